@@ -1,0 +1,87 @@
+"""ctypes binding of libparl_b200.so — the thin shim between PyTorch-held device
+memory and the C ABI declared in include/parl_b200.h.
+
+There is NO fallback: if the library is missing or a call fails, a RuntimeError
+is raised.  Tensors are passed as raw device pointers (``tensor.data_ptr()``) and
+the current torch CUDA stream as ``cudaStream_t``.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libparl_b200.so')
+
+_lib = None
+
+c_f = ctypes.c_float
+c_i = ctypes.c_int
+c_p = ctypes.c_void_p
+c_sz = ctypes.c_size_t
+c_u64 = ctypes.c_uint64
+c_u32 = ctypes.c_uint32
+c_i64 = ctypes.c_int64
+
+# name -> (restype, argtypes); must list every symbol include/parl_b200.h declares
+SIGNATURES = {
+    'rl_abi_version': (c_i, []),
+    'rl_last_error': (ctypes.c_char_p, []),
+    'rl_device_sm_count': (c_i, [c_i]),
+    'rl_loss_workspace_bytes': (c_sz, [c_i]),
+    'rl_vtrace_from_importance_weights': (c_i, [c_p] * 6 + [c_i, c_i, c_f, c_f, c_p, c_p, c_p]),
+    'rl_vtrace_loss_fwd_bwd': (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_i,
+                                     c_f, c_f, c_f, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    'rl_env_atari_synth_step': (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i,
+                                      c_i, c_i, c_u64, c_u32, c_u32, c_f, c_i, c_p]),
+    'rl_obs_stack_gather': (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p]),
+    'rl_env_mujoco_synth_step': (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i,
+                                       c_u64, c_u32, c_u32, c_f, c_i, c_p]),
+    'rl_env_cartpole_step': (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i,
+                                   c_u64, c_u32, c_u32, c_i, c_p]),
+    'rl_sample_categorical': (c_i, [c_p, c_i, c_i, c_u64, c_u32, c_u32, c_p, c_p, c_p]),
+    'rl_sample_gaussian': (c_i, [c_p, c_p, c_i, c_i, c_u64, c_u32, c_u32, c_p, c_p, c_p]),
+}
+
+
+def load():
+    """Load the shared library (building is a separate, explicit step)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            'parl_b200: CUDA library %s not found. Build it with `python -m parl_b200.build` '
+            '(there is no CPU fallback).' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().rl_last_error().decode()
+        raise RuntimeError('parl_b200.%s failed (code %d): %s' % (what, code, msg))
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('parl_b200 kernels need CUDA tensors (no CPU fallback); got a %s tensor' % t.device)
+        if t is not None and not t.is_contiguous():
+            raise RuntimeError('parl_b200 kernels need contiguous tensors')

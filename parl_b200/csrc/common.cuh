@@ -1,0 +1,58 @@
+// Shared device/host helpers for the parl_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/parl_b200.h"
+
+namespace rl {
+
+void set_error(const char* fmt, ...);
+
+#define RL_CHECK_ARG(cond, ...)            \
+  do {                                     \
+    if (!(cond)) {                         \
+      rl::set_error(__VA_ARGS__);          \
+      return RL_ERR_BAD_ARG;               \
+    }                                      \
+  } while (0)
+
+#define RL_CHECK_LAUNCH(name)                                              \
+  do {                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                  \
+    if (e__ != cudaSuccess) {                                              \
+      rl::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      return RL_ERR_CUDA;                                                  \
+    }                                                                      \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// streaming (evict-first) vector store / load for data touched exactly once
+__device__ __forceinline__ void st_cs_f4(float4* p, float4 v) { __stcs(p, v); }
+__device__ __forceinline__ float4 ld_cs_f4(const float4* p) { return __ldcs(p); }
+#endif
+
+}  // namespace rl

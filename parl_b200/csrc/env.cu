@@ -1,0 +1,459 @@
+// K5 / K7 — on-device vectorised actor pool: synthetic env steppers + action sampling.
+//
+// Replaces, for thousands of envs in lock-step, the reference's serial Python loop
+//   parl/env/vector_env.py:41-63      VectorEnv.step with auto-reset on done
+//   parl/tests/gym.py:117-207         mock CartPole / Pong / HalfCheetah distributions
+//   parl/env/atari_wrappers.py:270-307 FrameStack (reset fills all k slots)
+//   examples/IMPALA/atari_agent.py:39-40  per-row np.random.choice action sampling
+//   parl/algorithms/torch/ppo.py:164-177  Normal / Categorical sampling + log-prob
+// State is SoA in HBM ([B] arrays), frames are written once into a ring of
+// planes [P, B, H*W] uint8 (the 4-frame stack is virtual: age[t,b] says how many
+// older planes belong to the same episode), done masks are aggregated with
+// __ballot_sync for the episode statistics.
+// RNG contract: Philox4x32-10, counter (env_id, step, block, stream) — philox.cuh.
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace rl {
+
+struct EpisodeStats {
+  float* ep_ret;      // [B] running return
+  int* ep_len;        // [B] running length
+  float* totals;      // [4] completed episodes: count, sum return, sum length, (unused)
+  float* ring_ret;    // [ring_cap] most recent completed returns
+  int* ring_len;      // [ring_cap]
+  unsigned* ring_head;
+  int ring_cap;
+};
+
+// One warp-synchronous update of the episode bookkeeping for 32 envs.
+__device__ __forceinline__ void episode_update(const EpisodeStats& s, int b, bool valid, float reward, bool done) {
+  float ret = 0.f;
+  int len = 0;
+  if (valid) {
+    ret = s.ep_ret[b] + reward;
+    len = s.ep_len[b] + 1;
+    s.ep_ret[b] = done ? 0.f : ret;
+    s.ep_len[b] = done ? 0 : len;
+  }
+  const bool fin = valid && done;
+  const unsigned mask = __ballot_sync(0xffffffffu, fin);
+  if (mask == 0u) return;
+  const int lane = threadIdx.x & 31;
+  const float sret = warp_sum(fin ? ret : 0.f);
+  const float slen = warp_sum(fin ? (float)len : 0.f);
+  unsigned base = 0;
+  if (lane == 0) {
+    atomicAdd(s.totals + 0, (float)__popc(mask));
+    atomicAdd(s.totals + 1, sret);
+    atomicAdd(s.totals + 2, slen);
+    if (s.ring_cap > 0) base = atomicAdd(s.ring_head, (unsigned)__popc(mask));
+  }
+  if (s.ring_cap > 0) {
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (fin) {
+      const unsigned slot = (base + __popc(mask & ((1u << lane) - 1u))) % (unsigned)s.ring_cap;
+      s.ring_ret[slot] = ret;
+      s.ring_len[slot] = len;
+    }
+  }
+}
+
+// 16 pixels of frame n of env e: bytes of one Philox block mapped to U{0..254}.
+__device__ __forceinline__ uint4 frame_block(uint32_t env, uint32_t n, uint32_t blk, uint32_t k0, uint32_t k1) {
+  uint4 x = philox4x32_10(env, n, blk, STREAM_FRAME, k0, k1);
+  // per byte: max(b,1)-1  == (b*255)>>8  (parl/tests/gym.py:165 randint(0,255): high exclusive)
+  x.x = __vsub4(__vmaxu4(x.x, 0x01010101u), 0x01010101u);
+  x.y = __vsub4(__vmaxu4(x.y, 0x01010101u), 0x01010101u);
+  x.z = __vsub4(__vmaxu4(x.z, 0x01010101u), 0x01010101u);
+  x.w = __vsub4(__vmaxu4(x.w, 0x01010101u), 0x01010101u);
+  return x;
+}
+
+struct AtariStepArgs {
+  uint8_t* frame_out;       // [B, HW] plane receiving frame (step+1)
+  float* reward_out;        // [B]
+  uint8_t* done_out;        // [B]
+  const uint8_t* age_in;    // [B] (may be NULL on reset)
+  uint8_t* age_out;         // [B]
+  const float* logits;      // [B, A] or NULL
+  int* actions_out;         // [B] (written when logits != NULL)
+  EpisodeStats st;
+  int B, HW, A;
+  uint32_t k0, k1, step, env_offset, done_thr;
+  int reset;                // 1: only emit frame `step` and zero the state
+};
+
+__global__ void __launch_bounds__(256) atari_synth_step_kernel(const AtariStepArgs p) {
+  const int nblk = p.HW >> 4;
+  const long long total = (long long)p.B * nblk;
+  const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long gstride = (long long)gridDim.x * blockDim.x;
+  // ---- per-env scalars: reward, done, age, episode stats, (optional) action sampling ----
+  const int nwarp_env = (p.B + 31) >> 5;
+  if ((gtid >> 5) < nwarp_env) {
+    const int b = (int)gtid;
+    const bool valid = b < p.B;
+    if (p.reset) {
+      if (valid) {
+        p.age_out[b] = 0;
+        p.st.ep_ret[b] = 0.f;
+        p.st.ep_len[b] = 0;
+      }
+    } else {
+      float reward = 0.f;
+      bool done = false;
+      if (valid) {
+        const uint32_t env = p.env_offset + (uint32_t)b;
+        const uint4 x = philox4x32_10(env, p.step, 0u, STREAM_REWDONE, p.k0, p.k1);
+        reward = (float)(x.x & 1u);
+        done = x.y < p.done_thr;
+        p.reward_out[b] = reward;
+        p.done_out[b] = done ? 1 : 0;
+        const int age = p.age_in[b];
+        p.age_out[b] = done ? 0 : (uint8_t)min(age + 1, 3);
+        if (p.logits) {
+          const uint4 ua = philox4x32_10(env, p.step, 0u, STREAM_ACTION, p.k0, p.k1);
+          p.actions_out[b] = sample_categorical_exact(p.logits + (long long)b * p.A, p.A, u01_24(ua.x));
+        }
+      }
+      episode_update(p.st, b, valid, reward, done);
+    }
+  }
+  // ---- frame pixels: one 16-byte Philox block per thread, coalesced uint4 stores ----
+  const uint32_t n = p.reset ? p.step : p.step + 1u;
+  uint4* out = reinterpret_cast<uint4*>(p.frame_out);
+  for (long long i = gtid; i < total; i += gstride) {
+    const uint32_t b = (uint32_t)(i / nblk);
+    const uint32_t blk = (uint32_t)(i - (long long)b * nblk);
+    out[i] = frame_block(p.env_offset + b, n, blk, p.k0, p.k1);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Virtual frame stack -> materialised observations.
+// obs(t,b) channel j (0 = oldest) = plane[t + 3 - min(3 - j, age[t,b])].
+// ---------------------------------------------------------------------------
+template <typename OutT>
+__device__ __forceinline__ void store16(OutT* dst, uint4 v, float scale);
+template <>
+__device__ __forceinline__ void store16<uint8_t>(uint8_t* dst, uint4 v, float) {
+  *reinterpret_cast<uint4*>(dst) = v;
+}
+template <>
+__device__ __forceinline__ void store16<float>(float* dst, uint4 v, float scale) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float4 f;
+    f.x = (float)(w[k] & 0xffu) * scale;
+    f.y = (float)((w[k] >> 8) & 0xffu) * scale;
+    f.z = (float)((w[k] >> 16) & 0xffu) * scale;
+    f.w = (float)(w[k] >> 24) * scale;
+    reinterpret_cast<float4*>(dst)[k] = f;
+  }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) obs_stack_gather_kernel(const uint8_t* __restrict__ planes,
+                                                               const uint8_t* __restrict__ ages, int B, int HW,
+                                                               int t_begin, int t_count, int env_major, float scale,
+                                                               OutT* __restrict__ out) {
+  const int nblk = HW >> 4;
+  const long long total = (long long)t_count * B * 4 * nblk;
+  const long long gstride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gstride) {
+    const int blk = (int)(i % nblk);
+    long long r = i / nblk;
+    const int j = (int)(r & 3);
+    r >>= 2;                                   // sample index in output order
+    int t, b;
+    if (env_major) {
+      b = (int)(r / t_count), t = (int)(r - (long long)b * t_count);
+    } else {
+      t = (int)(r / B), b = (int)(r - (long long)t * B);
+    }
+    t += t_begin;
+    const int age = ages[(long long)t * B + b];
+    const int plane = t + 3 - min(3 - j, age);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(planes + ((long long)plane * B + b) * HW) + blk);
+    store16<OutT>(out + (r * 4 + j) * HW + (blk << 4), v, scale);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// MuJoCo-shaped synthetic env (obs N(0,1)^D) and CartPole physics: one lane per env.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float u_open(uint32_t x) { return ((float)(x >> 8) + 0.5f) * 5.9604644775390625e-08f; }
+
+__device__ __forceinline__ void gauss_block(uint32_t env, uint32_t n, uint32_t blk, uint32_t stream, uint32_t k0,
+                                            uint32_t k1, float z[4]) {
+  const uint4 x = philox4x32_10(env, n, blk, stream, k0, k1);
+  const float r0 = sqrtf(-2.0f * logf(u_open(x.x))), th0 = 6.283185307179586f * u_open(x.y);
+  const float r1 = sqrtf(-2.0f * logf(u_open(x.z))), th1 = 6.283185307179586f * u_open(x.w);
+  z[0] = r0 * cosf(th0), z[1] = r0 * sinf(th0), z[2] = r1 * cosf(th1), z[3] = r1 * sinf(th1);
+}
+
+struct VecStepArgs {
+  float* obs_out;           // [B, D]
+  float* reward_out;
+  uint8_t* done_out;
+  float* state;             // CartPole: [B,4] in/out
+  const void* actions;      // CartPole: [B] int32
+  EpisodeStats st;
+  int B, D, max_steps;
+  uint32_t k0, k1, step, env_offset, done_thr;
+  int reset;
+};
+
+__global__ void __launch_bounds__(128) mujoco_synth_step_kernel(const VecStepArgs p) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = b < p.B;
+  const uint32_t env = p.env_offset + (uint32_t)b;
+  float reward = 0.f;
+  bool done = false;
+  if (valid && !p.reset) {
+    const uint4 x = philox4x32_10(env, p.step, 0u, STREAM_REWDONE, p.k0, p.k1);
+    reward = (float)(x.x & 1u);
+    done = x.y < p.done_thr;
+    if (p.max_steps > 0 && p.st.ep_len[b] + 1 >= p.max_steps) done = true;
+    p.reward_out[b] = reward;
+    p.done_out[b] = done ? 1 : 0;
+  }
+  if (p.reset) {
+    if (valid) p.st.ep_ret[b] = 0.f, p.st.ep_len[b] = 0;
+  } else {
+    episode_update(p.st, b, valid, reward, done);
+  }
+  if (valid) {
+    const uint32_t n = p.reset ? p.step : p.step + 1u;
+    for (int blk = 0; blk * 4 < p.D; ++blk) {
+      float z[4];
+      gauss_block(env, n, (uint32_t)blk, STREAM_OBS, p.k0, p.k1, z);
+      for (int k = 0; k < 4 && blk * 4 + k < p.D; ++k) p.obs_out[(long long)b * p.D + blk * 4 + k] = z[k];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) cartpole_step_kernel(const VecStepArgs p) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = b < p.B;
+  const uint32_t env = p.env_offset + (uint32_t)b;
+  float reward = 0.f;
+  bool done = false;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid && !p.reset) {
+    s = reinterpret_cast<const float4*>(p.state)[b];
+    const int a = reinterpret_cast<const int*>(p.actions)[b];
+    // gym classic_control/cartpole.py constants (third party, restated: SURVEY.md §8c item 4)
+    const float force = a == 1 ? 10.0f : -10.0f;
+    const float total_mass = 1.1f, pml = 0.05f, tau = 0.02f;
+    const float c = cosf(s.z), sn = sinf(s.z);
+    const float temp = __fdiv_rn(__fadd_rn(force, __fmul_rn(__fmul_rn(__fmul_rn(pml, s.w), s.w), sn)), total_mass);
+    const float den = __fmul_rn(0.5f, __fsub_rn(1.3333334f, __fdiv_rn(__fmul_rn(__fmul_rn(0.1f, c), c), total_mass)));
+    const float thacc = __fdiv_rn(__fsub_rn(__fmul_rn(9.8f, sn), __fmul_rn(c, temp)), den);
+    const float xacc = __fsub_rn(temp, __fdiv_rn(__fmul_rn(__fmul_rn(pml, thacc), c), total_mass));
+    s.x = __fadd_rn(s.x, __fmul_rn(tau, s.y));
+    s.y = __fadd_rn(s.y, __fmul_rn(tau, xacc));
+    s.z = __fadd_rn(s.z, __fmul_rn(tau, s.w));
+    s.w = __fadd_rn(s.w, __fmul_rn(tau, thacc));
+    done = s.x < -2.4f || s.x > 2.4f || s.z < -0.20943951f || s.z > 0.20943951f;
+    reward = 1.0f;
+    if (p.max_steps > 0 && p.st.ep_len[b] + 1 >= p.max_steps) done = true;
+    p.reward_out[b] = reward;
+    p.done_out[b] = done ? 1 : 0;
+  }
+  if (p.reset) {
+    if (valid) p.st.ep_ret[b] = 0.f, p.st.ep_len[b] = 0;
+  } else {
+    episode_update(p.st, b, valid, reward, done);
+  }
+  if (valid) {
+    if (p.reset || done) {
+      const uint4 x = philox4x32_10(env, p.reset ? p.step : p.step + 1u, 0u, STREAM_OBS, p.k0, p.k1);
+      s.x = __fmul_rn(__fsub_rn(u01_24(x.x), 0.5f), 0.1f);
+      s.y = __fmul_rn(__fsub_rn(u01_24(x.y), 0.5f), 0.1f);
+      s.z = __fmul_rn(__fsub_rn(u01_24(x.z), 0.5f), 0.1f);
+      s.w = __fmul_rn(__fsub_rn(u01_24(x.w), 0.5f), 0.1f);
+    }
+    reinterpret_cast<float4*>(p.state)[b] = s;
+    reinterpret_cast<float4*>(p.obs_out)[b] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K7 standalone samplers.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) sample_categorical_kernel(const float* __restrict__ logits, int N, int A,
+                                                                 uint32_t k0, uint32_t k1, uint32_t step,
+                                                                 uint32_t env_offset, int* __restrict__ actions,
+                                                                 float* __restrict__ logp_out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= N) return;
+  const uint4 ua = philox4x32_10(env_offset + (uint32_t)b, step, 0u, STREAM_ACTION, k0, k1);
+  const float* row = logits + (long long)b * A;
+  const int a = sample_categorical_exact(row, A, u01_24(ua.x));
+  actions[b] = a;
+  if (logp_out) {
+    float m = row[0];
+    for (int j = 1; j < A; ++j) m = fmaxf(m, row[j]);
+    float S = 0.f;
+    for (int j = 0; j < A; ++j) S += expf(row[j] - m);
+    logp_out[b] = row[a] - m - logf(S);
+  }
+}
+
+// action = mean + exp(logstd) * z ; logp = sum_d [-(a-mu)^2/(2 s^2) - logstd - 0.5 log 2pi]  (ppo.py:164-169)
+__global__ void __launch_bounds__(128) sample_gaussian_kernel(const float* __restrict__ mean,
+                                                              const float* __restrict__ logstd, int N, int D,
+                                                              uint32_t k0, uint32_t k1, uint32_t step,
+                                                              uint32_t env_offset, float* __restrict__ action,
+                                                              float* __restrict__ logp_out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= N) return;
+  float lp = 0.f;
+  for (int blk = 0; blk * 4 < D; ++blk) {
+    float z[4];
+    gauss_block(env_offset + (uint32_t)b, step, (uint32_t)blk, STREAM_GAUSS, k0, k1, z);
+    for (int k = 0; k < 4 && blk * 4 + k < D; ++k) {
+      const int d = blk * 4 + k;
+      const float ls = logstd[d], sd = expf(ls);
+      const float a = fmaf(sd, z[k], mean[(long long)b * D + d]);
+      action[(long long)b * D + d] = a;
+      lp += -0.5f * z[k] * z[k] - ls - 0.9189385332046727f;
+    }
+  }
+  if (logp_out) logp_out[b] = lp;
+}
+
+static EpisodeStats make_stats(float* ep_ret, int* ep_len, float* totals, float* ring_ret, int* ring_len,
+                               unsigned* ring_head, int ring_cap) {
+  EpisodeStats s;
+  s.ep_ret = ep_ret, s.ep_len = ep_len, s.totals = totals, s.ring_ret = ring_ret, s.ring_len = ring_len;
+  s.ring_head = ring_head, s.ring_cap = (ring_ret && ring_len && ring_head) ? ring_cap : 0;
+  return s;
+}
+
+static uint32_t prob_thr(float p) {
+  double v = (double)p * 4294967296.0;
+  if (v < 0) v = 0;
+  if (v > 4294967295.0) v = 4294967295.0;
+  return (uint32_t)v;
+}
+
+}  // namespace rl
+
+using namespace rl;
+
+extern "C" int rl_env_atari_synth_step(uint8_t* frame_out, float* reward_out, uint8_t* done_out,
+                                       const uint8_t* age_in, uint8_t* age_out, const float* logits, int A,
+                                       int32_t* actions_out, float* ep_ret, int32_t* ep_len, float* totals,
+                                       float* ring_ret, int32_t* ring_len, uint32_t* ring_head, int ring_cap, int B,
+                                       int HW, uint64_t seed, uint32_t step, uint32_t env_offset, float p_done,
+                                       int reset, rl_stream_t stream) {
+  RL_CHECK_ARG(frame_out && age_out && ep_ret && ep_len && totals, "atari_synth_step: null pointer");
+  RL_CHECK_ARG(reset || (reward_out && done_out && age_in), "atari_synth_step: null pointer");
+  RL_CHECK_ARG(B > 0 && HW > 0 && HW % 16 == 0, "atari_synth_step: B=%d HW=%d (HW must be a multiple of 16)", B, HW);
+  RL_CHECK_ARG(aligned16(frame_out), "atari_synth_step: frame plane must be 16-byte aligned");
+  RL_CHECK_ARG(!logits || (A >= 1 && actions_out), "atari_synth_step: logits given but A=%d / actions_out null", A);
+  AtariStepArgs a;
+  a.frame_out = frame_out, a.reward_out = reward_out, a.done_out = done_out, a.age_in = age_in, a.age_out = age_out;
+  a.logits = logits, a.actions_out = actions_out, a.A = A;
+  a.st = make_stats(ep_ret, ep_len, totals, ring_ret, ring_len, ring_head, ring_cap);
+  a.B = B, a.HW = HW, a.k0 = (uint32_t)seed, a.k1 = (uint32_t)(seed >> 32), a.step = step, a.env_offset = env_offset;
+  a.done_thr = prob_thr(p_done), a.reset = reset;
+  const long long total = (long long)B * (HW / 16);
+  long long blocks = (total + 255) / 256;
+  const long long cap = 148LL * 8 * 4;      // 4 waves of 8 CTAs/SM, grid-stride beyond
+  if (blocks > cap) blocks = cap;
+  if (blocks < (B + 255) / 256) blocks = (B + 255) / 256;
+  atari_synth_step_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  RL_CHECK_LAUNCH("rl_env_atari_synth_step");
+  return RL_OK;
+}
+
+extern "C" int rl_obs_stack_gather(const uint8_t* planes, const uint8_t* ages, int B, int HW, int t_begin, int t_count,
+                                   int out_layout, int out_dtype, float scale, void* out, rl_stream_t stream) {
+  RL_CHECK_ARG(planes && ages && out, "obs_stack_gather: null pointer");
+  RL_CHECK_ARG(B > 0 && HW > 0 && HW % 16 == 0 && t_count > 0 && t_begin >= 0, "obs_stack_gather: bad shape");
+  RL_CHECK_ARG(aligned16(planes) && aligned16(out), "obs_stack_gather: 16-byte alignment required");
+  const long long total = (long long)t_count * B * 4 * (HW / 16);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  const int em = out_layout == RL_LAYOUT_ENV_MAJOR;
+  if (out_dtype == 0) {
+    obs_stack_gather_kernel<uint8_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        planes, ages, B, HW, t_begin, t_count, em, scale, (uint8_t*)out);
+  } else if (out_dtype == 1) {
+    obs_stack_gather_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        planes, ages, B, HW, t_begin, t_count, em, scale, (float*)out);
+  } else {
+    set_error("obs_stack_gather: out_dtype %d unsupported (0=u8, 1=f32)", out_dtype);
+    return RL_ERR_UNSUPPORTED;
+  }
+  RL_CHECK_LAUNCH("rl_obs_stack_gather");
+  return RL_OK;
+}
+
+static int vec_step(bool cartpole, float* obs_out, float* reward_out, uint8_t* done_out, float* state,
+                    const void* actions, float* ep_ret, int32_t* ep_len, float* totals, float* ring_ret,
+                    int32_t* ring_len, uint32_t* ring_head, int ring_cap, int B, int D, int max_steps, uint64_t seed,
+                    uint32_t step, uint32_t env_offset, float p_done, int reset, rl_stream_t stream) {
+  VecStepArgs a;
+  a.obs_out = obs_out, a.reward_out = reward_out, a.done_out = done_out, a.state = state, a.actions = actions;
+  a.st = make_stats(ep_ret, ep_len, totals, ring_ret, ring_len, ring_head, ring_cap);
+  a.B = B, a.D = D, a.max_steps = max_steps, a.k0 = (uint32_t)seed, a.k1 = (uint32_t)(seed >> 32);
+  a.step = step, a.env_offset = env_offset, a.done_thr = prob_thr(p_done), a.reset = reset;
+  const int blocks = (B + 127) / 128;
+  if (cartpole)
+    cartpole_step_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(a);
+  else
+    mujoco_synth_step_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(a);
+  return 0;
+}
+
+extern "C" int rl_env_mujoco_synth_step(float* obs_out, float* reward_out, uint8_t* done_out, float* ep_ret,
+                                        int32_t* ep_len, float* totals, float* ring_ret, int32_t* ring_len,
+                                        uint32_t* ring_head, int ring_cap, int B, int obs_dim, int max_episode_steps,
+                                        uint64_t seed, uint32_t step, uint32_t env_offset, float p_done, int reset,
+                                        rl_stream_t stream) {
+  RL_CHECK_ARG(obs_out && ep_ret && ep_len && totals && (reset || (reward_out && done_out)),
+               "mujoco_synth_step: null pointer");
+  RL_CHECK_ARG(B > 0 && obs_dim > 0, "mujoco_synth_step: bad shape");
+  vec_step(false, obs_out, reward_out, done_out, nullptr, nullptr, ep_ret, ep_len, totals, ring_ret, ring_len,
+           ring_head, ring_cap, B, obs_dim, max_episode_steps, seed, step, env_offset, p_done, reset, stream);
+  RL_CHECK_LAUNCH("rl_env_mujoco_synth_step");
+  return RL_OK;
+}
+
+extern "C" int rl_env_cartpole_step(float* state, float* obs_out, float* reward_out, uint8_t* done_out,
+                                    const int32_t* actions, float* ep_ret, int32_t* ep_len, float* totals,
+                                    float* ring_ret, int32_t* ring_len, uint32_t* ring_head, int ring_cap, int B,
+                                    int max_episode_steps, uint64_t seed, uint32_t step, uint32_t env_offset, int reset,
+                                    rl_stream_t stream) {
+  RL_CHECK_ARG(state && obs_out && ep_ret && ep_len && totals && (reset || (reward_out && done_out && actions)),
+               "cartpole_step: null pointer");
+  RL_CHECK_ARG(B > 0 && aligned16(state) && aligned16(obs_out), "cartpole_step: bad shape / alignment");
+  vec_step(true, obs_out, reward_out, done_out, state, actions, ep_ret, ep_len, totals, ring_ret, ring_len, ring_head,
+           ring_cap, B, 4, max_episode_steps, seed, step, env_offset, 0.f, reset, stream);
+  RL_CHECK_LAUNCH("rl_env_cartpole_step");
+  return RL_OK;
+}
+
+extern "C" int rl_sample_categorical(const float* logits, int N, int A, uint64_t seed, uint32_t step,
+                                     uint32_t env_offset, int32_t* actions, float* logp_out, rl_stream_t stream) {
+  RL_CHECK_ARG(logits && actions && N > 0 && A > 0, "sample_categorical: bad argument");
+  sample_categorical_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      logits, N, A, (uint32_t)seed, (uint32_t)(seed >> 32), step, env_offset, actions, logp_out);
+  RL_CHECK_LAUNCH("rl_sample_categorical");
+  return RL_OK;
+}
+
+extern "C" int rl_sample_gaussian(const float* mean, const float* logstd, int N, int D, uint64_t seed, uint32_t step,
+                                  uint32_t env_offset, float* action, float* logp_out, rl_stream_t stream) {
+  RL_CHECK_ARG(mean && logstd && action && N > 0 && D > 0, "sample_gaussian: bad argument");
+  sample_gaussian_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      mean, logstd, N, D, (uint32_t)seed, (uint32_t)(seed >> 32), step, env_offset, action, logp_out);
+  RL_CHECK_LAUNCH("rl_sample_gaussian");
+  return RL_OK;
+}
