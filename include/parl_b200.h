@@ -155,6 +155,92 @@ int rl_sample_gaussian(
     const float* mean, const float* logstd, int N, int D, uint64_t seed, uint32_t step, uint32_t env_offset,
     float* action, float* logp_out, rl_stream_t stream);
 
+/* Scratch for the flat (scan-free) loss kernels below: n_rows elements, `extra`
+ * additional per-CTA partial columns (PPO-Gaussian: D).  Zeroed once by the caller. */
+size_t rl_flat_workspace_bytes(long long n_rows, int extra);
+
+/* ------------------------------------------------------------------------
+ * a4  A2C loss + gradient.  Replaces parl/algorithms/torch/a2c.py:40-60
+ * (post-network part of A2C.learn; SUM reductions).
+ *   logits [N,A] f32, values [N], actions [N] i32/i64, advantages [N], target_values [N]
+ *   losses [4] = {total, pi_loss, vf_loss, entropy};  d_logits [N,A], d_values [N]
+ * ---------------------------------------------------------------------- */
+int rl_a2c_loss_fwd_bwd(
+    const float* logits, const float* values, const void* actions, int actions_i64,
+    const float* advantages, const float* target_values, long long N, int A,
+    float vf_loss_coeff, float entropy_coeff,
+    float* losses, float* d_logits, float* d_values,
+    void* workspace, size_t workspace_bytes, rl_stream_t stream);
+
+/* a5  Segment GAE of the A2C actor on a (T,B) rollout, float64 arithmetic.
+ * Replaces parl/utils/rl_utils.py:34-51 (calc_gae via scipy.signal.lfilter) as driven by
+ * benchmark/torch/a2c/actor.py:82-102: a segment ends at dones[t]==1 (next value 0) or at
+ * the rollout end (next value = bootstrap_value[b] = V(next_obs)).  Time-major [T,B]. */
+int rl_gae_scan_segments(
+    const float* rewards, const float* values, const uint8_t* dones, const float* bootstrap_value,
+    int T, int B, double gamma, double lam, float* advantages, float* target_values, rl_stream_t stream);
+
+/* a6  PPO GAE.  Replaces benchmark/torch/ppo/storage.py:45-64
+ * (RolloutStorage.compute_returns; float32, bit-exact operation order).  dones[t] is the
+ * done flag observed BEFORE step t (float32 0/1); last_value/last_done [B]. */
+int rl_gae_scan(
+    const float* rewards, const float* values, const float* dones,
+    const float* last_value, const float* last_done, int T, int B,
+    float gamma, float gae_lambda, float* advantages, float* returns, rl_stream_t stream);
+
+/* a7  PPO clipped-surrogate loss + gradient.  Replaces parl/algorithms/torch/ppo.py:102-138.
+ * Pass exactly one of `logits` [N,A] (Categorical, actions i32/i64) or `mean` [N,D] with
+ * `logstd` [D] (Normal(mean, exp(logstd)), actions = float32 [N,D]).
+ *   adv_stats : device {mean, 1/(unbiased std + 1e-8)} from rl_adv_stats (norm_adv=True),
+ *               or NULL (norm_adv=False).  Multi-GPU callers all-reduce the moments instead.
+ *   losses [4] = {value_loss, action_loss, entropy_loss, total}  (MEAN reductions)
+ *   d_logits_or_mean [N,A|D], d_logstd [D] (Gaussian only), d_values [N] */
+int rl_adv_stats(const float* adv, long long N, float* stats, rl_stream_t stream);
+int rl_ppo_loss_fwd_bwd(
+    const float* logits, const float* mean, const float* logstd, const void* actions, int actions_i64,
+    const float* values, const float* batch_value, const float* batch_return,
+    const float* batch_logprob, const float* batch_adv, const float* adv_stats,
+    long long N, int A_or_D, float clip_param, float value_loss_coef, float entropy_coef,
+    int use_clipped_value_loss,
+    float* losses, float* d_logits_or_mean, float* d_logstd, float* d_values,
+    void* workspace, size_t workspace_bytes, rl_stream_t stream);
+
+/* a8  TD target + (weighted) MSE loss + gradient.  Replaces parl/algorithms/torch/dqn.py:64-69;
+ * with q_online_next != NULL parl/algorithms/torch/ddqn.py:64-72; with weights != NULL the
+ * PER variant benchmark/fluid/Prioritized_DQN/per_alg.py:48-69 (td_abs = |target - Q(s,a)|).
+ *   q, q_target_next, q_online_next [M,A]; action [M]; reward, terminal (f32 0/1) [M]
+ *   losses [1] = mean loss; d_q [M,A]; td_abs [M] or NULL */
+int rl_td_loss_fwd_bwd(
+    const float* q, const float* q_target_next, const float* q_online_next,
+    const void* action, int action_i64, const float* reward, const float* terminal, const float* weights,
+    long long M, int A, float gamma, float* losses, float* d_q, float* td_abs,
+    void* workspace, size_t workspace_bytes, rl_stream_t stream);
+
+/* REINFORCE on probabilities.  Replaces parl/algorithms/torch/policy_gradient.py:54-75. */
+int rl_pg_loss_fwd_bwd(
+    const float* prob, const void* action, int action_i64, const float* reward, long long N, int A,
+    float* losses, float* d_prob, void* workspace, size_t workspace_bytes, rl_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * a9  HBM-resident replay.  Replaces benchmark/fluid/Prioritized_DQN/proportional_per.py:18-157
+ * (SumTree + ProportionalPER), benchmark/torch/dqn/replay_memory.py:59-113 (frame-context
+ * sampling) and parl/utils/replay_memory.py:51-95 (gather by index).
+ *   tree  : double[2*capacity-1], reference heap indexing (leaf i at capacity-1+i), zero-initialised
+ *   state : double[2] = {_min (init 10.0), _max_priority (init 1.0)}
+ * ---------------------------------------------------------------------- */
+int rl_per_store(double* tree, double* state, int capacity, int write_pos, int n, const float* delta,
+                 double alpha, double eps, rl_stream_t stream);
+int rl_per_update(double* tree, double* state, int capacity, const int32_t* tree_idx, const float* priorities,
+                  int n, double alpha, double eps, rl_stream_t stream);
+/* Stratified sample of seg_num leaves.  u [seg_num] float32 in [0,1) or NULL (Philox(seed, draw)).
+ * weights = (size*p/total / (size*_min/total))^-beta. */
+int rl_per_sample(const double* tree, const double* state, int capacity, int seg_num, const float* u,
+                  uint64_t seed, uint32_t draw, double beta, double size,
+                  int32_t* tree_idx, int32_t* elem_idx, float* weights, rl_stream_t stream);
+int rl_replay_gather_frames(const uint8_t* frames, const uint8_t* is_over, const int32_t* idx, int n,
+                            int curr_size, int context_len, int HW, uint8_t* out, rl_stream_t stream);
+int rl_gather_rows(const void* src, const int32_t* idx, long long n, int row_bytes, void* out, rl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,23 @@ SIGNATURES = {
                                    c_u64, c_u32, c_u32, c_i, c_p]),
     'rl_sample_categorical': (c_i, [c_p, c_i, c_i, c_u64, c_u32, c_u32, c_p, c_p, c_p]),
     'rl_sample_gaussian': (c_i, [c_p, c_p, c_i, c_i, c_u64, c_u32, c_u32, c_p, c_p, c_p]),
+    'rl_flat_workspace_bytes': (c_sz, [ctypes.c_longlong, c_i]),
+    'rl_a2c_loss_fwd_bwd': (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, ctypes.c_longlong, c_i, c_f, c_f, c_p, c_p, c_p,
+                                  c_p, c_sz, c_p]),
+    'rl_gae_scan_segments': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, ctypes.c_double, ctypes.c_double, c_p, c_p, c_p]),
+    'rl_gae_scan': (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_f, c_f, c_p, c_p, c_p]),
+    'rl_adv_stats': (c_i, [c_p, ctypes.c_longlong, c_p, c_p]),
+    'rl_ppo_loss_fwd_bwd': (c_i, [c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, ctypes.c_longlong, c_i,
+                                  c_f, c_f, c_f, c_i, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    'rl_td_loss_fwd_bwd': (c_i, [c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, ctypes.c_longlong, c_i, c_f, c_p, c_p,
+                                 c_p, c_p, c_sz, c_p]),
+    'rl_pg_loss_fwd_bwd': (c_i, [c_p, c_p, c_i, c_p, ctypes.c_longlong, c_i, c_p, c_p, c_p, c_sz, c_p]),
+    'rl_per_store': (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, ctypes.c_double, ctypes.c_double, c_p]),
+    'rl_per_update': (c_i, [c_p, c_p, c_i, c_p, c_p, c_i, ctypes.c_double, ctypes.c_double, c_p]),
+    'rl_per_sample': (c_i, [c_p, c_p, c_i, c_i, c_p, c_u64, c_u32, ctypes.c_double, ctypes.c_double, c_p, c_p,
+                            c_p, c_p]),
+    'rl_replay_gather_frames': (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
+    'rl_gather_rows': (c_i, [c_p, c_p, ctypes.c_longlong, c_i, c_p, c_p]),
 }
 
 

@@ -157,3 +157,177 @@ def sample_gaussian(mean, logstd, seed, step, env_offset=0):
     check(_lib.load().rl_sample_gaussian(ptr(mean), ptr(logstd), N, D, int(seed), int(step), int(env_offset),
                                          ptr(action), ptr(logp), stream()), 'sample_gaussian')
     return action, logp
+
+
+# --------------------------------------------------------------------------- flat losses / scans
+def _flat_ws(device, n_rows, extra=0):
+    need = _lib.load().rl_flat_workspace_bytes(int(n_rows), int(extra))
+    key = ('flat', device.index if device.index is not None else torch.cuda.current_device())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _act_flag(actions):
+    assert actions.dtype in (torch.int32, torch.int64)
+    return 1 if actions.dtype == torch.int64 else 0
+
+
+def a2c_loss_fwd_bwd(logits, values, actions, advantages, target_values, vf_loss_coeff, entropy_coeff):
+    """parl/algorithms/torch/a2c.py:40-60 -> dict(losses[4]={total,pi,vf,entropy}, d_logits, d_values)."""
+    require_cuda(logits, values, actions, advantages, target_values)
+    N, A = logits.shape
+    dev = logits.device
+    losses = torch.empty(4, dtype=torch.float32, device=dev)
+    d_logits, d_values = torch.empty_like(logits), torch.empty_like(values)
+    ws = _flat_ws(dev, N)
+    check(_lib.load().rl_a2c_loss_fwd_bwd(ptr(logits), ptr(values), ptr(actions), _act_flag(actions), ptr(advantages),
+                                          ptr(target_values), N, A, float(vf_loss_coeff), float(entropy_coeff),
+                                          ptr(losses), ptr(d_logits), ptr(d_values), ptr(ws), ws.numel(), stream()),
+          'a2c_loss_fwd_bwd')
+    return dict(losses=losses, d_logits=d_logits, d_values=d_values)
+
+
+def gae_scan_segments(rewards, values, dones, bootstrap_value, gamma, lam):
+    """calc_gae per episode segment (rl_utils.py:34-51, a2c/actor.py:82-102) on [T,B] -> (adv, target_values)."""
+    require_cuda(rewards, values, dones, bootstrap_value)
+    if dones.dtype == torch.bool:
+        dones = dones.view(torch.uint8)
+    T, B = rewards.shape
+    adv, tv = torch.empty_like(rewards), torch.empty_like(rewards)
+    check(_lib.load().rl_gae_scan_segments(ptr(rewards), ptr(values), ptr(dones), ptr(bootstrap_value), T, B,
+                                           float(gamma), float(lam), ptr(adv), ptr(tv), stream()), 'gae_scan_segments')
+    return adv, tv
+
+
+def gae_scan(rewards, values, dones, last_value, last_done, gamma=0.99, gae_lambda=0.95):
+    """RolloutStorage.compute_returns (benchmark/torch/ppo/storage.py:45-64) -> (advantages, returns)."""
+    require_cuda(rewards, values, dones, last_value, last_done)
+    T, B = rewards.shape
+    adv, ret = torch.empty_like(rewards), torch.empty_like(rewards)
+    check(_lib.load().rl_gae_scan(ptr(rewards), ptr(values), ptr(dones), ptr(last_value), ptr(last_done), T, B,
+                                  float(gamma), float(gae_lambda), ptr(adv), ptr(ret), stream()), 'gae_scan')
+    return adv, ret
+
+
+def adv_stats(adv):
+    require_cuda(adv)
+    stats = torch.empty(2, dtype=torch.float32, device=adv.device)
+    check(_lib.load().rl_adv_stats(ptr(adv), adv.numel(), ptr(stats), stream()), 'adv_stats')
+    return stats
+
+
+def ppo_loss_fwd_bwd(values, batch_action, batch_value, batch_return, batch_logprob, batch_adv, logits=None,
+                     mean=None, logstd=None, clip_param=0.1, value_loss_coef=0.5, entropy_coef=0.01,
+                     use_clipped_value_loss=True, norm_adv=True, stats=None):
+    """parl/algorithms/torch/ppo.py:102-138 -> dict(losses[4]={value,action,entropy,total}, d_values, d_logits|d_mean,d_logstd)."""
+    require_cuda(values, batch_action, batch_value, batch_return, batch_logprob, batch_adv, logits, mean, logstd)
+    dev = values.device
+    N = values.numel()
+    if norm_adv and stats is None:
+        stats = adv_stats(batch_adv)
+    if not norm_adv:
+        stats = None
+    losses = torch.empty(4, dtype=torch.float32, device=dev)
+    d_values = torch.empty_like(values)
+    if logits is not None:
+        AD = logits.shape[-1]
+        d_main, d_ls, flag = torch.empty_like(logits), None, _act_flag(batch_action)
+    else:
+        AD = mean.shape[-1]
+        assert batch_action.dtype == torch.float32
+        d_main, d_ls, flag = torch.empty_like(mean), torch.empty_like(logstd), 0
+    ws = _flat_ws(dev, N, AD)
+    check(_lib.load().rl_ppo_loss_fwd_bwd(
+        ptr(logits), ptr(mean), ptr(logstd), ptr(batch_action), flag, ptr(values), ptr(batch_value), ptr(batch_return),
+        ptr(batch_logprob), ptr(batch_adv), ptr(stats), N, AD, float(clip_param), float(value_loss_coef),
+        float(entropy_coef), 1 if use_clipped_value_loss else 0, ptr(losses), ptr(d_main), ptr(d_ls), ptr(d_values),
+        ptr(ws), ws.numel(), stream()), 'ppo_loss_fwd_bwd')
+    out = dict(losses=losses, d_values=d_values)
+    if logits is not None:
+        out['d_logits'] = d_main
+    else:
+        out['d_mean'], out['d_logstd'] = d_main, d_ls
+    return out
+
+
+def td_loss_fwd_bwd(q, q_target_next, action, reward, terminal, gamma, q_online_next=None, weights=None,
+                    want_td_abs=False):
+    """dqn.py:64-69 / ddqn.py:64-72 / per_alg.py:48-69 -> dict(losses[1], d_q, td_abs)."""
+    require_cuda(q, q_target_next, action, reward, terminal, q_online_next, weights)
+    M, A = q.shape
+    dev = q.device
+    losses = torch.empty(1, dtype=torch.float32, device=dev)
+    d_q = torch.empty_like(q)
+    td = torch.empty(M, dtype=torch.float32, device=dev) if want_td_abs else None
+    ws = _flat_ws(dev, M)
+    check(_lib.load().rl_td_loss_fwd_bwd(ptr(q), ptr(q_target_next), ptr(q_online_next), ptr(action), _act_flag(action),
+                                         ptr(reward), ptr(terminal), ptr(weights), M, A, float(gamma), ptr(losses),
+                                         ptr(d_q), ptr(td), ptr(ws), ws.numel(), stream()), 'td_loss_fwd_bwd')
+    return dict(losses=losses, d_q=d_q, td_abs=td)
+
+
+def pg_loss_fwd_bwd(prob, action, reward):
+    """policy_gradient.py:54-75 -> dict(losses[1], d_prob)."""
+    require_cuda(prob, action, reward)
+    N, A = prob.shape
+    losses = torch.empty(1, dtype=torch.float32, device=prob.device)
+    d_prob = torch.empty_like(prob)
+    ws = _flat_ws(prob.device, N)
+    check(_lib.load().rl_pg_loss_fwd_bwd(ptr(prob), ptr(action), _act_flag(action), ptr(reward), N, A, ptr(losses),
+                                         ptr(d_prob), ptr(ws), ws.numel(), stream()), 'pg_loss_fwd_bwd')
+    return dict(losses=losses, d_prob=d_prob)
+
+
+# --------------------------------------------------------------------------- replay
+class DeviceSumTree(object):
+    """fp64 sum-tree in HBM with the reference's heap indexing (proportional_per.py:18-70)."""
+
+    def __init__(self, capacity, device):
+        self.capacity = int(capacity)
+        self.tree = torch.zeros(2 * self.capacity - 1, dtype=torch.float64, device=device)
+        self.state = torch.tensor([10.0, 1.0], dtype=torch.float64, device=device)   # _min, _max_priority
+
+    def store(self, write_pos, n, alpha, eps, delta=None):
+        check(_lib.load().rl_per_store(ptr(self.tree), ptr(self.state), self.capacity, int(write_pos), int(n),
+                                       ptr(delta), float(alpha), float(eps), stream()), 'per_store')
+
+    def update(self, tree_idx, priorities, alpha, eps):
+        assert tree_idx.dtype == torch.int32 and priorities.dtype == torch.float32
+        check(_lib.load().rl_per_update(ptr(self.tree), ptr(self.state), self.capacity, ptr(tree_idx), ptr(priorities),
+                                        tree_idx.numel(), float(alpha), float(eps), stream()), 'per_update')
+
+    def sample(self, seg_num, beta, size, u=None, seed=0, draw=0):
+        dev = self.tree.device
+        tidx = torch.empty(seg_num, dtype=torch.int32, device=dev)
+        eidx = torch.empty(seg_num, dtype=torch.int32, device=dev)
+        w = torch.empty(seg_num, dtype=torch.float32, device=dev)
+        check(_lib.load().rl_per_sample(ptr(self.tree), ptr(self.state), self.capacity, int(seg_num), ptr(u), int(seed),
+                                        int(draw), float(beta), float(size), ptr(tidx), ptr(eidx), ptr(w), stream()),
+              'per_sample')
+        return tidx, eidx, w
+
+
+def replay_gather_frames(frames, is_over, idx, curr_size, context_len):
+    """benchmark/torch/dqn/replay_memory.py:59-85 for a batch of start indices -> [n, ctx+1, HW] uint8."""
+    require_cuda(frames, is_over, idx)
+    HW = frames[0].numel()
+    n = idx.numel()
+    out = torch.empty((n, context_len + 1, HW), dtype=torch.uint8, device=frames.device)
+    if is_over.dtype == torch.bool:
+        is_over = is_over.view(torch.uint8)
+    check(_lib.load().rl_replay_gather_frames(ptr(frames), ptr(is_over), ptr(idx), n, int(curr_size), int(context_len),
+                                              HW, ptr(out), stream()), 'replay_gather_frames')
+    return out
+
+
+def gather_rows(src, idx):
+    """out[i] = src[idx[i]] for a 2-D (or N-D, row-contiguous) tensor with 4-byte-multiple rows."""
+    require_cuda(src, idx)
+    assert idx.dtype == torch.int32
+    row_bytes = src[0].numel() * src.element_size()
+    out = torch.empty((idx.numel(), ) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    check(_lib.load().rl_gather_rows(ptr(src), ptr(idx), idx.numel(), row_bytes, ptr(out), stream()), 'gather_rows')
+    return out
