@@ -49,6 +49,10 @@ int rl_device_sm_count(int device);
  * The caller zeroes it ONCE (cudaMemset / torch.zeros); kernels leave it zeroed. */
 size_t rl_loss_workspace_bytes(int n_cols);
 
+/* Triage hook: 1 forces the cp.async tile path of rl_vtrace_loss_fwd_bwd, 0 (default) lets the
+ * TMA tensor-map path run when the layout allows it. */
+int rl_debug_set_tma(int disable);
+
 /* ------------------------------------------------------------------------
  * a1  V-trace returns.
  * Replaces parl/algorithms/paddle/impala/vtrace.py:36-139
@@ -110,14 +114,16 @@ int rl_vtrace_loss_fwd_bwd(
  * step `step`, and age_out = done ? 0 : min(age_in+1, 3) (frames of the virtual
  * 4-stack that belong to the current episode).  If `logits` != NULL also samples
  * actions_out[b] ~ Categorical(logits[b,:A]) with the exact inverse-CDF rule.
- * reset=1: only emit frame `step` into frame_out and zero age/episode state. */
+ * reset=1: only emit frame `step` into frame_out and zero age/episode state.
+ * step_dev: optional device-resident step index overriding `step` (lets a captured CUDA graph of
+ * a whole rollout be replayed with advancing counters). */
 int rl_env_atari_synth_step(
     uint8_t* frame_out, float* reward_out, uint8_t* done_out,
     const uint8_t* age_in, uint8_t* age_out,
     const float* logits, int A, int32_t* actions_out,
     float* ep_ret, int32_t* ep_len, float* totals,
     float* ring_ret, int32_t* ring_len, uint32_t* ring_head, int ring_cap,
-    int B, int HW, uint64_t seed, uint32_t step, uint32_t env_offset, float p_done,
+    int B, int HW, uint64_t seed, uint32_t step, const uint32_t* step_dev, uint32_t env_offset, float p_done,
     int reset, rl_stream_t stream);
 
 /* Materialise observations from the frame ring: obs(t,b) channel j (0 = oldest)
@@ -240,6 +246,24 @@ int rl_per_sample(const double* tree, const double* state, int capacity, int seg
 int rl_replay_gather_frames(const uint8_t* frames, const uint8_t* is_over, const int32_t* idx, int n,
                             int curr_size, int context_len, int HW, uint8_t* out, rl_stream_t stream);
 int rl_gather_rows(const void* src, const int32_t* idx, long long n, int row_bytes, void* out, rl_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Learner update on a flat parameter buffer (global-norm clip + Adam), no host sync.
+ * Replaces the optimizer calls of the reference learners:
+ *   parl/algorithms/paddle/impala/impala.py:113-117,210-213 (ClipGradByGlobalNorm(40) + Adam),
+ *   parl/algorithms/torch/a2c.py:65-69 / ppo.py:144-147 (clip_grad_norm_ + Adam), dqn.py:68-71.
+ * rl_grad_global_norm: out_norm[0] = ||grad||_2 (deterministic).  workspace >= 256+4*1184 B, zeroed once.
+ * rl_adam_step: grad is first divided by grad_div (e.g. world size for MEAN losses), then scaled by
+ *   clip_mode 0: 1 ; 1 (torch): min(1, max_norm/(norm+1e-6)) ; 2 (paddle): max_norm/max(norm, max_norm)
+ *   where norm = grad_norm[0]/grad_div; lr from lr_device[0] if non-NULL else `lr`;
+ *   step = 1-based update count (bias correction); zero_grad=1 clears grad in the same pass.
+ * ---------------------------------------------------------------------- */
+int rl_grad_global_norm(const float* grad, long long n, float* out_norm, void* workspace, size_t workspace_bytes,
+                        rl_stream_t stream);
+int rl_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                 const float* lr_device, float lr, float beta1, float beta2, float eps, int step,
+                 float grad_div, const float* grad_norm, float max_norm, int clip_mode, int zero_grad,
+                 rl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -29,11 +29,12 @@ SIGNATURES = {
     'rl_last_error': (ctypes.c_char_p, []),
     'rl_device_sm_count': (c_i, [c_i]),
     'rl_loss_workspace_bytes': (c_sz, [c_i]),
+    'rl_debug_set_tma': (c_i, [c_i]),
     'rl_vtrace_from_importance_weights': (c_i, [c_p] * 6 + [c_i, c_i, c_f, c_f, c_p, c_p, c_p]),
     'rl_vtrace_loss_fwd_bwd': (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_i,
                                      c_f, c_f, c_f, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
     'rl_env_atari_synth_step': (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i,
-                                      c_i, c_i, c_u64, c_u32, c_u32, c_f, c_i, c_p]),
+                                      c_i, c_i, c_u64, c_u32, c_p, c_u32, c_f, c_i, c_p]),
     'rl_obs_stack_gather': (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p]),
     'rl_env_mujoco_synth_step': (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i,
                                        c_u64, c_u32, c_u32, c_f, c_i, c_p]),
@@ -58,6 +59,9 @@ SIGNATURES = {
                             c_p, c_p]),
     'rl_replay_gather_frames': (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
     'rl_gather_rows': (c_i, [c_p, c_p, ctypes.c_longlong, c_i, c_p, c_p]),
+    'rl_grad_global_norm': (c_i, [c_p, ctypes.c_longlong, c_p, c_p, c_sz, c_p]),
+    'rl_adam_step': (c_i, [c_p, c_p, c_p, c_p, ctypes.c_longlong, c_p, c_f, c_f, c_f, c_f, c_i, c_f, c_p, c_f, c_i,
+                           c_i, c_p]),
 }
 
 

@@ -81,10 +81,12 @@ struct AtariStepArgs {
   EpisodeStats st;
   int B, HW, A;
   uint32_t k0, k1, step, env_offset, done_thr;
+  const uint32_t* step_dev; // if non-NULL the step index is read from device memory (CUDA-graph replay)
   int reset;                // 1: only emit frame `step` and zero the state
 };
 
-__global__ void __launch_bounds__(256) atari_synth_step_kernel(const AtariStepArgs p) {
+__global__ void __launch_bounds__(256) atari_synth_step_kernel(AtariStepArgs p) {
+  if (p.step_dev) p.step = *p.step_dev;
   const int nblk = p.HW >> 4;
   const long long total = (long long)p.B * nblk;
   const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -349,8 +351,8 @@ extern "C" int rl_env_atari_synth_step(uint8_t* frame_out, float* reward_out, ui
                                        const uint8_t* age_in, uint8_t* age_out, const float* logits, int A,
                                        int32_t* actions_out, float* ep_ret, int32_t* ep_len, float* totals,
                                        float* ring_ret, int32_t* ring_len, uint32_t* ring_head, int ring_cap, int B,
-                                       int HW, uint64_t seed, uint32_t step, uint32_t env_offset, float p_done,
-                                       int reset, rl_stream_t stream) {
+                                       int HW, uint64_t seed, uint32_t step, const uint32_t* step_dev,
+                                       uint32_t env_offset, float p_done, int reset, rl_stream_t stream) {
   RL_CHECK_ARG(frame_out && age_out && ep_ret && ep_len && totals, "atari_synth_step: null pointer");
   RL_CHECK_ARG(reset || (reward_out && done_out && age_in), "atari_synth_step: null pointer");
   RL_CHECK_ARG(B > 0 && HW > 0 && HW % 16 == 0, "atari_synth_step: B=%d HW=%d (HW must be a multiple of 16)", B, HW);
@@ -361,7 +363,7 @@ extern "C" int rl_env_atari_synth_step(uint8_t* frame_out, float* reward_out, ui
   a.logits = logits, a.actions_out = actions_out, a.A = A;
   a.st = make_stats(ep_ret, ep_len, totals, ring_ret, ring_len, ring_head, ring_cap);
   a.B = B, a.HW = HW, a.k0 = (uint32_t)seed, a.k1 = (uint32_t)(seed >> 32), a.step = step, a.env_offset = env_offset;
-  a.done_thr = prob_thr(p_done), a.reset = reset;
+  a.done_thr = prob_thr(p_done), a.reset = reset, a.step_dev = step_dev;
   const long long total = (long long)B * (HW / 16);
   long long blocks = (total + 255) / 256;
   const long long cap = 148LL * 8 * 4;      // 4 waves of 8 CTAs/SM, grid-stride beyond

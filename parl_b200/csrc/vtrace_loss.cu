@@ -16,8 +16,10 @@
 // is written back from shared memory with 16-byte coalesced stores.
 // Algorithmic traffic: (12A+17) bytes per kept (t,b) element.
 #include <stdarg.h>
+#include <string.h>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace rl {
 
@@ -44,136 +46,176 @@ struct VtraceLossArgs {
   float gamma, clip_rho, clip_pg, vf_coeff, ent_coeff;
 };
 
+// All index arithmetic is 32-bit (the host rejects T*B*A >= 2^31) and division-free:
+// element i of a chunk is (t_local, b_local) = (i >> 2, i & 3) for both layouts.
 template <bool EM>
-__device__ __forceinline__ long long gidx(int t, int b, int T, int B) {
-  return EM ? (long long)b * T + t : (long long)t * B + b;
+__device__ __forceinline__ int gidx(int t, int b, int T, int B) {
+  return EM ? b * T + t : t * B + b;
 }
 template <bool EM>
 __device__ __forceinline__ int sidx(int tl, int bl, int TC) {
   return EM ? bl * TC + tl : tl * kBW + bl;
 }
 
-// global <-> shared tile copy.  TM: nt row segments of nb*A floats; EM: nb column
-// segments of nt*A floats.  `to_smem` selects direction.
+// global <-> shared tile copy, one segment per warp iteration, lanes stride the segment.
+//   TM: nt row segments of nb*A floats (smem stride kBW*A);  EM: nb column segments of nt*A floats (stride TC*A).
 template <bool EM, bool TO_SMEM>
 __device__ __forceinline__ void copy_tile(float* s, const float* gsrc, float* gdst, int A, int T, int B, int TC,
                                           int t0, int nt, int b0, int nb, bool vec) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nseg = EM ? nb : nt;
   const int seglen = (EM ? nt : nb) * A;           // floats
-  const int sstride = (EM ? TC : kBW) * A;         // floats between segments in smem
-  if (vec) {
-    const int segv = seglen >> 2;
-    const int total = nseg * segv;
-    for (int i = threadIdx.x; i < total; i += kNT) {
-      const int sg = i / segv, k = i - sg * segv;
-      const long long goff = (EM ? ((long long)(b0 + sg) * T + t0) : ((long long)(t0 + sg) * B + b0)) * A + 4 * k;
-      float* sp = s + sg * sstride + 4 * k;
-      if (TO_SMEM) {
-        cp_async16(sp, gsrc + goff);
-      } else {
-        *reinterpret_cast<float4*>(gdst + goff) = *reinterpret_cast<const float4*>(sp);
+  const int sstride = (EM ? TC : kBW) * A;
+  const int gstride = (EM ? T : B) * A;            // floats between consecutive segments in global memory
+  int goff = (EM ? (b0 * T + t0) : (t0 * B + b0)) * A + warp * gstride;
+  float* sp = s + warp * sstride;
+  for (int sg = warp; sg < nseg; sg += kNT / 32, goff += (kNT / 32) * gstride, sp += (kNT / 32) * sstride) {
+    if (vec) {
+      for (int k = lane * 4; k < seglen; k += 128) {
+        if (TO_SMEM) cp_async16(sp + k, gsrc + goff + k);
+        else *reinterpret_cast<float4*>(gdst + goff + k) = *reinterpret_cast<const float4*>(sp + k);
       }
-    }
-  } else {
-    const int total = nseg * seglen;
-    for (int i = threadIdx.x; i < total; i += kNT) {
-      const int sg = i / seglen, k = i - sg * seglen;
-      const long long goff = (EM ? ((long long)(b0 + sg) * T + t0) : ((long long)(t0 + sg) * B + b0)) * A + k;
-      float* sp = s + sg * sstride + k;
-      if (TO_SMEM) {
-        cp_async4(sp, gsrc + goff);
-      } else {
-        gdst[goff] = *sp;
+    } else {
+      for (int k = lane; k < seglen; k += 32) {
+        if (TO_SMEM) cp_async4(sp + k, gsrc + goff + k);
+        else gdst[goff + k] = sp[k];
       }
     }
   }
 }
 
-// Per-element softmax statistics.  Reads the element's A target / behaviour
-// logits from shared memory, overwrites them with p_j and q_j = p_j * logp_j.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kL2E = 1.4426950408889634f;   // log2(e)
+constexpr float kLN2 = 0.6931471805599453f;   // ln(2)
+
+// Per-element softmax statistics.  Reads the element's A target (st) / behaviour (sb) logits from
+// shared memory and overwrites them with p_j and q2_j = p_j * log2(p_j) (base-2: phase C folds ln 2 into
+// its coefficient).  exp/log run as ex2/lg2 on pre-scaled arguments (one FFMA + one MUFU per logit); the
+// behaviour row is reduced to (max, logsumexp) first so only one A-long register array is live at a time.
 template <int A_>
 __device__ __forceinline__ void softmax_stats(float* st, float* sb, int A, int act, float& la, float& lma, float& H,
                                               float& KL) {
-  if constexpr (A_ > 0) {
-    float x[A_], y[A_];
-    if constexpr ((A_ & 1) == 0) {
+  if constexpr (A_ > 0 && (A_ & 1) == 0) {
+    float my, l2Sy;
+    {
+      float y[A_];
 #pragma unroll
       for (int j = 0; j < A_; j += 2) {
-        const float2 a = *reinterpret_cast<const float2*>(st + j);
         const float2 b = *reinterpret_cast<const float2*>(sb + j);
-        x[j] = a.x, x[j + 1] = a.y, y[j] = b.x, y[j + 1] = b.y;
+        y[j] = b.x, y[j + 1] = b.y;
       }
-    } else {
+      my = y[0];
 #pragma unroll
-      for (int j = 0; j < A_; ++j) x[j] = st[j], y[j] = sb[j];
+      for (int j = 1; j < A_; ++j) my = fmaxf(my, y[j]);
+      const float nmy = -my * kL2E;
+      float Sy = 0.f;
+#pragma unroll
+      for (int j = 0; j < A_; ++j) Sy += ex2_approx(fmaf(y[j], kL2E, nmy));
+      l2Sy = lg2_approx(Sy);
     }
-    float m = x[0], my = y[0];
+    const float y_act = sb[act], x_act = st[act];
+    float xs[A_], e[A_];
 #pragma unroll
-    for (int j = 1; j < A_; ++j) m = fmaxf(m, x[j]), my = fmaxf(my, y[j]);
-    float S = 0.f, Sy = 0.f;
+    for (int j = 0; j < A_; j += 2) {
+      const float2 a = *reinterpret_cast<const float2*>(st + j);
+      xs[j] = a.x, xs[j + 1] = a.y;
+    }
+    float m = xs[0];
+#pragma unroll
+    for (int j = 1; j < A_; ++j) m = fmaxf(m, xs[j]);
+    const float nm = -m * kL2E;
+    float S = 0.f;
 #pragma unroll
     for (int j = 0; j < A_; ++j) {
-      x[j] -= m;
-      y[j] -= my;
-      S += __expf(x[j]);
-      Sy += __expf(y[j]);
+      xs[j] = fmaf(xs[j], kL2E, nm);        // (x_j - m) * log2 e
+      e[j] = ex2_approx(xs[j]);
+      S += e[j];
     }
-    const float logS = __logf(S), logSy = __logf(Sy);
+    const float l2S = lg2_approx(S);
     const float inv = __fdividef(1.0f, S);
-    H = 0.f, KL = 0.f, la = 0.f, lma = 0.f;
+    float Hn2 = 0.f, Spy = 0.f;              // Hn2 = sum p_j log2 p_j ; Spy = sum p_j y_j
 #pragma unroll
-    for (int j = 0; j < A_; ++j) {
-      const float lj = x[j] - logS, lmj = y[j] - logSy;
-      const float pj = __expf(x[j]) * inv;
-      const float qj = pj * lj;
-      H -= qj;
-      KL = fmaf(pj, lj - lmj, KL);
-      if (j == act) la = lj, lma = lmj;
-      x[j] = pj, y[j] = qj;
+    for (int j = 0; j < A_; j += 2) {
+      const float2 yy = *reinterpret_cast<const float2*>(sb + j);
+      const float p0 = e[j] * inv, p1 = e[j + 1] * inv;
+      const float q0 = p0 * (xs[j] - l2S), q1 = p1 * (xs[j + 1] - l2S);
+      Hn2 += q0 + q1;
+      Spy = fmaf(p0, yy.x, fmaf(p1, yy.y, Spy));
+      *reinterpret_cast<float2*>(st + j) = make_float2(p0, p1);
+      *reinterpret_cast<float2*>(sb + j) = make_float2(q0, q1);
     }
-    if constexpr ((A_ & 1) == 0) {
-#pragma unroll
-      for (int j = 0; j < A_; j += 2) {
-        *reinterpret_cast<float2*>(st + j) = make_float2(x[j], x[j + 1]);
-        *reinterpret_cast<float2*>(sb + j) = make_float2(y[j], y[j + 1]);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < A_; ++j) st[j] = x[j], sb[j] = y[j];
-    }
+    const float Hn = Hn2 * kLN2;
+    const float logSy = l2Sy * kLN2;
+    H = -Hn;
+    KL = Hn - Spy + my + logSy;              // sum_j p_j (logp_j - logq_j)
+    la = (fmaf(x_act, kL2E, nm) - l2S) * kLN2;
+    lma = y_act - my - logSy;
   } else {
     float m = st[0], my = sb[0];
     for (int j = 1; j < A; ++j) m = fmaxf(m, st[j]), my = fmaxf(my, sb[j]);
+    const float nm = -m * kL2E, nmy = -my * kL2E;
     float S = 0.f, Sy = 0.f;
-    for (int j = 0; j < A; ++j) S += __expf(st[j] - m), Sy += __expf(sb[j] - my);
-    const float logS = __logf(S), logSy = __logf(Sy);
+    for (int j = 0; j < A; ++j) S += ex2_approx(fmaf(st[j], kL2E, nm)), Sy += ex2_approx(fmaf(sb[j], kL2E, nmy));
+    const float l2S = lg2_approx(S), logSy = lg2_approx(Sy) * kLN2;
     const float inv = __fdividef(1.0f, S);
-    H = 0.f, KL = 0.f, la = 0.f, lma = 0.f;
+    la = (fmaf(st[act], kL2E, nm) - l2S) * kLN2;
+    lma = sb[act] - my - logSy;
+    float Hn2 = 0.f, Spy = 0.f;
     for (int j = 0; j < A; ++j) {
-      const float xj = st[j] - m, yj = sb[j] - my;
-      const float lj = xj - logS, lmj = yj - logSy;
-      const float pj = __expf(xj) * inv;
-      const float qj = pj * lj;
-      H -= qj;
-      KL = fmaf(pj, lj - lmj, KL);
-      if (j == act) la = lj, lma = lmj;
+      const float xsj = fmaf(st[j], kL2E, nm);
+      const float pj = ex2_approx(xsj) * inv;
+      const float qj = pj * (xsj - l2S);
+      Hn2 += qj;
+      Spy = fmaf(pj, sb[j], Spy);
       st[j] = pj, sb[j] = qj;
     }
+    const float Hn = Hn2 * kLN2;
+    H = -Hn;
+    KL = Hn - Spy + my + logSy;
   }
 }
 
-template <int A_, bool EM>
-__global__ void __launch_bounds__(kNT, 7) vtrace_loss_kernel(const VtraceLossArgs p) {
-  extern __shared__ float4 smem4[];
+// Shared-memory carve-up (bytes): [tile_tl | pad to 128][tile_bl | pad to 128][s_acc][s_kc]
+__host__ __device__ inline int tile_bytes_padded(int TC, int A) { return (TC * kBW * A * 4 + 127) & ~127; }
+
+template <int A_, bool EM, bool TMA>
+__global__ void __launch_bounds__(kNT, 7) vtrace_loss_kernel(const VtraceLossArgs p,
+                                                            const __grid_constant__ CUtensorMap map_tl,
+                                                            const __grid_constant__ CUtensorMap map_bl,
+                                                            const __grid_constant__ CUtensorMap map_dl) {
+  static_assert(!(TMA && EM), "the TMA tile path is time-major only");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int A = A_ > 0 ? A_ : p.A;
   const int T = p.T, B = p.B, TC = p.TC;
-  float* s_tl = reinterpret_cast<float*>(smem4);
-  float* s_bl = s_tl + TC * kBW * A;
-  float* s_acc = s_bl + TC * kBW * A;   // delta, then acc = vs - V
-  float* s_kc = s_acc + TC * kBW;       // gamma_t * min(rho, 1)
+  const int tile_pad = tile_bytes_padded(TC, A);
+  float* s_tl = reinterpret_cast<float*>(smem_raw);
+  float* s_bl = reinterpret_cast<float*>(smem_raw + tile_pad);
+  float* s_acc = reinterpret_cast<float*>(smem_raw + 2 * tile_pad);   // delta, then acc = vs - V
+  float* s_kc = s_acc + TC * kBW;                                     // gamma_t * min(rho, 1)
   __shared__ float s_carry[kBW];        // acc at the first row of the chunk processed before (later in time)
   __shared__ float s_red[4][kNT / 32];
   __shared__ bool s_last;
+  __shared__ __align__(8) unsigned long long s_mbar;
+  uint32_t mbar_phase = 0;
+  if (TMA) {
+    if (threadIdx.x == 0) {
+      tma_prefetch_desc(&map_tl);
+      tma_prefetch_desc(&map_bl);
+      tma_prefetch_desc(&map_dl);
+      mbar_init(&s_mbar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+  }
 
   const int tid = threadIdx.x;
   const int b0 = blockIdx.x * kBW;
@@ -187,41 +229,56 @@ __global__ void __launch_bounds__(kNT, 7) vtrace_loss_kernel(const VtraceLossArg
     const int t0 = c * TC;
     const int nt = min(TC, T - t0);
     const bool vec = p.vec && (((EM ? nt : nb) * A) & 3) == 0;
-    copy_tile<EM, true>(s_tl, p.tl, nullptr, A, T, B, TC, t0, nt, b0, nb, vec);
-    copy_tile<EM, true>(s_bl, p.bl, nullptr, A, T, B, TC, t0, nt, b0, nb, vec);
-    cp_async_commit();
+    if (TMA) {
+      // one elected thread: two 2-D TMA tile loads (box = TC rows x kBW*A floats; rows/columns past the
+      // tensor edge are zero-filled by the hardware), completion signalled on the mbarrier
+      if (tid == 0) {
+        mbar_arrive_expect_tx(&s_mbar, 2u * (uint32_t)(TC * kBW * A * 4));
+        tma_load_2d(s_tl, &map_tl, b0 * A, t0, &s_mbar);
+        tma_load_2d(s_bl, &map_bl, b0 * A, t0, &s_mbar);
+      }
+    } else {
+      copy_tile<EM, true>(s_tl, p.tl, nullptr, A, T, B, TC, t0, nt, b0, nb, vec);
+      copy_tile<EM, true>(s_bl, p.bl, nullptr, A, T, B, TC, t0, nt, b0, nb, vec);
+      cp_async_commit();
+    }
 
     // ---- per-element scalars straight from global (overlaps the tile copy) ----
-    const int nel = nt * nb;
+    const int nel = nt * kBW;           // including the columns of a ragged last tile (masked below)
     int e_act[kEPT];
     float e_r[kEPT], e_v[kEPT], e_vn[kEPT], e_g[kEPT];
 #pragma unroll
     for (int k = 0; k < kEPT; ++k) {
       const int i = tid + k * kNT;
+      const int tl_ = i >> 2, bl_ = i & 3;
       e_act[k] = 0, e_r[k] = 0.f, e_v[k] = 0.f, e_vn[k] = 0.f, e_g[k] = 0.f;
-      if (i < nel) {
-        const int tl_ = EM ? i % nt : i / nb, bl_ = EM ? i / nt : i % nb;
+      if (i < nel && bl_ < nb) {
         const int t = t0 + tl_;
-        const long long g = gidx<EM>(t, b0 + bl_, T, B);
+        const int g = gidx<EM>(t, b0 + bl_, T, B);
         e_act[k] = p.act64 ? (int)reinterpret_cast<const long long*>(p.actions)[g]
                            : reinterpret_cast<const int*>(p.actions)[g];
         e_r[k] = p.rewards[g];
         e_v[k] = p.values[g];
         e_g[k] = p.dones[g] ? 0.0f : p.gamma;            // impala.py:59  (~dones) * discount
-        if (t + 1 < T) e_vn[k] = p.values[gidx<EM>(t + 1, b0 + bl_, T, B)];
+        if (t + 1 < T) e_vn[k] = p.values[g + (EM ? 1 : B)];
       }
     }
-    cp_async_wait<0>();
-    __syncthreads();
+    if (TMA) {
+      mbar_wait(&s_mbar, mbar_phase);
+      mbar_phase ^= 1u;
+    } else {
+      cp_async_wait<0>();
+      __syncthreads();
+    }
 
     // ---- phase A: softmax / entropy / KL / rho / delta (element-private) ----
     float e_la[kEPT], e_H[kEPT], e_rpg[kEPT];
 #pragma unroll
     for (int k = 0; k < kEPT; ++k) {
       const int i = tid + k * kNT;
+      const int tl_ = i >> 2, bl_ = i & 3;
       e_la[k] = 0.f, e_H[k] = 0.f, e_rpg[k] = 0.f;
-      if (i < nel) {
-        const int tl_ = EM ? i % nt : i / nb, bl_ = EM ? i / nt : i % nb;
+      if (i < nel && bl_ < nb) {
         const int si = sidx<EM>(tl_, bl_, TC);
         float la, lma, H, KL;
         softmax_stats<A_>(s_tl + si * A, s_bl + si * A, A, e_act[k], la, lma, H, KL);
@@ -246,8 +303,10 @@ __global__ void __launch_bounds__(kNT, 7) vtrace_loss_kernel(const VtraceLossArg
     if (tid < nb) {
       float acc = acc_carry;
       const int tl_hi = min(nt, T - 1 - t0) - 1;            // skip the bootstrap row
-      for (int tl_ = tl_hi; tl_ >= 0; --tl_) {
-        const int si = sidx<EM>(tl_, tid, TC);
+      const int step = EM ? 1 : kBW;
+      int si = sidx<EM>(tl_hi, tid, TC);
+#pragma unroll 8
+      for (int tl_ = tl_hi; tl_ >= 0; --tl_, si -= step) {
         acc = __fadd_rn(s_acc[si], __fmul_rn(s_kc[si], acc));   // vtrace.py:120
         s_acc[si] = acc;
       }
@@ -259,12 +318,12 @@ __global__ void __launch_bounds__(kNT, 7) vtrace_loss_kernel(const VtraceLossArg
 #pragma unroll
     for (int k = 0; k < kEPT; ++k) {
       const int i = tid + k * kNT;
-      if (i < nel) {
-        const int tl_ = EM ? i % nt : i / nb, bl_ = EM ? i / nt : i % nb;
+      const int tl_ = i >> 2, bl_ = i & 3;
+      if (i < nel && bl_ < nb) {
         const int t = t0 + tl_;
         const int si = sidx<EM>(tl_, bl_, TC);
         float* pt = s_tl + si * A;
-        const long long g = gidx<EM>(t, b0 + bl_, T, B);
+        const int g = gidx<EM>(t, b0 + bl_, T, B);
         if (t < T - 1) {
           const float acc_n = (t + 1 == T - 1) ? 0.f : (tl_ + 1 < nt ? s_acc[sidx<EM>(tl_ + 1, bl_, TC)] : s_carry[bl_]);
           const float vs = __fadd_rn(s_acc[si], e_v[k]);                 // vtrace.py:125
@@ -275,35 +334,46 @@ __global__ void __launch_bounds__(kNT, 7) vtrace_loss_kernel(const VtraceLossArg
           sum_pi -= e_la[k] * adv;                                        // impala.py:67-68
           sum_vf += 0.5f * dv * dv;                                       // :71-72
           p.d_values[g] = p.vf_coeff * dv;
-          if (p.vs_out) p.vs_out[(long long)t * B + b0 + bl_] = vs;
-          if (p.pg_out) p.pg_out[(long long)t * B + b0 + bl_] = adv;
+          if (p.vs_out) p.vs_out[t * B + b0 + bl_] = vs;
+          if (p.pg_out) p.pg_out[t * B + b0 + bl_] = adv;
           // dL/dz_j = p_j (adv - c_e H) - c_e p_j logp_j - adv [j == a]
           const float c0 = adv - p.ent_coeff * e_H[k];
+          const float nce = -p.ent_coeff * kLN2;                          // q is stored in base-2 units
           const float* pq = s_bl + si * A;
-          if constexpr (A_ > 0) {
+          if constexpr (A_ > 0 && (A_ & 1) == 0) {
 #pragma unroll
-            for (int j = 0; j < A_; ++j) {
-              float d = fmaf(pt[j], c0, -p.ent_coeff * pq[j]);
-              if (j == e_act[k]) d -= adv;
-              pt[j] = d;
+            for (int j = 0; j < A_; j += 2) {
+              const float2 pp = *reinterpret_cast<const float2*>(pt + j);
+              const float2 qq = *reinterpret_cast<const float2*>(pq + j);
+              *reinterpret_cast<float2*>(pt + j) =
+                  make_float2(fmaf(pp.x, c0, nce * qq.x), fmaf(pp.y, c0, nce * qq.y));
             }
           } else {
-            for (int j = 0; j < A; ++j) {
-              float d = fmaf(pt[j], c0, -p.ent_coeff * pq[j]);
-              if (j == e_act[k]) d -= adv;
-              pt[j] = d;
-            }
+            for (int j = 0; j < A; ++j) pt[j] = fmaf(pt[j], c0, nce * pq[j]);
           }
+          pt[e_act[k]] -= adv;
         } else {
           p.d_values[g] = 0.f;                                            // bootstrap row: no gradient
           for (int j = 0; j < A; ++j) pt[j] = 0.f;
         }
       }
     }
-    __syncthreads();
-    if (tid < nb) s_carry[tid] = acc_carry;
-    copy_tile<EM, false>(s_tl, nullptr, p.d_logits, A, T, B, TC, t0, nt, b0, nb, vec);
-    __syncthreads();
+    if (TMA) {
+      fence_proxy_async_smem();          // generic-proxy writes of the gradient tile -> visible to the TMA engine
+      __syncthreads();
+      if (tid < nb) s_carry[tid] = acc_carry;
+      if (tid == 0) {
+        tma_store_2d(&map_dl, b0 * A, t0, s_tl);
+        tma_store_commit();
+        tma_store_wait_read();           // smem tile may be overwritten / the CTA may exit afterwards
+      }
+      __syncthreads();
+    } else {
+      __syncthreads();
+      if (tid < nb) s_carry[tid] = acc_carry;
+      copy_tile<EM, false>(s_tl, nullptr, p.d_logits, A, T, B, TC, t0, nt, b0, nb, vec);
+      __syncthreads();
+    }
   }
 
   // ---- loss reduction: warp -> CTA -> (last CTA) grid, fixed order, fp64 at the end ----
@@ -390,18 +460,29 @@ __global__ void __launch_bounds__(128) vtrace_returns_kernel(const float* __rest
 }
 
 template <int A_>
-static int launch_vtrace_loss(const VtraceLossArgs& a, int layout, int grid, size_t smem, cudaStream_t st) {
+static int launch_vtrace_loss(const VtraceLossArgs& a, int layout, bool tma, const CUtensorMap* maps, int grid,
+                              size_t smem, cudaStream_t st) {
   if (layout == RL_LAYOUT_ENV_MAJOR) {
-    cudaFuncSetAttribute(vtrace_loss_kernel<A_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    vtrace_loss_kernel<A_, true><<<grid, kNT, smem, st>>>(a);
+    cudaFuncSetAttribute(vtrace_loss_kernel<A_, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    vtrace_loss_kernel<A_, true, false><<<grid, kNT, smem, st>>>(a, maps[0], maps[1], maps[2]);
+  } else if (tma) {
+    cudaFuncSetAttribute(vtrace_loss_kernel<A_, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    vtrace_loss_kernel<A_, false, true><<<grid, kNT, smem, st>>>(a, maps[0], maps[1], maps[2]);
   } else {
-    cudaFuncSetAttribute(vtrace_loss_kernel<A_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    vtrace_loss_kernel<A_, false><<<grid, kNT, smem, st>>>(a);
+    cudaFuncSetAttribute(vtrace_loss_kernel<A_, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    vtrace_loss_kernel<A_, false, false><<<grid, kNT, smem, st>>>(a, maps[0], maps[1], maps[2]);
   }
   return 0;
 }
 
 }  // namespace rl
+
+static bool g_disable_tma = false;
+// Test / triage hook: force the cp.async tile path (1) or allow the TMA path (0).
+extern "C" int rl_debug_set_tma(int disable) {
+  g_disable_tma = disable != 0;
+  return RL_OK;
+}
 
 extern "C" size_t rl_loss_workspace_bytes(int n_cols) {
   const size_t grid = (size_t)(n_cols > 0 ? n_cols : 1);   // >= any kernel's CTA count
@@ -432,6 +513,7 @@ extern "C" int rl_vtrace_loss_fwd_bwd(const float* target_logits, const float* b
                "vtrace_loss: null pointer");
   RL_CHECK_ARG(T >= 2 && B >= 1 && A >= 1 && A <= 1024, "vtrace_loss: bad shape T=%d B=%d A=%d (need T>=2)", T, B, A);
   RL_CHECK_ARG(layout == RL_LAYOUT_TIME_MAJOR || layout == RL_LAYOUT_ENV_MAJOR, "vtrace_loss: bad layout %d", layout);
+  RL_CHECK_ARG((long long)T * B * A < (1LL << 31), "vtrace_loss: T*B*A must be < 2^31 (32-bit indexing)");
   const int grid = (B + kBW - 1) / kBW;
   if (workspace_bytes < rl_loss_workspace_bytes(B)) {
     set_error("vtrace_loss: workspace too small (%zu < %zu)", workspace_bytes, rl_loss_workspace_bytes(B));
@@ -444,7 +526,7 @@ extern "C" int rl_vtrace_loss_fwd_bwd(const float* target_logits, const float* b
   if (TC > kNT * kEPT / kBW) TC = kNT * kEPT / kBW;
   if (TC >= T) TC = T; else TC &= ~3;                 // multi-chunk: keep chunk starts 16-byte aligned
   if (TC < 1) TC = 1;
-  const size_t smem = (size_t)TC * row_bytes;
+  const size_t smem = 2 * (size_t)tile_bytes_padded(TC, A) + (size_t)TC * kBW * 2 * sizeof(float);
   RL_CHECK_ARG(smem <= 200 * 1024, "vtrace_loss: A=%d too large for the shared-memory tile", A);
   VtraceLossArgs a;
   a.tl = target_logits, a.bl = behaviour_logits, a.actions = actions, a.rewards = rewards, a.dones = dones;
@@ -460,13 +542,27 @@ extern "C" int rl_vtrace_loss_fwd_bwd(const float* target_logits, const float* b
   } else {
     a.vec = ptr_ok && (((long long)T * A) % 4 == 0) && (((long long)TC * A) % 4 == 0);
   }
+  // TMA tile path: time-major, 16-byte aligned bases, row pitch a multiple of 16 bytes, box <= 256 elements
+  alignas(64) CUtensorMap maps[3];
+  memset(maps, 0, sizeof(maps));
+  bool tma = layout == RL_LAYOUT_TIME_MAJOR && ptr_ok && (((long long)B * A) % 4 == 0) && kBW * A <= 256 && TC <= 256 &&
+             !g_disable_tma;
+  if (tma) {
+    const char* err = nullptr;
+    const uint64_t pitch = (uint64_t)B * A * sizeof(float);
+    if (make_tensor_map_2d_f32(&maps[0], target_logits, (uint64_t)B * A, (uint64_t)T, pitch, kBW * A, TC, &err) ||
+        make_tensor_map_2d_f32(&maps[1], behaviour_logits, (uint64_t)B * A, (uint64_t)T, pitch, kBW * A, TC, &err) ||
+        make_tensor_map_2d_f32(&maps[2], d_logits, (uint64_t)B * A, (uint64_t)T, pitch, kBW * A, TC, &err)) {
+      tma = false;                       // fall back to the cp.async tile path
+    }
+  }
   cudaStream_t st = (cudaStream_t)stream;
   switch (A) {
-#define RL_CASE(N) case N: launch_vtrace_loss<N>(a, layout, grid, smem, st); break;
+#define RL_CASE(N) case N: launch_vtrace_loss<N>(a, layout, tma, maps, grid, smem, st); break;
     RL_CASE(2) RL_CASE(3) RL_CASE(4) RL_CASE(5) RL_CASE(6) RL_CASE(7) RL_CASE(8) RL_CASE(9) RL_CASE(10) RL_CASE(12)
     RL_CASE(14) RL_CASE(16) RL_CASE(18)
 #undef RL_CASE
-    default: launch_vtrace_loss<0>(a, layout, grid, smem, st); break;
+    default: launch_vtrace_loss<0>(a, layout, tma, maps, grid, smem, st); break;
   }
   RL_CHECK_LAUNCH("rl_vtrace_loss_fwd_bwd");
   return RL_OK;

@@ -1,0 +1,141 @@
+"""The IMPALA actor-learner loop on one B200 (one process per GPU): the on-device replacement of
+examples/IMPALA/{train.py:34-252, actor.py:27-105} + the xparl RPC data path
+(parl/remote/remote_wrapper.py:178-227).
+
+Rollout buffers live in HBM, time-major:
+    planes  [T+4, B, H*W] uint8   frame ring (obs t = planes t..t+3 via ages[t]); plane t+4 is
+                                  written by env step t, planes T..T+3 are carried to 0..3
+    ages    [T+1, B]      uint8
+    beh_logits [T,B,A] f32, actions [T,B] i32, rewards [T,B] f32, dones [T,B] u8
+Per step t: policy forward on obs_t -> logits straight into beh_logits[t] -> ONE kernel samples the
+actions and steps all B envs (rl_env_atari_synth_step).  The whole T-step rollout is captured in a
+CUDA graph (step counter resident on the device) and replayed.  ``learn`` runs the network over all
+T*B observations, the fused V-trace loss kernel, backward, (NCCL all-reduce of the flat gradient),
+clip + Adam.
+"""
+import torch
+
+from .. import kernels
+from ..algorithms import IMPALA
+from .nets import AtariActorCritic
+
+
+class ImpalaEngine(object):
+    def __init__(self, num_envs=4096, sample_batch_steps=50, act_dim=18, frame_hw=(84, 84), seed=0, device=None,
+                 env_offset=0, gamma=0.99, vf_loss_coeff=0.5, clip_rho_threshold=1.0, clip_pg_rho_threshold=1.0,
+                 p_done=0.1, model=None, learn_chunk_rows=5, use_graph=True):
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.B, self.T, self.A = int(num_envs), int(sample_batch_steps), int(act_dim)
+        self.h, self.w = frame_hw
+        self.hw = self.h * self.w
+        self.seed, self.env_offset, self.p_done = int(seed), int(env_offset), p_done
+        dev = self.device
+        B, T, A = self.B, self.T, self.A
+        self.planes = torch.zeros((T + 4, B, self.hw), dtype=torch.uint8, device=dev)
+        self.ages = torch.zeros((T + 1, B), dtype=torch.uint8, device=dev)
+        self.beh_logits = torch.zeros((T, B, A), dtype=torch.float32, device=dev)
+        self.actions = torch.zeros((T, B), dtype=torch.int32, device=dev)
+        self.rewards = torch.zeros((T, B), dtype=torch.float32, device=dev)
+        self.dones = torch.zeros((T, B), dtype=torch.uint8, device=dev)
+        self.stats = kernels.EpisodeStats(B, dev)
+        self.obs_step = torch.empty((B, 4, self.h, self.w), dtype=torch.uint8, device=dev)
+        self.step_dev = torch.zeros(T, dtype=torch.int32, device=dev)      # global env-step index of row t
+        self.step_dev.copy_(torch.arange(T, dtype=torch.int32))
+        self.model = model if model is not None else AtariActorCritic(A)
+        self.model.to(dev)
+        self.alg = IMPALA(self.model, sample_batch_steps=T, gamma=gamma, vf_loss_coeff=vf_loss_coeff,
+                          clip_rho_threshold=clip_rho_threshold, clip_pg_rho_threshold=clip_pg_rho_threshold)
+        self.learn_chunk_rows = int(learn_chunk_rows)
+        self.obs_chunk = torch.empty((self.learn_chunk_rows * B, 4, self.h, self.w), dtype=torch.uint8, device=dev)
+        self.tgt_logits = torch.empty((T, B, A), dtype=torch.float32, device=dev)
+        self.values = torch.empty((T, B), dtype=torch.float32, device=dev)
+        self.loss_out = dict(losses=torch.zeros(8, device=dev), d_logits=torch.empty((T * B, A), device=dev),
+                             d_values=torch.empty(T * B, device=dev))
+        self.sample_steps = 0
+        self.use_graph = use_graph
+        self._graph = None
+        self._kernel_launches = 0
+        self.reset()
+
+    # ------------------------------------------------------------------ env side
+    def reset(self):
+        # the reset frame goes where the carry at the start of the next rollout picks it up
+        T = self.T
+        kernels.env_atari_synth_step(self.planes[T + 3], None, None, None, self.ages[T], self.stats, self.seed, 0,
+                                     env_offset=self.env_offset, reset=True)
+        self.step_dev.copy_(torch.arange(T, dtype=torch.int32) - T)
+
+    def _rollout_body(self):
+        T = self.T
+        with torch.no_grad():
+            # carry the previous rollout's last observation (4 planes + age row) to the front; done HERE and
+            # not at the end of the previous rollout so that learn() still sees rows 0..3 intact
+            self.planes[0:4].copy_(self.planes[T:T + 4])
+            self.ages[0].copy_(self.ages[T])
+            self.step_dev.add_(T)
+            for t in range(T):
+                kernels.obs_stack_gather(self.planes, self.ages, t, 1, self.obs_step)
+                logits = self.model.policy(self.obs_step)
+                self.beh_logits[t].copy_(logits)
+                kernels.env_atari_synth_step(self.planes[t + 4], self.rewards[t], self.dones[t], self.ages[t],
+                                             self.ages[t + 1], self.stats, self.seed, 0, p_done=self.p_done,
+                                             env_offset=self.env_offset, logits=self.beh_logits[t],
+                                             actions_out=self.actions[t], step_dev=self.step_dev[t:])
+
+    def rollout(self):
+        """T lock-step env steps for all B envs (the device analogue of Actor.sample())."""
+        if self.use_graph:
+            if self._graph is None:
+                # warm up once eagerly (cuDNN autotune, allocator), then capture
+                self._rollout_body()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._rollout_body()
+                self._graph = g
+                self.sample_steps += self.T * self.B
+                return
+            self._graph.replay()
+        else:
+            self._rollout_body()
+        self.sample_steps += self.T * self.B
+
+    # ------------------------------------------------------------------ learner side
+    def learn(self, learning_rate=0.001, entropy_coeff=-0.01):
+        """One IMPALA update on the (T,B) rollout in HBM (impala.py:134-215 semantics)."""
+        T, B, A = self.T, self.B, self.A
+        rows = self.learn_chunk_rows
+        outs = []
+        for t0 in range(0, T, rows):
+            n = min(rows, T - t0)
+            obs = self.obs_chunk[:n * B]
+            kernels.obs_stack_gather(self.planes, self.ages, t0, n, obs)
+            logits, values = self.model.policy_and_value(obs)
+            self.tgt_logits[t0:t0 + n].copy_(logits.detach().view(n, B, A))
+            self.values[t0:t0 + n].copy_(values.detach().view(n, B))
+            outs.append((logits, values, t0, n))
+        res = kernels.vtrace_loss_fwd_bwd(self.tgt_logits.view(T * B, A), self.beh_logits.view(T * B, A),
+                                          self.actions.view(-1), self.rewards.view(-1), self.dones.view(-1),
+                                          self.values.view(-1), T, B, self.alg.gamma, self.alg.vf_loss_coeff,
+                                          entropy_coeff, self.alg.clip_rho_threshold, self.alg.clip_pg_rho_threshold,
+                                          layout=kernels.TIME_MAJOR, out=self.loss_out)
+        dl = res['d_logits'].view(T, B, A)
+        dv = res['d_values'].view(T, B)
+        tensors, grads = [], []
+        for logits, values, t0, n in outs:
+            tensors += [logits, values]
+            grads += [dl[t0:t0 + n].reshape(n * B, A), dv[t0:t0 + n].reshape(n * B)]
+        torch.autograd.backward(tensors, grads)
+        if self.alg.grad_sync is not None:
+            self.alg.grad_sync(self.alg.optimizer.grad)
+        self.alg.optimizer.step(lr=learning_rate)
+        return res['losses']
+
+    # ------------------------------------------------------------------ metrics (Actor.get_metrics analogue)
+    def get_metrics(self):
+        tot = self.stats.totals.tolist()
+        n = max(tot[0], 1.0)
+        return dict(sample_steps=self.sample_steps, episodes=int(tot[0]), mean_episode_rewards=tot[1] / n,
+                    mean_episode_steps=tot[2] / n)

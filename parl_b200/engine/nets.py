@@ -1,0 +1,108 @@
+"""Policy/value networks of the target examples as ``parl.Model`` subclasses (a13).
+
+AtariActorCritic  = the 84x84 actor-critic of benchmark/torch/a2c/atari_model.py:23-96 (conv 8x8/4,
+                    4x4/2, 3x3/1, fc 512, policy/value heads, xavier-normal init) — used for the C3
+                    IMPALA config because examples/IMPALA/atari_model.py is sized for 42x42 inputs.
+MujocoModel       = benchmark/torch/ppo/mujoco_model.py:27-53 (two 64-unit tanh MLPs, state-independent
+                    log-std parameter).
+CartPoleModel     = benchmark/torch/QuickStart/cartpole_model.py:21-38 (softmax policy) and an
+                    actor-critic variant for A2C on CartPole (C2).
+Observations arrive as uint8 [N,4,84,84] views of the device rollout buffer and are scaled by 1/255
+inside the model, as the reference models do (``obs / 255.0``).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..core import Model
+
+
+class AtariActorCritic(Model):
+    def __init__(self, act_dim, compute_dtype=torch.bfloat16):
+        super(AtariActorCritic, self).__init__()
+        self.conv1 = nn.Conv2d(4, 32, kernel_size=8, stride=4, padding=1)
+        self.conv2 = nn.Conv2d(32, 64, kernel_size=4, stride=2, padding=2)
+        self.conv3 = nn.Conv2d(64, 64, kernel_size=3, stride=1, padding=0)
+        self.fc = nn.Linear(64 * 9 * 9, 512)
+        self.fc_pi = nn.Linear(512, act_dim)
+        self.fc_v = nn.Linear(512, 1)
+        self.compute_dtype = compute_dtype
+        for m in self.modules():                       # atari_model.py:89-96
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                nn.init.xavier_normal_(m.weight)
+                nn.init.constant_(m.bias, 0)
+
+    def _trunk(self, x):
+        dt = self.compute_dtype if x.is_cuda else torch.float32
+        with torch.autocast(device_type=x.device.type, dtype=dt, enabled=dt != torch.float32):
+            x = x.to(dt) / 255.0
+            x = x.contiguous(memory_format=torch.channels_last)
+            x = F.relu(self.conv1(x))
+            x = F.relu(self.conv2(x))
+            x = F.relu(self.conv3(x))
+            return F.relu(self.fc(x.flatten(1)))       # (C,H,W) feature order, as nn.Flatten in the reference
+
+    def policy(self, x):
+        h = self._trunk(x)
+        return F.linear(h.float(), self.fc_pi.weight, self.fc_pi.bias)
+
+    def value(self, x):
+        h = self._trunk(x)
+        return F.linear(h.float(), self.fc_v.weight, self.fc_v.bias).squeeze(1)
+
+    def policy_and_value(self, x):
+        h = self._trunk(x).float()
+        logits = F.linear(h, self.fc_pi.weight, self.fc_pi.bias)
+        values = F.linear(h, self.fc_v.weight, self.fc_v.bias).squeeze(1)
+        return logits, values
+
+
+class MujocoModel(Model):
+    def __init__(self, obs_dim=17, act_dim=6):
+        super(MujocoModel, self).__init__()
+        self.fc_v1, self.fc_v2, self.fc_v3 = nn.Linear(obs_dim, 64), nn.Linear(64, 64), nn.Linear(64, 1)
+        self.fc_pi1, self.fc_pi2, self.fc_pi3 = nn.Linear(obs_dim, 64), nn.Linear(64, 64), nn.Linear(64, act_dim)
+        self.fc_pi_std = nn.Parameter(torch.zeros(1, act_dim))
+
+    def value(self, obs):
+        x = torch.tanh(self.fc_v1(obs))
+        x = torch.tanh(self.fc_v2(x))
+        return self.fc_v3(x)
+
+    def policy(self, obs):
+        x = torch.tanh(self.fc_pi1(obs))
+        x = torch.tanh(self.fc_pi2(x))
+        mean = self.fc_pi3(x)
+        return mean, torch.exp(self.fc_pi_std.expand_as(mean))
+
+
+class CartPoleActorCritic(Model):
+    def __init__(self, obs_dim=4, act_dim=2, hidden=64):
+        super(CartPoleActorCritic, self).__init__()
+        self.fc1, self.fc2 = nn.Linear(obs_dim, hidden), nn.Linear(hidden, hidden)
+        self.fc_pi, self.fc_v = nn.Linear(hidden, act_dim), nn.Linear(hidden, 1)
+
+    def _trunk(self, x):
+        return torch.tanh(self.fc2(torch.tanh(self.fc1(x))))
+
+    def policy(self, x):
+        return self.fc_pi(self._trunk(x))
+
+    def value(self, x):
+        return self.fc_v(self._trunk(x)).squeeze(1)
+
+    def policy_and_value(self, x):
+        h = self._trunk(x)
+        return self.fc_pi(h), self.fc_v(h).squeeze(1)
+
+
+class CartPolePolicy(Model):
+    """benchmark/torch/QuickStart/cartpole_model.py:21-38: forward returns action probabilities."""
+
+    def __init__(self, obs_dim=4, act_dim=2):
+        super(CartPolePolicy, self).__init__()
+        self.fc1 = nn.Linear(obs_dim, act_dim * 10)
+        self.fc2 = nn.Linear(act_dim * 10, act_dim)
+
+    def forward(self, x):
+        return F.softmax(self.fc2(torch.tanh(self.fc1(x))), dim=-1)

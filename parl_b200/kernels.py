@@ -103,13 +103,13 @@ class EpisodeStats(object):
 
 
 def env_atari_synth_step(frame_out, reward_out, done_out, age_in, age_out, stats, seed, step, p_done=0.1,
-                         env_offset=0, logits=None, actions_out=None, reset=False):
+                         env_offset=0, logits=None, actions_out=None, reset=False, step_dev=None):
     B, HW = frame_out.shape[0], frame_out[0].numel()
     A = logits.shape[-1] if logits is not None else 0
     check(_lib.load().rl_env_atari_synth_step(
         ptr(frame_out), ptr(reward_out), ptr(done_out), ptr(age_in), ptr(age_out), ptr(logits), A, ptr(actions_out),
-        *stats.args(), B, HW, int(seed), int(step), int(env_offset), float(p_done), 1 if reset else 0, stream()),
-        'env_atari_synth_step')
+        *stats.args(), B, HW, int(seed), int(step), ptr(step_dev), int(env_offset), float(p_done),
+        1 if reset else 0, stream()), 'env_atari_synth_step')
 
 
 def obs_stack_gather(planes, ages, t_begin, t_count, out, layout=TIME_MAJOR, scale=1.0):
@@ -331,3 +331,19 @@ def gather_rows(src, idx):
     out = torch.empty((idx.numel(), ) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
     check(_lib.load().rl_gather_rows(ptr(src), ptr(idx), idx.numel(), row_bytes, ptr(out), stream()), 'gather_rows')
     return out
+
+
+# --------------------------------------------------------------------------- optimizer
+def grad_global_norm(grad_flat, out_norm):
+    ws = _flat_ws(grad_flat.device, 1)
+    check(_lib.load().rl_grad_global_norm(ptr(grad_flat), grad_flat.numel(), ptr(out_norm), ptr(ws), ws.numel(),
+                                          stream()), 'grad_global_norm')
+    return out_norm
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_div=1.0, grad_norm=None,
+              max_norm=0.0, clip_mode=0, zero_grad=True, lr_device=None):
+    check(_lib.load().rl_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), ptr(lr_device),
+                                   float(lr), float(beta1), float(beta2), float(eps), int(step), float(grad_div),
+                                   ptr(grad_norm), float(max_norm), int(clip_mode), 1 if zero_grad else 0, stream()),
+          'adam_step')

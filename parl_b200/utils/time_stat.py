@@ -1,0 +1,31 @@
+"""TimeStat context manager (parl/utils/time_stat.py:21-52): windowed mean of wall-clock spans,
+e.g. ``with learn_time_stat: agent.learn(...)`` -> ``learn_time_s`` metric."""
+import time
+
+from .window_stat import WindowStat
+
+__all__ = ['TimeStat']
+
+
+class TimeStat(object):
+    def __init__(self, window_size=1):
+        self.time_samples = WindowStat(window_size)
+        self._start_time = None
+
+    def __enter__(self):
+        self._start_time = time.time()
+
+    def __exit__(self, exc_type, exc, tb):
+        self.time_samples.add(time.time() - self._start_time)
+
+    @property
+    def mean(self):
+        return self.time_samples.mean
+
+    @property
+    def min(self):
+        return self.time_samples.min
+
+    @property
+    def max(self):
+        return self.time_samples.max

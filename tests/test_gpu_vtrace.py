@@ -134,3 +134,24 @@ def test_vtrace_loss_full_size_properties():
     # determinism: same inputs, bit-identical outputs (fixed-order reduction)
     r2 = kernels.vtrace_loss_fwd_bwd(*args, T, B, 0.99, 0.5, -0.01)
     assert torch.equal(r['losses'][:5], r2['losses'][:5]) and torch.equal(r['d_logits'], r2['d_logits'])
+
+
+def test_tma_and_cpasync_tile_paths_agree():
+    """The TMA tensor-map tile path and the cp.async path of the fused kernel are the same arithmetic."""
+    from parl_b200 import kernels, _lib
+    lib = _lib.load()
+    for (T, B, A) in [(50, 512, 18), (50, 7 * 4, 6), (130, 64, 18), (20, 256, 2)]:
+        tl, bl, acts, rew, dones, vals = make_rollout(T, B, A, 11)
+        args = [_cuda(tl).reshape(T * B, A), _cuda(bl).reshape(T * B, A), _cuda(acts).reshape(-1),
+                _cuda(rew).reshape(-1), _cuda(dones).reshape(-1), _cuda(vals).reshape(-1)]
+        try:
+            lib.rl_debug_set_tma(1)
+            r0 = kernels.vtrace_loss_fwd_bwd(*args, T, B, 0.99, 0.5, -0.01, want_returns=True)
+            torch.cuda.synchronize()
+        finally:
+            lib.rl_debug_set_tma(0)
+        r1 = kernels.vtrace_loss_fwd_bwd(*args, T, B, 0.99, 0.5, -0.01, want_returns=True)
+        torch.cuda.synchronize()
+        for k in ('d_logits', 'd_values', 'vs', 'pg_advantages'):
+            assert torch.equal(r0[k], r1[k]), (k, T, B, A)
+        assert torch.equal(r0['losses'][:5], r1['losses'][:5])
