@@ -1,0 +1,256 @@
+#!/usr/bin/env python
+"""bench.py — IMPALA env-steps/s on synthetic Atari-shaped envs (BASELINE.json metric).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" = one full actor-learner iteration of the hot path: T=50 lock-step env steps of the whole
+actor pool (policy forward + fused sample/env-step kernel per time step, trajectories written straight
+into the (T,B) HBM rollout buffer) followed by one IMPALA learner update on the 50 x B batch (network
+forward, fused V-trace+loss kernel, backward, gradient all-reduce over NCCL when N>1, clip + Adam).
+Workload: configs[2] of BASELINE.json — 4096 actors in total, sharded B/N per GPU (strong scaling).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'env_steps_per_sec_impala_4096_actors'
+UNIT = 'env-steps/s'
+TOTAL_ENVS = 4096
+T_STEPS = 50
+ACT_DIM = 18
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--envs', type=int, default=TOTAL_ENVS, help='total env instances over all GPUs')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--cpu-seconds', type=float, default=15.0)
+    return ap.parse_args()
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self._stop, self._th = gpu_index, [], False, None
+
+    def _run(self):
+        while not self._stop:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def start(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+
+    def stop(self):
+        self._stop = True
+        if self._th:
+            self._th.join(timeout=6)
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace('.', '').isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(self.rows))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU actor-learner path (oracle port; the Python reference itself
+    cannot travel to the GPU box) on all host cores; each step = a bounded wall-clock sample."""
+    if rank != 0:
+        return
+    from oracle.actor_learner import run_cpu_impala
+    per = max(4.0, min(20.0, 100.0 / max(args.steps + args.warmup, 1)))
+    res = None
+    vals = []
+    for i in range(args.warmup + args.steps):
+        res = run_cpu_impala(seconds=per, seed=i)
+        if i >= args.warmup:
+            vals.append(res['env_steps_per_s'])
+    v = sum(vals) / len(vals)
+    sample = ('%d actor processes x %d envs x T=%d (lean 84x84 synthetic env + FrameStack4, torch-CPU 84x84 '
+              'actor-critic, numpy V-trace), %.0f s wall clock per step' % (res['actors'], res['env_num'], T_STEPS, per))
+    line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=per * 1e3, higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f32',
+                data='synthetic', impl='reference',
+                config=dict(workload='IMPALA synthetic Atari-shaped 84x84x4->18, CPU actor pool (oracle port of '
+                                     'examples/IMPALA on host cores)', total_envs=res['actors'] * res['env_num'],
+                            T=T_STEPS, train_batch_size=res['train_batch_size']),
+                cpu_baseline=dict(value=v, unit=UNIT, cores=res['cores'], kind='port', sample=sample,
+                                  learner_ms_per_batch=res['learn_ms_per_batch']),
+                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+    assert args.warmup >= 3, 'timing rules: at least 3 warm-up steps'
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    assert args.envs % world == 0
+    B = args.envs // world
+
+    from parl_b200 import kernels
+    from parl_b200.engine.impala import ImpalaEngine
+    torch.manual_seed(0)                      # identical initial weights on every rank
+    eng = ImpalaEngine(num_envs=B, sample_batch_steps=T_STEPS, act_dim=ACT_DIM, seed=1234, device=dev,
+                       env_offset=rank * B)
+    if world > 1:
+        # IMPALA's loss is a SUM over the global batch (impala.py:67-79) -> all-reduce SUM of the flat gradient
+        eng.alg.grad_sync = lambda g: dist.all_reduce(g, op=dist.ReduceOp.SUM)
+
+    def step():
+        eng.rollout()
+        return eng.learn(0.001, -0.01)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    kernels.reset_launch_count()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k1_events = []
+    eng.k1_events = k1_events
+    ev0.record()
+    for _ in range(args.steps):
+        losses = step()
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    elapsed_ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+    eng.k1_events = None
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed = elapsed_ms.item() * 1e-3
+    launches = kernels.launch_count()
+    total_steps = args.steps * T_STEPS * args.envs
+    value = total_steps / elapsed
+
+    # roofline of the dominant *hand-written HBM-bound* kernel named by the north star (K1), timed live
+    k1_ms = [a.elapsed_time(b) for a, b in k1_events]
+    k1_s = (sum(k1_ms) / len(k1_ms)) * 1e-3 if k1_ms else None
+    alg_bytes = (T_STEPS - 1) * B * (12 * ACT_DIM + 17) + 4 * B
+    peak, peak_src = measured_peaks()
+    roof = None
+    if k1_s:
+        ach = alg_bytes / k1_s / 1e9
+        roof = dict(bound='hbm', kernel='vtrace_loss_kernel (rl_vtrace_loss_fwd_bwd)', achieved=ach, peak=peak,
+                    unit='GB/s', frac=ach / peak, traffic=None, peak_source=peak_src,
+                    algorithmic_bytes_per_launch=alg_bytes, us_per_launch=k1_s * 1e6)
+
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(eng, args, world, dev)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.actor_learner import run_cpu_impala
+        r = run_cpu_impala(seconds=args.cpu_seconds)
+        cpu = dict(value=r['env_steps_per_s'], unit=UNIT, cores=r['cores'], kind='port',
+                   sample='%d actor processes x %d envs x T=%d lean synthetic 84x84 env, torch-CPU model, %.0f s'
+                          % (r['actors'], r['env_num'], T_STEPS, r['elapsed_s']),
+                   learner_ms_per_batch=r['learn_ms_per_batch'])
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=elapsed * 1e3 / args.steps, higher_is_better=True, scaling='strong', vs_baseline=None,
+                    dtype='bf16 network (fp32 accumulate, fp32 master weights) / f32 scans+losses', data='synthetic',
+                    config=dict(workload='IMPALA synthetic Atari-shaped (84x84x4 -> 18 discrete), %d actors total, '
+                                         'T=50, V-trace; configs[2] of BASELINE.json' % args.envs,
+                                envs_per_gpu=B, T=T_STEPS, learner_batch=T_STEPS * args.envs,
+                                model='84x84 actor-critic (benchmark/torch/a2c/atari_model.py), 2.74 M params',
+                                parallelism='dp%d' % world,
+                                l2_policy='per-step working set (obs ring %.1f GB/GPU) >> 126 MB L2' %
+                                          ((T_STEPS + 4) * B * 7056 / 1e9)),
+                    gpu_launches=launches, clocks=clocks, roofline=roof, e2e=e2e, cpu_baseline=cpu,
+                    learner_losses=[float(x) for x in losses[:5].tolist()])
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(eng, args, world, dev):
+    """The same metric through the reference-facing contract with HOST buffers: per step the rollout is
+    handed to the host as the numpy dict Actor.sample() returns (D2H into pinned memory) and
+    agent.learn() is fed from those host arrays (H2D) — copies inside the timed region."""
+    import torch
+    import torch.distributed as dist
+    steps = max(2, min(args.steps, 4))
+    host = eng.make_host_sample_buffers()
+    eng.sample_to_host(host)
+    eng.learn_from_host(host, 0.001, -0.01)           # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.time()
+    for _ in range(steps):
+        eng.sample_to_host(host)
+        losses = eng.learn_from_host(host, 0.001, -0.01)
+        _ = losses[:5].cpu()                          # D2H read of the step's result
+    torch.cuda.synchronize()
+    el = torch.tensor([time.time() - t0], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    nbytes = sum(v.numel() * v.element_size() for v in host.values())
+    return dict(value=steps * T_STEPS * args.envs / el.item(), unit=UNIT, h2d_bytes_per_step=nbytes,
+                d2h_bytes_per_step=nbytes + 20, steps=steps,
+                path='Actor.sample() numpy dict (uint8 obs) -> pinned host -> Agent.learn(numpy)')
+
+
+if __name__ == '__main__':
+    main()

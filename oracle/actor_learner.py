@@ -176,26 +176,50 @@ def run_cpu_impala(seconds=15.0, n_actors=None, env_num=5, T=50, act_dim=18, tra
 
     def weights():
         return {k: v.detach().numpy() for k, v in model.state_dict().items()}
-    w = weights()
+    import queue
+    import threading
+    state = dict(w=weights(), learn_steps=0, learn_time=0.0, stop=False)
+    sample_q = queue.Queue(maxsize=8)                 # sample_queue_max_size (impala_config.py:33)
+
+    def learner_loop():                               # Learner.run_learn thread (train.py:77-79,123-145)
+        pending = []
+        while not state['stop']:
+            try:
+                pending.append(sample_q.get(timeout=0.05))
+            except queue.Empty:
+                continue
+            if sum(len(s['actions']) for s in pending) >= train_batch_size:
+                batch = {k: np.concatenate([s[k] for s in pending]) for k in pending[0]}
+                pending = []
+                t1 = time.time()
+                impala_learn(model, opt, batch, T)
+                state['learn_time'] += time.time() - t1
+                state['learn_steps'] += 1
+                state['w'] = weights()
+
+    th = threading.Thread(target=learner_loop, daemon=True)
+    th.start()
     for c in conns:
-        c.send(w)
+        c.send(state['w'])
     t0 = time.time()
-    steps, learn_steps, learn_time, pending = 0, 0, 0.0, []
-    while time.time() - t0 < seconds:
+    steps = 0
+    while time.time() - t0 < seconds:                 # run_remote_sample threads (train.py:165-194), one loop
+        got = False
         for c in conns:
-            if c.poll(0.001):
-                pending.append(c.recv())
-                steps += env_num * T
-                c.send(w)
-        have = sum(len(s['actions']) for s in pending)
-        if have >= train_batch_size:
-            batch = {k: np.concatenate([s[k] for s in pending]) for k in pending[0]}
-            pending = []
-            t1 = time.time()
-            impala_learn(model, opt, batch, T)
-            learn_time += time.time() - t1
-            learn_steps += 1
-            w = weights()
+            if c.poll(0):
+                sample = c.recv()
+                steps += env_num * T                  # sample_total_steps += obs.shape[0]  (train.py:93)
+                c.send(state['w'])
+                try:
+                    sample_q.put(sample, timeout=max(0.0, seconds - (time.time() - t0)))
+                except queue.Full:
+                    pass
+                got = True
+        if not got:
+            time.sleep(0.002)
+    state['stop'] = True
+    th.join(timeout=30)
+    learn_steps, learn_time = state['learn_steps'], state['learn_time']
     elapsed = time.time() - t0
     for c in conns:
         try:

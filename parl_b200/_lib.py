@@ -94,7 +94,12 @@ def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+launches = 0          # number of C-ABI kernel-launching calls made by this process (bench.py gpu_launches)
+
+
 def check(code, what):
+    global launches
+    launches += 1
     if code != 0:
         msg = load().rl_last_error().decode()
         raise RuntimeError('parl_b200.%s failed (code %d): %s' % (what, code, msg))

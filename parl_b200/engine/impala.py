@@ -92,12 +92,16 @@ class ImpalaEngine(object):
                 self._rollout_body()
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
+                before = kernels.launch_count()
                 with torch.cuda.graph(g):
                     self._rollout_body()
+                self._graph_launches = kernels.launch_count() - before
+                kernels.add_graph_launches(-self._graph_launches)      # capture is not execution
                 self._graph = g
                 self.sample_steps += self.T * self.B
                 return
             self._graph.replay()
+            kernels.add_graph_launches(self._graph_launches)
         else:
             self._rollout_body()
         self.sample_steps += self.T * self.B
@@ -116,17 +120,89 @@ class ImpalaEngine(object):
             self.tgt_logits[t0:t0 + n].copy_(logits.detach().view(n, B, A))
             self.values[t0:t0 + n].copy_(values.detach().view(n, B))
             outs.append((logits, values, t0, n))
+        ev = getattr(self, 'k1_events', None)
+        if ev is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         res = kernels.vtrace_loss_fwd_bwd(self.tgt_logits.view(T * B, A), self.beh_logits.view(T * B, A),
                                           self.actions.view(-1), self.rewards.view(-1), self.dones.view(-1),
                                           self.values.view(-1), T, B, self.alg.gamma, self.alg.vf_loss_coeff,
                                           entropy_coeff, self.alg.clip_rho_threshold, self.alg.clip_pg_rho_threshold,
                                           layout=kernels.TIME_MAJOR, out=self.loss_out)
+        if ev is not None:
+            e1.record()
+            ev.append((e0, e1))
         dl = res['d_logits'].view(T, B, A)
         dv = res['d_values'].view(T, B)
         tensors, grads = [], []
         for logits, values, t0, n in outs:
             tensors += [logits, values]
             grads += [dl[t0:t0 + n].reshape(n * B, A), dv[t0:t0 + n].reshape(n * B)]
+        torch.autograd.backward(tensors, grads)
+        if self.alg.grad_sync is not None:
+            self.alg.grad_sync(self.alg.optimizer.grad)
+        self.alg.optimizer.step(lr=learning_rate)
+        return res['losses']
+
+    # ------------------------------------------------------------------ reference-facing host contract
+    def make_host_sample_buffers(self):
+        """Pinned host arrays with the keys / dtypes / env-major order of Actor.sample()
+        (examples/IMPALA/actor.py:54-91): obs [B*T,4,H,W] uint8, actions int64, behaviour_logits f32,
+        rewards f32, dones bool."""
+        N = self.B * self.T
+        pin = dict(pin_memory=True)
+        return dict(obs=torch.empty((N, 4, self.h, self.w), dtype=torch.uint8, **pin),
+                    actions=torch.empty(N, dtype=torch.int64, **pin),
+                    behaviour_logits=torch.empty((N, self.A), dtype=torch.float32, **pin),
+                    rewards=torch.empty(N, dtype=torch.float32, **pin),
+                    dones=torch.empty(N, dtype=torch.bool, **pin))
+
+    def sample_to_host(self, host):
+        """rollout() + device->host copy of the sample dict in the reference's env-major layout."""
+        self.rollout()
+        T, B = self.T, self.B
+        rows = self.learn_chunk_rows
+        # obs: gather env-major directly on the device in slabs of columns to bound scratch memory
+        em = lambda x: x.transpose(0, 1).contiguous()
+        obs_dev = getattr(self, '_obs_em', None)
+        if obs_dev is None:
+            obs_dev = self._obs_em = torch.empty((B * T, 4, self.h, self.w), dtype=torch.uint8, device=self.device)
+        kernels.obs_stack_gather(self.planes, self.ages, 0, T, obs_dev, layout=kernels.ENV_MAJOR)
+        host['obs'].copy_(obs_dev, non_blocking=True)
+        host['actions'].copy_(em(self.actions).view(-1).long(), non_blocking=True)
+        host['behaviour_logits'].copy_(em(self.beh_logits).view(B * T, self.A), non_blocking=True)
+        host['rewards'].copy_(em(self.rewards).view(-1), non_blocking=True)
+        host['dones'].copy_(em(self.dones).view(-1).bool(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host
+
+    def learn_from_host(self, host, learning_rate, entropy_coeff):
+        """Agent.learn(numpy...) contract (examples/IMPALA/atari_agent.py:44-74): host arrays -> H2D ->
+        IMPALA.learn in the reference's env-major order, processed in column slabs."""
+        T, B, A = self.T, self.B, self.A
+        dev = self.device
+        acts = host['actions'].to(dev, non_blocking=True)
+        bl = host['behaviour_logits'].to(dev, non_blocking=True)
+        rew = host['rewards'].to(dev, non_blocking=True)
+        dones = host['dones'].to(dev, non_blocking=True)
+        slab = max(1, (self.learn_chunk_rows * B) // T)          # env columns per forward slab
+        tgt = torch.empty((B * T, A), dtype=torch.float32, device=dev)
+        val = torch.empty(B * T, dtype=torch.float32, device=dev)
+        outs = []
+        for b0 in range(0, B, slab):
+            nb = min(slab, B - b0)
+            obs = host['obs'][b0 * T:(b0 + nb) * T].to(dev, non_blocking=True)
+            logits, values = self.model.policy_and_value(obs)
+            tgt[b0 * T:(b0 + nb) * T].copy_(logits.detach())
+            val[b0 * T:(b0 + nb) * T].copy_(values.detach())
+            outs.append((logits, values, b0 * T, nb * T))
+        res = kernels.vtrace_loss_fwd_bwd(tgt, bl, acts, rew, dones, val, T, B, self.alg.gamma, self.alg.vf_loss_coeff,
+                                          entropy_coeff, self.alg.clip_rho_threshold, self.alg.clip_pg_rho_threshold,
+                                          layout=kernels.ENV_MAJOR, out=self.loss_out)
+        tensors, grads = [], []
+        for logits, values, o, n in outs:
+            tensors += [logits, values]
+            grads += [res['d_logits'][o:o + n], res['d_values'][o:o + n]]
         torch.autograd.backward(tensors, grads)
         if self.alg.grad_sync is not None:
             self.alg.grad_sync(self.alg.optimizer.grad)

@@ -12,6 +12,23 @@ TIME_MAJOR = 0
 ENV_MAJOR = 1
 
 _workspaces = {}
+_graph_launches = 0
+
+
+def launch_count():
+    """C-ABI kernel launches issued so far (eager calls + launches replayed from captured CUDA graphs)."""
+    return _lib.launches + _graph_launches
+
+
+def reset_launch_count():
+    global _graph_launches
+    _lib.launches = 0
+    _graph_launches = 0
+
+
+def add_graph_launches(n):
+    global _graph_launches
+    _graph_launches += int(n)
 
 
 def loss_workspace(device, n_cols):

@@ -68,13 +68,15 @@ def bench_env(B=4096, HW=84 * 84, nplanes=16, iters=64):
 
 if __name__ == '__main__':
     which = sys.argv[1] if len(sys.argv) > 1 else 'all'
-    if which in ('vtrace', 'all'):
+    if which == 'vtrace_cpasync':
         from parl_b200 import _lib
         _lib.load().rl_debug_set_tma(1)
         r = bench_vtrace()
         r['path'] = 'cp.async'
         print(json.dumps(r))
-        _lib.load().rl_debug_set_tma(0)
+    if which == 'vtrace_c3':
+        print(json.dumps(bench_vtrace()))
+    if which in ('vtrace', 'all'):
         print(json.dumps(bench_vtrace()))
         print(json.dumps(bench_vtrace(B=65536, nbuf=2, iters=16)))
         print(json.dumps(bench_vtrace(B=512, nbuf=64)))
