@@ -265,6 +265,15 @@ int rl_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, l
                  float grad_div, const float* grad_norm, float max_norm, int clip_mode, int zero_grad,
                  rl_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * a13 / K6  Dense contraction on the tcgen05 tensor cores (TMA-staged tiles, fp32 accumulation in TMEM):
+ *   C[M,N] = act(A[M,K] . B[N,K]^T + bias[N])      A, B bf16 row-major ("x . W^T"), C bf16 or f32.
+ * Replaces the nn.Linear forward of the reference models (e.g. benchmark/torch/a2c/atari_model.py:46-49,
+ * executed there by cuBLAS through torch).  lda/ldb/ldc in elements; lda, ldb multiples of 8.
+ * ---------------------------------------------------------------------- */
+int rl_gemm_bf16_tn(const void* A, const void* B, const float* bias, void* C, int M, int N, int K,
+                    int lda, int ldb, int ldc, int relu, int out_f32, rl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,7 @@ SIGNATURES = {
     'rl_grad_global_norm': (c_i, [c_p, ctypes.c_longlong, c_p, c_p, c_sz, c_p]),
     'rl_adam_step': (c_i, [c_p, c_p, c_p, c_p, ctypes.c_longlong, c_p, c_f, c_f, c_f, c_f, c_i, c_f, c_p, c_f, c_i,
                            c_i, c_p]),
+    'rl_gemm_bf16_tn': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
 }
 
 

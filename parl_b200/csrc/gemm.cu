@@ -1,0 +1,274 @@
+// K6 (dense contractions) — bf16 GEMM on the 5th-gen tensor cores: C[M,N] = act(A[M,K] · B[N,K]^T + bias)
+// with fp32 accumulation in TMEM.  Used for the linear layers of the policy/value networks
+// (a13: benchmark/torch/a2c/atari_model.py:46-49 fc 5184->512 and the heads; forward x·W^T).
+//
+// sm_100a structure (one 128 x BN output tile per CTA, BK = 64 bf16 = one 128-byte swizzle atom):
+//   warp 0   : TMA producer — cp.async.bulk.tensor 2-D tiles of A and B (SWIZZLE_128B) into a
+//              4-stage shared-memory ring, completion on per-stage "full" mbarriers
+//   warp 1   : allocates TMEM, issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN, K=16) from
+//              ONE elected thread, 4 per stage; tcgen05.commit releases the stage ("empty") and,
+//              after the last k-block, signals "tmem_full"
+//   warps 2-5: epilogue — tcgen05.ld the 128 x BN fp32 accumulator (each warp its own 32-lane
+//              quarter), bias + optional ReLU, convert, store
+// Tensor-pipe bound: 2*M*N*K flops; operand traffic (M*K + N*K)*2 B + M*N*out B.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace rl {
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 64;          // bf16 elements per k-block = 128 bytes
+constexpr int kGemmStages = 4;
+constexpr int kGemmThreads = 192;    // 6 warps
+
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, int c0, int c1, void* mbar) {
+  tma_load_2d(smem_dst, map, c0, c1, mbar);
+}
+
+// ---- tcgen05 wrappers --------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(void* mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(mbar))
+               : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread (thread = lane/row)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major operand tile in shared memory, 128-byte rows, SWIZZLE_128B (cute::UMMA::SmemDescriptor):
+//   start_address[0,14) = addr>>4 ; LBO[16,30) = 1 (unused for swizzled K-major) ; SBO[32,46) = 1024>>4
+//   version[46,48) = 1 (Blackwell) ; layout_type[61,64) = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::f16, BF16 x BF16 -> F32, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct GemmArgs {
+  const float* bias;   // [N] or NULL
+  void* C;             // [M, ldc] bf16 or f32
+  int M, N, K, ldc;
+  int relu, out_f32;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                      const __grid_constant__ CUtensorMap map_b,
+                                                                      const GemmArgs g) {
+  constexpr int A_STAGE = kGemmBM * kGemmBK * 2;     // 16 KB
+  constexpr int B_STAGE = BN * kGemmBK * 2;
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  // SWIZZLE_128B atoms need 1024-byte alignment: align by hand (the launch reserves the slack)
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  unsigned char* sA = smem;                                     // [stages][128 rows][128 B]
+  unsigned char* sB = smem + kGemmStages * A_STAGE;             // [stages][BN rows][128 B]
+  __shared__ __align__(8) unsigned long long full_bar[kGemmStages], empty_bar[kGemmStages], tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * BN;
+  const int num_kb = (g.K + kGemmBK - 1) / kGemmBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < kGemmStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kGemmStages;
+        const uint32_t ph = (kb / kGemmStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1u);                                  // slot free (first pass: immediately)
+        mbar_arrive_expect_tx(&full_bar[s], A_STAGE + B_STAGE);
+        tma_load_2d(sA + s * A_STAGE, &map_a, kb * kGemmBK, m0, &full_bar[s]);
+        tma_load_2d(sB + s * B_STAGE, &map_b, kb * kGemmBK, n0, &full_bar[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kGemmBM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kGemmStages;
+        const uint32_t ph = (kb / kGemmStages) & 1;
+        mbar_wait(&full_bar[s], ph);                                        // TMA bytes have landed
+        tc_fence_after();
+        const uint64_t da = make_desc_sw128(smem_u32(sA + s * A_STAGE));
+        const uint64_t db = make_desc_sw128(smem_u32(sB + s * B_STAGE));
+#pragma unroll
+        for (int k = 0; k < kGemmBK / 16; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);                                         // frees the smem stage when the MMAs retire
+      }
+      umma_commit(&tmem_full_bar);                                          // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = m0 + q * 32 + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      float v[16];
+      tmem_ld16(tlane + (uint32_t)c0, v);
+      if (row < g.M) {
+        const int col = n0 + c0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float x = v[i] + ((g.bias && col + i < g.N) ? g.bias[col + i] : 0.f);
+          v[i] = g.relu ? fmaxf(x, 0.f) : x;
+        }
+        if (g.out_f32) {
+          float* dst = reinterpret_cast<float*>(g.C) + (size_t)row * g.ldc + col;
+          if (col + 16 <= g.N && (g.ldc & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+            for (int i = 0; i < 16 && col + i < g.N; ++i) dst[i] = v[i];
+          }
+        } else {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.C) + (size_t)row * g.ldc + col;
+          if (col + 16 <= g.N && (g.ldc & 7) == 0) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+              pk[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          } else {
+            for (int i = 0; i < 16 && col + i < g.N; ++i) dst[i] = __float2bfloat16(v[i]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// rank-2 bf16 tensor map {K (contiguous), rows}, box {64, box_rows}, SWIZZLE_128B
+static int make_tensor_map_bf16_sw128(CUtensorMap* map, const void* base, uint64_t K, uint64_t rows, uint64_t pitch_bytes,
+                                      uint32_t box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return -1;
+    fn = reinterpret_cast<EncodeFn>(p);
+  }
+  const cuuint64_t gdim[2] = {K, rows};
+  const cuuint64_t gstride[1] = {pitch_bytes};
+  const cuuint32_t box[2] = {(cuuint32_t)kGemmBK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+             ? 0
+             : -2;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, cudaStream_t st) {
+  const size_t smem = (size_t)kGemmStages * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 1024;
+  cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid((g.M + kGemmBM - 1) / kGemmBM, (g.N + BN - 1) / BN);
+  gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, smem, st>>>(ma, mb, g);
+  return 0;
+}
+
+}  // namespace rl
+
+using namespace rl;
+
+extern "C" int rl_gemm_bf16_tn(const void* A, const void* B, const float* bias, void* C, int M, int N, int K, int lda,
+                               int ldb, int ldc, int relu, int out_f32, rl_stream_t stream) {
+  RL_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "gemm_bf16_tn: bad argument");
+  RL_CHECK_ARG(aligned16(A) && aligned16(B) && aligned16(C), "gemm_bf16_tn: pointers must be 16-byte aligned");
+  RL_CHECK_ARG(lda >= K && ldb >= K && ldc >= N && (lda % 8) == 0 && (ldb % 8) == 0,
+               "gemm_bf16_tn: lda/ldb must be >= K and multiples of 8 elements (TMA row pitch)");
+  int BN = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
+  alignas(64) CUtensorMap ma, mb;
+  if (make_tensor_map_bf16_sw128(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kGemmBM) ||
+      make_tensor_map_bf16_sw128(&mb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, (uint32_t)BN)) {
+    set_error("gemm_bf16_tn: cuTensorMapEncodeTiled failed");
+    return RL_ERR_CUDA;
+  }
+  GemmArgs g;
+  g.bias = bias, g.C = C, g.M = M, g.N = N, g.K = K, g.ldc = ldc, g.relu = relu, g.out_f32 = out_f32;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (BN) {
+    case 256: launch_gemm<256>(ma, mb, g, st); break;
+    case 128: launch_gemm<128>(ma, mb, g, st); break;
+    case 64: launch_gemm<64>(ma, mb, g, st); break;
+    default: launch_gemm<32>(ma, mb, g, st); break;
+  }
+  RL_CHECK_LAUNCH("rl_gemm_bf16_tn");
+  return RL_OK;
+}

@@ -24,8 +24,7 @@
 namespace rl {
 
 constexpr int kBW = 4;     // env columns per CTA
-constexpr int kNT = 128;   // threads per CTA
-constexpr int kEPT = 2;    // max (t,b) elements per thread per chunk  (TC*BW <= kNT*kEPT)
+constexpr int kNT = 224;   // threads per CTA: one (t,b) element per thread, TC <= kNT / kBW = 56 rows per chunk
 
 struct VtraceLossArgs {
   const float* tl;
@@ -97,98 +96,86 @@ __device__ __forceinline__ float lg2_approx(float x) {
 constexpr float kL2E = 1.4426950408889634f;   // log2(e)
 constexpr float kLN2 = 0.6931471805599453f;   // ln(2)
 
-// Per-element softmax statistics.  Reads the element's A target (st) / behaviour (sb) logits from
-// shared memory and overwrites them with p_j and q2_j = p_j * log2(p_j) (base-2: phase C folds ln 2 into
-// its coefficient).  exp/log run as ex2/lg2 on pre-scaled arguments (one FFMA + one MUFU per logit); the
-// behaviour row is reduced to (max, logsumexp) first so only one A-long register array is live at a time.
+// Per-element softmax statistics in TWO array-free sweeps over the shared-memory rows (registers hold only
+// running scalars, so 7 CTAs x 7 warps stay resident per SM):
+//   sweep 1: m = max_j x_j, my = max_j y_j                                   (x target, y behaviour logits)
+//   sweep 2: with xs_j = (x_j - m) log2e, e_j = 2^xs_j:  S = sum e_j, W = sum e_j xs_j, Y = sum e_j y_j,
+//            Sy = sum 2^((y_j - my) log2e)
+// from which  log2 p_j = xs_j - log2 S,  sum_j p_j log2 p_j = W/S - log2 S,  sum_j p_j y_j = Y/S.
+// The tiles are left untouched; phase C recomputes p_j from x_j (one FFMA + MUFU.EX2 each).
+struct SoftmaxStats {
+  float nm;      // -m * log2e
+  float l2S;     // log2 sum_j 2^xs_j
+  float inv;     // 1 / S
+  float la;      // log pi(a)      (natural log)
+  float lma;     // log mu(a)
+  float H;       // entropy of pi  (natural log)
+  float KL;      // KL(pi || mu)
+};
+
 template <int A_>
-__device__ __forceinline__ void softmax_stats(float* st, float* sb, int A, int act, float& la, float& lma, float& H,
-                                              float& KL) {
+__device__ __forceinline__ SoftmaxStats softmax_stats(const float* __restrict__ st, const float* __restrict__ sb, int A,
+                                                      int act) {
+  SoftmaxStats r;
+  float m, my;
   if constexpr (A_ > 0 && (A_ & 1) == 0) {
-    float my, l2Sy;
-    {
-      float y[A_];
-#pragma unroll
-      for (int j = 0; j < A_; j += 2) {
-        const float2 b = *reinterpret_cast<const float2*>(sb + j);
-        y[j] = b.x, y[j + 1] = b.y;
-      }
-      my = y[0];
-#pragma unroll
-      for (int j = 1; j < A_; ++j) my = fmaxf(my, y[j]);
-      const float nmy = -my * kL2E;
-      float Sy = 0.f;
-#pragma unroll
-      for (int j = 0; j < A_; ++j) Sy += ex2_approx(fmaf(y[j], kL2E, nmy));
-      l2Sy = lg2_approx(Sy);
+    float2 a = *reinterpret_cast<const float2*>(st);
+    float2 b = *reinterpret_cast<const float2*>(sb);
+    m = fmaxf(a.x, a.y), my = fmaxf(b.x, b.y);
+#pragma unroll 4
+    for (int j = 2; j < A_; j += 2) {
+      a = *reinterpret_cast<const float2*>(st + j);
+      b = *reinterpret_cast<const float2*>(sb + j);
+      m = fmaxf(m, fmaxf(a.x, a.y));
+      my = fmaxf(my, fmaxf(b.x, b.y));
     }
-    const float y_act = sb[act], x_act = st[act];
-    float xs[A_], e[A_];
-#pragma unroll
+  } else {
+    m = st[0], my = sb[0];
+    for (int j = 1; j < A; ++j) m = fmaxf(m, st[j]), my = fmaxf(my, sb[j]);
+  }
+  const float nm = -m * kL2E, nmy = -my * kL2E;
+  float S0 = 0.f, S1 = 0.f, W0 = 0.f, W1 = 0.f, Y0 = 0.f, Y1 = 0.f, Sy0 = 0.f, Sy1 = 0.f;
+  if constexpr (A_ > 0 && (A_ & 1) == 0) {
+#pragma unroll 3
     for (int j = 0; j < A_; j += 2) {
       const float2 a = *reinterpret_cast<const float2*>(st + j);
-      xs[j] = a.x, xs[j + 1] = a.y;
+      const float2 b = *reinterpret_cast<const float2*>(sb + j);
+      const float xs0 = fmaf(a.x, kL2E, nm), xs1 = fmaf(a.y, kL2E, nm);
+      const float e0 = ex2_approx(xs0), e1 = ex2_approx(xs1);
+      S0 += e0, S1 += e1;
+      W0 = fmaf(e0, xs0, W0), W1 = fmaf(e1, xs1, W1);
+      Y0 = fmaf(e0, b.x, Y0), Y1 = fmaf(e1, b.y, Y1);
+      Sy0 += ex2_approx(fmaf(b.x, kL2E, nmy));
+      Sy1 += ex2_approx(fmaf(b.y, kL2E, nmy));
     }
-    float m = xs[0];
-#pragma unroll
-    for (int j = 1; j < A_; ++j) m = fmaxf(m, xs[j]);
-    const float nm = -m * kL2E;
-    float S = 0.f;
-#pragma unroll
-    for (int j = 0; j < A_; ++j) {
-      xs[j] = fmaf(xs[j], kL2E, nm);        // (x_j - m) * log2 e
-      e[j] = ex2_approx(xs[j]);
-      S += e[j];
-    }
-    const float l2S = lg2_approx(S);
-    const float inv = __fdividef(1.0f, S);
-    float Hn2 = 0.f, Spy = 0.f;              // Hn2 = sum p_j log2 p_j ; Spy = sum p_j y_j
-#pragma unroll
-    for (int j = 0; j < A_; j += 2) {
-      const float2 yy = *reinterpret_cast<const float2*>(sb + j);
-      const float p0 = e[j] * inv, p1 = e[j + 1] * inv;
-      const float q0 = p0 * (xs[j] - l2S), q1 = p1 * (xs[j + 1] - l2S);
-      Hn2 += q0 + q1;
-      Spy = fmaf(p0, yy.x, fmaf(p1, yy.y, Spy));
-      *reinterpret_cast<float2*>(st + j) = make_float2(p0, p1);
-      *reinterpret_cast<float2*>(sb + j) = make_float2(q0, q1);
-    }
-    const float Hn = Hn2 * kLN2;
-    const float logSy = l2Sy * kLN2;
-    H = -Hn;
-    KL = Hn - Spy + my + logSy;              // sum_j p_j (logp_j - logq_j)
-    la = (fmaf(x_act, kL2E, nm) - l2S) * kLN2;
-    lma = y_act - my - logSy;
   } else {
-    float m = st[0], my = sb[0];
-    for (int j = 1; j < A; ++j) m = fmaxf(m, st[j]), my = fmaxf(my, sb[j]);
-    const float nm = -m * kL2E, nmy = -my * kL2E;
-    float S = 0.f, Sy = 0.f;
-    for (int j = 0; j < A; ++j) S += ex2_approx(fmaf(st[j], kL2E, nm)), Sy += ex2_approx(fmaf(sb[j], kL2E, nmy));
-    const float l2S = lg2_approx(S), logSy = lg2_approx(Sy) * kLN2;
-    const float inv = __fdividef(1.0f, S);
-    la = (fmaf(st[act], kL2E, nm) - l2S) * kLN2;
-    lma = sb[act] - my - logSy;
-    float Hn2 = 0.f, Spy = 0.f;
     for (int j = 0; j < A; ++j) {
-      const float xsj = fmaf(st[j], kL2E, nm);
-      const float pj = ex2_approx(xsj) * inv;
-      const float qj = pj * (xsj - l2S);
-      Hn2 += qj;
-      Spy = fmaf(pj, sb[j], Spy);
-      st[j] = pj, sb[j] = qj;
+      const float xs0 = fmaf(st[j], kL2E, nm);
+      const float e0 = ex2_approx(xs0);
+      S0 += e0;
+      W0 = fmaf(e0, xs0, W0);
+      Y0 = fmaf(e0, sb[j], Y0);
+      Sy0 += ex2_approx(fmaf(sb[j], kL2E, nmy));
     }
-    const float Hn = Hn2 * kLN2;
-    H = -Hn;
-    KL = Hn - Spy + my + logSy;
   }
+  const float S = S0 + S1, W = W0 + W1, Y = Y0 + Y1, Sy = Sy0 + Sy1;
+  const float l2S = lg2_approx(S);
+  const float inv = __fdividef(1.0f, S);
+  const float logSy = lg2_approx(Sy) * kLN2;
+  const float Hn = (W * inv - l2S) * kLN2;            // sum_j p_j log p_j
+  r.nm = nm, r.l2S = l2S, r.inv = inv;
+  r.H = -Hn;
+  r.KL = Hn - Y * inv + my + logSy;                   // sum_j p_j (log p_j - log q_j)
+  r.la = (fmaf(st[act], kL2E, nm) - l2S) * kLN2;
+  r.lma = sb[act] - my - logSy;
+  return r;
 }
 
 // Shared-memory carve-up (bytes): [tile_tl | pad to 128][tile_bl | pad to 128][s_acc][s_kc]
 __host__ __device__ inline int tile_bytes_padded(int TC, int A) { return (TC * kBW * A * 4 + 127) & ~127; }
 
 template <int A_, bool EM, bool TMA>
-__global__ void __launch_bounds__(kNT, 7) vtrace_loss_kernel(const VtraceLossArgs p,
+__global__ void __launch_bounds__(kNT, 6) vtrace_loss_kernel(const VtraceLossArgs p,
                                                             const __grid_constant__ CUtensorMap map_tl,
                                                             const __grid_constant__ CUtensorMap map_bl,
                                                             const __grid_constant__ CUtensorMap map_dl) {
@@ -206,23 +193,26 @@ __global__ void __launch_bounds__(kNT, 7) vtrace_loss_kernel(const VtraceLossArg
   __shared__ bool s_last;
   __shared__ __align__(8) unsigned long long s_mbar;
   uint32_t mbar_phase = 0;
+  const int tid = threadIdx.x;
   if (TMA) {
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
       tma_prefetch_desc(&map_tl);
       tma_prefetch_desc(&map_bl);
       tma_prefetch_desc(&map_dl);
       mbar_init(&s_mbar, 1);
       fence_mbar_init();
     }
-    __syncthreads();
   }
+  if (tid < kBW) s_carry[tid] = 0.f;
+  __syncthreads();
 
-  const int tid = threadIdx.x;
   const int b0 = blockIdx.x * kBW;
   const int nb = min(kBW, B - b0);
+  // this thread's element of every chunk: (t_local, b_local) = (tid >> 2, tid & 3)
+  const int tl_ = tid >> 2, bl_ = tid & 3;
+  const int si = sidx<EM>(tl_, bl_, TC);
   float sum_pi = 0.f, sum_vf = 0.f, sum_ent = 0.f, sum_kl = 0.f;
   float acc_carry = 0.f;
-  if (tid < kBW) s_carry[tid] = 0.f;
 
   const int nchunks = (T + TC - 1) / TC;
   for (int c = nchunks - 1; c >= 0; --c) {
@@ -244,24 +234,18 @@ __global__ void __launch_bounds__(kNT, 7) vtrace_loss_kernel(const VtraceLossArg
     }
 
     // ---- per-element scalars straight from global (overlaps the tile copy) ----
-    const int nel = nt * kBW;           // including the columns of a ragged last tile (masked below)
-    int e_act[kEPT];
-    float e_r[kEPT], e_v[kEPT], e_vn[kEPT], e_g[kEPT];
-#pragma unroll
-    for (int k = 0; k < kEPT; ++k) {
-      const int i = tid + k * kNT;
-      const int tl_ = i >> 2, bl_ = i & 3;
-      e_act[k] = 0, e_r[k] = 0.f, e_v[k] = 0.f, e_vn[k] = 0.f, e_g[k] = 0.f;
-      if (i < nel && bl_ < nb) {
-        const int t = t0 + tl_;
-        const int g = gidx<EM>(t, b0 + bl_, T, B);
-        e_act[k] = p.act64 ? (int)reinterpret_cast<const long long*>(p.actions)[g]
-                           : reinterpret_cast<const int*>(p.actions)[g];
-        e_r[k] = p.rewards[g];
-        e_v[k] = p.values[g];
-        e_g[k] = p.dones[g] ? 0.0f : p.gamma;            // impala.py:59  (~dones) * discount
-        if (t + 1 < T) e_vn[k] = p.values[g + (EM ? 1 : B)];
-      }
+    const bool valid = tl_ < nt && bl_ < nb;
+    const int t = t0 + tl_;
+    const bool loss_row = valid && t < T - 1;
+    const int g = gidx<EM>(t, b0 + bl_, T, B);
+    int act = 0;
+    float e_r = 0.f, e_v = 0.f, e_vn = 0.f, e_g = 0.f;
+    if (valid) {
+      act = p.act64 ? (int)reinterpret_cast<const long long*>(p.actions)[g] : reinterpret_cast<const int*>(p.actions)[g];
+      e_r = p.rewards[g];
+      e_v = p.values[g];
+      e_g = p.dones[g] ? 0.0f : p.gamma;                  // impala.py:59  (~dones) * discount
+      if (t + 1 < T) e_vn = p.values[g + (EM ? 1 : B)];
     }
     if (TMA) {
       mbar_wait(&s_mbar, mbar_phase);
@@ -271,30 +255,23 @@ __global__ void __launch_bounds__(kNT, 7) vtrace_loss_kernel(const VtraceLossArg
       __syncthreads();
     }
 
-    // ---- phase A: softmax / entropy / KL / rho / delta (element-private) ----
-    float e_la[kEPT], e_H[kEPT], e_rpg[kEPT];
-#pragma unroll
-    for (int k = 0; k < kEPT; ++k) {
-      const int i = tid + k * kNT;
-      const int tl_ = i >> 2, bl_ = i & 3;
-      e_la[k] = 0.f, e_H[k] = 0.f, e_rpg[k] = 0.f;
-      if (i < nel && bl_ < nb) {
-        const int si = sidx<EM>(tl_, bl_, TC);
-        float la, lma, H, KL;
-        softmax_stats<A_>(s_tl + si * A, s_bl + si * A, A, e_act[k], la, lma, H, KL);
-        sum_kl += KL;                                       // impala.py:160-162: every row
-        if (t0 + tl_ < T - 1) {
-          const float rho = expf(la - lma);                 // vtrace.py:101-103
-          const float rhoc = p.clip_rho >= 0.f ? fminf(rho, p.clip_rho) : rho;
-          const float cs = fminf(rho, 1.0f);                // :109
-          e_rpg[k] = p.clip_pg >= 0.f ? fminf(rho, p.clip_pg) : rho;
-          // deltas = clipped_rhos * (rewards + discounts * values_t_plus_1 - values)   :115
-          const float td = __fsub_rn(__fadd_rn(e_r[k], __fmul_rn(e_g[k], e_vn[k])), e_v[k]);
-          s_acc[si] = __fmul_rn(rhoc, td);
-          s_kc[si] = __fmul_rn(e_g[k], cs);
-          e_la[k] = la, e_H[k] = H;
-          sum_ent += H;
-        }
+    // ---- phase A: softmax / entropy / KL / rho / delta (element-private, tiles read-only) ----
+    SoftmaxStats ss;
+    float e_rpg = 0.f;
+    ss.nm = 0.f, ss.l2S = 0.f, ss.inv = 0.f, ss.la = 0.f, ss.lma = 0.f, ss.H = 0.f, ss.KL = 0.f;
+    if (valid) {
+      ss = softmax_stats<A_>(s_tl + si * A, s_bl + si * A, A, act);
+      sum_kl += ss.KL;                                    // impala.py:160-162: every row
+      if (loss_row) {
+        const float rho = expf(ss.la - ss.lma);           // vtrace.py:101-103
+        const float rhoc = p.clip_rho >= 0.f ? fminf(rho, p.clip_rho) : rho;
+        const float cs = fminf(rho, 1.0f);                // :109
+        e_rpg = p.clip_pg >= 0.f ? fminf(rho, p.clip_pg) : rho;
+        // deltas = clipped_rhos * (rewards + discounts * values_t_plus_1 - values)   :115
+        const float td = __fsub_rn(__fadd_rn(e_r, __fmul_rn(e_g, e_vn)), e_v);
+        s_acc[si] = __fmul_rn(rhoc, td);
+        s_kc[si] = __fmul_rn(e_g, cs);
+        sum_ent += ss.H;
       }
     }
     __syncthreads();
@@ -302,60 +279,54 @@ __global__ void __launch_bounds__(kNT, 7) vtrace_loss_kernel(const VtraceLossArg
     // ---- phase B: backward scan, one lane per column, reference op order ----
     if (tid < nb) {
       float acc = acc_carry;
-      const int tl_hi = min(nt, T - 1 - t0) - 1;            // skip the bootstrap row
+      const int tl_hi = min(nt, T - 1 - t0) - 1;          // skip the bootstrap row
       const int step = EM ? 1 : kBW;
-      int si = sidx<EM>(tl_hi, tid, TC);
+      int sj = sidx<EM>(tl_hi, tid, TC);
 #pragma unroll 8
-      for (int tl_ = tl_hi; tl_ >= 0; --tl_, si -= step) {
-        acc = __fadd_rn(s_acc[si], __fmul_rn(s_kc[si], acc));   // vtrace.py:120
-        s_acc[si] = acc;
+      for (int q = tl_hi; q >= 0; --q, sj -= step) {
+        acc = __fadd_rn(s_acc[sj], __fmul_rn(s_kc[sj], acc));   // vtrace.py:120
+        s_acc[sj] = acc;
       }
       acc_carry = acc;
     }
     __syncthreads();
 
-    // ---- phase C: advantages, losses, gradient tile (in place over p_j) ----
-#pragma unroll
-    for (int k = 0; k < kEPT; ++k) {
-      const int i = tid + k * kNT;
-      const int tl_ = i >> 2, bl_ = i & 3;
-      if (i < nel && bl_ < nb) {
-        const int t = t0 + tl_;
-        const int si = sidx<EM>(tl_, bl_, TC);
-        float* pt = s_tl + si * A;
-        const int g = gidx<EM>(t, b0 + bl_, T, B);
-        if (t < T - 1) {
-          const float acc_n = (t + 1 == T - 1) ? 0.f : (tl_ + 1 < nt ? s_acc[sidx<EM>(tl_ + 1, bl_, TC)] : s_carry[bl_]);
-          const float vs = __fadd_rn(s_acc[si], e_v[k]);                 // vtrace.py:125
-          const float vs_n = __fadd_rn(acc_n, e_vn[k]);                  // :128-129 (bootstrap at the end)
-          const float adv =
-              __fmul_rn(e_rpg[k], __fsub_rn(__fadd_rn(e_r[k], __fmul_rn(e_g[k], vs_n)), e_v[k]));   // :136-137
-          const float dv = e_v[k] - vs;
-          sum_pi -= e_la[k] * adv;                                        // impala.py:67-68
-          sum_vf += 0.5f * dv * dv;                                       // :71-72
-          p.d_values[g] = p.vf_coeff * dv;
-          if (p.vs_out) p.vs_out[t * B + b0 + bl_] = vs;
-          if (p.pg_out) p.pg_out[t * B + b0 + bl_] = adv;
-          // dL/dz_j = p_j (adv - c_e H) - c_e p_j logp_j - adv [j == a]
-          const float c0 = adv - p.ent_coeff * e_H[k];
-          const float nce = -p.ent_coeff * kLN2;                          // q is stored in base-2 units
-          const float* pq = s_bl + si * A;
-          if constexpr (A_ > 0 && (A_ & 1) == 0) {
-#pragma unroll
-            for (int j = 0; j < A_; j += 2) {
-              const float2 pp = *reinterpret_cast<const float2*>(pt + j);
-              const float2 qq = *reinterpret_cast<const float2*>(pq + j);
-              *reinterpret_cast<float2*>(pt + j) =
-                  make_float2(fmaf(pp.x, c0, nce * qq.x), fmaf(pp.y, c0, nce * qq.y));
-            }
-          } else {
-            for (int j = 0; j < A; ++j) pt[j] = fmaf(pt[j], c0, nce * pq[j]);
+    // ---- phase C: advantages, losses, gradient tile (written over the target-logit tile) ----
+    if (valid) {
+      float* pt = s_tl + si * A;
+      if (loss_row) {
+        const float acc_n = (t + 1 == T - 1) ? 0.f : (tl_ + 1 < nt ? s_acc[sidx<EM>(tl_ + 1, bl_, TC)] : s_carry[bl_]);
+        const float vs = __fadd_rn(s_acc[si], e_v);                    // vtrace.py:125
+        const float vs_n = __fadd_rn(acc_n, e_vn);                     // :128-129 (bootstrap at the end)
+        const float adv = __fmul_rn(e_rpg, __fsub_rn(__fadd_rn(e_r, __fmul_rn(e_g, vs_n)), e_v));   // :136-137
+        const float dv = e_v - vs;
+        sum_pi -= ss.la * adv;                                          // impala.py:67-68
+        sum_vf += 0.5f * dv * dv;                                       // :71-72
+        p.d_values[g] = p.vf_coeff * dv;
+        if (p.vs_out) p.vs_out[t * B + b0 + bl_] = vs;
+        if (p.pg_out) p.pg_out[t * B + b0 + bl_] = adv;
+        // dL/dz_j = p_j (adv - c_e (H + log p_j)) - adv [j == a],  log p_j = ln2 (xs_j - log2 S)
+        const float ce2 = p.ent_coeff * kLN2;
+        const float c0 = fmaf(ce2, ss.l2S, adv - p.ent_coeff * ss.H) * ss.inv;   // folded with 1/S
+        const float c1 = -ce2 * ss.inv;
+        if constexpr (A_ > 0 && (A_ & 1) == 0) {
+#pragma unroll 3
+          for (int j = 0; j < A_; j += 2) {
+            const float2 a = *reinterpret_cast<const float2*>(pt + j);
+            const float xs0 = fmaf(a.x, kL2E, ss.nm), xs1 = fmaf(a.y, kL2E, ss.nm);
+            const float d0 = ex2_approx(xs0) * fmaf(c1, xs0, c0), d1 = ex2_approx(xs1) * fmaf(c1, xs1, c0);
+            *reinterpret_cast<float2*>(pt + j) = make_float2(d0, d1);
           }
-          pt[e_act[k]] -= adv;
         } else {
-          p.d_values[g] = 0.f;                                            // bootstrap row: no gradient
-          for (int j = 0; j < A; ++j) pt[j] = 0.f;
+          for (int j = 0; j < A; ++j) {
+            const float xs0 = fmaf(pt[j], kL2E, ss.nm);
+            pt[j] = ex2_approx(xs0) * fmaf(c1, xs0, c0);
+          }
         }
+        pt[act] -= adv;
+      } else {
+        p.d_values[g] = 0.f;                                            // bootstrap row: no gradient
+        for (int j = 0; j < A; ++j) pt[j] = 0.f;
       }
     }
     if (TMA) {
@@ -367,12 +338,12 @@ __global__ void __launch_bounds__(kNT, 7) vtrace_loss_kernel(const VtraceLossArg
         tma_store_commit();
         tma_store_wait_read();           // smem tile may be overwritten / the CTA may exit afterwards
       }
-      __syncthreads();
+      if (c > 0) __syncthreads();
     } else {
       __syncthreads();
       if (tid < nb) s_carry[tid] = acc_carry;
       copy_tile<EM, false>(s_tl, nullptr, p.d_logits, A, T, B, TC, t0, nt, b0, nb, vec);
-      __syncthreads();
+      if (c > 0) __syncthreads();
     }
   }
 
@@ -389,8 +360,8 @@ __global__ void __launch_bounds__(kNT, 7) vtrace_loss_kernel(const VtraceLossArg
 #pragma unroll
     for (int w = 0; w < kNT / 32; ++w) a += s_red[tid][w];
     p.partials[blockIdx.x * 4 + tid] = a;
+    __threadfence();
   }
-  __threadfence();
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
   __syncthreads();
@@ -519,11 +490,11 @@ extern "C" int rl_vtrace_loss_fwd_bwd(const float* target_logits, const float* b
     set_error("vtrace_loss: workspace too small (%zu < %zu)", workspace_bytes, rl_loss_workspace_bytes(B));
     return RL_ERR_WORKSPACE;
   }
-  // chunk of rows staged per pass: as many as fit ~30.5 KB (7 CTAs/SM) and kNT*kEPT elements
+  // chunk of rows staged per pass: as many as fit ~30.5 KB (7 CTAs/SM), one element per thread
   const size_t row_bytes = (size_t)kBW * (2 * A + 2) * sizeof(float);
   int TC = (int)(30500 / row_bytes);
   TC = TC < 1 ? 1 : TC;
-  if (TC > kNT * kEPT / kBW) TC = kNT * kEPT / kBW;
+  if (TC > kNT / kBW) TC = kNT / kBW;               // one (t,b) element per thread
   if (TC >= T) TC = T; else TC &= ~3;                 // multi-chunk: keep chunk starts 16-byte aligned
   if (TC < 1) TC = 1;
   const size_t smem = 2 * (size_t)tile_bytes_padded(TC, A) + (size_t)TC * kBW * 2 * sizeof(float);

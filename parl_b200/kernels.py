@@ -364,3 +364,19 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, gra
                                    float(lr), float(beta1), float(beta2), float(eps), int(step), float(grad_div),
                                    ptr(grad_norm), float(max_norm), int(clip_mode), 1 if zero_grad else 0, stream()),
           'adam_step')
+
+
+# --------------------------------------------------------------------------- tensor-core contractions
+def gemm_bf16_tn(a, b, bias=None, relu=False, out_dtype=torch.bfloat16, out=None):
+    """C = act(a @ b.T + bias) on tcgen05 (rl_gemm_bf16_tn): a [M,K] bf16, b [N,K] bf16 (nn.Linear weight layout)."""
+    require_cuda(a, b, bias)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.shape[1] == b.shape[1]
+    M, K = a.shape
+    N = b.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    assert out.dtype in (torch.bfloat16, torch.float32)
+    check(_lib.load().rl_gemm_bf16_tn(ptr(a), ptr(b), ptr(bias), ptr(out), M, N, K, a.stride(0), b.stride(0),
+                                      out.stride(0), 1 if relu else 0, 1 if out.dtype == torch.float32 else 0,
+                                      stream()), 'gemm_bf16_tn')
+    return out
