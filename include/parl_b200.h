@@ -129,7 +129,10 @@ int rl_env_atari_synth_step(
 /* Materialise observations from the frame ring: obs(t,b) channel j (0 = oldest)
  * = plane[t + 3 - min(3-j, age[t,b])].  planes [P,B,HW] u8, ages [>=t_begin+t_count, B] u8.
  * Output [t_count*B, 4, HW] in time-major or env-major sample order;
- * out_dtype 0 = uint8, 1 = float32 (value * scale). */
+ * out_dtype 0 = uint8, 1 = float32 (value * scale), both [n,4,HW] (NCHW);
+ * out_dtype 2 = bfloat16 [n,HW,4] (NHWC, value * scale) — the network input transform fused in;
+ * out_dtype 3 = bfloat16 [n,21,21,64]: conv1's space-to-depth form (8x8/4/pad-1 conv == 2x2/1 conv over 4x4
+ *               pixel blocks, channel = (dy*4+dx)*4+c, zero outside the image), 84x84 frames only. */
 int rl_obs_stack_gather(
     const uint8_t* planes, const uint8_t* ages, int B, int HW, int t_begin, int t_count,
     int out_layout, int out_dtype, float scale, void* out, rl_stream_t stream);

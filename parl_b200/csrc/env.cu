@@ -11,6 +11,8 @@
 // older planes belong to the same episode), done masks are aggregated with
 // __ballot_sync for the episode statistics.
 // RNG contract: Philox4x32-10, counter (env_id, step, block, stream) — philox.cuh.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -180,6 +182,109 @@ __global__ void __launch_bounds__(256) obs_stack_gather_kernel(const uint8_t* __
     const int plane = t + 3 - min(3 - j, age);
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(planes + ((long long)plane * B + b) * HW) + blk);
     store16<OutT>(out + (r * 4 + j) * HW + (blk << 4), v, scale);
+  }
+}
+
+
+// Same gather, fused with the network's input transform: out[sample, pixel, channel] (NHWC) in bf16,
+// value * scale (scale = 1/255 reproduces ``obs / 255.0`` of the reference models).  One thread = 16 pixels
+// x 4 channels: four 16-byte plane reads, one 128-byte contiguous write.
+__global__ void __launch_bounds__(256) obs_stack_gather_nhwc_bf16_kernel(const uint8_t* __restrict__ planes,
+                                                                         const uint8_t* __restrict__ ages, int B,
+                                                                         int HW, int t_begin, int t_count,
+                                                                         int env_major, float scale,
+                                                                         __nv_bfloat16* __restrict__ out) {
+  const int nblk = HW >> 4;
+  const long long total = (long long)t_count * B * nblk;
+  const long long gstride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gstride) {
+    const int blk = (int)(i % nblk);
+    const long long r = i / nblk;
+    int t, b;
+    if (env_major) {
+      b = (int)(r / t_count), t = (int)(r - (long long)b * t_count);
+    } else {
+      t = (int)(r / B), b = (int)(r - (long long)t * B);
+    }
+    t += t_begin;
+    const int age = ages[(long long)t * B + b];
+    uint32_t w[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int plane = t + 3 - min(3 - j, age);
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(planes + ((long long)plane * B + b) * HW) + blk);
+      w[j][0] = v.x, w[j][1] = v.y, w[j][2] = v.z, w[j][3] = v.w;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + (r * HW + (blk << 4)) * 4);
+#pragma unroll
+    for (int px = 0; px < 16; px += 2) {     // two pixels (8 bf16 = 16 bytes) per store
+      uint32_t pk[4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int p = px + h;
+        float c[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[j] = (float)((w[j][p >> 2] >> ((p & 3) * 8)) & 0xffu) * scale;
+        __nv_bfloat162 lo = __floats2bfloat162_rn(c[0], c[1]), hi = __floats2bfloat162_rn(c[2], c[3]);
+        pk[h * 2] = *reinterpret_cast<uint32_t*>(&lo), pk[h * 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
+      }
+      dst[px >> 1] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+// Gather fused with conv1's space-to-depth transform.  The first conv of the Atari models is 8x8 / stride 4 /
+// pad 1 on 84x84x4 (benchmark/torch/a2c/atari_model.py:26-27); it never reads the last image row/column, so it
+// equals a 2x2 / stride 1 conv on a 21x21 grid of 4x4 pixel blocks with 64 channels:
+//   out[sample, Y, X, (dy*4+dx)*4 + c] = scale * frame_c[4Y+dy-1][4X+dx-1]      (zero outside the image)
+// bf16, 128 contiguous bytes per block -> tensor-core friendly NHWC input.  One thread = one (sample,Y,X,dy).
+__global__ void __launch_bounds__(256) obs_stack_gather_s2d_bf16_kernel(const uint8_t* __restrict__ planes,
+                                                                        const uint8_t* __restrict__ ages, int B,
+                                                                        int t_begin, int t_count, int env_major,
+                                                                        float scale, __nv_bfloat16* __restrict__ out) {
+  constexpr int W = 84, G = 21;
+  const long long total = (long long)t_count * B * G * G * 4;
+  const long long gstride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gstride) {
+    const int dy = (int)(i & 3);
+    long long r = i >> 2;
+    const int X = (int)(r % G);
+    r /= G;
+    const int Y = (int)(r % G);
+    r /= G;                                   // sample index in output order
+    int t, b;
+    if (env_major) {
+      b = (int)(r / t_count), t = (int)(r - (long long)b * t_count);
+    } else {
+      t = (int)(r / B), b = (int)(r - (long long)t * B);
+    }
+    t += t_begin;
+    const int y = 4 * Y + dy - 1;
+    const int age = ages[(long long)t * B + b];
+    uint32_t px[4];                           // per channel: the 4 bytes at x = 4X-1 .. 4X+2
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      px[c] = 0u;
+      if (y >= 0) {
+        const int plane = t + 3 - min(3 - c, age);
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(planes + ((long long)plane * B + b) * (W * W) + y * W);
+        const uint32_t w0 = X > 0 ? __ldg(row + X - 1) : 0u;     // bytes 4X-4 .. 4X-1
+        const uint32_t w1 = __ldg(row + X);                      // bytes 4X   .. 4X+3
+        px[c] = (w0 >> 24) | (w1 << 8);
+      }
+    }
+    uint32_t pk[8];
+#pragma unroll
+    for (int dx = 0; dx < 4; ++dx) {
+      float v[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[c] = (float)((px[c] >> (8 * dx)) & 0xffu) * scale;
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+      pk[dx * 2] = *reinterpret_cast<uint32_t*>(&lo), pk[dx * 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + ((r * G + Y) * G + X) * 64 + dy * 16);
+    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
   }
 }
 
@@ -389,8 +494,21 @@ extern "C" int rl_obs_stack_gather(const uint8_t* planes, const uint8_t* ages, i
   } else if (out_dtype == 1) {
     obs_stack_gather_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         planes, ages, B, HW, t_begin, t_count, em, scale, (float*)out);
+  } else if (out_dtype == 2) {
+    const long long tot2 = (long long)t_count * B * (HW / 16);
+    long long b2 = (tot2 + 255) / 256;
+    if (b2 > 148LL * 32) b2 = 148LL * 32;
+    obs_stack_gather_nhwc_bf16_kernel<<<(unsigned)b2, 256, 0, (cudaStream_t)stream>>>(
+        planes, ages, B, HW, t_begin, t_count, em, scale, (__nv_bfloat16*)out);
+  } else if (out_dtype == 3) {
+    RL_CHECK_ARG(HW == 84 * 84, "obs_stack_gather: the space-to-depth layout is defined for 84x84 frames");
+    const long long tot3 = (long long)t_count * B * 21 * 21 * 4;
+    long long b3 = (tot3 + 255) / 256;
+    if (b3 > 148LL * 32) b3 = 148LL * 32;
+    obs_stack_gather_s2d_bf16_kernel<<<(unsigned)b3, 256, 0, (cudaStream_t)stream>>>(
+        planes, ages, B, t_begin, t_count, em, scale, (__nv_bfloat16*)out);
   } else {
-    set_error("obs_stack_gather: out_dtype %d unsupported (0=u8, 1=f32)", out_dtype);
+    set_error("obs_stack_gather: out_dtype %d unsupported (0=u8, 1=f32, 2=bf16 NHWC, 3=bf16 space-to-depth)", out_dtype);
     return RL_ERR_UNSUPPORTED;
   }
   RL_CHECK_LAUNCH("rl_obs_stack_gather");

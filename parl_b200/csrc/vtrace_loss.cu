@@ -175,7 +175,7 @@ __device__ __forceinline__ SoftmaxStats softmax_stats(const float* __restrict__ 
 __host__ __device__ inline int tile_bytes_padded(int TC, int A) { return (TC * kBW * A * 4 + 127) & ~127; }
 
 template <int A_, bool EM, bool TMA>
-__global__ void __launch_bounds__(kNT, 6) vtrace_loss_kernel(const VtraceLossArgs p,
+__global__ void __launch_bounds__(kNT, 7) vtrace_loss_kernel(const VtraceLossArgs p,
                                                             const __grid_constant__ CUtensorMap map_tl,
                                                             const __grid_constant__ CUtensorMap map_bl,
                                                             const __grid_constant__ CUtensorMap map_dl) {
@@ -276,18 +276,49 @@ __global__ void __launch_bounds__(kNT, 6) vtrace_loss_kernel(const VtraceLossArg
     }
     __syncthreads();
 
-    // ---- phase B: backward scan, one lane per column, reference op order ----
-    if (tid < nb) {
-      float acc = acc_carry;
-      const int tl_hi = min(nt, T - 1 - t0) - 1;          // skip the bootstrap row
+    // ---- phase B: backward-in-time scan acc_t = delta_t + k_t * acc_{t+1} as a warp-shuffle segmented prefix:
+    //      warp 0 = 4 columns x 8 time segments; each lane composes the affine maps of its rows, a 3-step
+    //      shuffle suffix-scan combines the segments (k_t = 0 at episode cuts makes the prefix segmented),
+    //      then each lane replays its rows with the incoming accumulator.
+    if (tid < 32) {
+      const int col = tid & 3, seg = tid >> 2;                 // lane = seg*4 + col
+      const int nrows = min(nt, T - 1 - t0);                   // loss rows of this chunk (bootstrap row skipped)
+      const int per = (nrows + 7) >> 3;
+      const int lo = min(seg * per, nrows), hi = min(lo + per, nrows);     // this lane's rows [lo, hi)
       const int step = EM ? 1 : kBW;
-      int sj = sidx<EM>(tl_hi, tid, TC);
-#pragma unroll 8
-      for (int q = tl_hi; q >= 0; --q, sj -= step) {
-        acc = __fadd_rn(s_acc[sj], __fmul_rn(s_kc[sj], acc));   // vtrace.py:120
-        s_acc[sj] = acc;
+      const bool colok = col < nb;
+      float D = 0.f, K = 1.f;
+      if (colok) {
+        int sj = sidx<EM>(hi - 1, col, TC);
+        for (int q = hi - 1; q >= lo; --q, sj -= step) {
+          const float k = s_kc[sj];
+          D = fmaf(k, D, s_acc[sj]);
+          K *= k;
+        }
       }
-      acc_carry = acc;
+      // inclusive suffix scan over segments (later time = higher seg): F_seg o F_{seg+off}
+#pragma unroll
+      for (int off = 1; off < 8; off <<= 1) {
+        const float Dn = __shfl_down_sync(0xffffffffu, D, off * 4);
+        const float Kn = __shfl_down_sync(0xffffffffu, K, off * 4);
+        if (seg + off < 8) {
+          D = fmaf(K, Dn, D);
+          K *= Kn;
+        }
+      }
+      // accumulator entering this lane's segment = composite of all later segments applied to the carry
+      const float Dx = __shfl_down_sync(0xffffffffu, D, 4), Kx = __shfl_down_sync(0xffffffffu, K, 4);
+      const float carry_in = __shfl_sync(0xffffffffu, acc_carry, col);       // lanes 0..3 hold the column carries
+      float acc = seg < 7 ? fmaf(Kx, carry_in, Dx) : carry_in;
+      if (colok) {
+        int sj = sidx<EM>(hi - 1, col, TC);
+        for (int q = hi - 1; q >= lo; --q, sj -= step) {
+          acc = fmaf(s_kc[sj], acc, s_acc[sj]);
+          s_acc[sj] = acc;
+        }
+      }
+      // lanes 0..3 (segment 0) end on row 0 of the chunk: that is the carry for the next (earlier) chunk
+      if (seg == 0) acc_carry = acc;
     }
     __syncthreads();
 
@@ -438,6 +469,8 @@ static int launch_vtrace_loss(const VtraceLossArgs& a, int layout, bool tma, con
     vtrace_loss_kernel<A_, true, false><<<grid, kNT, smem, st>>>(a, maps[0], maps[1], maps[2]);
   } else if (tma) {
     cudaFuncSetAttribute(vtrace_loss_kernel<A_, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(vtrace_loss_kernel<A_, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
     vtrace_loss_kernel<A_, false, true><<<grid, kNT, smem, st>>>(a, maps[0], maps[1], maps[2]);
   } else {
     cudaFuncSetAttribute(vtrace_loss_kernel<A_, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

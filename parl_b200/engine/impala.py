@@ -40,7 +40,9 @@ class ImpalaEngine(object):
         self.rewards = torch.zeros((T, B), dtype=torch.float32, device=dev)
         self.dones = torch.zeros((T, B), dtype=torch.uint8, device=dev)
         self.stats = kernels.EpisodeStats(B, dev)
-        self.obs_step = torch.empty((B, 4, self.h, self.w), dtype=torch.uint8, device=dev)
+        self.s2d = (self.h, self.w) == (84, 84)              # conv1 space-to-depth input [N,21,21,64]
+        obs_shape = (21, 21, 64) if self.s2d else (self.h, self.w, 4)
+        self.obs_step = torch.empty((B, ) + obs_shape, dtype=torch.bfloat16, device=dev)     # NHWC, pre-scaled
         self.step_dev = torch.zeros(T, dtype=torch.int32, device=dev)      # global env-step index of row t
         self.step_dev.copy_(torch.arange(T, dtype=torch.int32))
         self.model = model if model is not None else AtariActorCritic(A)
@@ -48,7 +50,11 @@ class ImpalaEngine(object):
         self.alg = IMPALA(self.model, sample_batch_steps=T, gamma=gamma, vf_loss_coeff=vf_loss_coeff,
                           clip_rho_threshold=clip_rho_threshold, clip_pg_rho_threshold=clip_pg_rho_threshold)
         self.learn_chunk_rows = int(learn_chunk_rows)
-        self.obs_chunk = torch.empty((self.learn_chunk_rows * B, 4, self.h, self.w), dtype=torch.uint8, device=dev)
+        # learner inputs: one pre-scaled bf16 NHWC buffer per chunk (each is saved by autograd for conv1's
+        # weight gradient, so chunks must not share storage): T*B*56 KB in total
+        self.obs_chunks = [torch.empty((min(self.learn_chunk_rows, T - t0) * B, ) + obs_shape,
+                                       dtype=torch.bfloat16, device=dev)
+                           for t0 in range(0, T, self.learn_chunk_rows)]
         self.tgt_logits = torch.empty((T, B, A), dtype=torch.float32, device=dev)
         self.values = torch.empty((T, B), dtype=torch.float32, device=dev)
         self.loss_out = dict(losses=torch.zeros(8, device=dev), d_logits=torch.empty((T * B, A), device=dev),
@@ -76,7 +82,7 @@ class ImpalaEngine(object):
             self.ages[0].copy_(self.ages[T])
             self.step_dev.add_(T)
             for t in range(T):
-                kernels.obs_stack_gather(self.planes, self.ages, t, 1, self.obs_step)
+                kernels.obs_stack_gather(self.planes, self.ages, t, 1, self.obs_step, scale=1.0 / 255.0, s2d=self.s2d)
                 logits = self.model.policy(self.obs_step)
                 self.beh_logits[t].copy_(logits)
                 kernels.env_atari_synth_step(self.planes[t + 4], self.rewards[t], self.dones[t], self.ages[t],
@@ -112,10 +118,10 @@ class ImpalaEngine(object):
         T, B, A = self.T, self.B, self.A
         rows = self.learn_chunk_rows
         outs = []
-        for t0 in range(0, T, rows):
+        for ci, t0 in enumerate(range(0, T, rows)):
             n = min(rows, T - t0)
-            obs = self.obs_chunk[:n * B]
-            kernels.obs_stack_gather(self.planes, self.ages, t0, n, obs)
+            obs = self.obs_chunks[ci]
+            kernels.obs_stack_gather(self.planes, self.ages, t0, n, obs, scale=1.0 / 255.0, s2d=self.s2d)
             logits, values = self.model.policy_and_value(obs)
             self.tgt_logits[t0:t0 + n].copy_(logits.detach().view(n, B, A))
             self.values[t0:t0 + n].copy_(values.detach().view(n, B))

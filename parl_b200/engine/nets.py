@@ -33,14 +33,29 @@ class AtariActorCritic(Model):
                 nn.init.constant_(m.bias, 0)
 
     def _trunk(self, x):
+        """Accepts (a) bf16 [N,21,21,64]: conv1's space-to-depth input from rl_obs_stack_gather(s2d=True),
+        already scaled by 1/255; (b) bf16 [N,84,84,4] NHWC, already scaled; (c) uint8/float [N,4,84,84] as in
+        the reference (scaled here by 1/255).  Activations stay NHWC (channels_last); the flatten before
+        ``fc`` is taken in (H,W,C) order with the weight columns permuted accordingly, which is the same
+        function as the reference's (C,H,W) nn.Flatten + nn.Linear."""
         dt = self.compute_dtype if x.is_cuda else torch.float32
         with torch.autocast(device_type=x.device.type, dtype=dt, enabled=dt != torch.float32):
-            x = x.to(dt) / 255.0
-            x = x.contiguous(memory_format=torch.channels_last)
-            x = F.relu(self.conv1(x))
+            if x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[-1] == 64:
+                # 8x8/4/pad-1 conv == 2x2/1 conv over 4x4 pixel blocks: W1[o,c,4a+dy,4b+dx] -> W1'[o,(dy,dx,c),a,b]
+                w1 = self.conv1.weight.view(32, 4, 2, 4, 2, 4).permute(0, 3, 5, 1, 2, 4).reshape(32, 64, 2, 2)
+                x = F.relu(F.conv2d(x.permute(0, 3, 1, 2), w1, self.conv1.bias))
+            else:
+                if x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[-1] == 4:
+                    x = x.permute(0, 3, 1, 2)              # zero-copy NCHW view with channels_last strides
+                else:
+                    x = (x.to(dt) / 255.0).contiguous(memory_format=torch.channels_last)
+                x = F.relu(self.conv1(x))
             x = F.relu(self.conv2(x))
             x = F.relu(self.conv3(x))
-            return F.relu(self.fc(x.flatten(1)))       # (C,H,W) feature order, as nn.Flatten in the reference
+            n = x.shape[0]
+            feat = x.permute(0, 2, 3, 1).reshape(n, -1)     # (H,W,C) order: a view for channels_last activations
+            wfc = self.fc.weight.view(512, 64, 9, 9).permute(0, 2, 3, 1).reshape(512, 64 * 9 * 9)
+            return F.relu(F.linear(feat, wfc, self.fc.bias))
 
     def policy(self, x):
         h = self._trunk(x)

@@ -129,11 +129,16 @@ def env_atari_synth_step(frame_out, reward_out, done_out, age_in, age_out, stats
         1 if reset else 0, stream()), 'env_atari_synth_step')
 
 
-def obs_stack_gather(planes, ages, t_begin, t_count, out, layout=TIME_MAJOR, scale=1.0):
-    """planes [P,B,HW] u8, ages [T+1,B] u8 -> out [t_count*B, 4, HW] (uint8 or float32)."""
+def obs_stack_gather(planes, ages, t_begin, t_count, out, layout=TIME_MAJOR, scale=1.0, s2d=False):
+    """planes [P,B,HW] u8, ages [T+1,B] u8 -> out [t_count*B, 4, HW] (uint8 / float32, NCHW) or
+    [t_count*B, HW, 4] (bfloat16, NHWC, value*scale)."""
     P, B, HW = planes.shape[0], planes.shape[1], planes[0, 0].numel()
-    dt = {torch.uint8: 0, torch.float32: 1}[out.dtype]
-    assert out.numel() == t_count * B * 4 * HW
+    dt = {torch.uint8: 0, torch.float32: 1, torch.bfloat16: 2}[out.dtype]
+    if s2d:
+        assert out.dtype == torch.bfloat16 and out.numel() == t_count * B * 21 * 21 * 64
+        dt = 3
+    else:
+        assert out.numel() == t_count * B * 4 * HW
     check(_lib.load().rl_obs_stack_gather(ptr(planes), ptr(ages), B, HW, int(t_begin), int(t_count), layout, dt,
                                           float(scale), ptr(out), stream()), 'obs_stack_gather')
     return out

@@ -172,3 +172,35 @@ def test_gaussian_sampler():
     assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
     want = oenv.gaussians(np.arange(N, dtype=np.uint32), 3, D, *oph.split_seed(7), stream=oph.STREAM_GAUSS)
     np.testing.assert_allclose(z, want, rtol=1e-3, atol=1e-4)
+
+
+def test_obs_gather_nhwc_and_space_to_depth():
+    """bf16 NHWC and conv1 space-to-depth gathers against the uint8 NCHW gather (itself checked bit-exactly above)."""
+    from parl_b200 import kernels as K
+    B, HW, T, seed = 9, 84 * 84, 6, 5
+    planes = torch.zeros(T + 4, B, HW, dtype=torch.uint8, device=DEV)
+    ages = torch.zeros(T + 1, B, dtype=torch.uint8, device=DEV)
+    rew = torch.zeros(B, device=DEV)
+    done = torch.zeros(B, dtype=torch.uint8, device=DEV)
+    st = K.EpisodeStats(B, DEV)
+    K.env_atari_synth_step(planes[3], None, None, None, ages[0], st, seed, 0, reset=True)
+    for t in range(T):
+        K.env_atari_synth_step(planes[t + 4], rew, done, ages[t], ages[t + 1], st, seed, t, p_done=0.3)
+    u8 = torch.empty(T * B, 4, 84, 84, dtype=torch.uint8, device=DEV)
+    K.obs_stack_gather(planes, ages, 0, T, u8)
+    ref = u8.cpu().float() * np.float32(1.0 / 255.0)                        # [N,4,84,84]
+    nhwc = torch.empty(T * B, 84, 84, 4, dtype=torch.bfloat16, device=DEV)
+    K.obs_stack_gather(planes, ages, 0, T, nhwc, scale=1.0 / 255.0)
+    want = ref.permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert torch.equal(nhwc.cpu(), want)
+    s2d = torch.empty(T * B, 21, 21, 64, dtype=torch.bfloat16, device=DEV)
+    K.obs_stack_gather(planes, ages, 0, T, s2d, scale=1.0 / 255.0, s2d=True)
+    pad = torch.zeros(T * B, 4, 85, 85)
+    pad[:, :, 1:, 1:] = ref
+    blocks = pad[:, :, :84, :84].reshape(T * B, 4, 21, 4, 21, 4)            # (n, c, Y, dy, X, dx)
+    want = blocks.permute(0, 2, 4, 3, 5, 1).reshape(T * B, 21, 21, 64).to(torch.bfloat16)
+    assert torch.equal(s2d.cpu(), want)
+    # env-major order
+    s2d_em = torch.empty(T * B, 21, 21, 64, dtype=torch.bfloat16, device=DEV)
+    K.obs_stack_gather(planes, ages, 0, T, s2d_em, layout=K.ENV_MAJOR, scale=1.0 / 255.0, s2d=True)
+    assert torch.equal(s2d_em.cpu().reshape(B, T, -1), want.reshape(T, B, -1).transpose(0, 1))
