@@ -277,6 +277,14 @@ int rl_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, l
 int rl_gemm_bf16_tn(const void* A, const void* B, const float* bias, void* C, int M, int N, int K,
                     int lda, int ldb, int ldc, int relu, int out_f32, rl_stream_t stream);
 
+/* NHWC bf16 convolution forward (+bias, optional ReLU) as an implicit GEMM on tcgen05: the conv layers of
+ * the Atari actor-critic (benchmark/torch/a2c/atari_model.py:26-44; executed there by cuDNN through torch).
+ *   in [N,Hin,Win,Cin] bf16, weight_krsc [Cout, KH*KW*Cin] bf16 with K ordered (r, s, c), bias [Cout] f32,
+ *   out [N,Hout,Wout,Cout] bf16.  Cin, Cout in {32, 64}; KH*KW*Cin a multiple of 64. */
+int rl_conv2d_nhwc_bf16_fwd(const void* in, const void* weight_krsc, const float* bias, void* out,
+                            int N, int Hin, int Win, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                            int relu, rl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

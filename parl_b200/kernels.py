@@ -385,3 +385,17 @@ def gemm_bf16_tn(a, b, bias=None, relu=False, out_dtype=torch.bfloat16, out=None
                                       out.stride(0), 1 if relu else 0, 1 if out.dtype == torch.float32 else 0,
                                       stream()), 'gemm_bf16_tn')
     return out
+
+
+def conv2d_nhwc_bf16_fwd(x, weight_krsc, bias, KH, KW, stride, pad, relu=True, out=None):
+    """NHWC bf16 conv forward on tcgen05 (rl_conv2d_nhwc_bf16_fwd): x [N,H,W,Cin], weight [Cout, KH*KW*Cin] (r,s,c)."""
+    require_cuda(x, weight_krsc, bias)
+    assert x.dtype == torch.bfloat16 and weight_krsc.dtype == torch.bfloat16 and bias.dtype == torch.float32
+    N, H, W, Cin = x.shape
+    Cout = weight_krsc.shape[0]
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    if out is None:
+        out = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().rl_conv2d_nhwc_bf16_fwd(ptr(x), ptr(weight_krsc), ptr(bias), ptr(out), N, H, W, Cin, Cout, KH, KW,
+                                              stride, pad, 1 if relu else 0, stream()), 'conv2d_nhwc_bf16_fwd')
+    return out
