@@ -254,6 +254,9 @@ extern "C" int rl_gemm_bf16_tn(const void* A, const void* B, const float* bias, 
   RL_CHECK_ARG(lda >= K && ldb >= K && ldc >= N && (lda % 8) == 0 && (ldb % 8) == 0,
                "gemm_bf16_tn: lda/ldb must be >= K and multiples of 8 elements (TMA row pitch)");
   int BN = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
+  // small problems: prefer more, narrower tiles so that the grid covers the 148 SMs
+  const long long mt = (M + kGemmBM - 1) / kGemmBM;
+  while (BN > 64 && mt * ((N + BN - 1) / BN) < 148) BN >>= 1;
   alignas(64) CUtensorMap ma, mb;
   if (make_tensor_map_bf16_sw128(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kGemmBM) ||
       make_tensor_map_bf16_sw128(&mb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, (uint32_t)BN)) {

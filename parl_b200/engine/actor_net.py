@@ -1,0 +1,69 @@
+"""Actor-side inference of the Atari actor-critic entirely on hand-written tcgen05 kernels
+(rl_conv2d_nhwc_bf16_fwd x3 + rl_gemm_bf16_tn x2): the policy forward the reference runs on CPU, batch 5,
+inside every remote actor (examples/IMPALA/actor.py:60-62, atari_agent.py:35-42) — here once per time
+step for the whole pool, reading the space-to-depth observation written by rl_obs_stack_gather and writing
+the logits straight into the (T,B,A) rollout buffer.
+
+The bf16 operand copies of the parameters are re-packed from the fp32 master weights after every learner
+update (``pack``): conv kernels in (r,s,c)-ordered [Cout, K] form, conv1 in its space-to-depth form, the
+fc weight with (H,W,C)-ordered columns.
+"""
+import torch
+
+from .. import kernels
+
+
+class AtariActorNet(object):
+    def __init__(self, model, batch, device):
+        self.model = model
+        self.B = int(batch)
+        dev = self.device = torch.device(device)
+        bf = torch.bfloat16
+        self.a1 = torch.empty((self.B, 20, 20, 32), dtype=bf, device=dev)
+        self.a2 = torch.empty((self.B, 11, 11, 64), dtype=bf, device=dev)
+        self.a3 = torch.empty((self.B, 9, 9, 64), dtype=bf, device=dev)
+        self.h = torch.empty((self.B, 512), dtype=bf, device=dev)
+        A = model.fc_pi.weight.shape[0]
+        self.A = A
+        self.w1 = torch.empty((32, 256), dtype=bf, device=dev)
+        self.w2 = torch.empty((64, 512), dtype=bf, device=dev)
+        self.w3 = torch.empty((64, 576), dtype=bf, device=dev)
+        self.wfc = torch.empty((512, 5184), dtype=bf, device=dev)
+        self.wpi = torch.empty((A, 512), dtype=bf, device=dev)
+        self.wv = torch.empty((1, 512), dtype=bf, device=dev)
+        self.b1 = torch.empty(32, dtype=torch.float32, device=dev)
+        self.b2 = torch.empty(64, dtype=torch.float32, device=dev)
+        self.b3 = torch.empty(64, dtype=torch.float32, device=dev)
+        self.bfc = torch.empty(512, dtype=torch.float32, device=dev)
+        self.bpi = torch.empty(A, dtype=torch.float32, device=dev)
+        self.bv = torch.empty(1, dtype=torch.float32, device=dev)
+        self.pack()
+
+    @torch.no_grad()
+    def pack(self):
+        """fp32 master weights -> bf16 kernel operands (in place: safe to call between CUDA-graph replays)."""
+        m = self.model
+        # conv1 8x8/4 -> 2x2/1 on 4x4 pixel blocks: W1[o,c,4a+dy,4b+dx] -> [o, (a,b), (dy,dx,c)]
+        w1 = m.conv1.weight.view(32, 4, 2, 4, 2, 4).permute(0, 2, 4, 3, 5, 1)      # (o, a, b, dy, dx, c)
+        self.w1.copy_(w1.reshape(32, 256))
+        self.w2.copy_(m.conv2.weight.permute(0, 2, 3, 1).reshape(64, 512))         # (o, r, s, c)
+        self.w3.copy_(m.conv3.weight.permute(0, 2, 3, 1).reshape(64, 576))
+        self.wfc.copy_(m.fc.weight.view(512, 64, 9, 9).permute(0, 2, 3, 1).reshape(512, 5184))
+        self.wpi.copy_(m.fc_pi.weight)
+        self.wv.copy_(m.fc_v.weight)
+        self.b1.copy_(m.conv1.bias), self.b2.copy_(m.conv2.bias), self.b3.copy_(m.conv3.bias)
+        self.bfc.copy_(m.fc.bias), self.bpi.copy_(m.fc_pi.bias), self.bv.copy_(m.fc_v.bias)
+
+    def policy(self, obs_s2d, logits_out):
+        """obs_s2d [B,21,21,64] bf16 (already scaled by 1/255) -> logits_out [B,A] float32."""
+        K = kernels
+        K.conv2d_nhwc_bf16_fwd(obs_s2d, self.w1, self.b1, 2, 2, 1, 0, relu=True, out=self.a1)
+        K.conv2d_nhwc_bf16_fwd(self.a1, self.w2, self.b2, 4, 4, 2, 2, relu=True, out=self.a2)
+        K.conv2d_nhwc_bf16_fwd(self.a2, self.w3, self.b3, 3, 3, 1, 0, relu=True, out=self.a3)
+        K.gemm_bf16_tn(self.a3.view(self.B, 5184), self.wfc, self.bfc, relu=True, out=self.h)
+        K.gemm_bf16_tn(self.h, self.wpi, self.bpi, relu=False, out=logits_out)
+        return logits_out
+
+    def value(self, values_out):
+        """Value head on the trunk features of the last ``policy`` call -> values_out [B,1] float32."""
+        return kernels.gemm_bf16_tn(self.h, self.wv, self.bv, relu=False, out=values_out)

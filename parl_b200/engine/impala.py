@@ -18,12 +18,13 @@ import torch
 from .. import kernels
 from ..algorithms import IMPALA
 from .nets import AtariActorCritic
+from .actor_net import AtariActorNet
 
 
 class ImpalaEngine(object):
     def __init__(self, num_envs=4096, sample_batch_steps=50, act_dim=18, frame_hw=(84, 84), seed=0, device=None,
                  env_offset=0, gamma=0.99, vf_loss_coeff=0.5, clip_rho_threshold=1.0, clip_pg_rho_threshold=1.0,
-                 p_done=0.1, model=None, learn_chunk_rows=5, use_graph=True):
+                 p_done=0.1, model=None, learn_chunk_rows=5, use_graph=True, actor_kernels='auto'):
         if device is None:
             device = torch.device('cuda', torch.cuda.current_device())
         self.device = torch.device(device)
@@ -59,6 +60,11 @@ class ImpalaEngine(object):
         self.values = torch.empty((T, B), dtype=torch.float32, device=dev)
         self.loss_out = dict(losses=torch.zeros(8, device=dev), d_logits=torch.empty((T * B, A), device=dev),
                              d_values=torch.empty(T * B, device=dev))
+        # actor-side policy forward: hand-written tcgen05 conv/GEMM kernels when the model is the Atari
+        # actor-critic on 84x84 frames ('auto'), else the user's torch Model
+        use_native = actor_kernels is True or (actor_kernels == 'auto' and self.s2d and
+                                               isinstance(self.model, AtariActorCritic))
+        self.actor_net = AtariActorNet(self.model, B, dev) if use_native else None
         self.sample_steps = 0
         self.use_graph = use_graph
         self._graph = None
@@ -83,8 +89,10 @@ class ImpalaEngine(object):
             self.step_dev.add_(T)
             for t in range(T):
                 kernels.obs_stack_gather(self.planes, self.ages, t, 1, self.obs_step, scale=1.0 / 255.0, s2d=self.s2d)
-                logits = self.model.policy(self.obs_step)
-                self.beh_logits[t].copy_(logits)
+                if self.actor_net is not None:
+                    self.actor_net.policy(self.obs_step, self.beh_logits[t])
+                else:
+                    self.beh_logits[t].copy_(self.model.policy(self.obs_step))
                 kernels.env_atari_synth_step(self.planes[t + 4], self.rewards[t], self.dones[t], self.ages[t],
                                              self.ages[t + 1], self.stats, self.seed, 0, p_done=self.p_done,
                                              env_offset=self.env_offset, logits=self.beh_logits[t],
@@ -148,6 +156,8 @@ class ImpalaEngine(object):
         if self.alg.grad_sync is not None:
             self.alg.grad_sync(self.alg.optimizer.grad)
         self.alg.optimizer.step(lr=learning_rate)
+        if self.actor_net is not None:
+            self.actor_net.pack()              # refresh the actor's bf16 operand copies (weights never leave HBM)
         return res['losses']
 
     # ------------------------------------------------------------------ reference-facing host contract
@@ -213,6 +223,8 @@ class ImpalaEngine(object):
         if self.alg.grad_sync is not None:
             self.alg.grad_sync(self.alg.optimizer.grad)
         self.alg.optimizer.step(lr=learning_rate)
+        if self.actor_net is not None:
+            self.actor_net.pack()
         return res['losses']
 
     # ------------------------------------------------------------------ metrics (Actor.get_metrics analogue)

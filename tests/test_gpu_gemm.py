@@ -43,3 +43,41 @@ def test_conv2d_nhwc_bf16_fwd(N, H, Cin, Cout, k, stride, pad):
     ref = ref.permute(0, 2, 3, 1)
     err = (out.float() - ref).abs().max().item()
     assert out.shape == ref.shape and err < 2e-2 * max(1.0, ref.abs().max().item()), err
+
+
+def test_native_actor_net_matches_torch_model():
+    """The tcgen05 inference path (s2d conv1 -> conv2 -> conv3 -> fc -> policy head) against the torch model
+    (bf16 autocast) on real observations from the device env pool."""
+    from parl_b200 import kernels as K_
+    from parl_b200.engine.nets import AtariActorCritic
+    from parl_b200.engine.actor_net import AtariActorNet
+    torch.manual_seed(0)
+    B = 300
+    model = AtariActorCritic(18).to(DEV)
+    net = AtariActorNet(model, B, DEV)
+    planes = torch.zeros(5, B, 84 * 84, dtype=torch.uint8, device=DEV)
+    ages = torch.zeros(2, B, dtype=torch.uint8, device=DEV)
+    st = K_.EpisodeStats(B, DEV)
+    for p in range(4):
+        K_.env_atari_synth_step(planes[p], None, None, None, ages[0], st, 7, p, reset=True)
+    ages[0] = 3
+    obs = torch.empty(B, 21, 21, 64, dtype=torch.bfloat16, device=DEV)
+    K_.obs_stack_gather(planes, ages, 0, 1, obs, scale=1.0 / 255.0, s2d=True)
+    logits = torch.empty(B, 18, dtype=torch.float32, device=DEV)
+    net.policy(obs, logits)
+    val = torch.empty(B, 1, dtype=torch.float32, device=DEV)
+    net.value(val)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref_l, ref_v = model.policy_and_value(obs)
+    scale = max(1.0, ref_l.abs().max().item())
+    assert (logits - ref_l).abs().max().item() < 3e-2 * scale
+    assert (val.squeeze(1) - ref_v).abs().max().item() < 3e-2 * max(1.0, ref_v.abs().max().item())
+    # fp32 reference of the same function (reference-form network on uint8 NCHW obs)
+    u8 = torch.empty(B, 4, 84, 84, dtype=torch.uint8, device=DEV)
+    K_.obs_stack_gather(planes, ages, 0, 1, u8)
+    m32 = AtariActorCritic(18, compute_dtype=torch.float32).to(DEV)
+    m32.load_state_dict(model.state_dict())
+    with torch.no_grad():
+        l32 = m32.policy(u8)
+    assert (logits - l32).abs().max().item() < 5e-2 * scale
