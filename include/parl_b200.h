@@ -285,6 +285,18 @@ int rl_conv2d_nhwc_bf16_fwd(const void* in, const void* weight_krsc, const float
                             int N, int Hin, int Win, int Cin, int Cout, int KH, int KW, int stride, int pad,
                             int relu, rl_stream_t stream);
 
+/* Stride-1 NHWC bf16 convolution forward in TMA-window form (no operand gather): a conv over the flattened
+ * pixel sequence is a sum of shifted GEMMs; one TMA load per 128-position tile brings the input window into
+ * shared memory and every filter tap is a tcgen05.mma whose descriptor starts (r*W+s) rows further down.
+ * Stride-2/4 layers use it through space-to-depth of their input.  in [N,H,W,Cin], weight [Cout, KH*KW*Cin]
+ * ordered (r,s,c); out_mode 0: out [N,H-KH+1,W-KW+1,Cout]; out_mode 1 (20x20 outputs only): out is the
+ * zero-padded 2x2 space-to-depth tensor [N,12,12,4*Cout] that feeds a following 4x4/stride-2/pad-2 conv.
+ * Cin in {64,128}, Cout in {32,64}, 128+(KH-1)*W+(KW-1) <= 256. */
+int rl_conv2d_s1_nhwc_bf16_fwd(const void* in, const void* weight_krsc, const float* bias, void* out,
+                               int N, int H, int W, int Cin, int Cout, int KH, int KW, int relu, int out_mode,
+                               rl_stream_t stream);
+int rl_debug_set_shiftconv_base_offset(int enable);
+
 #ifdef __cplusplus
 }
 #endif

@@ -125,12 +125,17 @@ __global__ void __launch_bounds__(256) atari_synth_step_kernel(AtariStepArgs p) 
     }
   }
   // ---- frame pixels: one 16-byte Philox block per thread, coalesced uint4 stores ----
+  // 32-bit, division-free walk: (env, blk) advance by (gstride / nblk, gstride % nblk) per grid stride
   const uint32_t n = p.reset ? p.step : p.step + 1u;
   uint4* out = reinterpret_cast<uint4*>(p.frame_out);
-  for (long long i = gtid; i < total; i += gstride) {
-    const uint32_t b = (uint32_t)(i / nblk);
-    const uint32_t blk = (uint32_t)(i - (long long)b * nblk);
+  const uint32_t unblk = (uint32_t)nblk;
+  const uint32_t ustride = (uint32_t)gstride;
+  const uint32_t db = ustride / unblk, dk = ustride - db * unblk;
+  uint32_t b = (uint32_t)gtid / unblk, blk = (uint32_t)gtid - b * unblk;
+  for (uint32_t i = (uint32_t)gtid; i < (uint32_t)total; i += ustride) {
     out[i] = frame_block(p.env_offset + b, n, blk, p.k0, p.k1);
+    b += db, blk += dk;
+    if (blk >= unblk) blk -= unblk, ++b;
   }
 }
 
@@ -461,6 +466,7 @@ extern "C" int rl_env_atari_synth_step(uint8_t* frame_out, float* reward_out, ui
   RL_CHECK_ARG(frame_out && age_out && ep_ret && ep_len && totals, "atari_synth_step: null pointer");
   RL_CHECK_ARG(reset || (reward_out && done_out && age_in), "atari_synth_step: null pointer");
   RL_CHECK_ARG(B > 0 && HW > 0 && HW % 16 == 0, "atari_synth_step: B=%d HW=%d (HW must be a multiple of 16)", B, HW);
+  RL_CHECK_ARG((long long)B * (HW / 16) < (1LL << 31), "atari_synth_step: B*HW/16 must be < 2^31");
   RL_CHECK_ARG(aligned16(frame_out), "atari_synth_step: frame plane must be 16-byte aligned");
   RL_CHECK_ARG(!logits || (A >= 1 && actions_out), "atari_synth_step: logits given but A=%d / actions_out null", A);
   AtariStepArgs a;

@@ -1,0 +1,307 @@
+// K6 (convolutions, TMA-window form) — stride-1 NHWC bf16 convolution forward on tcgen05 where the A operand
+// is never gathered: a stride-1 conv over the row-major flattened pixel sequence is a sum of SHIFTED GEMMs
+//     out[q, :] = bias + sum_{r,s} in[q + r*W + s, :] . W[(r,s)]^T        q = n*H*W + y*W + x
+// (positions with y >= Hout or x >= Wout are computed and dropped).  Per 128-position tile ONE 2-D TMA load
+// brings the input window rows [q0, q0 + 128 + (KH-1)*W + (KW-1)) into shared memory (SWIZZLE_128B); every
+// filter tap then issues tcgen05.mma with an smem descriptor that simply starts (r*W+s) rows further down
+// (matrix-descriptor base_offset carries the swizzle phase).  Each input byte crosses L2->SM once per tile
+// instead of once per tap.  Stride-2/4 layers are brought to this form by space-to-depth of their INPUT
+// (conv1: rl_obs_stack_gather out_dtype 3; conv2: conv1's epilogue writes the padded 2x2-block layout).
+//
+// Layers of the Atari actor-critic (a13: benchmark/torch/a2c/atari_model.py:26-44):
+//   conv1  8x8/4/p1, 4->32   == 2x2/1 on [21,21,64]   -> [20,20,32] written as s2d2-padded [12,12,128]
+//   conv2  4x4/2/p2, 32->64  == 2x2/1 on [12,12,128]  -> [11,11,64]
+//   conv3  3x3/1,    64->64  == 3x3/1 on [11,11,64]   -> [9,9,64]
+// Roles: warp 0 TMA producer (3-stage window ring), warp 1 MMA issuer (weights resident in smem, TMEM
+// accumulator double-buffered), warps 2-5 epilogue (bias, ReLU, bf16, layout-aware row store).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace rl {
+
+__device__ __forceinline__ void s_tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void s_tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void s_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void s_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void s_umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void s_commit(void* mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(mbar))
+               : "memory");
+}
+__device__ __forceinline__ void s_tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void s_mbar_arrive(void* mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(mbar)) : "memory");
+}
+// K-major SWIZZLE_128B operand starting at an arbitrary 128-byte row of a 1024-byte aligned swizzled buffer:
+// base_offset (bits 49-51) = (addr >> 7) & 7 tells the tensor core the swizzle phase of the first row.
+__device__ __forceinline__ uint64_t s_desc_sw128(uint32_t smem_addr, uint32_t use_base_offset) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  if (use_base_offset) d |= (uint64_t)((smem_addr >> 7) & 7) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t s_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int kScBM = 128;
+constexpr int kScStages = 3;
+constexpr int kScThreads = 192;
+
+struct ShiftConvArgs {
+  const float* bias;
+  __nv_bfloat16* out;
+  int H, W, KH, KW, Hout, Wout;   // input grid per image, filter, valid output grid
+  int Q;                           // N * H * W flattened input positions
+  int wrows;                       // window rows = 128 + (KH-1)*W + (KW-1)
+  int num_tiles, relu;
+  int base_offset;                 // 1: set the descriptor base_offset field for shifted windows (default)
+  int out_mode;                    // 0: compact NHWC [N,Hout,Wout,Cout]; 1: conv1 -> conv2 s2d2-padded [N,12,12,4*Cout]
+};
+
+template <int COUT, int CBLK>
+__global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __grid_constant__ CUtensorMap map_in,
+                                                                      const __grid_constant__ CUtensorMap map_w,
+                                                                      const ShiftConvArgs g) {
+  constexpr int W_KB = COUT * 128;                        // one 64-wide weight k-block
+  constexpr int TMEM_COLS = 2 * COUT < 32 ? 32 : 2 * COUT;
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const int ntaps = g.KH * g.KW;
+  const int num_kb = ntaps * CBLK;
+  const int win_bytes = (g.wrows * 128 + 1023) & ~1023;   // one 64-channel column block of the window
+  unsigned char* sW = smem;                               // [num_kb][COUT][128 B]
+  unsigned char* sWin = smem + ((num_kb * W_KB + 1023) & ~1023);   // [stages][CBLK][wrows][128 B]
+  __shared__ __align__(8) unsigned long long full_bar[kScStages], empty_bar[kScStages], w_bar, tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_in);
+    tma_prefetch_desc(&map_w);
+    for (int s = 0; s < kScStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&w_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) s_tmem_alloc(&tmem_base_smem, TMEM_COLS);
+  s_fence_before();
+  __syncthreads();
+  s_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer: one window (CBLK column blocks) per tile =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t s = it % kScStages;
+        mbar_wait(&empty_bar[s], ((it / kScStages) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(CBLK * g.wrows * 128));
+        for (int cb = 0; cb < CBLK; ++cb)
+          tma_load_2d(sWin + (s * CBLK + cb) * win_bytes, &map_in, cb * 64, tile * kScBM, &full_bar[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== resident weights + MMA issue =====
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&w_bar, (uint32_t)(num_kb * W_KB));
+      for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sW + kb * W_KB, &map_w, kb * 64, 0, &w_bar);
+      mbar_wait(&w_bar, 0);
+      constexpr uint32_t idesc = s_idesc_bf16(kScBM, COUT);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t s = it % kScStages, buf = it & 1u;
+        mbar_wait(&tmem_empty[buf], ((it >> 1) & 1u) ^ 1u);
+        mbar_wait(&full_bar[s], (it / kScStages) & 1u);
+        s_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * COUT;
+        uint32_t first = 0;
+        for (int r = 0; r < g.KH; ++r) {
+          for (int sx = 0; sx < g.KW; ++sx) {
+            const uint32_t row_off = (uint32_t)(r * g.W + sx) * 128u;        // shift by (r*W + s) window rows
+            const int tap = r * g.KW + sx;
+#pragma unroll
+            for (int cb = 0; cb < CBLK; ++cb) {
+              const uint32_t a_addr = smem_u32(sWin + (s * CBLK + cb) * win_bytes) + row_off;
+              const uint32_t b_addr = smem_u32(sW + (tap * CBLK + cb) * W_KB);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                s_umma(d_tmem, s_desc_sw128(a_addr + 32u * k, (uint32_t)g.base_offset), s_desc_sw128(b_addr + 32u * k, 0u), idesc, first);
+                first = 1u;
+              }
+            }
+          }
+        }
+        s_commit(&empty_bar[s]);
+        s_commit(&tmem_full[buf]);
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int qd = warp & 3;
+    const int HW = g.H * g.W;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u;
+      mbar_wait(&tmem_full[buf], (it >> 1) & 1u);
+      s_fence_after();
+      const int q = tile * kScBM + qd * 32 + lane;
+      const int n = q / HW;
+      const int rem = q - n * HW;
+      const int y = rem / g.W, x = rem - y * g.W;
+      const bool valid = q < g.Q && y < g.Hout && x < g.Wout;
+      size_t obase;
+      if (g.out_mode == 0) {
+        obase = ((size_t)(n * g.Hout + y) * g.Wout + x) * COUT;
+      } else {
+        // conv1 -> conv2 input: zero-padded by 2, 2x2 space-to-depth: [n, (y+2)/2, (x+2)/2, ((y&1)*2 + (x&1))*COUT + c]
+        const int yp = y + 2, xp = x + 2;
+        obase = (((size_t)n * 12 + (yp >> 1)) * 12 + (xp >> 1)) * (4 * COUT) + (size_t)(((yp & 1) * 2 + (xp & 1)) * COUT);
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + buf * COUT;
+#pragma unroll
+      for (int c0 = 0; c0 < COUT; c0 += 16) {
+        float v[16];
+        s_tmem_ld16(taddr + (uint32_t)c0, v);
+        if (valid) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float x0 = v[2 * i] + __ldg(g.bias + c0 + 2 * i), x1 = v[2 * i + 1] + __ldg(g.bias + c0 + 2 * i + 1);
+            if (g.relu) x0 = fmaxf(x0, 0.f), x1 = fmaxf(x1, 0.f);
+            __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(g.out + obase + c0);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      s_fence_before();
+      s_mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+  s_fence_before();
+  __syncthreads();
+  if (warp == 1) s_tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+static int sc_make_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return -1;
+    fn = reinterpret_cast<EncodeFn>(p);
+  }
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {cols * 2};
+  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+             ? 0
+             : -2;
+}
+
+template <int COUT, int CBLK>
+static void launch_shiftconv(const CUtensorMap& mi, const CUtensorMap& mw, const ShiftConvArgs& g, int num_kb, int sms,
+                             cudaStream_t st) {
+  const size_t win = (size_t)((g.wrows * 128 + 1023) & ~1023);
+  const size_t smem = (size_t)((num_kb * COUT * 128 + 1023) & ~1023) + (size_t)kScStages * CBLK * win + 1024;
+  cudaFuncSetAttribute(shiftconv_fwd_kernel<COUT, CBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int grid = g.num_tiles < sms ? g.num_tiles : sms;
+  shiftconv_fwd_kernel<COUT, CBLK><<<grid, kScThreads, smem, st>>>(mi, mw, g);
+}
+
+}  // namespace rl
+
+using namespace rl;
+
+static int g_sc_base_offset = 1;
+// Triage hook: 0 builds the shifted-window descriptors WITHOUT the base_offset field.
+extern "C" int rl_debug_set_shiftconv_base_offset(int enable) {
+  g_sc_base_offset = enable ? 1 : 0;
+  return RL_OK;
+}
+
+extern "C" int rl_conv2d_s1_nhwc_bf16_fwd(const void* in, const void* weight_krsc, const float* bias, void* out, int N,
+                                          int H, int W, int Cin, int Cout, int KH, int KW, int relu, int out_mode,
+                                          rl_stream_t stream) {
+  RL_CHECK_ARG(in && weight_krsc && bias && out && N > 0, "conv2d_s1: bad argument");
+  RL_CHECK_ARG(aligned16(in) && aligned16(weight_krsc) && aligned16(out), "conv2d_s1: 16-byte alignment required");
+  RL_CHECK_ARG((Cout == 32 || Cout == 64) && (Cin == 64 || Cin == 128), "conv2d_s1: Cin in {64,128}, Cout in {32,64}");
+  RL_CHECK_ARG(KH >= 1 && KW >= 1 && KH <= H && KW <= W, "conv2d_s1: bad filter");
+  RL_CHECK_ARG(out_mode == 0 || (out_mode == 1 && H - KH + 1 == 20 && W - KW + 1 == 20),
+               "conv2d_s1: out_mode 1 is the 20x20 -> [12,12,4*Cout] layout");
+  ShiftConvArgs g;
+  g.bias = bias, g.out = (__nv_bfloat16*)out, g.H = H, g.W = W, g.KH = KH, g.KW = KW;
+  g.Hout = H - KH + 1, g.Wout = W - KW + 1;
+  const long long Q = (long long)N * H * W;
+  RL_CHECK_ARG(Q < (1LL << 31), "conv2d_s1: too many positions");
+  g.Q = (int)Q, g.wrows = kScBM + (KH - 1) * W + (KW - 1), g.relu = relu, g.out_mode = out_mode, g.base_offset = g_sc_base_offset;
+  RL_CHECK_ARG(g.wrows <= 256, "conv2d_s1: window of %d rows exceeds the TMA box limit", g.wrows);
+  g.num_tiles = (int)((Q + kScBM - 1) / kScBM);
+  const int cblk = Cin / 64, num_kb = KH * KW * cblk;
+  const size_t win = (size_t)((g.wrows * 128 + 1023) & ~1023);
+  RL_CHECK_ARG((size_t)num_kb * Cout * 128 + (size_t)kScStages * cblk * win + 4096 <= 227 * 1024,
+               "conv2d_s1: weights + windows do not fit in shared memory");
+  alignas(64) CUtensorMap mi, mw;
+  if (sc_make_map(&mi, in, (uint64_t)Cin, (uint64_t)Q, (uint32_t)g.wrows) ||
+      sc_make_map(&mw, weight_krsc, (uint64_t)KH * KW * Cin, (uint64_t)Cout, (uint32_t)Cout)) {
+    set_error("conv2d_s1: cuTensorMapEncodeTiled failed");
+    return RL_ERR_CUDA;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Cout == 32 && cblk == 1) launch_shiftconv<32, 1>(mi, mw, g, num_kb, sms, st);
+  else if (Cout == 32) launch_shiftconv<32, 2>(mi, mw, g, num_kb, sms, st);
+  else if (cblk == 1) launch_shiftconv<64, 1>(mi, mw, g, num_kb, sms, st);
+  else launch_shiftconv<64, 2>(mi, mw, g, num_kb, sms, st);
+  RL_CHECK_LAUNCH("rl_conv2d_s1_nhwc_bf16_fwd");
+  return RL_OK;
+}

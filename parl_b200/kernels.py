@@ -399,3 +399,17 @@ def conv2d_nhwc_bf16_fwd(x, weight_krsc, bias, KH, KW, stride, pad, relu=True, o
     check(_lib.load().rl_conv2d_nhwc_bf16_fwd(ptr(x), ptr(weight_krsc), ptr(bias), ptr(out), N, H, W, Cin, Cout, KH, KW,
                                               stride, pad, 1 if relu else 0, stream()), 'conv2d_nhwc_bf16_fwd')
     return out
+
+
+def conv2d_s1_nhwc_bf16_fwd(x, weight_krsc, bias, KH, KW, relu=True, out=None, out_mode=0):
+    """Stride-1 NHWC bf16 conv forward in TMA-window form (rl_conv2d_s1_nhwc_bf16_fwd)."""
+    require_cuda(x, weight_krsc, bias)
+    assert x.dtype == torch.bfloat16 and weight_krsc.dtype == torch.bfloat16 and bias.dtype == torch.float32
+    N, H, W, Cin = x.shape
+    Cout = weight_krsc.shape[0]
+    if out is None:
+        assert out_mode == 0
+        out = torch.empty((N, H - KH + 1, W - KW + 1, Cout), dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().rl_conv2d_s1_nhwc_bf16_fwd(ptr(x), ptr(weight_krsc), ptr(bias), ptr(out), N, H, W, Cin, Cout, KH,
+                                                 KW, 1 if relu else 0, int(out_mode), stream()), 'conv2d_s1_nhwc_bf16_fwd')
+    return out

@@ -81,3 +81,47 @@ def test_native_actor_net_matches_torch_model():
     with torch.no_grad():
         l32 = m32.policy(u8)
     assert (logits - l32).abs().max().item() < 5e-2 * scale
+
+
+@pytest.mark.parametrize('N,H,Cin,Cout,k', [(3, 21, 64, 32, 2), (300, 21, 64, 32, 2), (5, 12, 128, 64, 2),
+                                            (200, 12, 128, 64, 2), (7, 11, 64, 64, 3), (300, 11, 64, 64, 3)])
+def test_conv2d_s1_tma_window_form(N, H, Cin, Cout, k):
+    """The TMA-window (shifted-descriptor) conv against torch conv2d in float32 on the same bf16 operands."""
+    from parl_b200 import kernels as K_
+    g = torch.Generator(device=DEV).manual_seed(N + H + Cin)
+    x = torch.randn(N, H, H, Cin, device=DEV, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, k, k, device=DEV, generator=g) / (Cin * k * k) ** 0.5).to(torch.bfloat16)
+    b = torch.randn(Cout, device=DEV, generator=g)
+    w_krsc = w.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).contiguous()
+    out = K_.conv2d_s1_nhwc_bf16_fwd(x, w_krsc, b, k, k, relu=True)
+    torch.cuda.synchronize()
+    ref = torch.relu(torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b)).permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs().max().item()
+    assert out.shape == ref.shape and err < 2e-2 * max(1.0, ref.abs().max().item()), err
+
+
+def test_conv1_to_conv2_space_to_depth_chain():
+    """conv1 (s2d form) writing conv2's padded 2x2-block input, then conv2 as a 2x2/1 conv: equals the
+    reference pair conv(8x8/4/p1) -> relu -> conv(4x4/2/p2) -> relu."""
+    from parl_b200 import kernels as K_
+    torch.manual_seed(1)
+    N = 37
+    x = torch.rand(N, 4, 84, 84, device=DEV)
+    w1 = (torch.randn(32, 4, 8, 8, device=DEV) / 16).to(torch.bfloat16)
+    w2 = (torch.randn(64, 32, 4, 4, device=DEV) / 22).to(torch.bfloat16)
+    b1, b2 = torch.randn(32, device=DEV) * 0.1, torch.randn(64, device=DEV) * 0.1
+    F = torch.nn.functional
+    xb = x.to(torch.bfloat16)
+    r1 = torch.relu(F.conv2d(xb.float(), w1.float(), b1, stride=4, padding=1)).to(torch.bfloat16)
+    ref = torch.relu(F.conv2d(r1.float(), w2.float(), b2, stride=2, padding=2)).permute(0, 2, 3, 1)
+    pad = torch.zeros(N, 4, 85, 85, device=DEV, dtype=torch.bfloat16)
+    pad[:, :, 1:, 1:] = xb
+    s2d = pad[:, :, :84, :84].reshape(N, 4, 21, 4, 21, 4).permute(0, 2, 4, 3, 5, 1).reshape(N, 21, 21, 64).contiguous()
+    w1p = w1.view(32, 4, 2, 4, 2, 4).permute(0, 2, 4, 3, 5, 1).reshape(32, 256).contiguous()      # (o,a,b,dy,dx,c)
+    w2p = w2.view(64, 32, 2, 2, 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(64, 512).contiguous()     # (o,a,b,dy,dx,c)
+    a1 = torch.zeros(N, 12, 12, 128, device=DEV, dtype=torch.bfloat16)
+    K_.conv2d_s1_nhwc_bf16_fwd(s2d, w1p, b1, 2, 2, relu=True, out=a1, out_mode=1)
+    out = K_.conv2d_s1_nhwc_bf16_fwd(a1, w2p, b2, 2, 2, relu=True)
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert out.shape == ref.shape and err < 3e-2 * max(1.0, ref.abs().max().item()), err
