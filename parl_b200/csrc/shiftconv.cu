@@ -4,7 +4,7 @@
 // (positions with y >= Hout or x >= Wout are computed and dropped).  Per 128-position tile ONE 2-D TMA load
 // brings the input window rows [q0, q0 + 128 + (KH-1)*W + (KW-1)) into shared memory (SWIZZLE_128B); every
 // filter tap then issues tcgen05.mma with an smem descriptor that simply starts (r*W+s) rows further down
-// (matrix-descriptor base_offset carries the swizzle phase).  Each input byte crosses L2->SM once per tile
+// (the swizzle phase follows from the absolute shared-memory address).  Each input byte crosses L2->SM once per tile
 // instead of once per tap.  Stride-2/4 layers are brought to this form by space-to-depth of their INPUT
 // (conv1: rl_obs_stack_gather out_dtype 3; conv2: conv1's epilogue writes the padded 2x2-block layout).
 //
@@ -59,8 +59,9 @@ __device__ __forceinline__ void s_tmem_ld16(uint32_t taddr, float (&v)[16]) {
 __device__ __forceinline__ void s_mbar_arrive(void* mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(mbar)) : "memory");
 }
-// K-major SWIZZLE_128B operand starting at an arbitrary 128-byte row of a 1024-byte aligned swizzled buffer:
-// base_offset (bits 49-51) = (addr >> 7) & 7 tells the tensor core the swizzle phase of the first row.
+// K-major SWIZZLE_128B operand starting at an arbitrary 128-byte row of a 1024-byte aligned swizzled buffer.
+// The hardware derives the swizzle phase from the absolute address, so base_offset (bits 49-51) stays 0
+// (verified on B200, see rl_debug_set_shiftconv_base_offset).
 __device__ __forceinline__ uint64_t s_desc_sw128(uint32_t smem_addr, uint32_t use_base_offset) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
@@ -86,7 +87,7 @@ struct ShiftConvArgs {
   int Q;                           // N * H * W flattened input positions
   int wrows;                       // window rows = 128 + (KH-1)*W + (KW-1)
   int num_tiles, relu;
-  int base_offset;                 // 1: set the descriptor base_offset field for shifted windows (default)
+  int base_offset;                 // triage only: 1 sets the descriptor base_offset field (wrong on B200)
   int out_mode;                    // 0: compact NHWC [N,Hout,Wout,Cout]; 1: conv1 -> conv2 s2d2-padded [N,12,12,4*Cout]
 };
 
@@ -260,8 +261,10 @@ static void launch_shiftconv(const CUtensorMap& mi, const CUtensorMap& mw, const
 
 using namespace rl;
 
-static int g_sc_base_offset = 1;
-// Triage hook: 0 builds the shifted-window descriptors WITHOUT the base_offset field.
+static int g_sc_base_offset = 0;
+// Triage hook.  Measured on B200: the tensor core swizzles on ABSOLUTE shared-memory address bits, so a
+// descriptor that starts at an arbitrary 128-byte row of a 1024-byte aligned swizzled buffer needs NO
+// base_offset (setting it double-counts the phase: max error 4.3 vs 0.016).  1 re-enables the field.
 extern "C" int rl_debug_set_shiftconv_base_offset(int enable) {
   g_sc_base_offset = enable ? 1 : 0;
   return RL_OK;

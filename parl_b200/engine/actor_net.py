@@ -1,5 +1,5 @@
 """Actor-side inference of the Atari actor-critic entirely on hand-written tcgen05 kernels
-(rl_conv2d_nhwc_bf16_fwd x3 + rl_gemm_bf16_tn x2): the policy forward the reference runs on CPU, batch 5,
+(rl_conv2d_s1_nhwc_bf16_fwd x3 in TMA-window form + rl_gemm_bf16_tn x2): the policy forward the reference runs on CPU, batch 5,
 inside every remote actor (examples/IMPALA/actor.py:60-62, atari_agent.py:35-42) — here once per time
 step for the whole pool, reading the space-to-depth observation written by rl_obs_stack_gather and writing
 the logits straight into the (T,B,A) rollout buffer.
@@ -14,12 +14,15 @@ from .. import kernels
 
 
 class AtariActorNet(object):
-    def __init__(self, model, batch, device):
+    def __init__(self, model, batch, device, window_form=True):
         self.model = model
         self.B = int(batch)
         dev = self.device = torch.device(device)
         bf = torch.bfloat16
-        self.a1 = torch.empty((self.B, 20, 20, 32), dtype=bf, device=dev)
+        self.window_form = window_form
+        # window form: conv1 writes conv2's zero-padded 2x2-block input [B,12,12,128] (border stays zero)
+        self.a1 = (torch.zeros((self.B, 12, 12, 128), dtype=bf, device=dev) if window_form else
+                   torch.empty((self.B, 20, 20, 32), dtype=bf, device=dev))
         self.a2 = torch.empty((self.B, 11, 11, 64), dtype=bf, device=dev)
         self.a3 = torch.empty((self.B, 9, 9, 64), dtype=bf, device=dev)
         self.h = torch.empty((self.B, 512), dtype=bf, device=dev)
@@ -46,7 +49,11 @@ class AtariActorNet(object):
         # conv1 8x8/4 -> 2x2/1 on 4x4 pixel blocks: W1[o,c,4a+dy,4b+dx] -> [o, (a,b), (dy,dx,c)]
         w1 = m.conv1.weight.view(32, 4, 2, 4, 2, 4).permute(0, 2, 4, 3, 5, 1)      # (o, a, b, dy, dx, c)
         self.w1.copy_(w1.reshape(32, 256))
-        self.w2.copy_(m.conv2.weight.permute(0, 2, 3, 1).reshape(64, 512))         # (o, r, s, c)
+        if self.window_form:
+            # conv2 4x4/2/p2 -> 2x2/1 on 2x2 pixel blocks: W2[o,c,2a+dy,2b+dx] -> [o, (a,b), (dy,dx,c)]
+            self.w2.copy_(m.conv2.weight.view(64, 32, 2, 2, 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(64, 512))
+        else:
+            self.w2.copy_(m.conv2.weight.permute(0, 2, 3, 1).reshape(64, 512))     # (o, r, s, c)
         self.w3.copy_(m.conv3.weight.permute(0, 2, 3, 1).reshape(64, 576))
         self.wfc.copy_(m.fc.weight.view(512, 64, 9, 9).permute(0, 2, 3, 1).reshape(512, 5184))
         self.wpi.copy_(m.fc_pi.weight)
@@ -57,9 +64,14 @@ class AtariActorNet(object):
     def policy(self, obs_s2d, logits_out):
         """obs_s2d [B,21,21,64] bf16 (already scaled by 1/255) -> logits_out [B,A] float32."""
         K = kernels
-        K.conv2d_nhwc_bf16_fwd(obs_s2d, self.w1, self.b1, 2, 2, 1, 0, relu=True, out=self.a1)
-        K.conv2d_nhwc_bf16_fwd(self.a1, self.w2, self.b2, 4, 4, 2, 2, relu=True, out=self.a2)
-        K.conv2d_nhwc_bf16_fwd(self.a2, self.w3, self.b3, 3, 3, 1, 0, relu=True, out=self.a3)
+        if self.window_form:
+            K.conv2d_s1_nhwc_bf16_fwd(obs_s2d, self.w1, self.b1, 2, 2, relu=True, out=self.a1, out_mode=1)
+            K.conv2d_s1_nhwc_bf16_fwd(self.a1, self.w2, self.b2, 2, 2, relu=True, out=self.a2)
+            K.conv2d_s1_nhwc_bf16_fwd(self.a2, self.w3, self.b3, 3, 3, relu=True, out=self.a3)
+        else:
+            K.conv2d_nhwc_bf16_fwd(obs_s2d, self.w1, self.b1, 2, 2, 1, 0, relu=True, out=self.a1)
+            K.conv2d_nhwc_bf16_fwd(self.a1, self.w2, self.b2, 4, 4, 2, 2, relu=True, out=self.a2)
+            K.conv2d_nhwc_bf16_fwd(self.a2, self.w3, self.b3, 3, 3, 1, 0, relu=True, out=self.a3)
         K.gemm_bf16_tn(self.a3.view(self.B, 5184), self.wfc, self.bfc, relu=True, out=self.h)
         K.gemm_bf16_tn(self.h, self.wpi, self.bpi, relu=False, out=logits_out)
         return logits_out

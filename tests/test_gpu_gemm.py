@@ -45,7 +45,8 @@ def test_conv2d_nhwc_bf16_fwd(N, H, Cin, Cout, k, stride, pad):
     assert out.shape == ref.shape and err < 2e-2 * max(1.0, ref.abs().max().item()), err
 
 
-def test_native_actor_net_matches_torch_model():
+@pytest.mark.parametrize('window_form', [True, False])
+def test_native_actor_net_matches_torch_model(window_form):
     """The tcgen05 inference path (s2d conv1 -> conv2 -> conv3 -> fc -> policy head) against the torch model
     (bf16 autocast) on real observations from the device env pool."""
     from parl_b200 import kernels as K_
@@ -54,7 +55,7 @@ def test_native_actor_net_matches_torch_model():
     torch.manual_seed(0)
     B = 300
     model = AtariActorCritic(18).to(DEV)
-    net = AtariActorNet(model, B, DEV)
+    net = AtariActorNet(model, B, DEV, window_form=window_form)
     planes = torch.zeros(5, B, 84 * 84, dtype=torch.uint8, device=DEV)
     ages = torch.zeros(2, B, dtype=torch.uint8, device=DEV)
     st = K_.EpisodeStats(B, DEV)
