@@ -297,6 +297,30 @@ int rl_conv2d_s1_nhwc_bf16_fwd(const void* in, const void* weight_krsc, const fl
                                rl_stream_t stream);
 int rl_debug_set_shiftconv_base_offset(int enable);
 
+/* Data gradient of rl_conv2d_s1_nhwc_bf16_fwd in the same TMA-window form (transposed conv = shifted GEMMs run
+ * backwards).  dout_grid [N,H,W,Cout] is the output gradient ON THE INPUT GRID (zeros where y>=H-KH+1 or
+ * x>=W-KW+1); weight_t_krsc [Cin, KH*KW*Cout] with element [ci][(r,s,co)] = W[co][(r,s,ci)];
+ * act_mask (optional) [N,H,W,Cin] is the saved post-ReLU input activation: din *= (act_mask > 0).
+ * out_mode 0: din on a [N,OGH,OGW,Cin] grid (OGH>=H, OGW>=W; untouched cells stay as they are);
+ * out_mode 2 (H=W=12, Cin=128): din of the 2x2-block conv scattered to the [N,21,21,32] grid of conv1. */
+int rl_conv2d_s1_nhwc_bf16_dgrad(const void* dout_grid, const void* weight_t_krsc, const void* act_mask, void* din,
+                                 int N, int H, int W, int Cout, int Cin, int KH, int KW, int out_mode,
+                                 int OGH, int OGW, rl_stream_t stream);
+
+/* Weight gradient of rl_conv2d_s1_nhwc_bf16_fwd in TMA-window form: dW[co][(r,s,ci)] = sum_q dout_grid[q,co] *
+ * in[q + r*W + s, ci] with the position index as the GEMM reduction dimension (tcgen05, MN-major operands,
+ * accumulators resident in TMEM over the CTA's whole position range, deterministic two-stage reduction).
+ * dout_grid [N,H,W,Cout] on the input grid (zeros at invalid positions), in [N,H,W,Cin], dw_krsc [Cout, KH*KW*Cin]
+ * float32 (accumulate=1 adds to it).  Cout = 64, Cin in {64,128}.  Workspace: rl_conv_wgrad_workspace_bytes. */
+size_t rl_conv_wgrad_workspace_bytes(int KH, int KW, int Cin);
+int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* in, float* dw_krsc, int N, int H, int W,
+                                 int Cin, int Cout, int KH, int KW, int accumulate,
+                                 void* workspace, size_t workspace_bytes, rl_stream_t stream);
+int rl_debug_set_wgrad_lane_map(int mode);
+/* out[c] = sum_r x[r,c] for a [rows, C] bf16 matrix (bias gradients); C divides 256; workspace >= 592*C*4 bytes. */
+int rl_colsum_bf16(const void* x, long long rows, int C, float* out, void* workspace, size_t workspace_bytes,
+                   rl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,7 +88,13 @@ struct ShiftConvArgs {
   int wrows;                       // window rows = 128 + (KH-1)*W + (KW-1)
   int num_tiles, relu;
   int base_offset;                 // triage only: 1 sets the descriptor base_offset field (wrong on B200)
-  int out_mode;                    // 0: compact NHWC [N,Hout,Wout,Cout]; 1: conv1 -> conv2 s2d2-padded [N,12,12,4*Cout]
+  int out_mode;                    // 0: NHWC grid [N,OGH,OGW,Cout] (valid y<Hout, x<Wout);
+                                   // 1: conv1 -> conv2 s2d2-padded [N,12,12,4*Cout];
+                                   // 2: (dgrad of the s2d2 conv) [N,12,12,128] blocks -> full grid [N,21,21,32]
+  int OGH, OGW;                    // output grid of out_mode 0
+  int row_shift;                   // TMA row coordinate of a tile = tile*128 + row_shift (dgrad: -((KH-1)*W+KW-1))
+  int flip;                        // 1: tap (r,s) reads window row (KH-1-r)*W + (KW-1-s)  (transposed conv)
+  const __nv_bfloat16* mask;       // optional activation on the accumulator grid [Q, COUT]: out *= (mask > 0)
 };
 
 template <int COUT, int CBLK>
@@ -137,7 +143,7 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
         mbar_wait(&empty_bar[s], ((it / kScStages) & 1u) ^ 1u);
         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(CBLK * g.wrows * 128));
         for (int cb = 0; cb < CBLK; ++cb)
-          tma_load_2d(sWin + (s * CBLK + cb) * win_bytes, &map_in, cb * 64, tile * kScBM, &full_bar[s]);
+          tma_load_2d(sWin + (s * CBLK + cb) * win_bytes, &map_in, cb * 64, tile * kScBM + g.row_shift, &full_bar[s]);
       }
     }
   } else if (warp == 1) {
@@ -157,7 +163,8 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
         uint32_t first = 0;
         for (int r = 0; r < g.KH; ++r) {
           for (int sx = 0; sx < g.KW; ++sx) {
-            const uint32_t row_off = (uint32_t)(r * g.W + sx) * 128u;        // shift by (r*W + s) window rows
+            const int wr = g.flip ? (g.KH - 1 - r) * g.W + (g.KW - 1 - sx) : r * g.W + sx;
+            const uint32_t row_off = (uint32_t)wr * 128u;                     // shift by that many window rows
             const int tap = r * g.KW + sx;
 #pragma unroll
             for (int cb = 0; cb < CBLK; ++cb) {
@@ -189,29 +196,50 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
       const int rem = q - n * HW;
       const int y = rem / g.W, x = rem - y * g.W;
       const bool valid = q < g.Q && y < g.Hout && x < g.Wout;
-      size_t obase;
+      size_t obase = 0;
       if (g.out_mode == 0) {
-        obase = ((size_t)(n * g.Hout + y) * g.Wout + x) * COUT;
-      } else {
+        obase = ((size_t)(n * g.OGH + y) * g.OGW + x) * COUT;
+      } else if (g.out_mode == 1) {
         // conv1 -> conv2 input: zero-padded by 2, 2x2 space-to-depth: [n, (y+2)/2, (x+2)/2, ((y&1)*2 + (x&1))*COUT + c]
         const int yp = y + 2, xp = x + 2;
         obase = (((size_t)n * 12 + (yp >> 1)) * 12 + (xp >> 1)) * (4 * COUT) + (size_t)(((yp & 1) * 2 + (xp & 1)) * COUT);
       }
+      const size_t mbase = (size_t)q * COUT;             // the ReLU mask is indexed on the accumulator grid [Q, COUT]
       const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + buf * COUT;
 #pragma unroll
       for (int c0 = 0; c0 < COUT; c0 += 16) {
         float v[16];
         s_tmem_ld16(taddr + (uint32_t)c0, v);
-        if (valid) {
+        bool ok = valid;
+        size_t dst_off = obase + c0;
+        if (g.out_mode == 2) {
+          // channel block (dy,dx) of position (Y,X) is pixel (2Y+dy-2, 2X+dx-2) of the 20x20 image, 32 channels
+          const int blk = c0 >> 5, py = 2 * y + (blk >> 1) - 2, px = 2 * x + (blk & 1) - 2;
+          ok = q < g.Q && py >= 0 && py < 20 && px >= 0 && px < 20;
+          dst_off = (((size_t)n * 21 + py) * 21 + px) * 32 + (c0 & 31);
+        }
+        if (ok) {
           uint32_t pk[8];
+          uint4 mk0 = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), mk1 = mk0;   // bf16 1.0
+          if (g.mask) {
+            const uint4* mp = reinterpret_cast<const uint4*>(g.mask + mbase + c0);
+            mk0 = __ldg(mp), mk1 = __ldg(mp + 1);
+          }
+          const uint32_t mw[8] = {mk0.x, mk0.y, mk0.z, mk0.w, mk1.x, mk1.y, mk1.z, mk1.w};
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float x0 = v[2 * i] + __ldg(g.bias + c0 + 2 * i), x1 = v[2 * i + 1] + __ldg(g.bias + c0 + 2 * i + 1);
+            float x0 = v[2 * i], x1 = v[2 * i + 1];
+            if (g.bias) x0 += __ldg(g.bias + c0 + 2 * i), x1 += __ldg(g.bias + c0 + 2 * i + 1);
             if (g.relu) x0 = fmaxf(x0, 0.f), x1 = fmaxf(x1, 0.f);
+            // ReLU backward: keep the gradient where the saved post-ReLU activation is positive (bf16 sign/zero test)
+            if (g.mask) {
+              if ((mw[i] & 0x7fffu) == 0u || (mw[i] & 0x8000u)) x0 = 0.f;
+              if ((mw[i] & 0x7fff0000u) == 0u || (mw[i] & 0x80000000u)) x1 = 0.f;
+            }
             __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
             pk[i] = *reinterpret_cast<uint32_t*>(&h);
           }
-          uint4* dst = reinterpret_cast<uint4*>(g.out + obase + c0);
+          uint4* dst = reinterpret_cast<uint4*>(g.out + dst_off);
           dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
@@ -270,31 +298,34 @@ extern "C" int rl_debug_set_shiftconv_base_offset(int enable) {
   return RL_OK;
 }
 
-extern "C" int rl_conv2d_s1_nhwc_bf16_fwd(const void* in, const void* weight_krsc, const float* bias, void* out, int N,
-                                          int H, int W, int Cin, int Cout, int KH, int KW, int relu, int out_mode,
-                                          rl_stream_t stream) {
-  RL_CHECK_ARG(in && weight_krsc && bias && out && N > 0, "conv2d_s1: bad argument");
-  RL_CHECK_ARG(aligned16(in) && aligned16(weight_krsc) && aligned16(out), "conv2d_s1: 16-byte alignment required");
-  RL_CHECK_ARG((Cout == 32 || Cout == 64) && (Cin == 64 || Cin == 128), "conv2d_s1: Cin in {64,128}, Cout in {32,64}");
-  RL_CHECK_ARG(KH >= 1 && KW >= 1 && KH <= H && KW <= W, "conv2d_s1: bad filter");
-  RL_CHECK_ARG(out_mode == 0 || (out_mode == 1 && H - KH + 1 == 20 && W - KW + 1 == 20),
-               "conv2d_s1: out_mode 1 is the 20x20 -> [12,12,4*Cout] layout");
+static int shiftconv_launch(const void* in, const void* weight, const float* bias, void* out, int N, int H, int W,
+                            int Cin, int Cout, int KH, int KW, int relu, int out_mode, int Hout, int Wout, int OGH, int OGW,
+                            int transposed, const void* mask, rl_stream_t stream, const char* name) {
+  RL_CHECK_ARG(in && weight && out && N > 0, "%s: bad argument", name);
+  RL_CHECK_ARG(aligned16(in) && aligned16(weight) && aligned16(out) && (!mask || aligned16(mask)),
+               "%s: 16-byte alignment required", name);
+  RL_CHECK_ARG((Cout == 32 || Cout == 64 || Cout == 128) && (Cin == 64 || Cin == 128),
+               "%s: Cin in {64,128}, Cout in {32,64,128}", name);
+  RL_CHECK_ARG(KH >= 1 && KW >= 1 && KH <= H && KW <= W, "%s: bad filter", name);
   ShiftConvArgs g;
   g.bias = bias, g.out = (__nv_bfloat16*)out, g.H = H, g.W = W, g.KH = KH, g.KW = KW;
-  g.Hout = H - KH + 1, g.Wout = W - KW + 1;
+  g.Hout = Hout, g.Wout = Wout, g.OGH = OGH, g.OGW = OGW;
   const long long Q = (long long)N * H * W;
-  RL_CHECK_ARG(Q < (1LL << 31), "conv2d_s1: too many positions");
-  g.Q = (int)Q, g.wrows = kScBM + (KH - 1) * W + (KW - 1), g.relu = relu, g.out_mode = out_mode, g.base_offset = g_sc_base_offset;
-  RL_CHECK_ARG(g.wrows <= 256, "conv2d_s1: window of %d rows exceeds the TMA box limit", g.wrows);
+  RL_CHECK_ARG(Q < (1LL << 31), "%s: too many positions", name);
+  g.Q = (int)Q, g.wrows = kScBM + (KH - 1) * W + (KW - 1), g.relu = relu, g.out_mode = out_mode;
+  g.base_offset = g_sc_base_offset;
+  g.row_shift = transposed ? -((KH - 1) * W + (KW - 1)) : 0, g.flip = transposed;
+  g.mask = (const __nv_bfloat16*)mask;
+  RL_CHECK_ARG(g.wrows <= 256, "%s: window of %d rows exceeds the TMA box limit", name, g.wrows);
   g.num_tiles = (int)((Q + kScBM - 1) / kScBM);
   const int cblk = Cin / 64, num_kb = KH * KW * cblk;
   const size_t win = (size_t)((g.wrows * 128 + 1023) & ~1023);
   RL_CHECK_ARG((size_t)num_kb * Cout * 128 + (size_t)kScStages * cblk * win + 4096 <= 227 * 1024,
-               "conv2d_s1: weights + windows do not fit in shared memory");
+               "%s: weights + windows do not fit in shared memory", name);
   alignas(64) CUtensorMap mi, mw;
   if (sc_make_map(&mi, in, (uint64_t)Cin, (uint64_t)Q, (uint32_t)g.wrows) ||
-      sc_make_map(&mw, weight_krsc, (uint64_t)KH * KW * Cin, (uint64_t)Cout, (uint32_t)Cout)) {
-    set_error("conv2d_s1: cuTensorMapEncodeTiled failed");
+      sc_make_map(&mw, weight, (uint64_t)KH * KW * Cin, (uint64_t)Cout, (uint32_t)Cout)) {
+    set_error("%s: cuTensorMapEncodeTiled failed", name);
     return RL_ERR_CUDA;
   }
   int dev = 0, sms = 148;
@@ -303,8 +334,35 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_fwd(const void* in, const void* weight_krs
   cudaStream_t st = (cudaStream_t)stream;
   if (Cout == 32 && cblk == 1) launch_shiftconv<32, 1>(mi, mw, g, num_kb, sms, st);
   else if (Cout == 32) launch_shiftconv<32, 2>(mi, mw, g, num_kb, sms, st);
-  else if (cblk == 1) launch_shiftconv<64, 1>(mi, mw, g, num_kb, sms, st);
-  else launch_shiftconv<64, 2>(mi, mw, g, num_kb, sms, st);
-  RL_CHECK_LAUNCH("rl_conv2d_s1_nhwc_bf16_fwd");
+  else if (Cout == 64 && cblk == 1) launch_shiftconv<64, 1>(mi, mw, g, num_kb, sms, st);
+  else if (Cout == 64) launch_shiftconv<64, 2>(mi, mw, g, num_kb, sms, st);
+  else if (cblk == 1) launch_shiftconv<128, 1>(mi, mw, g, num_kb, sms, st);
+  else launch_shiftconv<128, 2>(mi, mw, g, num_kb, sms, st);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", name, cudaGetErrorString(e));
+    return RL_ERR_CUDA;
+  }
   return RL_OK;
+}
+
+extern "C" int rl_conv2d_s1_nhwc_bf16_fwd(const void* in, const void* weight_krsc, const float* bias, void* out, int N,
+                                          int H, int W, int Cin, int Cout, int KH, int KW, int relu, int out_mode,
+                                          rl_stream_t stream) {
+  RL_CHECK_ARG(bias, "conv2d_s1: bias required");
+  RL_CHECK_ARG(out_mode == 0 || (out_mode == 1 && H - KH + 1 == 20 && W - KW + 1 == 20),
+               "conv2d_s1: out_mode 1 is the 20x20 -> [12,12,4*Cout] layout");
+  return shiftconv_launch(in, weight_krsc, bias, out, N, H, W, Cin, Cout, KH, KW, relu, out_mode, H - KH + 1, W - KW + 1,
+                          H - KH + 1, W - KW + 1, 0, nullptr, stream, "conv2d_s1");
+}
+
+extern "C" int rl_conv2d_s1_nhwc_bf16_dgrad(const void* dout_grid, const void* weight_t_krsc, const void* act_mask,
+                                            void* din, int N, int H, int W, int Cout, int Cin, int KH, int KW,
+                                            int out_mode, int OGH, int OGW, rl_stream_t stream) {
+  RL_CHECK_ARG(out_mode == 0 || (out_mode == 2 && H == 12 && W == 12 && Cin == 128),
+               "conv2d_s1_dgrad: out_mode 2 is the [12,12,128] -> [21,21,32] layout");
+  // the data gradient of a stride-1 conv is the same shifted-GEMM sum run backwards: window starts
+  // (KH-1)*W+(KW-1) rows earlier, taps flipped, weights transposed ([Cin, (r,s,co)]); every grid position is an output
+  return shiftconv_launch(dout_grid, weight_t_krsc, nullptr, din, N, H, W, Cout, Cin, KH, KW, 0, out_mode, H, W,
+                          out_mode == 0 ? OGH : 0, out_mode == 0 ? OGW : 0, 1, act_mask, stream, "conv2d_s1_dgrad");
 }

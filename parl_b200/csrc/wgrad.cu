@@ -1,0 +1,327 @@
+// K6 (convolution weight gradient, TMA-window form) — for a stride-1 NHWC conv written as shifted GEMMs
+//     out[q, co] = sum_t sum_ci in[q + off_t, ci] W_t[co, ci]
+// the weight gradient is a sum over ALL positions of outer products
+//     dW_t[co, ci] = sum_q dout_grid[q, co] * in[q + off_t, ci]
+// i.e. per tap a GEMM whose reduction (K) dimension is the position index q.  Both operands are read exactly
+// as they lie in HBM — rows = positions, 128 contiguous bytes = 64 channels — through the same TMA windows as
+// the forward kernel and consumed by tcgen05.mma as MN-MAJOR operands (a_major = b_major = 1): A = dout tile
+// (M = 64 output channels), B = input window starting off_t rows down (N = 64 input channels), K = 16
+// positions per instruction.  Accumulators for all (tap, channel-block) pairs stay in TMEM across the CTA's
+// whole persistent loop over position tiles; taps are split over CTA groups when they exceed 512 columns.
+// Partials are dumped once per CTA and reduced in fixed order by a second kernel (deterministic).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace rl {
+
+__device__ __forceinline__ void w_tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void w_tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void w_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void w_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void w_umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void w_commit(void* mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(mbar))
+               : "memory");
+}
+__device__ __forceinline__ void w_tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// MN-major SWIZZLE_128B operand (cute canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): 64 MN-elements
+// = one 128-byte row per K index, 8 rows per 1024-byte swizzle atom (SBO = 1024 B between K-groups of 8).
+__device__ __forceinline__ uint64_t w_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                       // LBO: single 64-element MN block, unused
+  d |= (uint64_t)(1024 >> 4) << 32;             // SBO
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16, BF16 x BF16 -> F32, A and B MN-major (bits 15, 16)
+__host__ __device__ constexpr uint32_t w_idesc_bf16_mn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int kWgBM = 128;            // positions (K of the GEMM) per tile
+constexpr int kWgStages = 3;
+constexpr int kWgThreads = 192;
+
+struct WgradArgs {
+  float* partials;                    // [gridDim.x][128 lanes][ncols_max] raw TMEM dumps
+  int W, KH, KW;
+  int Q, wrows, num_tiles;
+  int ngroups, taps_per_group, ncols_max;
+};
+
+template <int CBLK>
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_window_kernel(const __grid_constant__ CUtensorMap map_dout,
+                                                                     const __grid_constant__ CUtensorMap map_x,
+                                                                     const WgradArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const int win_bytes = (g.wrows * 128 + 1023) & ~1023;
+  const int stage_bytes = kWgBM * 128 + CBLK * win_bytes;           // dout tile + input window blocks
+  __shared__ __align__(8) unsigned long long full_bar[kWgStages], empty_bar[kWgStages], done_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntaps = g.KH * g.KW;
+  const int gid = blockIdx.x % g.ngroups;                           // which slice of the filter taps
+  const int tb = gid * g.taps_per_group, te = min(ntaps, tb + g.taps_per_group);
+  const int cta_in_group = blockIdx.x / g.ngroups, ctas_per_group = (gridDim.x + g.ngroups - 1 - gid) / g.ngroups;
+  const int ncols = (te - tb) * CBLK * 64;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)g.ncols_max) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_dout);
+    tma_prefetch_desc(&map_x);
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) w_tmem_alloc(&tmem_base_smem, tmem_cols);
+  w_fence_before();
+  __syncthreads();
+  w_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = cta_in_group; tile < g.num_tiles; tile += ctas_per_group, ++it) {
+        const uint32_t s = it % kWgStages;
+        mbar_wait(&empty_bar[s], ((it / kWgStages) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(kWgBM * 128 + CBLK * g.wrows * 128));
+        unsigned char* st = smem + s * stage_bytes;
+        tma_load_2d(st, &map_dout, 0, tile * kWgBM, &full_bar[s]);
+        for (int cb = 0; cb < CBLK; ++cb)
+          tma_load_2d(st + kWgBM * 128 + cb * win_bytes, &map_x, cb * 64, tile * kWgBM, &full_bar[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = w_idesc_bf16_mn(64, 64);
+      uint32_t it = 0;
+      for (int tile = cta_in_group; tile < g.num_tiles; tile += ctas_per_group, ++it) {
+        const uint32_t s = it % kWgStages;
+        mbar_wait(&full_bar[s], (it / kWgStages) & 1u);
+        w_fence_after();
+        const uint32_t a_base = smem_u32(smem + s * stage_bytes);
+        const uint32_t x_base = a_base + kWgBM * 128;
+        for (int tap = tb; tap < te; ++tap) {
+          const int r = tap / g.KW, sx = tap - r * g.KW;
+          const uint32_t row_off = (uint32_t)(r * g.W + sx) * 128u;
+#pragma unroll
+          for (int cb = 0; cb < CBLK; ++cb) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)(((tap - tb) * CBLK + cb) * 64);
+            const uint32_t b_base = x_base + cb * win_bytes + row_off;
+#pragma unroll
+            for (int kk = 0; kk < kWgBM / 16; ++kk) {
+              // K advances by 16 positions = 16 rows of 128 bytes in both operands
+              w_umma(d_tmem, w_desc_mn_sw128(a_base + kk * 2048u), w_desc_mn_sw128(b_base + kk * 2048u), idesc,
+                     (it | (uint32_t)kk) != 0u ? 1u : 0u);
+            }
+          }
+        }
+        w_commit(&empty_bar[s]);
+      }
+      w_commit(&done_bar);
+    }
+  } else {
+    // ===== dump the TMEM accumulators once: [128 lanes][ncols] raw (the reduce kernel maps lanes -> rows) =====
+    const int qd = warp & 3;
+    mbar_wait(&done_bar, 0);
+    w_fence_after();
+    float* dst = g.partials + ((size_t)blockIdx.x * 128 + qd * 32 + lane) * g.ncols_max;
+    const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
+      float v[16];
+      w_tmem_ld16(taddr + (uint32_t)c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+  }
+  w_fence_before();
+  __syncthreads();
+  if (warp == 1) w_tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// dW[co][(tap, ci)] = sum over the CTAs of the tap's group, in CTA order (deterministic).
+// lane_map 0: accumulator row i of an M=64 tile lives in TMEM lane 32*(i/16) + i%16 ; 1: lane i.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partials, int nctas, int ngroups,
+                                                           int taps_per_group, int ntaps, int cblk, int ncols_max,
+                                                           int lane_map, float* __restrict__ dw, int accumulate) {
+  const int K = ntaps * cblk * 64;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 64 * K) return;
+  const int co = idx / K, k = idx - co * K;
+  const int tap = k / (cblk * 64), within = k - tap * cblk * 64;
+  const int gid = tap / taps_per_group;
+  const int col = (tap - gid * taps_per_group) * cblk * 64 + within;
+  const int ln = lane_map == 0 ? 32 * (co >> 4) + (co & 15) : co;
+  float acc = 0.f;
+  for (int c = gid; c < nctas; c += ngroups) acc += partials[((size_t)c * 128 + ln) * ncols_max + col];
+  dw[idx] = accumulate ? dw[idx] + acc : acc;
+}
+
+// column sums of a [rows, C] bf16 matrix (bias gradients): deterministic two-stage
+__global__ void __launch_bounds__(256) colsum_bf16_stage1(const __nv_bfloat16* __restrict__ x, long long rows, int C,
+                                                          float* __restrict__ part) {
+  // block b sums rows [b*chunk, (b+1)*chunk); thread t handles column t % C, row phase t / C
+  const int c = threadIdx.x % C, ph = threadIdx.x / C, nph = blockDim.x / C;
+  const long long chunk = (rows + gridDim.x - 1) / gridDim.x;
+  const long long r0 = (long long)blockIdx.x * chunk, r1 = min(rows, r0 + chunk);
+  float acc = 0.f;
+  if (ph < nph)
+    for (long long r = r0 + ph; r < r1; r += nph) acc += __bfloat162float(x[r * C + c]);
+  __shared__ float sm[256];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float a = 0.f;
+    for (int p = 0; p < nph; ++p) a += sm[p * C + threadIdx.x];
+    part[(size_t)blockIdx.x * C + threadIdx.x] = a;
+  }
+}
+__global__ void colsum_stage2(const float* __restrict__ part, int nblocks, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f;
+  for (int b = 0; b < nblocks; ++b) a += part[(size_t)b * C + c];
+  out[c] = a;
+}
+
+static int wg_make_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return -1;
+    fn = reinterpret_cast<EncodeFn>(p);
+  }
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {cols * 2};
+  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+             ? 0
+             : -2;
+}
+
+}  // namespace rl
+
+using namespace rl;
+
+static int g_wg_lane_map = 0;
+extern "C" int rl_debug_set_wgrad_lane_map(int mode) {
+  g_wg_lane_map = mode;
+  return RL_OK;
+}
+
+extern "C" size_t rl_conv_wgrad_workspace_bytes(int KH, int KW, int Cin) {
+  const int cblk = Cin / 64, ntaps = KH * KW;
+  int per = 512 / (cblk * 64);
+  if (per > ntaps) per = ntaps;
+  return (size_t)148 * 128 * (size_t)(per * cblk * 64) * sizeof(float) + 4096;
+}
+
+extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* in, float* dw_krsc, int N, int H, int W,
+                                            int Cin, int Cout, int KH, int KW, int accumulate, void* workspace,
+                                            size_t workspace_bytes, rl_stream_t stream) {
+  RL_CHECK_ARG(dout_grid && in && dw_krsc && workspace && N > 0, "conv2d_s1_wgrad: bad argument");
+  RL_CHECK_ARG(aligned16(dout_grid) && aligned16(in) && aligned16(workspace), "conv2d_s1_wgrad: alignment");
+  RL_CHECK_ARG(Cout == 64 && (Cin == 64 || Cin == 128), "conv2d_s1_wgrad: Cout must be 64 and Cin in {64,128}");
+  const long long Q = (long long)N * H * W;
+  RL_CHECK_ARG(Q < (1LL << 31), "conv2d_s1_wgrad: too many positions");
+  const int cblk = Cin / 64, ntaps = KH * KW;
+  WgradArgs g;
+  g.partials = reinterpret_cast<float*>(workspace);
+  g.W = W, g.KH = KH, g.KW = KW, g.Q = (int)Q;
+  g.wrows = kWgBM + (KH - 1) * W + (KW - 1);
+  RL_CHECK_ARG(g.wrows <= 256, "conv2d_s1_wgrad: window too tall");
+  g.num_tiles = (int)((Q + kWgBM - 1) / kWgBM);
+  g.taps_per_group = 512 / (cblk * 64);
+  if (g.taps_per_group > ntaps) g.taps_per_group = ntaps;
+  g.ngroups = (ntaps + g.taps_per_group - 1) / g.taps_per_group;
+  g.ncols_max = g.taps_per_group * cblk * 64;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = sms;
+  if (grid > g.num_tiles * g.ngroups) grid = g.num_tiles * g.ngroups;
+  if (grid < g.ngroups) grid = g.ngroups;
+  if (workspace_bytes < (size_t)grid * 128 * g.ncols_max * sizeof(float)) {
+    set_error("conv2d_s1_wgrad: workspace too small");
+    return RL_ERR_WORKSPACE;
+  }
+  alignas(64) CUtensorMap md, mx;
+  if (wg_make_map(&md, dout_grid, (uint64_t)Cout, (uint64_t)Q, kWgBM) ||
+      wg_make_map(&mx, in, (uint64_t)Cin, (uint64_t)Q, (uint32_t)g.wrows)) {
+    set_error("conv2d_s1_wgrad: cuTensorMapEncodeTiled failed");
+    return RL_ERR_CUDA;
+  }
+  const size_t win = (size_t)((g.wrows * 128 + 1023) & ~1023);
+  const size_t smem = (size_t)kWgStages * (kWgBM * 128 + cblk * win) + 1024;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cblk == 1) {
+    cudaFuncSetAttribute(wgrad_window_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    wgrad_window_kernel<1><<<grid, kWgThreads, smem, st>>>(md, mx, g);
+  } else {
+    cudaFuncSetAttribute(wgrad_window_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    wgrad_window_kernel<2><<<grid, kWgThreads, smem, st>>>(md, mx, g);
+  }
+  const int K = ntaps * cblk * 64;
+  wgrad_reduce_kernel<<<(64 * K + 255) / 256, 256, 0, st>>>(g.partials, grid, g.ngroups, g.taps_per_group, ntaps, cblk,
+                                                           g.ncols_max, g_wg_lane_map, dw_krsc, accumulate);
+  RL_CHECK_LAUNCH("rl_conv2d_s1_nhwc_bf16_wgrad");
+  return RL_OK;
+}
+
+extern "C" int rl_colsum_bf16(const void* x, long long rows, int C, float* out, void* workspace, size_t workspace_bytes,
+                              rl_stream_t stream) {
+  RL_CHECK_ARG(x && out && workspace && rows > 0 && C > 0 && C <= 256 && 256 % C == 0, "colsum_bf16: bad argument (C | 256)");
+  const int nblocks = 592;
+  if (workspace_bytes < (size_t)nblocks * C * sizeof(float)) {
+    set_error("colsum_bf16: workspace too small");
+    return RL_ERR_WORKSPACE;
+  }
+  colsum_bf16_stage1<<<nblocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, rows, C, (float*)workspace);
+  colsum_stage2<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>((const float*)workspace, nblocks, C, out);
+  RL_CHECK_LAUNCH("rl_colsum_bf16");
+  return RL_OK;
+}

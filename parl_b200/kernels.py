@@ -413,3 +413,52 @@ def conv2d_s1_nhwc_bf16_fwd(x, weight_krsc, bias, KH, KW, relu=True, out=None, o
     check(_lib.load().rl_conv2d_s1_nhwc_bf16_fwd(ptr(x), ptr(weight_krsc), ptr(bias), ptr(out), N, H, W, Cin, Cout, KH,
                                                  KW, 1 if relu else 0, int(out_mode), stream()), 'conv2d_s1_nhwc_bf16_fwd')
     return out
+
+
+def conv2d_s1_nhwc_bf16_dgrad(dout_grid, weight_t_krsc, KH, KW, out, act_mask=None, out_mode=0):
+    """Data gradient of the TMA-window conv (rl_conv2d_s1_nhwc_bf16_dgrad).  dout_grid [N,H,W,Cout] on the
+    input grid, weight_t_krsc [Cin, KH*KW*Cout]; out [N,OGH,OGW,Cin] (mode 0) or [N,21,21,32] (mode 2)."""
+    require_cuda(dout_grid, weight_t_krsc, out, act_mask)
+    N, H, W, Cout = dout_grid.shape
+    Cin = weight_t_krsc.shape[0]
+    OGH, OGW = (out.shape[1], out.shape[2]) if out_mode == 0 else (0, 0)
+    check(_lib.load().rl_conv2d_s1_nhwc_bf16_dgrad(ptr(dout_grid), ptr(weight_t_krsc), ptr(act_mask), ptr(out), N, H, W,
+                                                   Cout, Cin, KH, KW, int(out_mode), OGH, OGW, stream()),
+          'conv2d_s1_nhwc_bf16_dgrad')
+    return out
+
+
+def _raw_ws(device, nbytes, key):
+    k = (key, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _workspaces.get(k)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _workspaces[k] = ws
+    return ws
+
+
+def conv2d_s1_nhwc_bf16_wgrad(dout_grid, x, KH, KW, dw_krsc=None, accumulate=False):
+    """Weight gradient of the TMA-window conv (rl_conv2d_s1_nhwc_bf16_wgrad) -> dw [Cout, KH*KW*Cin] float32."""
+    require_cuda(dout_grid, x, dw_krsc)
+    N, H, W, Cout = dout_grid.shape
+    Cin = x.shape[-1]
+    assert x.shape[:3] == dout_grid.shape[:3]
+    if dw_krsc is None:
+        dw_krsc = torch.empty((Cout, KH * KW * Cin), dtype=torch.float32, device=x.device)
+    ws = _raw_ws(x.device, _lib.load().rl_conv_wgrad_workspace_bytes(KH, KW, Cin), 'wgrad')
+    check(_lib.load().rl_conv2d_s1_nhwc_bf16_wgrad(ptr(dout_grid), ptr(x), ptr(dw_krsc), N, H, W, Cin, Cout, KH, KW,
+                                                   1 if accumulate else 0, ptr(ws), ws.numel(), stream()),
+          'conv2d_s1_nhwc_bf16_wgrad')
+    return dw_krsc
+
+
+def colsum_bf16(x, out=None):
+    """Column sums of a [rows, C] bf16 matrix -> float32 [C] (rl_colsum_bf16)."""
+    require_cuda(x, out)
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if out is None:
+        out = torch.empty(C, dtype=torch.float32, device=x.device)
+    ws = _raw_ws(x.device, 592 * C * 4, 'colsum')
+    check(_lib.load().rl_colsum_bf16(ptr(x), rows, C, ptr(out), ptr(ws), ws.numel(), stream()), 'colsum_bf16')
+    return out

@@ -126,3 +126,25 @@ def test_conv1_to_conv2_space_to_depth_chain():
     torch.cuda.synchronize()
     err = (out.float() - ref).abs().max().item()
     assert out.shape == ref.shape and err < 3e-2 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize('N,H,Cin,Cout,k', [(5, 11, 64, 64, 3), (150, 11, 64, 64, 3), (40, 12, 128, 64, 2)])
+def test_conv2d_s1_dgrad_tma_window_form(N, H, Cin, Cout, k):
+    """dgrad of the window-form conv (+ ReLU mask) against torch autograd on the same bf16 operands."""
+    from parl_b200 import kernels as K_
+    g = torch.Generator(device=DEV).manual_seed(N + H)
+    Ho = H - k + 1
+    x = torch.randn(N, H, H, Cin, device=DEV, generator=g).to(torch.bfloat16)          # saved (post-ReLU-like) input
+    w = (torch.randn(Cout, Cin, k, k, device=DEV, generator=g) / (Cin * k * k) ** 0.5).to(torch.bfloat16)
+    dout = torch.randn(N, Ho, Ho, Cout, device=DEV, generator=g).to(torch.bfloat16)
+    xin = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    torch.nn.functional.conv2d(xin, w.float()).backward(dout.float().permute(0, 3, 1, 2))
+    ref = (xin.grad.permute(0, 2, 3, 1) * (x.float() > 0))
+    dgrid = torch.zeros(N, H, H, Cout, device=DEV, dtype=torch.bfloat16)
+    dgrid[:, :Ho, :Ho] = dout
+    wt = w.permute(1, 2, 3, 0).reshape(Cin, k * k * Cout).contiguous()                 # [ci][(r,s,co)]
+    out = torch.zeros(N, H, H, Cin, device=DEV, dtype=torch.bfloat16)
+    K_.conv2d_s1_nhwc_bf16_dgrad(dgrid, wt, k, k, out, act_mask=x)
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert err < 3e-2 * max(1.0, ref.abs().max().item()), err
