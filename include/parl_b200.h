@@ -132,7 +132,8 @@ int rl_env_atari_synth_step(
  * out_dtype 0 = uint8, 1 = float32 (value * scale), both [n,4,HW] (NCHW);
  * out_dtype 2 = bfloat16 [n,HW,4] (NHWC, value * scale) — the network input transform fused in;
  * out_dtype 3 = bfloat16 [n,21,21,64]: conv1's space-to-depth form (8x8/4/pad-1 conv == 2x2/1 conv over 4x4
- *               pixel blocks, channel = (dy*4+dx)*4+c, zero outside the image), 84x84 frames only. */
+ *               pixel blocks, channel = (dy*4+dx)*4+c, zero outside the image), 84x84 frames only; with
+ *               ages == NULL `planes` is an already stacked uint8 tensor [t_count*B, 4, 84, 84]. */
 int rl_obs_stack_gather(
     const uint8_t* planes, const uint8_t* ages, int B, int HW, int t_begin, int t_count,
     int out_layout, int out_dtype, float scale, void* out, rl_stream_t stream);
@@ -276,6 +277,10 @@ int rl_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, l
  * ---------------------------------------------------------------------- */
 int rl_gemm_bf16_tn(const void* A, const void* B, const float* bias, void* C, int M, int N, int K,
                     int lda, int ldb, int ldc, int relu, int out_f32, rl_stream_t stream);
+/* Backward-through-ReLU form: C[M,N] = (A . B^T) * (mask > 0), mask [M, ldm] bf16 = the saved post-ReLU activation
+ * of the layer whose input gradient is being formed (dX = dY . W, B = W^T stored [N, K]). */
+int rl_gemm_bf16_tn_masked(const void* A, const void* B, void* C, const void* mask, int M, int N, int K,
+                           int lda, int ldb, int ldc, int ldm, int out_f32, rl_stream_t stream);
 
 /* NHWC bf16 convolution forward (+bias, optional ReLU) as an implicit GEMM on tcgen05: the conv layers of
  * the Atari actor-critic (benchmark/torch/a2c/atari_model.py:26-44; executed there by cuDNN through torch).
@@ -302,7 +307,8 @@ int rl_debug_set_shiftconv_base_offset(int enable);
  * x>=W-KW+1); weight_t_krsc [Cin, KH*KW*Cout] with element [ci][(r,s,co)] = W[co][(r,s,ci)];
  * act_mask (optional) [N,H,W,Cin] is the saved post-ReLU input activation: din *= (act_mask > 0).
  * out_mode 0: din on a [N,OGH,OGW,Cin] grid (OGH>=H, OGW>=W; untouched cells stay as they are);
- * out_mode 2 (H=W=12, Cin=128): din of the 2x2-block conv scattered to the [N,21,21,32] grid of conv1. */
+ * out_mode 2 (H=W=12, Cin=128): din of the 2x2-block conv scattered to conv1's gradient grid [N,21,21,64]
+ * (channels 0..31 of each cell; 32..63 are zero padding so that the weight-gradient kernel sees M = 64). */
 int rl_conv2d_s1_nhwc_bf16_dgrad(const void* dout_grid, const void* weight_t_krsc, const void* act_mask, void* din,
                                  int N, int H, int W, int Cout, int Cin, int KH, int KW, int out_mode,
                                  int OGH, int OGW, rl_stream_t stream);
@@ -317,7 +323,8 @@ int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* in, float* d
                                  int Cin, int Cout, int KH, int KW, int accumulate,
                                  void* workspace, size_t workspace_bytes, rl_stream_t stream);
 int rl_debug_set_wgrad_lane_map(int mode);
-/* out[c] = sum_r x[r,c] for a [rows, C] bf16 matrix (bias gradients); C divides 256; workspace >= 592*C*4 bytes. */
+/* out[c] = sum_r x[r,c] for a [rows, C] bf16 matrix (bias gradients); C divides 256 or is a multiple of it;
+ * workspace >= 592*C*4 bytes. */
 int rl_colsum_bf16(const void* x, long long rows, int C, float* out, void* workspace, size_t workspace_bytes,
                    rl_stream_t stream);
 

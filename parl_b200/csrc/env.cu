@@ -265,14 +265,15 @@ __global__ void __launch_bounds__(256) obs_stack_gather_s2d_bf16_kernel(const ui
     }
     t += t_begin;
     const int y = 4 * Y + dy - 1;
-    const int age = ages[(long long)t * B + b];
+    const int age = ages ? ages[(long long)t * B + b] : 0;
     uint32_t px[4];                           // per channel: the 4 bytes at x = 4X-1 .. 4X+2
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       px[c] = 0u;
       if (y >= 0) {
-        const int plane = t + 3 - min(3 - c, age);
-        const uint32_t* row = reinterpret_cast<const uint32_t*>(planes + ((long long)plane * B + b) * (W * W) + y * W);
+        // ages == NULL: the source is an already stacked observation tensor [n, 4, 84, 84] (host contract path)
+        const long long img = ages ? ((long long)(t + 3 - min(3 - c, age)) * B + b) : (r * 4 + c);
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(planes + img * (W * W) + y * W);
         const uint32_t w0 = X > 0 ? __ldg(row + X - 1) : 0u;     // bytes 4X-4 .. 4X-1
         const uint32_t w1 = __ldg(row + X);                      // bytes 4X   .. 4X+3
         px[c] = (w0 >> 24) | (w1 << 8);
@@ -487,7 +488,7 @@ extern "C" int rl_env_atari_synth_step(uint8_t* frame_out, float* reward_out, ui
 
 extern "C" int rl_obs_stack_gather(const uint8_t* planes, const uint8_t* ages, int B, int HW, int t_begin, int t_count,
                                    int out_layout, int out_dtype, float scale, void* out, rl_stream_t stream) {
-  RL_CHECK_ARG(planes && ages && out, "obs_stack_gather: null pointer");
+  RL_CHECK_ARG(planes && out && (ages || out_dtype == 3), "obs_stack_gather: null pointer");
   RL_CHECK_ARG(B > 0 && HW > 0 && HW % 16 == 0 && t_count > 0 && t_begin >= 0, "obs_stack_gather: bad shape");
   RL_CHECK_ARG(aligned16(planes) && aligned16(out), "obs_stack_gather: 16-byte alignment required");
   const long long total = (long long)t_count * B * 4 * (HW / 16);

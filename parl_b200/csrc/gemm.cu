@@ -92,6 +92,8 @@ struct GemmArgs {
   void* C;             // [M, ldc] bf16 or f32
   int M, N, K, ldc;
   int relu, out_f32;
+  const __nv_bfloat16* mask;   // optional [M, ldm] saved post-ReLU activation: C *= (mask > 0)  (ReLU backward)
+  int ldm;
 };
 
 template <int BN>
@@ -179,6 +181,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tn_kernel(const __g
           float x = v[i] + ((g.bias && col + i < g.N) ? g.bias[col + i] : 0.f);
           v[i] = g.relu ? fmaxf(x, 0.f) : x;
         }
+        if (g.mask) {
+          const __nv_bfloat16* mrow = g.mask + (size_t)row * g.ldm + col;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (col + i < g.N && !(__bfloat162float(mrow[i]) > 0.f)) v[i] = 0.f;
+        }
         if (g.out_f32) {
           float* dst = reinterpret_cast<float*>(g.C) + (size_t)row * g.ldc + col;
           if (col + 16 <= g.N && (g.ldc & 3) == 0) {
@@ -247,8 +255,22 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmA
 
 using namespace rl;
 
+static int gemm_launch(const void* A, const void* B, const float* bias, void* C, int M, int N, int K, int lda, int ldb,
+                       int ldc, int relu, int out_f32, const void* mask, int ldm, rl_stream_t stream);
+
 extern "C" int rl_gemm_bf16_tn(const void* A, const void* B, const float* bias, void* C, int M, int N, int K, int lda,
                                int ldb, int ldc, int relu, int out_f32, rl_stream_t stream) {
+  return gemm_launch(A, B, bias, C, M, N, K, lda, ldb, ldc, relu, out_f32, nullptr, 0, stream);
+}
+
+extern "C" int rl_gemm_bf16_tn_masked(const void* A, const void* B, void* C, const void* mask, int M, int N, int K,
+                                      int lda, int ldb, int ldc, int ldm, int out_f32, rl_stream_t stream) {
+  RL_CHECK_ARG(mask && ldm >= N, "gemm_bf16_tn_masked: mask required, ldm >= N");
+  return gemm_launch(A, B, nullptr, C, M, N, K, lda, ldb, ldc, 0, out_f32, mask, ldm, stream);
+}
+
+static int gemm_launch(const void* A, const void* B, const float* bias, void* C, int M, int N, int K, int lda, int ldb,
+                       int ldc, int relu, int out_f32, const void* mask, int ldm, rl_stream_t stream) {
   RL_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "gemm_bf16_tn: bad argument");
   RL_CHECK_ARG(aligned16(A) && aligned16(B) && aligned16(C), "gemm_bf16_tn: pointers must be 16-byte aligned");
   RL_CHECK_ARG(lda >= K && ldb >= K && ldc >= N && (lda % 8) == 0 && (ldb % 8) == 0,
@@ -265,6 +287,7 @@ extern "C" int rl_gemm_bf16_tn(const void* A, const void* B, const float* bias, 
   }
   GemmArgs g;
   g.bias = bias, g.C = C, g.M = M, g.N = N, g.K = K, g.ldc = ldc, g.relu = relu, g.out_f32 = out_f32;
+  g.mask = (const __nv_bfloat16*)mask, g.ldm = ldm;
   cudaStream_t st = (cudaStream_t)stream;
   switch (BN) {
     case 256: launch_gemm<256>(ma, mb, g, st); break;

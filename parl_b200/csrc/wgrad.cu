@@ -197,10 +197,19 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 // column sums of a [rows, C] bf16 matrix (bias gradients): deterministic two-stage
 __global__ void __launch_bounds__(256) colsum_bf16_stage1(const __nv_bfloat16* __restrict__ x, long long rows, int C,
                                                           float* __restrict__ part) {
-  // block b sums rows [b*chunk, (b+1)*chunk); thread t handles column t % C, row phase t / C
-  const int c = threadIdx.x % C, ph = threadIdx.x / C, nph = blockDim.x / C;
   const long long chunk = (rows + gridDim.x - 1) / gridDim.x;
   const long long r0 = (long long)blockIdx.x * chunk, r1 = min(rows, r0 + chunk);
+  if (C >= 256) {
+    // thread t owns columns t, t+256, ...; rows of the block's chunk are walked sequentially (coalesced over t)
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float acc = 0.f;
+      for (long long r = r0; r < r1; ++r) acc += __bfloat162float(x[r * C + c]);
+      part[(size_t)blockIdx.x * C + c] = acc;
+    }
+    return;
+  }
+  // C < 256: thread t handles column t % C, row phase t / C
+  const int c = threadIdx.x % C, ph = threadIdx.x / C, nph = blockDim.x / C;
   float acc = 0.f;
   if (ph < nph)
     for (long long r = r0 + ph; r < r1; r += nph) acc += __bfloat162float(x[r * C + c]);
@@ -314,7 +323,8 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
 
 extern "C" int rl_colsum_bf16(const void* x, long long rows, int C, float* out, void* workspace, size_t workspace_bytes,
                               rl_stream_t stream) {
-  RL_CHECK_ARG(x && out && workspace && rows > 0 && C > 0 && C <= 256 && 256 % C == 0, "colsum_bf16: bad argument (C | 256)");
+  RL_CHECK_ARG(x && out && workspace && rows > 0 && C > 0 && (C % 256 == 0 || (C < 256 && 256 % C == 0)),
+               "colsum_bf16: C must divide 256 or be a multiple of 256");
   const int nblocks = 592;
   if (workspace_bytes < (size_t)nblocks * C * sizeof(float)) {
     set_error("colsum_bf16: workspace too small");

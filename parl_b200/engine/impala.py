@@ -19,12 +19,14 @@ from .. import kernels
 from ..algorithms import IMPALA
 from .nets import AtariActorCritic
 from .actor_net import AtariActorNet
+from .train_net import AtariTrainNet
 
 
 class ImpalaEngine(object):
     def __init__(self, num_envs=4096, sample_batch_steps=50, act_dim=18, frame_hw=(84, 84), seed=0, device=None,
                  env_offset=0, gamma=0.99, vf_loss_coeff=0.5, clip_rho_threshold=1.0, clip_pg_rho_threshold=1.0,
-                 p_done=0.1, model=None, learn_chunk_rows=5, use_graph=True, actor_kernels='auto'):
+                 p_done=0.1, model=None, learn_chunk_rows=5, use_graph=True, actor_kernels='auto',
+                 learner_kernels='auto'):
         if device is None:
             device = torch.device('cuda', torch.cuda.current_device())
         self.device = torch.device(device)
@@ -51,11 +53,15 @@ class ImpalaEngine(object):
         self.alg = IMPALA(self.model, sample_batch_steps=T, gamma=gamma, vf_loss_coeff=vf_loss_coeff,
                           clip_rho_threshold=clip_rho_threshold, clip_pg_rho_threshold=clip_pg_rho_threshold)
         self.learn_chunk_rows = int(learn_chunk_rows)
+        native_ok = (self.h, self.w) == (84, 84) and isinstance(self.model, AtariActorCritic)
+        use_native_learner = learner_kernels is True or (learner_kernels == 'auto' and native_ok)
+        # learner forward+backward on hand-written tcgen05 kernels (no autograd) when the model is the Atari net
+        self.train_net = AtariTrainNet(self.model, T * B, dev) if use_native_learner else None
         # learner inputs: one pre-scaled bf16 NHWC buffer per chunk (each is saved by autograd for conv1's
         # weight gradient, so chunks must not share storage): T*B*56 KB in total
-        self.obs_chunks = [torch.empty((min(self.learn_chunk_rows, T - t0) * B, ) + obs_shape,
-                                       dtype=torch.bfloat16, device=dev)
-                           for t0 in range(0, T, self.learn_chunk_rows)]
+        self.obs_chunks = [] if self.train_net is not None else [
+            torch.empty((min(self.learn_chunk_rows, T - t0) * B, ) + obs_shape, dtype=torch.bfloat16, device=dev)
+            for t0 in range(0, T, self.learn_chunk_rows)]
         self.tgt_logits = torch.empty((T, B, A), dtype=torch.float32, device=dev)
         self.values = torch.empty((T, B), dtype=torch.float32, device=dev)
         self.loss_out = dict(losses=torch.zeros(8, device=dev), d_logits=torch.empty((T * B, A), device=dev),
@@ -124,6 +130,8 @@ class ImpalaEngine(object):
     def learn(self, learning_rate=0.001, entropy_coeff=-0.01):
         """One IMPALA update on the (T,B) rollout in HBM (impala.py:134-215 semantics)."""
         T, B, A = self.T, self.B, self.A
+        if self.train_net is not None:
+            return self._learn_native(learning_rate, entropy_coeff)
         rows = self.learn_chunk_rows
         outs = []
         for ci, t0 in enumerate(range(0, T, rows)):
@@ -158,6 +166,33 @@ class ImpalaEngine(object):
         self.alg.optimizer.step(lr=learning_rate)
         if self.actor_net is not None:
             self.actor_net.pack()              # refresh the actor's bf16 operand copies (weights never leave HBM)
+        return res['losses']
+
+    def _learn_native(self, learning_rate, entropy_coeff):
+        """learn() with the network forward/backward on the hand-written kernels (AtariTrainNet)."""
+        T, B, A = self.T, self.B, self.A
+        net = self.train_net
+        logits, values = net.forward(self.planes, self.ages, T)
+        ev = getattr(self, 'k1_events', None)
+        if ev is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        res = kernels.vtrace_loss_fwd_bwd(logits, self.beh_logits.view(T * B, A), self.actions.view(-1),
+                                          self.rewards.view(-1), self.dones.view(-1), values.view(-1), T, B,
+                                          self.alg.gamma, self.alg.vf_loss_coeff, entropy_coeff,
+                                          self.alg.clip_rho_threshold, self.alg.clip_pg_rho_threshold,
+                                          layout=kernels.TIME_MAJOR, out=self.loss_out)
+        if ev is not None:
+            e1.record()
+            ev.append((e0, e1))
+        self.tgt_logits, self.values = logits.view(T, B, A), values.view(T, B)
+        net.backward(res['d_logits'], res['d_values'])
+        if self.alg.grad_sync is not None:
+            self.alg.grad_sync(self.alg.optimizer.grad)
+        self.alg.optimizer.step(lr=learning_rate)
+        net.pack()
+        if self.actor_net is not None:
+            self.actor_net.pack()
         return res['losses']
 
     # ------------------------------------------------------------------ reference-facing host contract
@@ -201,28 +236,44 @@ class ImpalaEngine(object):
         bl = host['behaviour_logits'].to(dev, non_blocking=True)
         rew = host['rewards'].to(dev, non_blocking=True)
         dones = host['dones'].to(dev, non_blocking=True)
-        slab = max(1, (self.learn_chunk_rows * B) // T)          # env columns per forward slab
-        tgt = torch.empty((B * T, A), dtype=torch.float32, device=dev)
-        val = torch.empty(B * T, dtype=torch.float32, device=dev)
-        outs = []
-        for b0 in range(0, B, slab):
-            nb = min(slab, B - b0)
-            obs = host['obs'][b0 * T:(b0 + nb) * T].to(dev, non_blocking=True)
-            logits, values = self.model.policy_and_value(obs)
-            tgt[b0 * T:(b0 + nb) * T].copy_(logits.detach())
-            val[b0 * T:(b0 + nb) * T].copy_(values.detach())
-            outs.append((logits, values, b0 * T, nb * T))
-        res = kernels.vtrace_loss_fwd_bwd(tgt, bl, acts, rew, dones, val, T, B, self.alg.gamma, self.alg.vf_loss_coeff,
-                                          entropy_coeff, self.alg.clip_rho_threshold, self.alg.clip_pg_rho_threshold,
-                                          layout=kernels.ENV_MAJOR, out=self.loss_out)
-        tensors, grads = [], []
-        for logits, values, o, n in outs:
-            tensors += [logits, values]
-            grads += [res['d_logits'][o:o + n], res['d_values'][o:o + n]]
-        torch.autograd.backward(tensors, grads)
+        if self.train_net is not None:
+            # native learner: stacked uint8 observations -> conv1's space-to-depth input -> tcgen05 forward/backward
+            net = self.train_net
+            slab = 16384
+            for s0 in range(0, B * T, slab):
+                n = min(slab, B * T - s0)
+                obs = host['obs'][s0:s0 + n].to(dev, non_blocking=True)
+                kernels.obs_stack_gather(obs, None, 0, 1, net.x0[s0:s0 + n], scale=1.0 / 255.0, s2d=True)
+            logits, values = net.forward_from_x0()
+            res = kernels.vtrace_loss_fwd_bwd(logits, bl, acts, rew, dones, values.view(-1), T, B, self.alg.gamma,
+                                              self.alg.vf_loss_coeff, entropy_coeff, self.alg.clip_rho_threshold,
+                                              self.alg.clip_pg_rho_threshold, layout=kernels.ENV_MAJOR, out=self.loss_out)
+            net.backward(res['d_logits'], res['d_values'])
+        else:
+            slab = max(1, (self.learn_chunk_rows * B) // T)          # env columns per forward slab
+            tgt = torch.empty((B * T, A), dtype=torch.float32, device=dev)
+            val = torch.empty(B * T, dtype=torch.float32, device=dev)
+            outs = []
+            for b0 in range(0, B, slab):
+                nb = min(slab, B - b0)
+                obs = host['obs'][b0 * T:(b0 + nb) * T].to(dev, non_blocking=True)
+                logits, values = self.model.policy_and_value(obs)
+                tgt[b0 * T:(b0 + nb) * T].copy_(logits.detach())
+                val[b0 * T:(b0 + nb) * T].copy_(values.detach())
+                outs.append((logits, values, b0 * T, nb * T))
+            res = kernels.vtrace_loss_fwd_bwd(tgt, bl, acts, rew, dones, val, T, B, self.alg.gamma,
+                                              self.alg.vf_loss_coeff, entropy_coeff, self.alg.clip_rho_threshold,
+                                              self.alg.clip_pg_rho_threshold, layout=kernels.ENV_MAJOR, out=self.loss_out)
+            tensors, grads = [], []
+            for logits, values, o, n in outs:
+                tensors += [logits, values]
+                grads += [res['d_logits'][o:o + n], res['d_values'][o:o + n]]
+            torch.autograd.backward(tensors, grads)
         if self.alg.grad_sync is not None:
             self.alg.grad_sync(self.alg.optimizer.grad)
         self.alg.optimizer.step(lr=learning_rate)
+        if self.train_net is not None:
+            self.train_net.pack()
         if self.actor_net is not None:
             self.actor_net.pack()
         return res['losses']

@@ -1,0 +1,126 @@
+"""Learner-side forward AND backward of the Atari actor-critic on hand-written tcgen05 kernels — no autograd,
+no cuDNN on the convolution path.
+
+Layers (a13: benchmark/torch/a2c/atari_model.py:23-96), all stride-1 in TMA-window form after space-to-depth:
+    x0 [N,21,21,64] --conv1' 2x2--> a1 (padded 2x2-block layout [N,12,12,128]) --conv2' 2x2--> a2 [N,11,11,64]
+       --conv3 3x3--> a3 [N,9,9,64] == [N,5184] --fc--> h [N,512] --heads--> logits [N,A], values [N]
+Backward (after the fused loss kernel delivered d_logits / d_values):
+    heads/fc data gradients : rl_gemm_bf16_tn_masked (ReLU masks fused in the epilogue)
+    conv data gradients     : rl_conv2d_s1_nhwc_bf16_dgrad (same windows, flipped taps, ReLU mask fused)
+    conv weight gradients   : rl_conv2d_s1_nhwc_bf16_wgrad (positions as the GEMM K dimension, TMEM-resident)
+    bias gradients          : rl_colsum_bf16
+    fc / head weight gradients: two plain library GEMMs (torch.matmul -> cuBLAS), the only library calls left
+Activations for the whole learner batch stay resident in HBM (about 120 KB per sample in bf16).
+Gradients are written into the parameters' ``.grad`` views of the FlatAdam buffer in the reference layouts.
+"""
+import torch
+
+from .. import kernels as K
+
+
+class AtariTrainNet(object):
+    def __init__(self, model, n_samples, device):
+        self.model = model
+        N = self.N = int(n_samples)
+        dev = self.device = torch.device(device)
+        bf, f32 = torch.bfloat16, torch.float32
+        A = self.A = model.fc_pi.weight.shape[0]
+        z = lambda *s: torch.zeros(s, dtype=bf, device=dev)
+        e = lambda *s: torch.empty(s, dtype=bf, device=dev)
+        # activations
+        self.x0, self.a1, self.a2, self.a3 = e(N, 21, 21, 64), z(N, 12, 12, 128), e(N, 11, 11, 64), e(N, 9, 9, 64)
+        self.h = e(N, 512)
+        self.logits = torch.empty((N, A), dtype=f32, device=dev)
+        self.values = torch.empty((N, 1), dtype=f32, device=dev)
+        # gradients of activations (grids are zero where no valid output exists and are never written there)
+        self.dheads, self.dh = z(N, 32), e(N, 512)
+        self.da3g, self.da2g, self.da1g = z(N, 11, 11, 64), z(N, 12, 12, 64), z(N, 21, 21, 64)
+        # operand copies of the weights
+        self.w1, self.w2, self.w3 = e(32, 256), e(64, 512), e(64, 576)
+        self.wfc, self.wpi, self.wv = e(512, 5184), e(A, 512), e(1, 512)
+        self.wfcT, self.whT = e(5184, 512), z(512, 32)
+        self.w3T, self.w2T = e(64, 576), e(128, 256)
+        self.b1, self.b2, self.b3 = [torch.empty(n, dtype=f32, device=dev) for n in (32, 64, 64)]
+        self.bfc, self.bpi, self.bv = [torch.empty(n, dtype=f32, device=dev) for n in (512, A, 1)]
+        # weight-gradient scratch (KRSC, float32)
+        self.dw1 = torch.empty((64, 256), dtype=f32, device=dev)
+        self.dw2 = torch.empty((64, 512), dtype=f32, device=dev)
+        self.dw3 = torch.empty((64, 576), dtype=f32, device=dev)
+        self.db = torch.empty(64, dtype=f32, device=dev)
+        self.pack()
+
+    @torch.no_grad()
+    def pack(self):
+        m = self.model
+        self.w1.copy_(m.conv1.weight.view(32, 4, 2, 4, 2, 4).permute(0, 2, 4, 3, 5, 1).reshape(32, 256))
+        w2p = m.conv2.weight.view(64, 32, 2, 2, 2, 2).permute(0, 2, 4, 3, 5, 1)          # (o, a, b, dy, dx, c)
+        self.w2.copy_(w2p.reshape(64, 512))
+        self.w2T.copy_(w2p.permute(3, 4, 5, 1, 2, 0).reshape(128, 256))                  # [(dy,dx,c)][(a,b,o)]
+        self.w3.copy_(m.conv3.weight.permute(0, 2, 3, 1).reshape(64, 576))               # (o, r, s, c)
+        self.w3T.copy_(m.conv3.weight.permute(1, 2, 3, 0).reshape(64, 576))              # [c][(r,s,o)]
+        wfc = m.fc.weight.view(512, 64, 9, 9).permute(0, 2, 3, 1).reshape(512, 5184)     # columns in (h,w,c) order
+        self.wfc.copy_(wfc)
+        self.wfcT.copy_(wfc.t())
+        self.wpi.copy_(m.fc_pi.weight)
+        self.wv.copy_(m.fc_v.weight)
+        self.whT[:, :self.A].copy_(m.fc_pi.weight.t())
+        self.whT[:, self.A:self.A + 1].copy_(m.fc_v.weight.t())
+        self.b1.copy_(m.conv1.bias), self.b2.copy_(m.conv2.bias), self.b3.copy_(m.conv3.bias)
+        self.bfc.copy_(m.fc.bias), self.bpi.copy_(m.fc_pi.bias), self.bv.copy_(m.fc_v.bias)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, planes, ages, t_count, layout=K.TIME_MAJOR):
+        """Observations of rows [0, t_count) of the frame ring -> self.logits [N,A], self.values [N,1]."""
+        N = self.N
+        K.obs_stack_gather(planes, ages, 0, t_count, self.x0, layout=layout, scale=1.0 / 255.0, s2d=True)
+        return self.forward_from_x0()
+
+    def forward_from_x0(self):
+        N = self.N
+        K.conv2d_s1_nhwc_bf16_fwd(self.x0, self.w1, self.b1, 2, 2, relu=True, out=self.a1, out_mode=1)
+        K.conv2d_s1_nhwc_bf16_fwd(self.a1, self.w2, self.b2, 2, 2, relu=True, out=self.a2)
+        K.conv2d_s1_nhwc_bf16_fwd(self.a2, self.w3, self.b3, 3, 3, relu=True, out=self.a3)
+        K.gemm_bf16_tn(self.a3.view(N, 5184), self.wfc, self.bfc, relu=True, out=self.h)
+        K.gemm_bf16_tn(self.h, self.wpi, self.bpi, relu=False, out=self.logits)
+        K.gemm_bf16_tn(self.h, self.wv, self.bv, relu=False, out=self.values)
+        return self.logits, self.values
+
+    # ------------------------------------------------------------------ backward
+    @torch.no_grad()
+    def backward(self, d_logits, d_values):
+        """d_logits [N,A] f32, d_values [N] f32 -> fills ``p.grad`` of every model parameter."""
+        N, A, m = self.N, self.A, self.model
+        self.dheads[:, :A].copy_(d_logits)
+        self.dheads[:, A].copy_(d_values.reshape(-1))
+        # heads
+        dwh = self.dheads[:, :A + 1].t().float() @ self.h.float() if N <= 4096 else \
+            (self.dheads[:, :A + 1].t() @ self.h).float()
+        m.fc_pi.weight.grad.copy_(dwh[:A])
+        m.fc_v.weight.grad.copy_(dwh[A:A + 1])
+        dbh = K.colsum_bf16(self.dheads)
+        m.fc_pi.bias.grad.copy_(dbh[:A])
+        m.fc_v.bias.grad.copy_(dbh[A:A + 1])
+        K.gemm_bf16_tn_masked(self.dheads, self.whT, self.h, self.dh)                       # dh = (dheads.Wh) * (h>0)
+        # fc
+        a3f = self.a3.view(N, 5184)
+        dwfc = (self.dh.t() @ a3f).float()                                                   # [512, 5184] (h,w,c) cols
+        m.fc.weight.grad.copy_(dwfc.view(512, 9, 9, 64).permute(0, 3, 1, 2).reshape(512, 5184))
+        m.fc.bias.grad.copy_(K.colsum_bf16(self.dh))
+        da3 = self.da3g.view(N, 121 * 64)
+        for y in range(9):   # image row y of the 9x9 output = 576 contiguous columns of the 11x11 gradient grid
+            K.gemm_bf16_tn_masked(self.dh, self.wfcT[y * 576:(y + 1) * 576], a3f[:, y * 576:(y + 1) * 576],
+                                  da3[:, y * 704:y * 704 + 576])
+        # conv3
+        K.conv2d_s1_nhwc_bf16_wgrad(self.da3g, self.a2, 3, 3, dw_krsc=self.dw3)
+        m.conv3.weight.grad.copy_(self.dw3.view(64, 3, 3, 64).permute(0, 3, 1, 2))
+        m.conv3.bias.grad.copy_(K.colsum_bf16(self.da3g, out=self.db))
+        K.conv2d_s1_nhwc_bf16_dgrad(self.da3g, self.w3T, 3, 3, self.da2g, act_mask=self.a2)   # onto the 12x12 grid
+        # conv2 (2x2 block form)
+        K.conv2d_s1_nhwc_bf16_wgrad(self.da2g, self.a1, 2, 2, dw_krsc=self.dw2)
+        m.conv2.weight.grad.copy_(self.dw2.view(64, 2, 2, 2, 2, 32).permute(0, 5, 1, 3, 2, 4).reshape(64, 32, 4, 4))
+        m.conv2.bias.grad.copy_(K.colsum_bf16(self.da2g, out=self.db))
+        K.conv2d_s1_nhwc_bf16_dgrad(self.da2g, self.w2T, 2, 2, self.da1g, act_mask=self.a1, out_mode=2)
+        # conv1 (4x4 block form); the gradient grid carries 64 channels, the upper 32 are zero padding
+        K.conv2d_s1_nhwc_bf16_wgrad(self.da1g, self.x0, 2, 2, dw_krsc=self.dw1)
+        m.conv1.weight.grad.copy_(self.dw1[:32].view(32, 2, 2, 4, 4, 4).permute(0, 5, 1, 3, 2, 4).reshape(32, 4, 8, 8))
+        m.conv1.bias.grad.copy_(K.colsum_bf16(self.da1g, out=self.db)[:32])

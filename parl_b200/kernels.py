@@ -132,7 +132,11 @@ def env_atari_synth_step(frame_out, reward_out, done_out, age_in, age_out, stats
 def obs_stack_gather(planes, ages, t_begin, t_count, out, layout=TIME_MAJOR, scale=1.0, s2d=False):
     """planes [P,B,HW] u8, ages [T+1,B] u8 -> out [t_count*B, 4, HW] (uint8 / float32, NCHW) or
     [t_count*B, HW, 4] (bfloat16, NHWC, value*scale)."""
-    P, B, HW = planes.shape[0], planes.shape[1], planes[0, 0].numel()
+    if ages is None:        # already stacked observations [n,4,84,84] -> space-to-depth (host-contract path)
+        assert s2d and planes.dim() == 4 and planes.shape[1] == 4
+        B, HW, t_begin, t_count = planes.shape[0], planes[0, 0].numel(), 0, 1
+    else:
+        P, B, HW = planes.shape[0], planes.shape[1], planes[0, 0].numel()
     dt = {torch.uint8: 0, torch.float32: 1, torch.bfloat16: 2}[out.dtype]
     if s2d:
         assert out.dtype == torch.bfloat16 and out.numel() == t_count * B * 21 * 21 * 64
@@ -417,7 +421,7 @@ def conv2d_s1_nhwc_bf16_fwd(x, weight_krsc, bias, KH, KW, relu=True, out=None, o
 
 def conv2d_s1_nhwc_bf16_dgrad(dout_grid, weight_t_krsc, KH, KW, out, act_mask=None, out_mode=0):
     """Data gradient of the TMA-window conv (rl_conv2d_s1_nhwc_bf16_dgrad).  dout_grid [N,H,W,Cout] on the
-    input grid, weight_t_krsc [Cin, KH*KW*Cout]; out [N,OGH,OGW,Cin] (mode 0) or [N,21,21,32] (mode 2)."""
+    input grid, weight_t_krsc [Cin, KH*KW*Cout]; out [N,OGH,OGW,Cin] (mode 0) or [N,21,21,64] (mode 2)."""
     require_cuda(dout_grid, weight_t_krsc, out, act_mask)
     N, H, W, Cout = dout_grid.shape
     Cin = weight_t_krsc.shape[0]
@@ -461,4 +465,17 @@ def colsum_bf16(x, out=None):
         out = torch.empty(C, dtype=torch.float32, device=x.device)
     ws = _raw_ws(x.device, 592 * C * 4, 'colsum')
     check(_lib.load().rl_colsum_bf16(ptr(x), rows, C, ptr(out), ptr(ws), ws.numel(), stream()), 'colsum_bf16')
+    return out
+
+
+def gemm_bf16_tn_masked(a, b, mask, out):
+    """out = (a @ b.T) * (mask > 0) on tcgen05 (rl_gemm_bf16_tn_masked); row strides of a / b / out / mask may
+    exceed their widths (sub-matrix views)."""
+    require_cuda(a, b)
+    M, K = a.shape
+    N = b.shape[0]
+    assert out.shape == (M, N) and mask.shape == (M, N) and a.stride(1) == 1 and out.stride(1) == 1 and mask.stride(1) == 1
+    check(_lib.load().rl_gemm_bf16_tn_masked(ptr(a), ptr(b), ptr(out), ptr(mask), M, N, K, a.stride(0), b.stride(0),
+                                             out.stride(0), mask.stride(0), 1 if out.dtype == torch.float32 else 0,
+                                             stream()), 'gemm_bf16_tn_masked')
     return out
