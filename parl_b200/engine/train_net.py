@@ -97,9 +97,8 @@ class AtariTrainNet(object):
             (self.dheads[:, :A + 1].t() @ self.h).float()
         m.fc_pi.weight.grad.copy_(dwh[:A])
         m.fc_v.weight.grad.copy_(dwh[A:A + 1])
-        dbh = K.colsum_bf16(self.dheads)
-        m.fc_pi.bias.grad.copy_(dbh[:A])
-        m.fc_v.bias.grad.copy_(dbh[A:A + 1])
+        m.fc_pi.bias.grad.copy_(d_logits.sum(0))          # head bias gradients straight from the fp32 loss gradients
+        m.fc_v.bias.grad.copy_(d_values.sum().reshape(1))
         K.gemm_bf16_tn_masked(self.dheads, self.whT, self.h, self.dh)                       # dh = (dheads.Wh) * (h>0)
         # fc
         a3f = self.a3.view(N, 5184)
