@@ -323,10 +323,18 @@ int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* in, float* d
                                  int Cin, int Cout, int KH, int KW, int accumulate,
                                  void* workspace, size_t workspace_bytes, rl_stream_t stream);
 int rl_debug_set_wgrad_lane_map(int mode);
-/* out[c] = sum_r x[r,c] for a [rows, C] bf16 matrix (bias gradients); C divides 256 or is a multiple of it;
- * workspace >= 592*C*4 bytes. */
+/* out[c] = sum_r x[r,c] for a [rows, C] bf16 matrix (bias gradients); C a multiple of 8 with C/8 dividing 256;
+ * workspace >= 1184*C*4 bytes. */
 int rl_colsum_bf16(const void* x, long long rows, int C, float* out, void* workspace, size_t workspace_bytes,
                    rl_stream_t stream);
+
+/* Bandwidth-bound glue of the learner network (bf16, in HBM):
+ *   rl_bias_act_bf16          x[M,N] = act(x + bias[N]) in place (epilogue of a library GEMM);
+ *   rl_mask_scatter_grid_bf16 ReLU backward + re-gridding: dst[n,y,x,:] = src[n,y,x,:] * (act[n,y,x,:] > 0) from a
+ *                             compact [N,PH,PW,C] gradient onto a [N,GH,GW,C] grid (other cells untouched). */
+int rl_bias_act_bf16(void* x, const float* bias, long long M, int N, int relu, rl_stream_t stream);
+int rl_mask_scatter_grid_bf16(const void* src, const void* act, void* dst, long long N, int PH, int PW, int GH, int GW,
+                              int C, rl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,8 @@ SIGNATURES = {
     'rl_debug_set_wgrad_lane_map': (c_i, [c_i]),
     'rl_colsum_bf16': (c_i, [c_p, ctypes.c_longlong, c_i, c_p, c_p, c_sz, c_p]),
     'rl_gemm_bf16_tn_masked': (c_i, [c_p, c_p, c_p, c_p] + [c_i] * 8 + [c_p]),
+    'rl_bias_act_bf16': (c_i, [c_p, c_p, ctypes.c_longlong, c_i, c_i, c_p]),
+    'rl_mask_scatter_grid_bf16': (c_i, [c_p, c_p, c_p, ctypes.c_longlong, c_i, c_i, c_i, c_i, c_i, c_p]),
 }
 
 

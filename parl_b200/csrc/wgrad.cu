@@ -194,32 +194,50 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   dw[idx] = accumulate ? dw[idx] + acc : acc;
 }
 
-// column sums of a [rows, C] bf16 matrix (bias gradients): deterministic two-stage
+// column sums of a [rows, C] bf16 matrix (bias gradients): deterministic two-stage, 16-byte loads.
+// A thread owns 8 adjacent columns (one uint4) and walks the rows of its block's chunk with stride
+// (256 / (C/8)) so that a warp reads whole 128-byte lines.
 __global__ void __launch_bounds__(256) colsum_bf16_stage1(const __nv_bfloat16* __restrict__ x, long long rows, int C,
                                                           float* __restrict__ part) {
+  const int vpr = C >> 3;                              // uint4 vectors per row
   const long long chunk = (rows + gridDim.x - 1) / gridDim.x;
   const long long r0 = (long long)blockIdx.x * chunk, r1 = min(rows, r0 + chunk);
-  if (C >= 256) {
-    // thread t owns columns t, t+256, ...; rows of the block's chunk are walked sequentially (coalesced over t)
-    for (int c = threadIdx.x; c < C; c += 256) {
-      float acc = 0.f;
-      for (long long r = r0; r < r1; ++r) acc += __bfloat162float(x[r * C + c]);
-      part[(size_t)blockIdx.x * C + c] = acc;
+  __shared__ float sm[256][8];
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (vpr <= 256) {
+    const int nph = 256 / vpr;                         // row phases handled concurrently by the block
+    const int v = threadIdx.x % vpr, ph = threadIdx.x / vpr;
+    if (ph < nph) {
+      const uint4* base = reinterpret_cast<const uint4*>(x) + v;
+      for (long long r = r0 + ph; r < r1; r += nph) {
+        const uint4 q = __ldcs(base + r * vpr);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[2 * i] += __uint_as_float(w[i] << 16);
+          acc[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+        }
+      }
     }
-    return;
-  }
-  // C < 256: thread t handles column t % C, row phase t / C
-  const int c = threadIdx.x % C, ph = threadIdx.x / C, nph = blockDim.x / C;
-  float acc = 0.f;
-  if (ph < nph)
-    for (long long r = r0 + ph; r < r1; r += nph) acc += __bfloat162float(x[r * C + c]);
-  __shared__ float sm[256];
-  sm[threadIdx.x] = acc;
-  __syncthreads();
-  if (threadIdx.x < C) {
-    float a = 0.f;
-    for (int p = 0; p < nph; ++p) a += sm[p * C + threadIdx.x];
-    part[(size_t)blockIdx.x * C + threadIdx.x] = a;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm[threadIdx.x][i] = acc[i];
+    __syncthreads();
+    if (threadIdx.x < vpr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float a = 0.f;
+        for (int p = 0; p < nph; ++p) a += sm[p * vpr + threadIdx.x][i];
+        part[(size_t)blockIdx.x * C + threadIdx.x * 8 + i] = a;
+      }
+    }
+  } else {
+    for (int c = threadIdx.x; c < C; c += 256) {       // very wide matrices: scalar fallback
+      float a = 0.f;
+      for (long long r = r0; r < r1; ++r) a += __bfloat162float(x[r * C + c]);
+      part[(size_t)blockIdx.x * C + c] = a;
+    }
   }
 }
 __global__ void colsum_stage2(const float* __restrict__ part, int nblocks, int C, float* __restrict__ out) {
@@ -266,7 +284,7 @@ extern "C" size_t rl_conv_wgrad_workspace_bytes(int KH, int KW, int Cin) {
   const int cblk = Cin / 64, ntaps = KH * KW;
   int per = 512 / (cblk * 64);
   if (per > ntaps) per = ntaps;
-  return (size_t)148 * 128 * (size_t)(per * cblk * 64) * sizeof(float) + 4096;
+  return (size_t)160 * 128 * (size_t)(per * cblk * 64) * sizeof(float) + 4096;
 }
 
 extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* in, float* dw_krsc, int N, int H, int W,
@@ -284,9 +302,10 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
   g.wrows = kWgBM + (KH - 1) * W + (KW - 1);
   RL_CHECK_ARG(g.wrows <= 256, "conv2d_s1_wgrad: window too tall");
   g.num_tiles = (int)((Q + kWgBM - 1) / kWgBM);
-  g.taps_per_group = 512 / (cblk * 64);
-  if (g.taps_per_group > ntaps) g.taps_per_group = ntaps;
-  g.ngroups = (ntaps + g.taps_per_group - 1) / g.taps_per_group;
+  int cap = 512 / (cblk * 64);                       // taps whose accumulators fit the 512 TMEM columns
+  if (cap > ntaps) cap = ntaps;
+  g.ngroups = (ntaps + cap - 1) / cap;
+  g.taps_per_group = (ntaps + g.ngroups - 1) / g.ngroups;   // balanced split (e.g. 9 taps -> 5 + 4)
   g.ncols_max = g.taps_per_group * cblk * 64;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -323,11 +342,12 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
 
 extern "C" int rl_colsum_bf16(const void* x, long long rows, int C, float* out, void* workspace, size_t workspace_bytes,
                               rl_stream_t stream) {
-  RL_CHECK_ARG(x && out && workspace && rows > 0 && C > 0 && (C % 256 == 0 || (C < 256 && 256 % C == 0)),
-               "colsum_bf16: C must divide 256 or be a multiple of 256");
-  const int nblocks = 592;
+  RL_CHECK_ARG(x && out && workspace && rows > 0 && C >= 8 && C % 8 == 0 && aligned16(x) &&
+                   ((C / 8) > 256 || 256 % (C / 8) == 0),
+               "colsum_bf16: C must be a multiple of 8 with C/8 dividing 256 (or C > 2048)");
+  const int nblocks = 1184;
   if (workspace_bytes < (size_t)nblocks * C * sizeof(float)) {
-    set_error("colsum_bf16: workspace too small");
+    set_error("colsum_bf16: workspace too small (need %d*C*4 bytes)", nblocks);
     return RL_ERR_WORKSPACE;
   }
   colsum_bf16_stage1<<<nblocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, rows, C, (float*)workspace);

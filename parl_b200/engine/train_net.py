@@ -19,7 +19,7 @@ from .. import kernels as K
 
 
 class AtariTrainNet(object):
-    def __init__(self, model, n_samples, device):
+    def __init__(self, model, n_samples, device, fc_backend='auto'):
         self.model = model
         N = self.N = int(n_samples)
         dev = self.device = torch.device(device)
@@ -47,6 +47,10 @@ class AtariTrainNet(object):
         self.dw2 = torch.empty((64, 512), dtype=f32, device=dev)
         self.dw3 = torch.empty((64, 576), dtype=f32, device=dev)
         self.db = torch.empty(64, dtype=f32, device=dev)
+        # the two big fc contractions (K=5184 / N=5184 over all samples): our single-tile tcgen05 GEMM is L2-bound
+        # at this size, so by default they go to the library GEMM with our fused epilogue kernels around it
+        self.fc_library = fc_backend == 'library' or (fc_backend == 'auto' and N > 16384)
+        self.da3c = e(N, 5184) if self.fc_library else None
         self.pack()
 
     @torch.no_grad()
@@ -80,7 +84,11 @@ class AtariTrainNet(object):
         K.conv2d_s1_nhwc_bf16_fwd(self.x0, self.w1, self.b1, 2, 2, relu=True, out=self.a1, out_mode=1)
         K.conv2d_s1_nhwc_bf16_fwd(self.a1, self.w2, self.b2, 2, 2, relu=True, out=self.a2)
         K.conv2d_s1_nhwc_bf16_fwd(self.a2, self.w3, self.b3, 3, 3, relu=True, out=self.a3)
-        K.gemm_bf16_tn(self.a3.view(N, 5184), self.wfc, self.bfc, relu=True, out=self.h)
+        if self.fc_library:
+            torch.matmul(self.a3.view(N, 5184), self.wfcT, out=self.h)
+            K.bias_act_bf16(self.h, self.bfc, relu=True)
+        else:
+            K.gemm_bf16_tn(self.a3.view(N, 5184), self.wfc, self.bfc, relu=True, out=self.h)
         K.gemm_bf16_tn(self.h, self.wpi, self.bpi, relu=False, out=self.logits)
         K.gemm_bf16_tn(self.h, self.wv, self.bv, relu=False, out=self.values)
         return self.logits, self.values
@@ -105,10 +113,14 @@ class AtariTrainNet(object):
         dwfc = (self.dh.t() @ a3f).float()                                                   # [512, 5184] (h,w,c) cols
         m.fc.weight.grad.copy_(dwfc.view(512, 9, 9, 64).permute(0, 3, 1, 2).reshape(512, 5184))
         m.fc.bias.grad.copy_(K.colsum_bf16(self.dh))
-        da3 = self.da3g.view(N, 121 * 64)
-        for y in range(9):   # image row y of the 9x9 output = 576 contiguous columns of the 11x11 gradient grid
-            K.gemm_bf16_tn_masked(self.dh, self.wfcT[y * 576:(y + 1) * 576], a3f[:, y * 576:(y + 1) * 576],
-                                  da3[:, y * 704:y * 704 + 576])
+        if self.fc_library:
+            torch.matmul(self.dh, self.wfc, out=self.da3c)                                   # [N, 5184] compact
+            K.mask_scatter_grid_bf16(self.da3c, self.a3, self.da3g, N, 9, 9, 11, 11, 64)    # ReLU mask + 11x11 grid
+        else:
+            da3 = self.da3g.view(N, 121 * 64)
+            for y in range(9):   # image row y of the 9x9 output = 576 contiguous columns of the 11x11 gradient grid
+                K.gemm_bf16_tn_masked(self.dh, self.wfcT[y * 576:(y + 1) * 576], a3f[:, y * 576:(y + 1) * 576],
+                                      da3[:, y * 704:y * 704 + 576])
         # conv3
         K.conv2d_s1_nhwc_bf16_wgrad(self.da3g, self.a2, 3, 3, dw_krsc=self.dw3)
         m.conv3.weight.grad.copy_(self.dw3.view(64, 3, 3, 64).permute(0, 3, 1, 2))

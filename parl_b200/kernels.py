@@ -463,7 +463,7 @@ def colsum_bf16(x, out=None):
     rows = x.numel() // C
     if out is None:
         out = torch.empty(C, dtype=torch.float32, device=x.device)
-    ws = _raw_ws(x.device, 592 * C * 4, 'colsum')
+    ws = _raw_ws(x.device, 1184 * C * 4, 'colsum')
     check(_lib.load().rl_colsum_bf16(ptr(x), rows, C, ptr(out), ptr(ws), ws.numel(), stream()), 'colsum_bf16')
     return out
 
@@ -479,3 +479,18 @@ def gemm_bf16_tn_masked(a, b, mask, out):
                                              out.stride(0), mask.stride(0), 1 if out.dtype == torch.float32 else 0,
                                              stream()), 'gemm_bf16_tn_masked')
     return out
+
+
+def bias_act_bf16(x, bias, relu=True):
+    require_cuda(x, bias)
+    assert x.dtype == torch.bfloat16 and bias.dtype == torch.float32
+    N = x.shape[-1]
+    check(_lib.load().rl_bias_act_bf16(ptr(x), ptr(bias), x.numel() // N, N, 1 if relu else 0, stream()), 'bias_act_bf16')
+    return x
+
+
+def mask_scatter_grid_bf16(src, act, dst, n, PH, PW, GH, GW, C):
+    require_cuda(src, act, dst)
+    check(_lib.load().rl_mask_scatter_grid_bf16(ptr(src), ptr(act), ptr(dst), int(n), PH, PW, GH, GW, C, stream()),
+          'mask_scatter_grid_bf16')
+    return dst

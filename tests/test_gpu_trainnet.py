@@ -12,7 +12,8 @@ def _rel(a, b):
     return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
 
 
-def test_train_net_forward_backward_matches_autograd():
+@pytest.mark.parametrize('fc_backend', ['native', 'library'])
+def test_train_net_forward_backward_matches_autograd(fc_backend):
     from parl_b200 import kernels as K
     from parl_b200.engine.nets import AtariActorCritic
     from parl_b200.engine.train_net import AtariTrainNet
@@ -25,7 +26,7 @@ def test_train_net_forward_backward_matches_autograd():
                 p.normal_(0, 0.1)
     for p in model.parameters():
         p.grad = torch.zeros_like(p)
-    net = AtariTrainNet(model, N, DEV)
+    net = AtariTrainNet(model, N, DEV, fc_backend=fc_backend)
     obs = torch.randint(0, 255, (N, 4, 84, 84), dtype=torch.uint8, device=DEV)
     K.obs_stack_gather(obs, None, 0, 1, net.x0, scale=1.0 / 255.0, s2d=True)
     logits, values = net.forward_from_x0()
