@@ -39,6 +39,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
+    ap.add_argument('--no-pipeline', action='store_true', help='strictly sequential rollout -> learn')
     return ap.parse_args()
 
 
@@ -143,14 +144,13 @@ def main():
     from parl_b200.engine.impala import ImpalaEngine
     torch.manual_seed(0)                      # identical initial weights on every rank
     eng = ImpalaEngine(num_envs=B, sample_batch_steps=T_STEPS, act_dim=ACT_DIM, seed=1234, device=dev,
-                       env_offset=rank * B)
+                       env_offset=rank * B, pipeline=not args.no_pipeline)
     if world > 1:
         # IMPALA's loss is a SUM over the global batch (impala.py:67-79) -> all-reduce SUM of the flat gradient
         eng.alg.grad_sync = lambda g: dist.all_reduce(g, op=dist.ReduceOp.SUM)
 
     def step():
-        eng.rollout()
-        return eng.learn(0.001, -0.01)
+        return eng.step(0.001, -0.01)
 
     for _ in range(args.warmup):
         step()
@@ -214,6 +214,10 @@ def main():
                                 envs_per_gpu=B, T=T_STEPS, learner_batch=T_STEPS * args.envs,
                                 model='84x84 actor-critic (benchmark/torch/a2c/atari_model.py), 2.74 M params',
                                 parallelism='dp%d' % world,
+                                actor_learner='pipelined (rollout k+1 || learn k, policy lag 1)' if eng.pipeline
+                                else 'sequential',
+                                network='hand-written tcgen05 kernels (actor fwd; learner fwd+dgrad+wgrad)' if
+                                eng.train_net is not None else 'torch',
                                 l2_policy='per-step working set (obs ring %.1f GB/GPU) >> 126 MB L2' %
                                           ((T_STEPS + 4) * B * 7056 / 1e9)),
                     gpu_launches=launches, clocks=clocks, roofline=roof, e2e=e2e, cpu_baseline=cpu,
@@ -230,17 +234,32 @@ def run_e2e(eng, args, world, dev):
     import torch
     import torch.distributed as dist
     steps = max(2, min(args.steps, 4))
-    host = eng.make_host_sample_buffers()
-    eng.sample_to_host(host)
-    eng.learn_from_host(host, 0.001, -0.01)           # warm-up
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.time()
-    for _ in range(steps):
+    if eng.pipeline:
+        hosts = [eng.make_host_sample_buffers() for _ in range(2)]
+        host = hosts[0]
+        eng._k = 0                                        # restart the pipeline on the host path
+        eng._learn_done = [None, None]
+        for _ in range(2):                                # warm-up (prologue + one steady-state iteration)
+            eng.step_host(hosts, 0.001, -0.01)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.time()
+        for _ in range(steps):
+            losses = eng.step_host(hosts, 0.001, -0.01)
+            _ = losses[:5].cpu()                          # D2H read of the step's result
+    else:
+        host = eng.make_host_sample_buffers()
         eng.sample_to_host(host)
-        losses = eng.learn_from_host(host, 0.001, -0.01)
-        _ = losses[:5].cpu()                          # D2H read of the step's result
+        eng.learn_from_host(host, 0.001, -0.01)           # warm-up
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.time()
+        for _ in range(steps):
+            eng.sample_to_host(host)
+            losses = eng.learn_from_host(host, 0.001, -0.01)
+            _ = losses[:5].cpu()                          # D2H read of the step's result
     torch.cuda.synchronize()
     el = torch.tensor([time.time() - t0], device=dev)
     if world > 1:

@@ -77,7 +77,7 @@ __host__ __device__ constexpr uint32_t s_idesc_bf16(int M, int N) {
 }
 
 constexpr int kScBM = 128;
-constexpr int kScStages = 3;
+constexpr int kScMaxStages = 8;      // window ring depth is chosen at launch from the shared memory left by the weights
 constexpr int kScThreads = 192;
 
 struct ShiftConvArgs {
@@ -87,6 +87,7 @@ struct ShiftConvArgs {
   int Q;                           // N * H * W flattened input positions
   int wrows;                       // window rows = 128 + (KH-1)*W + (KW-1)
   int num_tiles, relu;
+  int stages;                      // depth of the TMA window ring (2..kScMaxStages)
   int base_offset;                 // triage only: 1 sets the descriptor base_offset field (wrong on B200)
   int out_mode;                    // 0: NHWC grid [N,OGH,OGW,Cout] (valid y<Hout, x<Wout);
                                    // 1: conv1 -> conv2 s2d2-padded [N,12,12,4*Cout];
@@ -110,14 +111,15 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
   const int win_bytes = (g.wrows * 128 + 1023) & ~1023;   // one 64-channel column block of the window
   unsigned char* sW = smem;                               // [num_kb][COUT][128 B]
   unsigned char* sWin = smem + ((num_kb * W_KB + 1023) & ~1023);   // [stages][CBLK][wrows][128 B]
-  __shared__ __align__(8) unsigned long long full_bar[kScStages], empty_bar[kScStages], w_bar, tmem_full[2], tmem_empty[2];
+  __shared__ __align__(8) unsigned long long full_bar[kScMaxStages], empty_bar[kScMaxStages], w_bar, tmem_full[2], tmem_empty[2];
+  const uint32_t nstages = (uint32_t)g.stages;
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_in);
     tma_prefetch_desc(&map_w);
-    for (int s = 0; s < kScStages; ++s) {
+    for (int s = 0; s < kScMaxStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -139,8 +141,8 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t s = it % kScStages;
-        mbar_wait(&empty_bar[s], ((it / kScStages) & 1u) ^ 1u);
+        const uint32_t s = it % nstages;
+        mbar_wait(&empty_bar[s], ((it / nstages) & 1u) ^ 1u);
         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(CBLK * g.wrows * 128));
         for (int cb = 0; cb < CBLK; ++cb)
           tma_load_2d(sWin + (s * CBLK + cb) * win_bytes, &map_in, cb * 64, tile * kScBM + g.row_shift, &full_bar[s]);
@@ -155,9 +157,9 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
       constexpr uint32_t idesc = s_idesc_bf16(kScBM, COUT);
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t s = it % kScStages, buf = it & 1u;
+        const uint32_t s = it % nstages, buf = it & 1u;
         mbar_wait(&tmem_empty[buf], ((it >> 1) & 1u) ^ 1u);
-        mbar_wait(&full_bar[s], (it / kScStages) & 1u);
+        mbar_wait(&full_bar[s], (it / nstages) & 1u);
         s_fence_after();
         const uint32_t d_tmem = tmem_base + buf * COUT;
         uint32_t first = 0;
@@ -279,7 +281,7 @@ template <int COUT, int CBLK>
 static void launch_shiftconv(const CUtensorMap& mi, const CUtensorMap& mw, const ShiftConvArgs& g, int num_kb, int sms,
                              cudaStream_t st) {
   const size_t win = (size_t)((g.wrows * 128 + 1023) & ~1023);
-  const size_t smem = (size_t)((num_kb * COUT * 128 + 1023) & ~1023) + (size_t)kScStages * CBLK * win + 1024;
+  const size_t smem = (size_t)((num_kb * COUT * 128 + 1023) & ~1023) + (size_t)g.stages * CBLK * win + 1024;
   cudaFuncSetAttribute(shiftconv_fwd_kernel<COUT, CBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = g.num_tiles < sms ? g.num_tiles : sms;
   shiftconv_fwd_kernel<COUT, CBLK><<<grid, kScThreads, smem, st>>>(mi, mw, g);
@@ -320,8 +322,13 @@ static int shiftconv_launch(const void* in, const void* weight, const float* bia
   g.num_tiles = (int)((Q + kScBM - 1) / kScBM);
   const int cblk = Cin / 64, num_kb = KH * KW * cblk;
   const size_t win = (size_t)((g.wrows * 128 + 1023) & ~1023);
-  RL_CHECK_ARG((size_t)num_kb * Cout * 128 + (size_t)kScStages * cblk * win + 4096 <= 227 * 1024,
-               "%s: weights + windows do not fit in shared memory", name);
+  {
+    const size_t budget = 220 * 1024 - ((size_t)num_kb * Cout * 128 + 2048);
+    long long st = (long long)(budget / ((size_t)cblk * win));
+    if (st > kScMaxStages) st = kScMaxStages;
+    RL_CHECK_ARG(st >= 2, "%s: weights + windows do not fit in shared memory", name);
+    g.stages = (int)st;
+  }
   alignas(64) CUtensorMap mi, mw;
   if (sc_make_map(&mi, in, (uint64_t)Cin, (uint64_t)Q, (uint32_t)g.wrows) ||
       sc_make_map(&mw, weight, (uint64_t)KH * KW * Cin, (uint64_t)Cout, (uint32_t)Cout)) {

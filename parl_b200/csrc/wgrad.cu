@@ -69,7 +69,7 @@ __host__ __device__ constexpr uint32_t w_idesc_bf16_mn(int M, int N) {
 }
 
 constexpr int kWgBM = 128;            // positions (K of the GEMM) per tile
-constexpr int kWgStages = 3;
+constexpr int kWgMaxStages = 6;
 constexpr int kWgThreads = 192;
 
 struct WgradArgs {
@@ -77,6 +77,7 @@ struct WgradArgs {
   int W, KH, KW;
   int Q, wrows, num_tiles;
   int ngroups, taps_per_group, ncols_max;
+  int stages;
 };
 
 template <int CBLK>
@@ -87,7 +88,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_window_kernel(const __gri
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int win_bytes = (g.wrows * 128 + 1023) & ~1023;
   const int stage_bytes = kWgBM * 128 + CBLK * win_bytes;           // dout tile + input window blocks
-  __shared__ __align__(8) unsigned long long full_bar[kWgStages], empty_bar[kWgStages], done_bar;
+  __shared__ __align__(8) unsigned long long full_bar[kWgMaxStages], empty_bar[kWgMaxStages], done_bar;
+  const uint32_t nstages = (uint32_t)g.stages;
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_window_kernel(const __gri
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_dout);
     tma_prefetch_desc(&map_x);
-    for (int s = 0; s < kWgStages; ++s) {
+    for (int s = 0; s < kWgMaxStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -119,8 +121,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_window_kernel(const __gri
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = cta_in_group; tile < g.num_tiles; tile += ctas_per_group, ++it) {
-        const uint32_t s = it % kWgStages;
-        mbar_wait(&empty_bar[s], ((it / kWgStages) & 1u) ^ 1u);
+        const uint32_t s = it % nstages;
+        mbar_wait(&empty_bar[s], ((it / nstages) & 1u) ^ 1u);
         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(kWgBM * 128 + CBLK * g.wrows * 128));
         unsigned char* st = smem + s * stage_bytes;
         tma_load_2d(st, &map_dout, 0, tile * kWgBM, &full_bar[s]);
@@ -133,8 +135,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_window_kernel(const __gri
       constexpr uint32_t idesc = w_idesc_bf16_mn(64, 64);
       uint32_t it = 0;
       for (int tile = cta_in_group; tile < g.num_tiles; tile += ctas_per_group, ++it) {
-        const uint32_t s = it % kWgStages;
-        mbar_wait(&full_bar[s], (it / kWgStages) & 1u);
+        const uint32_t s = it % nstages;
+        mbar_wait(&full_bar[s], (it / nstages) & 1u);
         w_fence_after();
         const uint32_t a_base = smem_u32(smem + s * stage_bytes);
         const uint32_t x_base = a_base + kWgBM * 128;
@@ -324,7 +326,9 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
     return RL_ERR_CUDA;
   }
   const size_t win = (size_t)((g.wrows * 128 + 1023) & ~1023);
-  const size_t smem = (size_t)kWgStages * (kWgBM * 128 + cblk * win) + 1024;
+  long long nst = (long long)((218 * 1024) / (kWgBM * 128 + cblk * win));
+  g.stages = (int)(nst > kWgMaxStages ? kWgMaxStages : (nst < 2 ? 2 : nst));
+  const size_t smem = (size_t)g.stages * (kWgBM * 128 + cblk * win) + 1024;
   cudaStream_t st = (cudaStream_t)stream;
   if (cblk == 1) {
     cudaFuncSetAttribute(wgrad_window_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -26,7 +26,7 @@ class ImpalaEngine(object):
     def __init__(self, num_envs=4096, sample_batch_steps=50, act_dim=18, frame_hw=(84, 84), seed=0, device=None,
                  env_offset=0, gamma=0.99, vf_loss_coeff=0.5, clip_rho_threshold=1.0, clip_pg_rho_threshold=1.0,
                  p_done=0.1, model=None, learn_chunk_rows=5, use_graph=True, actor_kernels='auto',
-                 learner_kernels='auto'):
+                 learner_kernels='auto', pipeline=False):
         if device is None:
             device = torch.device('cuda', torch.cuda.current_device())
         self.device = torch.device(device)
@@ -36,12 +36,18 @@ class ImpalaEngine(object):
         self.seed, self.env_offset, self.p_done = int(seed), int(env_offset), p_done
         dev = self.device
         B, T, A = self.B, self.T, self.A
-        self.planes = torch.zeros((T + 4, B, self.hw), dtype=torch.uint8, device=dev)
-        self.ages = torch.zeros((T + 1, B), dtype=torch.uint8, device=dev)
-        self.beh_logits = torch.zeros((T, B, A), dtype=torch.float32, device=dev)
-        self.actions = torch.zeros((T, B), dtype=torch.int32, device=dev)
-        self.rewards = torch.zeros((T, B), dtype=torch.float32, device=dev)
-        self.dones = torch.zeros((T, B), dtype=torch.uint8, device=dev)
+        # rollout buffer sets: one, or two when actor and learner are pipelined (double buffering)
+        self.pipeline = bool(pipeline)
+        self._sets = []
+        for _ in range(2 if self.pipeline else 1):
+            self._sets.append(dict(
+                planes=torch.zeros((T + 4, B, self.hw), dtype=torch.uint8, device=dev),
+                ages=torch.zeros((T + 1, B), dtype=torch.uint8, device=dev),
+                beh_logits=torch.zeros((T, B, A), dtype=torch.float32, device=dev),
+                actions=torch.zeros((T, B), dtype=torch.int32, device=dev),
+                rewards=torch.zeros((T, B), dtype=torch.float32, device=dev),
+                dones=torch.zeros((T, B), dtype=torch.uint8, device=dev)))
+        self._bind(0)
         self.stats = kernels.EpisodeStats(B, dev)
         self.s2d = (self.h, self.w) == (84, 84)              # conv1 space-to-depth input [N,21,21,64]
         obs_shape = (21, 21, 64) if self.s2d else (self.h, self.w, 4)
@@ -73,25 +79,39 @@ class ImpalaEngine(object):
         self.actor_net = AtariActorNet(self.model, B, dev) if use_native else None
         self.sample_steps = 0
         self.use_graph = use_graph
-        self._graph = None
-        self._kernel_launches = 0
+        self._graphs = [None] * len(self._sets)
+        self._graph_launches = 0
+        self._k = 0
+        if self.pipeline:
+            self.actor_stream = torch.cuda.Stream(device=dev)
+            self._roll_done = [torch.cuda.Event() for _ in range(2)]
+            self._learn_done = [None, None]
+            self._ev_pack = torch.cuda.Event()
         self.reset()
+
+    def _bind(self, i):
+        """Make buffer set i the one the attribute names (planes, ages, beh_logits, ...) refer to."""
+        self._cur_set = i
+        for k, v in self._sets[i].items():
+            setattr(self, k, v)
 
     # ------------------------------------------------------------------ env side
     def reset(self):
         # the reset frame goes where the carry at the start of the next rollout picks it up
         T = self.T
-        kernels.env_atari_synth_step(self.planes[T + 3], None, None, None, self.ages[T], self.stats, self.seed, 0,
+        last = self._sets[-1]               # rollout 0 goes into set 0 and carries from the last set's tail
+        kernels.env_atari_synth_step(last['planes'][T + 3], None, None, None, last['ages'][T], self.stats, self.seed, 0,
                                      env_offset=self.env_offset, reset=True)
         self.step_dev.copy_(torch.arange(T, dtype=torch.int32) - T)
 
     def _rollout_body(self):
         T = self.T
+        prev = self._sets[(self._cur_set - 1) % len(self._sets)]      # the set the previous rollout filled
         with torch.no_grad():
             # carry the previous rollout's last observation (4 planes + age row) to the front; done HERE and
             # not at the end of the previous rollout so that learn() still sees rows 0..3 intact
-            self.planes[0:4].copy_(self.planes[T:T + 4])
-            self.ages[0].copy_(self.ages[T])
+            self.planes[0:4].copy_(prev['planes'][T:T + 4])
+            self.ages[0].copy_(prev['ages'][T])
             self.step_dev.add_(T)
             for t in range(T):
                 kernels.obs_stack_gather(self.planes, self.ages, t, 1, self.obs_step, scale=1.0 / 255.0, s2d=self.s2d)
@@ -104,12 +124,12 @@ class ImpalaEngine(object):
                                              env_offset=self.env_offset, logits=self.beh_logits[t],
                                              actions_out=self.actions[t], step_dev=self.step_dev[t:])
 
-    def rollout(self):
-        """T lock-step env steps for all B envs (the device analogue of Actor.sample())."""
+    def _run_rollout(self, i):
+        """Rollout into buffer set i on the current stream (graph replay after the first, eager, run)."""
+        self._bind(i)
         if self.use_graph:
-            if self._graph is None:
-                # warm up once eagerly (cuDNN autotune, allocator), then capture
-                self._rollout_body()
+            if self._graphs[i] is None:
+                self._rollout_body()                      # eager once (allocator / autotune warm-up), then capture
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 before = kernels.launch_count()
@@ -117,14 +137,52 @@ class ImpalaEngine(object):
                     self._rollout_body()
                 self._graph_launches = kernels.launch_count() - before
                 kernels.add_graph_launches(-self._graph_launches)      # capture is not execution
-                self._graph = g
-                self.sample_steps += self.T * self.B
-                return
-            self._graph.replay()
-            kernels.add_graph_launches(self._graph_launches)
+                self._graphs[i] = g
+            else:
+                self._graphs[i].replay()
+                kernels.add_graph_launches(self._graph_launches)
         else:
             self._rollout_body()
         self.sample_steps += self.T * self.B
+
+    def rollout(self):
+        """T lock-step env steps for all B envs (the device analogue of Actor.sample())."""
+        assert not self.pipeline, 'pipelined engines are driven by step()'
+        self._run_rollout(0)
+
+    def step(self, learning_rate=0.001, entropy_coeff=-0.01):
+        """One actor-learner iteration.  Sequential engines: rollout then learn.  Pipelined engines (SURVEY.md
+        8f-1, the device analogue of the reference's sample queue + stale parameter broadcast,
+        examples/IMPALA/train.py:37-38,182-194): rollout k+1 runs on the actor stream into the other buffer
+        set, with the weights of update k-1, WHILE the learner stream trains on rollout k."""
+        if not self.pipeline:
+            self.rollout()
+            return self.learn(learning_rate, entropy_coeff)
+        cur_stream = torch.cuda.current_stream()
+        k = self._k
+        if k == 0:                                        # prologue: rollout 0
+            self.actor_stream.wait_stream(cur_stream)
+            with torch.cuda.stream(self.actor_stream):
+                self._run_rollout(0)
+                self._roll_done[0].record(self.actor_stream)
+        cur, nxt = k % 2, (k + 1) % 2
+        with torch.cuda.stream(self.actor_stream):
+            if self._learn_done[nxt] is not None:          # update k-1 finished: its weights are final, set nxt is free
+                self.actor_stream.wait_event(self._learn_done[nxt])
+            if self.actor_net is not None:
+                self.actor_net.pack()
+            self._ev_pack.record(self.actor_stream)
+            self._run_rollout(nxt)
+            self._roll_done[nxt].record(self.actor_stream)
+        cur_stream.wait_event(self._ev_pack)              # the actor has taken its copy of the weights
+        cur_stream.wait_event(self._roll_done[cur])
+        self._bind(cur)
+        losses = self.learn(learning_rate, entropy_coeff)
+        ev = torch.cuda.Event()
+        ev.record(cur_stream)
+        self._learn_done[cur] = ev
+        self._k += 1
+        return losses
 
     # ------------------------------------------------------------------ learner side
     def learn(self, learning_rate=0.001, entropy_coeff=-0.01):
@@ -164,7 +222,7 @@ class ImpalaEngine(object):
         if self.alg.grad_sync is not None:
             self.alg.grad_sync(self.alg.optimizer.grad)
         self.alg.optimizer.step(lr=learning_rate)
-        if self.actor_net is not None:
+        if self.actor_net is not None and not self.pipeline:
             self.actor_net.pack()              # refresh the actor's bf16 operand copies (weights never leave HBM)
         return res['losses']
 
@@ -191,7 +249,7 @@ class ImpalaEngine(object):
             self.alg.grad_sync(self.alg.optimizer.grad)
         self.alg.optimizer.step(lr=learning_rate)
         net.pack()
-        if self.actor_net is not None:
+        if self.actor_net is not None and not self.pipeline:
             self.actor_net.pack()
         return res['losses']
 
@@ -208,12 +266,9 @@ class ImpalaEngine(object):
                     rewards=torch.empty(N, dtype=torch.float32, **pin),
                     dones=torch.empty(N, dtype=torch.bool, **pin))
 
-    def sample_to_host(self, host):
-        """rollout() + device->host copy of the sample dict in the reference's env-major layout."""
-        self.rollout()
+    def _sample_dict_to_host(self, host):
+        """Enqueue the device->host copies of the current buffer set as the reference's env-major sample dict."""
         T, B = self.T, self.B
-        rows = self.learn_chunk_rows
-        # obs: gather env-major directly on the device in slabs of columns to bound scratch memory
         em = lambda x: x.transpose(0, 1).contiguous()
         obs_dev = getattr(self, '_obs_em', None)
         if obs_dev is None:
@@ -224,8 +279,47 @@ class ImpalaEngine(object):
         host['behaviour_logits'].copy_(em(self.beh_logits).view(B * T, self.A), non_blocking=True)
         host['rewards'].copy_(em(self.rewards).view(-1), non_blocking=True)
         host['dones'].copy_(em(self.dones).view(-1).bool(), non_blocking=True)
+
+    def sample_to_host(self, host):
+        """rollout() + device->host copy of the sample dict in the reference's env-major layout."""
+        self.rollout()
+        self._sample_dict_to_host(host)
         torch.cuda.current_stream().synchronize()
         return host
+
+    def step_host(self, hosts, learning_rate=0.001, entropy_coeff=-0.01):
+        """Pipelined iteration THROUGH HOST MEMORY (the reference-facing contract, examples/IMPALA/train.py:165-194):
+        the actor stream produces rollout k+1 and copies its numpy-layout sample dict to pinned host buffers
+        hosts[(k+1)%2] while the learner stream uploads hosts[k%2] and trains on it."""
+        assert self.pipeline and len(hosts) == 2
+        cur_stream = torch.cuda.current_stream()
+        k = self._k
+        if not hasattr(self, '_host_ready'):
+            self._host_ready = [torch.cuda.Event() for _ in range(2)]
+        if k == 0:
+            self.actor_stream.wait_stream(cur_stream)
+            with torch.cuda.stream(self.actor_stream):
+                self._run_rollout(0)
+                self._sample_dict_to_host(hosts[0])
+                self._host_ready[0].record(self.actor_stream)
+        cur, nxt = k % 2, (k + 1) % 2
+        with torch.cuda.stream(self.actor_stream):
+            if self._learn_done[nxt] is not None:
+                self.actor_stream.wait_event(self._learn_done[nxt])
+            if self.actor_net is not None:
+                self.actor_net.pack()
+            self._ev_pack.record(self.actor_stream)
+            self._run_rollout(nxt)
+            self._sample_dict_to_host(hosts[nxt])
+            self._host_ready[nxt].record(self.actor_stream)
+        cur_stream.wait_event(self._ev_pack)
+        cur_stream.wait_event(self._host_ready[cur])
+        losses = self.learn_from_host(hosts[cur], learning_rate, entropy_coeff)
+        ev = torch.cuda.Event()
+        ev.record(cur_stream)
+        self._learn_done[cur] = ev
+        self._k += 1
+        return losses
 
     def learn_from_host(self, host, learning_rate, entropy_coeff):
         """Agent.learn(numpy...) contract (examples/IMPALA/atari_agent.py:44-74): host arrays -> H2D ->
@@ -274,7 +368,7 @@ class ImpalaEngine(object):
         self.alg.optimizer.step(lr=learning_rate)
         if self.train_net is not None:
             self.train_net.pack()
-        if self.actor_net is not None:
+        if self.actor_net is not None and not self.pipeline:
             self.actor_net.pack()
         return res['losses']
 
