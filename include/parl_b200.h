@@ -307,8 +307,7 @@ int rl_debug_set_shiftconv_base_offset(int enable);
  * x>=W-KW+1); weight_t_krsc [Cin, KH*KW*Cout] with element [ci][(r,s,co)] = W[co][(r,s,ci)];
  * act_mask (optional) [N,H,W,Cin] is the saved post-ReLU input activation: din *= (act_mask > 0).
  * out_mode 0: din on a [N,OGH,OGW,Cin] grid (OGH>=H, OGW>=W; untouched cells stay as they are);
- * out_mode 2 (H=W=12, Cin=128): din of the 2x2-block conv scattered to conv1's gradient grid [N,21,21,64]
- * (channels 0..31 of each cell; 32..63 are zero padding so that the weight-gradient kernel sees M = 64). */
+ * out_mode 2 (H=W=12, Cin=128): din of the 2x2-block conv scattered to conv1's gradient grid [N,21,21,32]. */
 int rl_conv2d_s1_nhwc_bf16_dgrad(const void* dout_grid, const void* weight_t_krsc, const void* act_mask, void* din,
                                  int N, int H, int W, int Cout, int Cin, int KH, int KW, int out_mode,
                                  int OGH, int OGW, rl_stream_t stream);
@@ -317,7 +316,8 @@ int rl_conv2d_s1_nhwc_bf16_dgrad(const void* dout_grid, const void* weight_t_krs
  * in[q + r*W + s, ci] with the position index as the GEMM reduction dimension (tcgen05, MN-major operands,
  * accumulators resident in TMEM over the CTA's whole position range, deterministic two-stage reduction).
  * dout_grid [N,H,W,Cout] on the input grid (zeros at invalid positions), in [N,H,W,Cin], dw_krsc [Cout, KH*KW*Cin]
- * float32 (accumulate=1 adds to it).  Cout = 64, Cin in {64,128}.  Workspace: rl_conv_wgrad_workspace_bytes. */
+ * float32 (accumulate=1 adds to it).  (Cout, Cin) = (64, 64|128), or (32, 64) where the 64-byte dout rows are the
+ * SWIZZLE_64B N-operand of a role-swapped product.  Workspace: rl_conv_wgrad_workspace_bytes. */
 size_t rl_conv_wgrad_workspace_bytes(int KH, int KW, int Cin);
 int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* in, float* dw_krsc, int N, int H, int W,
                                  int Cin, int Cout, int KH, int KW, int accumulate,

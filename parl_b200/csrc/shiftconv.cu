@@ -91,7 +91,7 @@ struct ShiftConvArgs {
   int base_offset;                 // triage only: 1 sets the descriptor base_offset field (wrong on B200)
   int out_mode;                    // 0: NHWC grid [N,OGH,OGW,Cout] (valid y<Hout, x<Wout);
                                    // 1: conv1 -> conv2 s2d2-padded [N,12,12,4*Cout];
-                                   // 2: (dgrad of the s2d2 conv) [N,12,12,128] blocks -> grid [N,21,21,64] (32 used)
+                                   // 2: (dgrad of the s2d2 conv) [N,12,12,128] blocks -> grid [N,21,21,32]
   int OGH, OGW;                    // output grid of out_mode 0
   int row_shift;                   // TMA row coordinate of a tile = tile*128 + row_shift (dgrad: -((KH-1)*W+KW-1))
   int flip;                        // 1: tap (r,s) reads window row (KH-1-r)*W + (KW-1-s)  (transposed conv)
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
           // channel block (dy,dx) of position (Y,X) is pixel (2Y+dy-2, 2X+dx-2) of the 20x20 image, 32 channels
           const int blk = c0 >> 5, py = 2 * y + (blk >> 1) - 2, px = 2 * x + (blk & 1) - 2;
           ok = q < g.Q && py >= 0 && py < 20 && px >= 0 && px < 20;
-          dst_off = (((size_t)n * 21 + py) * 21 + px) * 64 + (c0 & 31);   // 64-wide rows: channels 32..63 stay zero
+          dst_off = (((size_t)n * 21 + py) * 21 + px) * 32 + (c0 & 31);   // a lane writes 2 x 128 contiguous bytes
         }
         if (ok) {
           uint32_t pk[8];

@@ -62,6 +62,17 @@ __device__ __forceinline__ uint64_t w_desc_mn_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major SWIZZLE_64B operand: 32 MN-elements = one 64-byte row per K index, 8 rows per 512-byte swizzle atom
+// (cute canonical ((4,n),(8,k)):((1,LBO),(4,SBO)) in 16-byte units; layout_type 4).
+__device__ __forceinline__ uint64_t w_desc_mn_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;              // SBO
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
 // kind::f16, BF16 x BF16 -> F32, A and B MN-major (bits 15, 16)
 __host__ __device__ constexpr uint32_t w_idesc_bf16_mn(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
@@ -196,6 +207,106 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   dw[idx] = accumulate ? dw[idx] + acc : acc;
 }
 
+// Cout = 32 variant (conv1 of the Atari net): the roles are swapped so that the 64-byte dout rows become the
+// N = 32 operand:  D_t[ci, co] = sum_q in[q + off_t, ci] * dout[q, co];  A = input window (MN-major, SW128, M = 64),
+// B = dout tile (MN-major, SWIZZLE_64B, N = 32).  One group: KH*KW taps x 32 columns of TMEM.
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_window_n32_kernel(const __grid_constant__ CUtensorMap map_dout,
+                                                                         const __grid_constant__ CUtensorMap map_x,
+                                                                         const WgradArgs g) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const int win_bytes = (g.wrows * 128 + 1023) & ~1023;
+  const int stage_bytes = kWgBM * 64 + win_bytes;                    // 8 KB dout tile + input window
+  __shared__ __align__(8) unsigned long long full_bar[kWgMaxStages], empty_bar[kWgMaxStages], done_bar;
+  __shared__ uint32_t tmem_base_smem;
+  const uint32_t nstages = (uint32_t)g.stages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntaps = g.KH * g.KW;
+  const int ncols = ntaps * 32;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)ncols) tmem_cols <<= 1;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_dout);
+    tma_prefetch_desc(&map_x);
+    for (int s = 0; s < kWgMaxStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) w_tmem_alloc(&tmem_base_smem, tmem_cols);
+  w_fence_before();
+  __syncthreads();
+  w_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t s = it % nstages;
+        mbar_wait(&empty_bar[s], ((it / nstages) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(kWgBM * 64 + g.wrows * 128));
+        unsigned char* st = smem + s * stage_bytes;
+        tma_load_2d(st + kWgBM * 64, &map_x, 0, tile * kWgBM, &full_bar[s]);     // window first: 1024-byte aligned
+        tma_load_2d(st, &map_dout, 0, tile * kWgBM, &full_bar[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = w_idesc_bf16_mn(64, 32);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t s = it % nstages;
+        mbar_wait(&full_bar[s], (it / nstages) & 1u);
+        w_fence_after();
+        const uint32_t b_base = smem_u32(smem + s * stage_bytes);            // dout tile, 64-byte rows
+        const uint32_t x_base = b_base + kWgBM * 64;
+        for (int tap = 0; tap < ntaps; ++tap) {
+          const int r = tap / g.KW, sx = tap - r * g.KW;
+          const uint32_t a_base = x_base + (uint32_t)(r * g.W + sx) * 128u;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(tap * 32);
+#pragma unroll
+          for (int kk = 0; kk < kWgBM / 16; ++kk)
+            w_umma(d_tmem, w_desc_mn_sw128(a_base + kk * 2048u), w_desc_mn_sw64(b_base + kk * 1024u), idesc,
+                   (it | (uint32_t)kk) != 0u ? 1u : 0u);
+        }
+        w_commit(&empty_bar[s]);
+      }
+      w_commit(&done_bar);
+    }
+  } else {
+    const int qd = warp & 3;
+    mbar_wait(&done_bar, 0);
+    w_fence_after();
+    float* dst = g.partials + ((size_t)blockIdx.x * 128 + qd * 32 + lane) * g.ncols_max;
+    const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
+      float v[16];
+      w_tmem_ld16(taddr + (uint32_t)c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+  }
+  w_fence_before();
+  __syncthreads();
+  if (warp == 1) w_tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// dW[co][(tap, ci)] (Cout = 32, Cin = 64) from the [ci lanes][tap*32 + co] partials, CTA order (deterministic)
+__global__ void __launch_bounds__(256) wgrad_reduce_n32_kernel(const float* __restrict__ partials, int nctas, int ntaps,
+                                                               int ncols_max, float* __restrict__ dw, int accumulate) {
+  const int K = ntaps * 64;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 32 * K) return;
+  const int co = idx / K, k = idx - co * K;
+  const int tap = k >> 6, ci = k & 63;
+  const int ln = 32 * (ci >> 4) + (ci & 15);
+  float acc = 0.f;
+  for (int c = 0; c < nctas; ++c) acc += partials[((size_t)c * 128 + ln) * ncols_max + tap * 32 + co];
+  dw[idx] = accumulate ? dw[idx] + acc : acc;
+}
+
 // column sums of a [rows, C] bf16 matrix (bias gradients): deterministic two-stage, 16-byte loads.
 // A thread owns 8 adjacent columns (one uint4) and walks the rows of its block's chunk with stride
 // (256 / (C/8)) so that a warp reads whole 128-byte lines.
@@ -250,7 +361,8 @@ __global__ void colsum_stage2(const float* __restrict__ part, int nblocks, int C
   out[c] = a;
 }
 
-static int wg_make_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+static int wg_make_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows,
+                       uint32_t box_cols = 64, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -263,10 +375,10 @@ static int wg_make_map(CUtensorMap* map, const void* base, uint64_t cols, uint64
   }
   const cuuint64_t gdim[2] = {cols, rows};
   const cuuint64_t gstride[1] = {cols * 2};
-  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
              ? 0
              : -2;
@@ -294,7 +406,8 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
                                             size_t workspace_bytes, rl_stream_t stream) {
   RL_CHECK_ARG(dout_grid && in && dw_krsc && workspace && N > 0, "conv2d_s1_wgrad: bad argument");
   RL_CHECK_ARG(aligned16(dout_grid) && aligned16(in) && aligned16(workspace), "conv2d_s1_wgrad: alignment");
-  RL_CHECK_ARG(Cout == 64 && (Cin == 64 || Cin == 128), "conv2d_s1_wgrad: Cout must be 64 and Cin in {64,128}");
+  RL_CHECK_ARG((Cout == 64 && (Cin == 64 || Cin == 128)) || (Cout == 32 && Cin == 64),
+               "conv2d_s1_wgrad: (Cout, Cin) must be (64, 64|128) or (32, 64)");
   const long long Q = (long long)N * H * W;
   RL_CHECK_ARG(Q < (1LL << 31), "conv2d_s1_wgrad: too many positions");
   const int cblk = Cin / 64, ntaps = KH * KW;
@@ -304,6 +417,35 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
   g.wrows = kWgBM + (KH - 1) * W + (KW - 1);
   RL_CHECK_ARG(g.wrows <= 256, "conv2d_s1_wgrad: window too tall");
   g.num_tiles = (int)((Q + kWgBM - 1) / kWgBM);
+  if (Cout == 32) {
+    // swapped-role variant: D[ci, co], dout rows are 64 bytes (SWIZZLE_64B operand)
+    RL_CHECK_ARG(ntaps * 32 <= 512, "conv2d_s1_wgrad: too many taps for Cout = 32");
+    g.ngroups = 1, g.taps_per_group = ntaps, g.ncols_max = ntaps * 32;
+    int dev32 = 0, sms32 = 148;
+    cudaGetDevice(&dev32);
+    cudaDeviceGetAttribute(&sms32, cudaDevAttrMultiProcessorCount, dev32);
+    int grid32 = sms32 < g.num_tiles ? sms32 : g.num_tiles;
+    if (workspace_bytes < (size_t)grid32 * 128 * g.ncols_max * sizeof(float)) {
+      set_error("conv2d_s1_wgrad: workspace too small");
+      return RL_ERR_WORKSPACE;
+    }
+    alignas(64) CUtensorMap md32, mx32;
+    if (wg_make_map(&md32, dout_grid, 32, (uint64_t)Q, kWgBM, 32, CU_TENSOR_MAP_SWIZZLE_64B) ||
+        wg_make_map(&mx32, in, 64, (uint64_t)Q, (uint32_t)g.wrows)) {
+      set_error("conv2d_s1_wgrad: cuTensorMapEncodeTiled failed");
+      return RL_ERR_CUDA;
+    }
+    const size_t win32 = (size_t)((g.wrows * 128 + 1023) & ~1023);
+    long long nst32 = (long long)((218 * 1024) / (kWgBM * 64 + win32));
+    g.stages = (int)(nst32 > kWgMaxStages ? kWgMaxStages : (nst32 < 2 ? 2 : nst32));
+    const size_t smem32 = (size_t)g.stages * (kWgBM * 64 + win32) + 1024;
+    cudaFuncSetAttribute(wgrad_window_n32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+    wgrad_window_n32_kernel<<<grid32, kWgThreads, smem32, (cudaStream_t)stream>>>(md32, mx32, g);
+    wgrad_reduce_n32_kernel<<<(32 * ntaps * 64 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        g.partials, grid32, ntaps, g.ncols_max, dw_krsc, accumulate);
+    RL_CHECK_LAUNCH("rl_conv2d_s1_nhwc_bf16_wgrad");
+    return RL_OK;
+  }
   int cap = 512 / (cblk * 64);                       // taps whose accumulators fit the 512 TMEM columns
   if (cap > ntaps) cap = ntaps;
   g.ngroups = (ntaps + cap - 1) / cap;

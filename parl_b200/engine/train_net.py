@@ -34,7 +34,7 @@ class AtariTrainNet(object):
         self.values = torch.empty((N, 1), dtype=f32, device=dev)
         # gradients of activations (grids are zero where no valid output exists and are never written there)
         self.dheads, self.dh = z(N, 32), e(N, 512)
-        self.da3g, self.da2g, self.da1g = z(N, 11, 11, 64), z(N, 12, 12, 64), z(N, 21, 21, 64)
+        self.da3g, self.da2g, self.da1g = z(N, 11, 11, 64), z(N, 12, 12, 64), z(N, 21, 21, 32)
         # operand copies of the weights
         self.w1, self.w2, self.w3 = e(32, 256), e(64, 512), e(64, 576)
         self.wfc, self.wpi, self.wv = e(512, 5184), e(A, 512), e(1, 512)
@@ -43,7 +43,7 @@ class AtariTrainNet(object):
         self.b1, self.b2, self.b3 = [torch.empty(n, dtype=f32, device=dev) for n in (32, 64, 64)]
         self.bfc, self.bpi, self.bv = [torch.empty(n, dtype=f32, device=dev) for n in (512, A, 1)]
         # weight-gradient scratch (KRSC, float32)
-        self.dw1 = torch.empty((64, 256), dtype=f32, device=dev)
+        self.dw1 = torch.empty((32, 256), dtype=f32, device=dev)
         self.dw2 = torch.empty((64, 512), dtype=f32, device=dev)
         self.dw3 = torch.empty((64, 576), dtype=f32, device=dev)
         self.db = torch.empty(64, dtype=f32, device=dev)
@@ -131,7 +131,7 @@ class AtariTrainNet(object):
         m.conv2.weight.grad.copy_(self.dw2.view(64, 2, 2, 2, 2, 32).permute(0, 5, 1, 3, 2, 4).reshape(64, 32, 4, 4))
         m.conv2.bias.grad.copy_(K.colsum_bf16(self.da2g, out=self.db))
         K.conv2d_s1_nhwc_bf16_dgrad(self.da2g, self.w2T, 2, 2, self.da1g, act_mask=self.a1, out_mode=2)
-        # conv1 (4x4 block form); the gradient grid carries 64 channels, the upper 32 are zero padding
+        # conv1 (4x4 block form): 64-byte gradient rows -> role-swapped weight-gradient kernel (SWIZZLE_64B operand)
         K.conv2d_s1_nhwc_bf16_wgrad(self.da1g, self.x0, 2, 2, dw_krsc=self.dw1)
-        m.conv1.weight.grad.copy_(self.dw1[:32].view(32, 2, 2, 4, 4, 4).permute(0, 5, 1, 3, 2, 4).reshape(32, 4, 8, 8))
-        m.conv1.bias.grad.copy_(K.colsum_bf16(self.da1g, out=self.db)[:32])
+        m.conv1.weight.grad.copy_(self.dw1.view(32, 2, 2, 4, 4, 4).permute(0, 5, 1, 3, 2, 4).reshape(32, 4, 8, 8))
+        m.conv1.bias.grad.copy_(K.colsum_bf16(self.da1g, out=self.db[:32]))

@@ -421,7 +421,7 @@ def conv2d_s1_nhwc_bf16_fwd(x, weight_krsc, bias, KH, KW, relu=True, out=None, o
 
 def conv2d_s1_nhwc_bf16_dgrad(dout_grid, weight_t_krsc, KH, KW, out, act_mask=None, out_mode=0):
     """Data gradient of the TMA-window conv (rl_conv2d_s1_nhwc_bf16_dgrad).  dout_grid [N,H,W,Cout] on the
-    input grid, weight_t_krsc [Cin, KH*KW*Cout]; out [N,OGH,OGW,Cin] (mode 0) or [N,21,21,64] (mode 2)."""
+    input grid, weight_t_krsc [Cin, KH*KW*Cout]; out [N,OGH,OGW,Cin] (mode 0) or [N,21,21,32] (mode 2)."""
     require_cuda(dout_grid, weight_t_krsc, out, act_mask)
     N, H, W, Cout = dout_grid.shape
     Cin = weight_t_krsc.shape[0]

@@ -148,3 +148,25 @@ def test_conv2d_s1_dgrad_tma_window_form(N, H, Cin, Cout, k):
     torch.cuda.synchronize()
     err = (out.float() - ref).abs().max().item()
     assert err < 3e-2 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize('N,H,Cin,Cout,k', [(5, 11, 64, 64, 3), (150, 11, 64, 64, 3), (9, 12, 128, 64, 2),
+                                            (7, 21, 64, 32, 2), (160, 21, 64, 32, 2)])
+def test_conv2d_s1_wgrad_tma_window_form(N, H, Cin, Cout, k):
+    """Window-form weight gradient (positions as the GEMM K dimension, MN-major tcgen05 operands; the Cout=32
+    case uses the role-swapped SWIZZLE_64B variant) against torch autograd on the same bf16 operands."""
+    from parl_b200 import kernels as K_
+    g = torch.Generator(device=DEV).manual_seed(N + H + Cout)
+    Ho = H - k + 1
+    x = torch.randn(N, H, H, Cin, device=DEV, generator=g).to(torch.bfloat16)
+    dout = torch.randn(N, Ho, Ho, Cout, device=DEV, generator=g).to(torch.bfloat16)
+    w = torch.zeros(Cout, Cin, k, k, device=DEV, requires_grad=True)
+    torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w).backward(dout.float().permute(0, 3, 1, 2))
+    ref = w.grad.permute(0, 2, 3, 1).reshape(Cout, -1)
+    dgrid = torch.zeros(N, H, H, Cout, device=DEV, dtype=torch.bfloat16)
+    dgrid[:, :Ho, :Ho] = dout
+    dw = K_.conv2d_s1_nhwc_bf16_wgrad(dgrid, x, k, k)
+    torch.cuda.synchronize()
+    assert (dw - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
+    db = K_.colsum_bf16(dgrid)
+    assert (db - dgrid.float().sum((0, 1, 2))).abs().max().item() < 1e-2

@@ -4,7 +4,7 @@ from parl_b200 import kernels as K, _lib
 DEV = 'cuda:0'
 for lm in (0, 1):
     _lib.load().rl_debug_set_wgrad_lane_map(lm)
-    for (N, H, Cin, Cout, k) in [(5, 11, 64, 64, 3), (9, 12, 128, 64, 2), (150, 11, 64, 64, 3)]:
+    for (N, H, Cin, Cout, k) in [(5, 11, 64, 64, 3), (9, 12, 128, 64, 2), (150, 11, 64, 64, 3), (7, 21, 64, 32, 2), (160, 21, 64, 32, 2)]:
         g = torch.Generator(device=DEV).manual_seed(1)
         Ho = H - k + 1
         x = torch.randn(N, H, H, Cin, device=DEV, generator=g).to(torch.bfloat16)
