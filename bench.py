@@ -190,9 +190,25 @@ def main():
     roof = None
     if k1_s:
         ach = alg_bytes / k1_s / 1e9
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch at B=4096 from the committed
+        # `ncu --set full` capture (profiles/r01_k1_vtrace_loss_*.txt); the gradient tile stays in L2 past the launch
+        traffic = 42.9e6 if B == 4096 else None
         roof = dict(bound='hbm', kernel='vtrace_loss_kernel (rl_vtrace_loss_fwd_bwd)', achieved=ach, peak=peak,
-                    unit='GB/s', frac=ach / peak, traffic=None, peak_source=peak_src,
+                    unit='GB/s', frac=ach / peak, traffic=traffic, peak_source=peak_src,
                     algorithmic_bytes_per_launch=alg_bytes, us_per_launch=k1_s * 1e6)
+
+    # tensor-pipe view of the whole step: policy/value network FLOPs (actor forward + learner forward/backward
+    # = 4 x 25.8 MFLOP per env-step) over the step time, against the measured sustained bf16 peak
+    net_roof = None
+    try:
+        pk = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        tpeak, tsrc = float(pk['bf16_tflops_sustained']), 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)'
+    except Exception:
+        tpeak, tsrc = 1400.0, 'fallback (B200_PROFILING.md sustained)'
+    flops_per_step = 4 * 25.8e6 * T_STEPS * B
+    ach_tf = flops_per_step * args.steps / elapsed / 1e12
+    net_roof = dict(bound='tensor', what='policy/value network (tcgen05 conv/GEMM kernels), per GPU', achieved=ach_tf,
+                    peak=tpeak, unit='TFLOP/s', frac=ach_tf / tpeak, peak_source=tsrc)
 
     e2e = None
     if not args.no_e2e:
@@ -220,7 +236,8 @@ def main():
                                 eng.train_net is not None else 'torch',
                                 l2_policy='per-step working set (obs ring %.1f GB/GPU) >> 126 MB L2' %
                                           ((T_STEPS + 4) * B * 7056 / 1e9)),
-                    gpu_launches=launches, clocks=clocks, roofline=roof, e2e=e2e, cpu_baseline=cpu,
+                    gpu_launches=launches, clocks=clocks, roofline=roof, roofline_network=net_roof, e2e=e2e,
+                    cpu_baseline=cpu,
                     learner_losses=[float(x) for x in losses[:5].tolist()])
         print(json.dumps(line))
     if world > 1:

@@ -326,6 +326,8 @@ static int shiftconv_launch(const void* in, const void* weight, const float* bia
     const size_t budget = 220 * 1024 - ((size_t)num_kb * Cout * 128 + 2048);
     long long st = (long long)(budget / ((size_t)cblk * win));
     if (st > kScMaxStages) st = kScMaxStages;
+    // the dgrad epilogue reads the ReLU mask through L1: leave the unified L1/shared array some cache
+    if (mask && st > 4) st = 4;
     RL_CHECK_ARG(st >= 2, "%s: weights + windows do not fit in shared memory", name);
     g.stages = (int)st;
   }
