@@ -191,12 +191,20 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1u;
-      mbar_wait(&tmem_full[buf], (it >> 1) & 1u);
-      s_fence_after();
       const int q = tile * kScBM + qd * 32 + lane;
+      // ReLU mask of this row (accumulator grid [Q, COUT]): issued BEFORE waiting for the accumulator so that the
+      // global-memory latency overlaps the MMAs of this tile
+      uint4 mk[COUT / 8];
+      if (g.mask && q < g.Q) {
+        const uint4* mp = reinterpret_cast<const uint4*>(g.mask + (size_t)q * COUT);
+#pragma unroll
+        for (int i = 0; i < COUT / 8; ++i) mk[i] = __ldg(mp + i);
+      }
       const int n = q / HW;
       const int rem = q - n * HW;
       const int y = rem / g.W, x = rem - y * g.W;
+      mbar_wait(&tmem_full[buf], (it >> 1) & 1u);
+      s_fence_after();
       const bool valid = q < g.Q && y < g.Hout && x < g.Wout;
       size_t obase = 0;
       if (g.out_mode == 0) {
@@ -206,7 +214,6 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
         const int yp = y + 2, xp = x + 2;
         obase = (((size_t)n * 12 + (yp >> 1)) * 12 + (xp >> 1)) * (4 * COUT) + (size_t)(((yp & 1) * 2 + (xp & 1)) * COUT);
       }
-      const size_t mbase = (size_t)q * COUT;             // the ReLU mask is indexed on the accumulator grid [Q, COUT]
       const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + buf * COUT;
 #pragma unroll
       for (int c0 = 0; c0 < COUT; c0 += 16) {
@@ -222,11 +229,7 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
         }
         if (ok) {
           uint32_t pk[8];
-          uint4 mk0 = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), mk1 = mk0;   // bf16 1.0
-          if (g.mask) {
-            const uint4* mp = reinterpret_cast<const uint4*>(g.mask + mbase + c0);
-            mk0 = __ldg(mp), mk1 = __ldg(mp + 1);
-          }
+          const uint4 mk0 = mk[c0 / 8], mk1 = mk[c0 / 8 + 1];
           const uint32_t mw[8] = {mk0.x, mk0.y, mk0.z, mk0.w, mk1.x, mk1.y, mk1.z, mk1.w};
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
