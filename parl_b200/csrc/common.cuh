@@ -29,6 +29,29 @@ void set_error(const char* fmt, ...);
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Opt a kernel in to the device's whole dynamic shared-memory range (227 KB minus its static use) ONCE per
+// device and never lower it again: the per-launch size is then free to vary between streams (actor: deep
+// pipelines, learner: shallower ones that leave L1 for the mask reads) without re-programming the function
+// while another launch of it is still queued.
+template <class Kernel>
+static inline void opt_in_max_dynamic_smem(Kernel kernel, unsigned long long* done_mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*done_mask & bit) return;
+  int optin = 0;
+  cudaFuncAttributes fa;
+  if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess &&
+      cudaFuncGetAttributes(&fa, kernel) == cudaSuccess)
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+  *done_mask |= bit;
+}
+#define RL_SMEM_OPTIN(...)                                  \
+  do {                                                      \
+    static unsigned long long done__ = 0;                   \
+    rl::opt_in_max_dynamic_smem(__VA_ARGS__, &done__);      \
+  } while (0)
+
 #ifdef __CUDACC__
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));

@@ -261,7 +261,7 @@ static int make_weight_map(CUtensorMap* map, const void* w, int K, int Cout) {
 template <int COUT, int CIN>
 static void launch_conv(const CUtensorMap& mw, const ConvArgs& g, int sms, cudaStream_t st) {
   const size_t smem = (size_t)((g.num_kb * COUT * 128 + 1023) & ~1023) + (size_t)kCvStages * kCvBM * 128 + 1024;
-  cudaFuncSetAttribute(conv_igemm_fwd_kernel<COUT, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  RL_SMEM_OPTIN(conv_igemm_fwd_kernel<COUT, CIN>);
   const int grid = g.num_tiles < sms ? g.num_tiles : sms;
   conv_igemm_fwd_kernel<COUT, CIN><<<grid, kCvThreads, smem, st>>>(mw, g);
 }

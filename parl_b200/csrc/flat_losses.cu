@@ -410,10 +410,10 @@ static int launch_flat(int mode, const FlatArgs& a, cudaStream_t st) {
   const unsigned grid = (unsigned)((a.N + kEPB - 1) / kEPB);
   const size_t smem = (size_t)kEPB * a.A * sizeof(float);
   if (mode == MODE_A2C) {
-    cudaFuncSetAttribute(flat_categorical_loss_kernel<MODE_A2C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RL_SMEM_OPTIN(flat_categorical_loss_kernel<MODE_A2C>);
     flat_categorical_loss_kernel<MODE_A2C><<<grid, kFT, smem, st>>>(a);
   } else {
-    cudaFuncSetAttribute(flat_categorical_loss_kernel<MODE_PPO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RL_SMEM_OPTIN(flat_categorical_loss_kernel<MODE_PPO>);
     flat_categorical_loss_kernel<MODE_PPO><<<grid, kFT, smem, st>>>(a);
   }
   return 0;

@@ -245,7 +245,7 @@ static int make_tensor_map_bf16_sw128(CUtensorMap* map, const void* base, uint64
 template <int BN>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, cudaStream_t st) {
   const size_t smem = (size_t)kGemmStages * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 1024;
-  cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  RL_SMEM_OPTIN(gemm_bf16_tn_kernel<BN>);
   dim3 grid((g.M + kGemmBM - 1) / kGemmBM, (g.N + BN - 1) / BN);
   gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, smem, st>>>(ma, mb, g);
   return 0;

@@ -285,7 +285,7 @@ static void launch_shiftconv(const CUtensorMap& mi, const CUtensorMap& mw, const
                              cudaStream_t st) {
   const size_t win = (size_t)((g.wrows * 128 + 1023) & ~1023);
   const size_t smem = (size_t)((num_kb * COUT * 128 + 1023) & ~1023) + (size_t)g.stages * CBLK * win + 1024;
-  cudaFuncSetAttribute(shiftconv_fwd_kernel<COUT, CBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  RL_SMEM_OPTIN(shiftconv_fwd_kernel<COUT, CBLK>);
   const int grid = g.num_tiles < sms ? g.num_tiles : sms;
   shiftconv_fwd_kernel<COUT, CBLK><<<grid, kScThreads, smem, st>>>(mi, mw, g);
 }

@@ -465,15 +465,15 @@ template <int A_>
 static int launch_vtrace_loss(const VtraceLossArgs& a, int layout, bool tma, const CUtensorMap* maps, int grid,
                               size_t smem, cudaStream_t st) {
   if (layout == RL_LAYOUT_ENV_MAJOR) {
-    cudaFuncSetAttribute(vtrace_loss_kernel<A_, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RL_SMEM_OPTIN(vtrace_loss_kernel<A_, true, false>);
     vtrace_loss_kernel<A_, true, false><<<grid, kNT, smem, st>>>(a, maps[0], maps[1], maps[2]);
   } else if (tma) {
-    cudaFuncSetAttribute(vtrace_loss_kernel<A_, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RL_SMEM_OPTIN(vtrace_loss_kernel<A_, false, true>);
     cudaFuncSetAttribute(vtrace_loss_kernel<A_, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     vtrace_loss_kernel<A_, false, true><<<grid, kNT, smem, st>>>(a, maps[0], maps[1], maps[2]);
   } else {
-    cudaFuncSetAttribute(vtrace_loss_kernel<A_, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RL_SMEM_OPTIN(vtrace_loss_kernel<A_, false, false>);
     vtrace_loss_kernel<A_, false, false><<<grid, kNT, smem, st>>>(a, maps[0], maps[1], maps[2]);
   }
   return 0;

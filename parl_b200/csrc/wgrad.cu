@@ -439,7 +439,7 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
     long long nst32 = (long long)((218 * 1024) / (kWgBM * 64 + win32));
     g.stages = (int)(nst32 > kWgMaxStages ? kWgMaxStages : (nst32 < 2 ? 2 : nst32));
     const size_t smem32 = (size_t)g.stages * (kWgBM * 64 + win32) + 1024;
-    cudaFuncSetAttribute(wgrad_window_n32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32);
+    RL_SMEM_OPTIN(wgrad_window_n32_kernel);
     wgrad_window_n32_kernel<<<grid32, kWgThreads, smem32, (cudaStream_t)stream>>>(md32, mx32, g);
     wgrad_reduce_n32_kernel<<<(32 * ntaps * 64 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
         g.partials, grid32, ntaps, g.ncols_max, dw_krsc, accumulate);
@@ -473,10 +473,10 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
   const size_t smem = (size_t)g.stages * (kWgBM * 128 + cblk * win) + 1024;
   cudaStream_t st = (cudaStream_t)stream;
   if (cblk == 1) {
-    cudaFuncSetAttribute(wgrad_window_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RL_SMEM_OPTIN(wgrad_window_kernel<1>);
     wgrad_window_kernel<1><<<grid, kWgThreads, smem, st>>>(md, mx, g);
   } else {
-    cudaFuncSetAttribute(wgrad_window_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RL_SMEM_OPTIN(wgrad_window_kernel<2>);
     wgrad_window_kernel<2><<<grid, kWgThreads, smem, st>>>(md, mx, g);
   }
   const int K = ntaps * cblk * 64;

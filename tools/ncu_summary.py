@@ -39,6 +39,8 @@ def launches(path):
             v = float(r[ci['Metric Value']].replace(',', ''))
         except ValueError:
             continue
+        if v != v:          # 'nan': a launch ncu could not time
+            continue
         v *= {'ns': 1e-6, 'us': 1e-3, 'ms': 1.0, 's': 1e3}.get(r[ci['Metric Unit']], 1.0)
         name = r[ci['Kernel Name']][:90]
         agg[name][0] += 1
