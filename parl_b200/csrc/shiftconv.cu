@@ -12,8 +12,11 @@
 //   conv1  8x8/4/p1, 4->32   == 2x2/1 on [21,21,64]   -> [20,20,32] written as s2d2-padded [12,12,128]
 //   conv2  4x4/2/p2, 32->64  == 2x2/1 on [12,12,128]  -> [11,11,64]
 //   conv3  3x3/1,    64->64  == 3x3/1 on [11,11,64]   -> [9,9,64]
-// Roles: warp 0 TMA producer (3-stage window ring), warp 1 MMA issuer (weights resident in smem, TMEM
-// accumulator double-buffered), warps 2-5 epilogue (bias, ReLU, bf16, layout-aware row store).
+// Roles: warp 0 TMA producer (window ring), warps 1 and 10 MMA issuers taking alternate tiles (weights
+// resident in smem, FOUR TMEM accumulators in flight; one issuing thread needs ~50 cycles per tcgen05.mma of
+// 16-64 tensor-core cycles, so a single issuer was the bound — ncu round 1), warps 2-9 epilogue in TWO groups of four warps that take alternate tiles (bias,
+// ReLU, bf16, layout-aware row store) — one group's tcgen05.ld -> convert -> store latency chain hides behind
+// the other's, which is what bounds these small-N tiles (16..72 MMAs of 128xNx16 per tile).
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -61,16 +64,13 @@ __device__ __forceinline__ void s_mbar_arrive(void* mbar) {
 }
 // K-major SWIZZLE_128B operand starting at an arbitrary 128-byte row of a 1024-byte aligned swizzled buffer.
 // The hardware derives the swizzle phase from the absolute address, so base_offset (bits 49-51) stays 0
-// (verified on B200, see rl_debug_set_shiftconv_base_offset).
-__device__ __forceinline__ uint64_t s_desc_sw128(uint32_t smem_addr, uint32_t use_base_offset) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  if (use_base_offset) d |= (uint64_t)((smem_addr >> 7) & 7) << 49;
-  d |= (uint64_t)2 << 61;
-  return d;
+// (measured on B200: setting it double-counts the phase, max error 4.3 vs 0.016).  Everything but the 14-bit
+// start-address field (address >> 4; shared memory is < 256 KB so the field never overflows) is constant, so the
+// issuing thread only ADDS 16-byte units to the low word: tap shift, k step (32 B) and weight block.
+constexpr uint32_t kDescHiSw128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO, version 1, SWIZZLE_128B
+constexpr uint32_t kDescLoLbo1 = 1u << 16;                                            // LBO field = 1
+__device__ __forceinline__ uint64_t s_desc_from_lo(uint32_t lo) {                     // lo = (addr >> 4) + kDescLoLbo1
+  return ((uint64_t)kDescHiSw128 << 32) | (uint64_t)lo;
 }
 __host__ __device__ constexpr uint32_t s_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -78,7 +78,10 @@ __host__ __device__ constexpr uint32_t s_idesc_bf16(int M, int N) {
 
 constexpr int kScBM = 128;
 constexpr int kScMaxStages = 8;      // window ring depth is chosen at launch from the shared memory left by the weights
-constexpr int kScThreads = 192;
+constexpr int kScEpiGroups = 2;      // epilogue warp groups (4 warps each) working on alternate tiles
+constexpr int kScAcc = 4;            // TMEM accumulators in flight (kScAcc * COUT <= 512 columns)
+constexpr int kScIssuer2 = 2 + 4 * kScEpiGroups;   // warp index of the second MMA issuer (odd tiles)
+constexpr int kScThreads = 32 * (kScIssuer2 + 1);
 
 struct ShiftConvArgs {
   const float* bias;
@@ -88,7 +91,6 @@ struct ShiftConvArgs {
   int wrows;                       // window rows = 128 + (KH-1)*W + (KW-1)
   int num_tiles, relu;
   int stages;                      // depth of the TMA window ring (2..kScMaxStages)
-  int base_offset;                 // triage only: 1 sets the descriptor base_offset field (wrong on B200)
   int out_mode;                    // 0: NHWC grid [N,OGH,OGW,Cout] (valid y<Hout, x<Wout);
                                    // 1: conv1 -> conv2 s2d2-padded [N,12,12,4*Cout];
                                    // 2: (dgrad of the s2d2 conv) [N,12,12,128] blocks -> grid [N,21,21,32]
@@ -98,20 +100,19 @@ struct ShiftConvArgs {
   const __nv_bfloat16* mask;       // optional activation on the accumulator grid [Q, COUT]: out *= (mask > 0)
 };
 
-template <int COUT, int CBLK>
+template <int COUT, int CBLK, int KS>
 __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __grid_constant__ CUtensorMap map_in,
                                                                       const __grid_constant__ CUtensorMap map_w,
                                                                       const ShiftConvArgs g) {
   constexpr int W_KB = COUT * 128;                        // one 64-wide weight k-block
-  constexpr int TMEM_COLS = 2 * COUT < 32 ? 32 : 2 * COUT;
+  constexpr int TMEM_COLS = kScAcc * COUT;                // 128 / 256 / 512: powers of two
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-  const int ntaps = g.KH * g.KW;
-  const int num_kb = ntaps * CBLK;
+  constexpr int num_kb = KS * KS * CBLK;                  // square KS x KS filter
   const int win_bytes = (g.wrows * 128 + 1023) & ~1023;   // one 64-channel column block of the window
   unsigned char* sW = smem;                               // [num_kb][COUT][128 B]
   unsigned char* sWin = smem + ((num_kb * W_KB + 1023) & ~1023);   // [stages][CBLK][wrows][128 B]
-  __shared__ __align__(8) unsigned long long full_bar[kScMaxStages], empty_bar[kScMaxStages], w_bar, tmem_full[2], tmem_empty[2];
+  __shared__ __align__(8) unsigned long long full_bar[kScMaxStages], empty_bar[kScMaxStages], w_bar, tmem_full[kScAcc], tmem_empty[kScAcc];
   const uint32_t nstages = (uint32_t)g.stages;
   __shared__ uint32_t tmem_base_smem;
 
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&w_bar, 1);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kScAcc; ++b) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], 128);
     }
@@ -139,58 +140,70 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
   if (warp == 0) {
     // ===== TMA producer: one window (CBLK column blocks) per tile =====
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t s = it % nstages;
-        mbar_wait(&empty_bar[s], ((it / nstages) & 1u) ^ 1u);
+      uint32_t s = 0, par = 1;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        mbar_wait(&empty_bar[s], par);
         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(CBLK * g.wrows * 128));
+#pragma unroll
         for (int cb = 0; cb < CBLK; ++cb)
           tma_load_2d(sWin + (s * CBLK + cb) * win_bytes, &map_in, cb * 64, tile * kScBM + g.row_shift, &full_bar[s]);
+        if (++s == nstages) s = 0, par ^= 1u;
       }
     }
-  } else if (warp == 1) {
-    // ===== resident weights + MMA issue =====
+  } else if (warp == 1 || warp == kScIssuer2) {
+    // ===== resident weights + MMA issue (issuer 0: even tiles of this CTA, issuer 1: odd tiles) =====
     if (lane == 0) {
-      mbar_arrive_expect_tx(&w_bar, (uint32_t)(num_kb * W_KB));
-      for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sW + kb * W_KB, &map_w, kb * 64, 0, &w_bar);
+      const uint32_t issuer = warp == 1 ? 0u : 1u;
+      if (issuer == 0) {
+        mbar_arrive_expect_tx(&w_bar, (uint32_t)(num_kb * W_KB));
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sW + kb * W_KB, &map_w, kb * 64, 0, &w_bar);
+      }
       mbar_wait(&w_bar, 0);
       constexpr uint32_t idesc = s_idesc_bf16(kScBM, COUT);
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t s = it % nstages, buf = it & 1u;
-        mbar_wait(&tmem_empty[buf], ((it >> 1) & 1u) ^ 1u);
-        mbar_wait(&full_bar[s], (it / nstages) & 1u);
+      // the issue loop is ONE thread's instruction stream: keep it to "add, add, mma" — tap shifts are
+      // loop-invariant registers (16-byte units: 8 per window row), weight offsets are compile-time constants
+      uint32_t tap_off[KS * KS];
+#pragma unroll
+      for (int r = 0; r < KS; ++r)
+#pragma unroll
+        for (int sx = 0; sx < KS; ++sx)
+          tap_off[r * KS + sx] = (uint32_t)(g.flip ? (KS - 1 - r) * g.W + (KS - 1 - sx) : r * g.W + sx) * 8u;
+      const uint32_t w_lo = (smem_u32(sW) >> 4) + kDescLoLbo1, win_lo0 = (smem_u32(sWin) >> 4) + kDescLoLbo1;
+      const uint32_t win16 = (uint32_t)win_bytes >> 4;
+      uint32_t s = issuer, buf = issuer, full_par = 0, empty_par = 1;        // nstages >= 2, kScAcc = 4
+      for (long long tile = blockIdx.x + (long long)issuer * gridDim.x; tile < g.num_tiles; tile += 2 * gridDim.x) {
+        mbar_wait(&tmem_empty[buf], empty_par);
+        mbar_wait(&full_bar[s], full_par);
         s_fence_after();
         const uint32_t d_tmem = tmem_base + buf * COUT;
-        uint32_t first = 0;
-        for (int r = 0; r < g.KH; ++r) {
-          for (int sx = 0; sx < g.KW; ++sx) {
-            const int wr = g.flip ? (g.KH - 1 - r) * g.W + (g.KW - 1 - sx) : r * g.W + sx;
-            const uint32_t row_off = (uint32_t)wr * 128u;                     // shift by that many window rows
-            const int tap = r * g.KW + sx;
+        const uint32_t a_lo = win_lo0 + s * (CBLK * win16);
 #pragma unroll
-            for (int cb = 0; cb < CBLK; ++cb) {
-              const uint32_t a_addr = smem_u32(sWin + (s * CBLK + cb) * win_bytes) + row_off;
-              const uint32_t b_addr = smem_u32(sW + (tap * CBLK + cb) * W_KB);
+        for (int tap = 0; tap < KS * KS; ++tap) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                s_umma(d_tmem, s_desc_sw128(a_addr + 32u * k, (uint32_t)g.base_offset), s_desc_sw128(b_addr + 32u * k, 0u), idesc, first);
-                first = 1u;
-              }
-            }
+          for (int cb = 0; cb < CBLK; ++cb) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              s_umma(d_tmem, s_desc_from_lo(a_lo + cb * win16 + tap_off[tap] + 2u * k),
+                     s_desc_from_lo(w_lo + (uint32_t)((tap * CBLK + cb) * (W_KB >> 4) + 2 * k)), idesc,
+                     (tap | cb | k) != 0 ? 1u : 0u);
           }
         }
         s_commit(&empty_bar[s]);
         s_commit(&tmem_full[buf]);
+        s += 2;
+        if (s >= nstages) s -= nstages, full_par ^= 1u;
+        buf += 2;
+        if (buf >= kScAcc) buf -= kScAcc, empty_par ^= 1u;
       }
     }
   } else {
-    // ===== epilogue =====
-    const int qd = warp & 3;
+    // ===== epilogue (warps 2 .. 2 + 4 * kScEpiGroups - 1) =====
+    const int qd = warp & 3;                        // TMEM lane quarter this warp may read
+    const int grp = (warp - 2) >> 2;                // epilogue group: tiles it = grp, grp + 2, ...
     const int HW = g.H * g.W;
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t buf = it & 1u;
+    for (uint32_t it = (uint32_t)grp; blockIdx.x + (long long)it * gridDim.x < g.num_tiles; it += kScEpiGroups) {
+      const int tile = blockIdx.x + (int)it * gridDim.x;
+      const uint32_t buf = it % kScAcc;
       const int q = tile * kScBM + qd * 32 + lane;
       // ReLU mask of this row (accumulator grid [Q, COUT]): issued BEFORE waiting for the accumulator so that the
       // global-memory latency overlaps the MMAs of this tile
@@ -203,7 +216,7 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
       const int n = q / HW;
       const int rem = q - n * HW;
       const int y = rem / g.W, x = rem - y * g.W;
-      mbar_wait(&tmem_full[buf], (it >> 1) & 1u);
+      mbar_wait(&tmem_full[buf], (it / kScAcc) & 1u);
       s_fence_after();
       const bool valid = q < g.Q && y < g.Hout && x < g.Wout;
       size_t obase = 0;
@@ -280,26 +293,26 @@ static int sc_make_map(CUtensorMap* map, const void* base, uint64_t cols, uint64
              : -2;
 }
 
-template <int COUT, int CBLK>
+template <int COUT, int CBLK, int KS>
 static void launch_shiftconv(const CUtensorMap& mi, const CUtensorMap& mw, const ShiftConvArgs& g, int num_kb, int sms,
                              cudaStream_t st) {
   const size_t win = (size_t)((g.wrows * 128 + 1023) & ~1023);
   const size_t smem = (size_t)((num_kb * COUT * 128 + 1023) & ~1023) + (size_t)g.stages * CBLK * win + 1024;
-  RL_SMEM_OPTIN(shiftconv_fwd_kernel<COUT, CBLK>);
+  RL_SMEM_OPTIN(shiftconv_fwd_kernel<COUT, CBLK, KS>);
   const int grid = g.num_tiles < sms ? g.num_tiles : sms;
-  shiftconv_fwd_kernel<COUT, CBLK><<<grid, kScThreads, smem, st>>>(mi, mw, g);
+  shiftconv_fwd_kernel<COUT, CBLK, KS><<<grid, kScThreads, smem, st>>>(mi, mw, g);
 }
 
 }  // namespace rl
 
 using namespace rl;
 
-static int g_sc_base_offset = 0;
-// Triage hook.  Measured on B200: the tensor core swizzles on ABSOLUTE shared-memory address bits, so a
-// descriptor that starts at an arbitrary 128-byte row of a 1024-byte aligned swizzled buffer needs NO
-// base_offset (setting it double-counts the phase: max error 4.3 vs 0.016).  1 re-enables the field.
+// Former triage hook.  Measured on B200 (round 1): the tensor core swizzles on ABSOLUTE shared-memory address
+// bits, so a descriptor that starts at an arbitrary 128-byte row of a 1024-byte aligned swizzled buffer needs NO
+// base_offset (setting it double-counted the phase: max error 4.3 vs 0.016).  The field is now hard-wired to 0
+// in the issue loop; asking for 1 is an error.
 extern "C" int rl_debug_set_shiftconv_base_offset(int enable) {
-  g_sc_base_offset = enable ? 1 : 0;
+  RL_CHECK_ARG(enable == 0, "shiftconv base_offset=1 was measured wrong on B200 and has been removed");
   return RL_OK;
 }
 
@@ -311,14 +324,13 @@ static int shiftconv_launch(const void* in, const void* weight, const float* bia
                "%s: 16-byte alignment required", name);
   RL_CHECK_ARG((Cout == 32 || Cout == 64 || Cout == 128) && (Cin == 64 || Cin == 128),
                "%s: Cin in {64,128}, Cout in {32,64,128}", name);
-  RL_CHECK_ARG(KH >= 1 && KW >= 1 && KH <= H && KW <= W, "%s: bad filter", name);
+  RL_CHECK_ARG(KH == KW && (KH == 2 || KH == 3) && KH <= H && KW <= W, "%s: filter must be 2x2 or 3x3", name);
   ShiftConvArgs g;
   g.bias = bias, g.out = (__nv_bfloat16*)out, g.H = H, g.W = W, g.KH = KH, g.KW = KW;
   g.Hout = Hout, g.Wout = Wout, g.OGH = OGH, g.OGW = OGW;
   const long long Q = (long long)N * H * W;
   RL_CHECK_ARG(Q < (1LL << 31), "%s: too many positions", name);
   g.Q = (int)Q, g.wrows = kScBM + (KH - 1) * W + (KW - 1), g.relu = relu, g.out_mode = out_mode;
-  g.base_offset = g_sc_base_offset;
   g.row_shift = transposed ? -((KH - 1) * W + (KW - 1)) : 0, g.flip = transposed;
   g.mask = (const __nv_bfloat16*)mask;
   RL_CHECK_ARG(g.wrows <= 256, "%s: window of %d rows exceeds the TMA box limit", name, g.wrows);
@@ -344,12 +356,22 @@ static int shiftconv_launch(const void* in, const void* weight, const float* bia
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaStream_t st = (cudaStream_t)stream;
-  if (Cout == 32 && cblk == 1) launch_shiftconv<32, 1>(mi, mw, g, num_kb, sms, st);
-  else if (Cout == 32) launch_shiftconv<32, 2>(mi, mw, g, num_kb, sms, st);
-  else if (Cout == 64 && cblk == 1) launch_shiftconv<64, 1>(mi, mw, g, num_kb, sms, st);
-  else if (Cout == 64) launch_shiftconv<64, 2>(mi, mw, g, num_kb, sms, st);
-  else if (cblk == 1) launch_shiftconv<128, 1>(mi, mw, g, num_kb, sms, st);
-  else launch_shiftconv<128, 2>(mi, mw, g, num_kb, sms, st);
+  // instantiations: the layers of the Atari actor-critic and their data gradients (2x2 and 3x3 filters)
+  const int key = Cout * 100 + cblk * 10 + KH;
+  switch (key) {
+    case 3212: launch_shiftconv<32, 1, 2>(mi, mw, g, num_kb, sms, st); break;     // conv1 fwd
+    case 6422: launch_shiftconv<64, 2, 2>(mi, mw, g, num_kb, sms, st); break;     // conv2 fwd
+    case 6413: launch_shiftconv<64, 1, 3>(mi, mw, g, num_kb, sms, st); break;     // conv3 fwd / dgrad
+    case 12812: launch_shiftconv<128, 1, 2>(mi, mw, g, num_kb, sms, st); break;   // conv2 dgrad
+    case 6412: launch_shiftconv<64, 1, 2>(mi, mw, g, num_kb, sms, st); break;
+    case 3213: launch_shiftconv<32, 1, 3>(mi, mw, g, num_kb, sms, st); break;
+    case 6423: launch_shiftconv<64, 2, 3>(mi, mw, g, num_kb, sms, st); break;
+    case 12813: launch_shiftconv<128, 1, 3>(mi, mw, g, num_kb, sms, st); break;
+    case 12822: launch_shiftconv<128, 2, 2>(mi, mw, g, num_kb, sms, st); break;
+    default:
+      set_error("%s: no instantiation for Cout=%d Cin=%d %dx%d", name, Cout, Cin, KH, KW);
+      return RL_ERR_BAD_ARG;
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: launch failed: %s", name, cudaGetErrorString(e));

@@ -9,6 +9,12 @@
 // positions per instruction.  Accumulators for all (tap, channel-block) pairs stay in TMEM across the CTA's
 // whole persistent loop over position tiles; taps are split over CTA groups when they exceed 512 columns.
 // Partials are dumped once per CTA and reduced in fixed order by a second kernel (deterministic).
+//
+// Issue rate.  With M = 64 tiles of K = 16 the tensor core needs only 16-32 cycles per instruction, so ONE
+// issuing thread (about 50 cycles per tcgen05.mma even with the descriptors reduced to "add to the low word")
+// was the bound (ncu round 1: tensor pipe 18-40 % active, issuer never waiting on data).  Two warps issue now,
+// each owning a disjoint half of the CTA's filter taps (= disjoint TMEM columns); both wait on the same "full"
+// barrier and both commit to the stage's "empty" barrier (count 2).
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -51,28 +57,16 @@ __device__ __forceinline__ void w_tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-// MN-major SWIZZLE_128B operand (cute canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): 64 MN-elements
-// = one 128-byte row per K index, 8 rows per 1024-byte swizzle atom (SBO = 1024 B between K-groups of 8).
-__device__ __forceinline__ uint64_t w_desc_mn_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;                       // LBO: single 64-element MN block, unused
-  d |= (uint64_t)(1024 >> 4) << 32;             // SBO
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// MN-major SWIZZLE_64B operand: 32 MN-elements = one 64-byte row per K index, 8 rows per 512-byte swizzle atom
-// (cute canonical ((4,n),(8,k)):((1,LBO),(4,SBO)) in 16-byte units; layout_type 4).
-__device__ __forceinline__ uint64_t w_desc_mn_sw64(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(512 >> 4) << 32;              // SBO
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;
-  return d;
-}
+// Shared-memory descriptors.  Only the 14-bit start-address field (address >> 4, shared memory < 256 KB) varies,
+// so the issuing threads keep "lo" words = (address >> 4) + kWgLoLbo1 and ADD 16-byte offsets to them.
+//   MN-major SWIZZLE_128B (cute canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): 64 MN-elements = one
+//     128-byte row per K index, 8 rows per 1024-byte swizzle atom (SBO = 1024 B between K-groups of 8); LBO unused.
+//   MN-major SWIZZLE_64B  (((4,n),(8,k)):((1,LBO),(4,SBO)), layout_type 4): 32 MN-elements = one 64-byte row per
+//     K index, 8 rows per 512-byte atom.
+constexpr uint32_t kWgLoLbo1 = 1u << 16;
+constexpr uint32_t kWgHiSw128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t kWgHiSw64 = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);
+__device__ __forceinline__ uint64_t w_desc(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
 // kind::f16, BF16 x BF16 -> F32, A and B MN-major (bits 15, 16)
 __host__ __device__ constexpr uint32_t w_idesc_bf16_mn(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
@@ -81,7 +75,8 @@ __host__ __device__ constexpr uint32_t w_idesc_bf16_mn(int M, int N) {
 
 constexpr int kWgBM = 128;            // positions (K of the GEMM) per tile
 constexpr int kWgMaxStages = 6;
-constexpr int kWgThreads = 192;
+constexpr int kWgThreads = 224;       // warp 0 TMA, warps 1 and 6 MMA issuers (disjoint taps), warps 2-5 TMEM dump
+constexpr int kWgTapsPerIssuer = 5;   // <= 10 filter taps per CTA group
 
 struct WgradArgs {
   float* partials;                    // [gridDim.x][128 lanes][ncols_max] raw TMEM dumps
@@ -117,9 +112,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_window_kernel(const __gri
     tma_prefetch_desc(&map_x);
     for (int s = 0; s < kWgMaxStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], 2);          // both issuers commit
     }
-    mbar_init(&done_bar, 1);
+    mbar_init(&done_bar, 2);
     fence_mbar_init();
   }
   if (warp == 1) w_tmem_alloc(&tmem_base_smem, tmem_cols);
@@ -141,36 +136,46 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_window_kernel(const __gri
           tma_load_2d(st + kWgBM * 128 + cb * win_bytes, &map_x, cb * 64, tile * kWgBM, &full_bar[s]);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 6) {
     if (lane == 0) {
       constexpr uint32_t idesc = w_idesc_bf16_mn(64, 64);
-      uint32_t it = 0;
-      for (int tile = cta_in_group; tile < g.num_tiles; tile += ctas_per_group, ++it) {
-        const uint32_t s = it % nstages;
-        mbar_wait(&full_bar[s], (it / nstages) & 1u);
+      // this issuer's taps of the group: local indices [j0, j0 + nmine)
+      const int ntg = te - tb, half = (ntg + 1) >> 1;
+      const int j0 = warp == 1 ? 0 : half, nmine = warp == 1 ? half : ntg - half;
+      uint32_t tap_off[kWgTapsPerIssuer];                    // window shift of each tap in 16-byte units
+#pragma unroll
+      for (int j = 0; j < kWgTapsPerIssuer; ++j) {
+        const int tap = tb + j0 + j, r = tap / g.KW;
+        tap_off[j] = (uint32_t)(r * g.W + tap - r * g.KW) * 8u;
+      }
+      const uint32_t lo0 = (smem_u32(smem) >> 4) + kWgLoLbo1, stage16 = (uint32_t)stage_bytes >> 4;
+      const uint32_t win16 = (uint32_t)win_bytes >> 4;
+      uint32_t s = 0, par = 0, acc0 = 0;
+      for (int tile = cta_in_group; tile < g.num_tiles; tile += ctas_per_group) {
+        mbar_wait(&full_bar[s], par);
         w_fence_after();
-        const uint32_t a_base = smem_u32(smem + s * stage_bytes);
-        const uint32_t x_base = a_base + kWgBM * 128;
-        for (int tap = tb; tap < te; ++tap) {
-          const int r = tap / g.KW, sx = tap - r * g.KW;
-          const uint32_t row_off = (uint32_t)(r * g.W + sx) * 128u;
+        const uint32_t a_lo = lo0 + s * stage16, x_lo = a_lo + (uint32_t)(kWgBM * 128 >> 4);
 #pragma unroll
-          for (int cb = 0; cb < CBLK; ++cb) {
-            const uint32_t d_tmem = tmem_base + (uint32_t)(((tap - tb) * CBLK + cb) * 64);
-            const uint32_t b_base = x_base + cb * win_bytes + row_off;
+        for (int j = 0; j < kWgTapsPerIssuer; ++j) {
+          if (j < nmine) {
 #pragma unroll
-            for (int kk = 0; kk < kWgBM / 16; ++kk) {
-              // K advances by 16 positions = 16 rows of 128 bytes in both operands
-              w_umma(d_tmem, w_desc_mn_sw128(a_base + kk * 2048u), w_desc_mn_sw128(b_base + kk * 2048u), idesc,
-                     (it | (uint32_t)kk) != 0u ? 1u : 0u);
+            for (int cb = 0; cb < CBLK; ++cb) {
+              const uint32_t d_tmem = tmem_base + (uint32_t)(((j0 + j) * CBLK + cb) * 64);
+              const uint32_t b_lo = x_lo + cb * win16 + tap_off[j];
+#pragma unroll
+              for (int kk = 0; kk < kWgBM / 16; ++kk)   // K advances by 16 positions = 16 rows of 128 bytes (128 units)
+                w_umma(d_tmem, w_desc(kWgHiSw128, a_lo + kk * 128u), w_desc(kWgHiSw128, b_lo + kk * 128u), idesc,
+                       kk == 0 ? acc0 : 1u);
             }
           }
         }
         w_commit(&empty_bar[s]);
+        acc0 = 1u;
+        if (++s == nstages) s = 0, par ^= 1u;
       }
       w_commit(&done_bar);
     }
-  } else {
+  } else if (warp < 6) {
     // ===== dump the TMEM accumulators once: [128 lanes][ncols] raw (the reduce kernel maps lanes -> rows) =====
     const int qd = warp & 3;
     mbar_wait(&done_bar, 0);
@@ -230,9 +235,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_window_n32_kernel(const _
     tma_prefetch_desc(&map_x);
     for (int s = 0; s < kWgMaxStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], 2);          // both issuers commit
     }
-    mbar_init(&done_bar, 1);
+    mbar_init(&done_bar, 2);
     fence_mbar_init();
   }
   if (warp == 1) w_tmem_alloc(&tmem_base_smem, tmem_cols);
@@ -252,30 +257,42 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_window_n32_kernel(const _
         tma_load_2d(st, &map_dout, 0, tile * kWgBM, &full_bar[s]);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 6) {
     if (lane == 0) {
       constexpr uint32_t idesc = w_idesc_bf16_mn(64, 32);
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-        const uint32_t s = it % nstages;
-        mbar_wait(&full_bar[s], (it / nstages) & 1u);
-        w_fence_after();
-        const uint32_t b_base = smem_u32(smem + s * stage_bytes);            // dout tile, 64-byte rows
-        const uint32_t x_base = b_base + kWgBM * 64;
-        for (int tap = 0; tap < ntaps; ++tap) {
-          const int r = tap / g.KW, sx = tap - r * g.KW;
-          const uint32_t a_base = x_base + (uint32_t)(r * g.W + sx) * 128u;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(tap * 32);
+      const int half = (ntaps + 1) >> 1;
+      const int j0 = warp == 1 ? 0 : half, nmine = warp == 1 ? half : ntaps - half;
+      uint32_t tap_off[kWgTapsPerIssuer];
 #pragma unroll
-          for (int kk = 0; kk < kWgBM / 16; ++kk)
-            w_umma(d_tmem, w_desc_mn_sw128(a_base + kk * 2048u), w_desc_mn_sw64(b_base + kk * 1024u), idesc,
-                   (it | (uint32_t)kk) != 0u ? 1u : 0u);
+      for (int j = 0; j < kWgTapsPerIssuer; ++j) {
+        const int tap = j0 + j, r = tap / g.KW;
+        tap_off[j] = (uint32_t)(r * g.W + tap - r * g.KW) * 8u;
+      }
+      const uint32_t lo0 = (smem_u32(smem) >> 4) + kWgLoLbo1, stage16 = (uint32_t)stage_bytes >> 4;
+      uint32_t s = 0, par = 0, acc0 = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        mbar_wait(&full_bar[s], par);
+        w_fence_after();
+        const uint32_t b_lo = lo0 + s * stage16;                              // dout tile, 64-byte rows
+        const uint32_t x_lo = b_lo + (uint32_t)(kWgBM * 64 >> 4);
+#pragma unroll
+        for (int j = 0; j < kWgTapsPerIssuer; ++j) {
+          if (j < nmine) {
+            const uint32_t a_lo = x_lo + tap_off[j];
+            const uint32_t d_tmem = tmem_base + (uint32_t)((j0 + j) * 32);
+#pragma unroll
+            for (int kk = 0; kk < kWgBM / 16; ++kk)     // 16 positions = 2048 B of window rows, 1024 B of dout rows
+              w_umma(d_tmem, w_desc(kWgHiSw128, a_lo + kk * 128u), w_desc(kWgHiSw64, b_lo + kk * 64u), idesc,
+                     kk == 0 ? acc0 : 1u);
+          }
         }
         w_commit(&empty_bar[s]);
+        acc0 = 1u;
+        if (++s == nstages) s = 0, par ^= 1u;
       }
       w_commit(&done_bar);
     }
-  } else {
+  } else if (warp < 6) {
     const int qd = warp & 3;
     mbar_wait(&done_bar, 0);
     w_fence_after();
@@ -419,7 +436,7 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
   g.num_tiles = (int)((Q + kWgBM - 1) / kWgBM);
   if (Cout == 32) {
     // swapped-role variant: D[ci, co], dout rows are 64 bytes (SWIZZLE_64B operand)
-    RL_CHECK_ARG(ntaps * 32 <= 512, "conv2d_s1_wgrad: too many taps for Cout = 32");
+    RL_CHECK_ARG(ntaps <= 2 * kWgTapsPerIssuer, "conv2d_s1_wgrad: too many taps for Cout = 32");
     g.ngroups = 1, g.taps_per_group = ntaps, g.ncols_max = ntaps * 32;
     int dev32 = 0, sms32 = 148;
     cudaGetDevice(&dev32);
@@ -451,6 +468,7 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
   g.ngroups = (ntaps + cap - 1) / cap;
   g.taps_per_group = (ntaps + g.ngroups - 1) / g.ngroups;   // balanced split (e.g. 9 taps -> 5 + 4)
   g.ncols_max = g.taps_per_group * cblk * 64;
+  RL_CHECK_ARG(g.taps_per_group <= 2 * kWgTapsPerIssuer, "conv2d_s1_wgrad: too many taps per CTA group");
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -28,7 +28,10 @@ class AtariTrainNet(object):
         z = lambda *s: torch.zeros(s, dtype=bf, device=dev)
         e = lambda *s: torch.empty(s, dtype=bf, device=dev)
         # activations
-        self.x0, self.a1, self.a2, self.a3 = e(N, 21, 21, 64), z(N, 12, 12, 128), e(N, 11, 11, 64), e(N, 9, 9, 64)
+        # x0 (conv1's space-to-depth input) is allocated on first use: the on-device engine hands in the rollout
+        # buffer's own observation plane (written by the actor at step t) instead, see ImpalaEngine.share_obs
+        self._x0 = self._x0_in = None
+        self.a1, self.a2, self.a3 = z(N, 12, 12, 128), e(N, 11, 11, 64), e(N, 9, 9, 64)
         self.h = e(N, 512)
         self.logits = torch.empty((N, A), dtype=f32, device=dev)
         self.values = torch.empty((N, 1), dtype=f32, device=dev)
@@ -52,6 +55,12 @@ class AtariTrainNet(object):
         self.fc_library = fc_backend == 'library' or (fc_backend == 'auto' and N > 16384)
         self.da3c = e(N, 5184) if self.fc_library else None
         self.pack()
+
+    @property
+    def x0(self):
+        if self._x0 is None:
+            self._x0 = torch.empty((self.N, 21, 21, 64), dtype=torch.bfloat16, device=self.device)
+        return self._x0
 
     @torch.no_grad()
     def pack(self):
@@ -79,9 +88,11 @@ class AtariTrainNet(object):
         K.obs_stack_gather(planes, ages, 0, t_count, self.x0, layout=layout, scale=1.0 / 255.0, s2d=True)
         return self.forward_from_x0()
 
-    def forward_from_x0(self):
+    def forward_from_x0(self, x0=None):
+        """x0 [N,21,21,64] bf16 (default: this net's own buffer); kept by reference for conv1's weight gradient."""
         N = self.N
-        K.conv2d_s1_nhwc_bf16_fwd(self.x0, self.w1, self.b1, 2, 2, relu=True, out=self.a1, out_mode=1)
+        x0 = self._x0_in = self.x0 if x0 is None else x0
+        K.conv2d_s1_nhwc_bf16_fwd(x0, self.w1, self.b1, 2, 2, relu=True, out=self.a1, out_mode=1)
         K.conv2d_s1_nhwc_bf16_fwd(self.a1, self.w2, self.b2, 2, 2, relu=True, out=self.a2)
         K.conv2d_s1_nhwc_bf16_fwd(self.a2, self.w3, self.b3, 3, 3, relu=True, out=self.a3)
         if self.fc_library:
@@ -132,6 +143,6 @@ class AtariTrainNet(object):
         m.conv2.bias.grad.copy_(K.colsum_bf16(self.da2g, out=self.db))
         K.conv2d_s1_nhwc_bf16_dgrad(self.da2g, self.w2T, 2, 2, self.da1g, act_mask=self.a1, out_mode=2)
         # conv1 (4x4 block form): 64-byte gradient rows -> role-swapped weight-gradient kernel (SWIZZLE_64B operand)
-        K.conv2d_s1_nhwc_bf16_wgrad(self.da1g, self.x0, 2, 2, dw_krsc=self.dw1)
+        K.conv2d_s1_nhwc_bf16_wgrad(self.da1g, self._x0_in, 2, 2, dw_krsc=self.dw1)
         m.conv1.weight.grad.copy_(self.dw1.view(32, 2, 2, 4, 4, 4).permute(0, 5, 1, 3, 2, 4).reshape(32, 4, 8, 8))
         m.conv1.bias.grad.copy_(K.colsum_bf16(self.da1g, out=self.db[:32]))

@@ -20,7 +20,8 @@ for _ in range(2):
     out = eng.learn(1e-3, -0.01)
 torch.cuda.synchronize()
 print('sequential ok', [float(x) for x in out[:3]] if isinstance(out, (tuple, list)) else out)
-for _ in range(4):
+eng = ImpalaEngine(num_envs=B, sample_batch_steps=T, act_dim=18, seed=3, device=dev, pipeline=True)
+for _ in range(5):
     out = eng.step(1e-3, -0.01)
 torch.cuda.synchronize()
 print('pipelined ok')
