@@ -242,21 +242,16 @@ __global__ void __launch_bounds__(256) obs_stack_gather_nhwc_bf16_kernel(const u
 // pad 1 on 84x84x4 (benchmark/torch/a2c/atari_model.py:26-27); it never reads the last image row/column, so it
 // equals a 2x2 / stride 1 conv on a 21x21 grid of 4x4 pixel blocks with 64 channels:
 //   out[sample, Y, X, (dy*4+dx)*4 + c] = scale * frame_c[4Y+dy-1][4X+dx-1]      (zero outside the image)
-// bf16, 128 contiguous bytes per block -> tensor-core friendly NHWC input.  One thread = one (sample,Y,X,dy).
+// bf16, 128 contiguous bytes per block -> tensor-core friendly NHWC input.  One CTA walks whole samples (the
+// (t,b) / plane lookups are per-sample scalars, all per-item index math is 32-bit with constant divisors: the
+// first version spent most of its time in 64-bit div/mod); one thread = one (Y,X,dy) item = 32 output bytes.
 __global__ void __launch_bounds__(256) obs_stack_gather_s2d_bf16_kernel(const uint8_t* __restrict__ planes,
                                                                         const uint8_t* __restrict__ ages, int B,
                                                                         int t_begin, int t_count, int env_major,
                                                                         float scale, __nv_bfloat16* __restrict__ out) {
-  constexpr int W = 84, G = 21;
-  const long long total = (long long)t_count * B * G * G * 4;
-  const long long gstride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gstride) {
-    const int dy = (int)(i & 3);
-    long long r = i >> 2;
-    const int X = (int)(r % G);
-    r /= G;
-    const int Y = (int)(r % G);
-    r /= G;                                   // sample index in output order
+  constexpr int W = 84, G = 21, ITEMS = G * G * 4;
+  const long long nsamples = (long long)t_count * B;
+  for (long long r = blockIdx.x; r < nsamples; r += gridDim.x) {      // sample index in output order
     int t, b;
     if (env_major) {
       b = (int)(r / t_count), t = (int)(r - (long long)b * t_count);
@@ -264,33 +259,42 @@ __global__ void __launch_bounds__(256) obs_stack_gather_s2d_bf16_kernel(const ui
       t = (int)(r / B), b = (int)(r - (long long)t * B);
     }
     t += t_begin;
-    const int y = 4 * Y + dy - 1;
     const int age = ages ? ages[(long long)t * B + b] : 0;
-    uint32_t px[4];                           // per channel: the 4 bytes at x = 4X-1 .. 4X+2
+    const uint8_t* img[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      px[c] = 0u;
-      if (y >= 0) {
-        // ages == NULL: the source is an already stacked observation tensor [n, 4, 84, 84] (host contract path)
-        const long long img = ages ? ((long long)(t + 3 - min(3 - c, age)) * B + b) : (r * 4 + c);
-        const uint32_t* row = reinterpret_cast<const uint32_t*>(planes + img * (W * W) + y * W);
-        const uint32_t w0 = X > 0 ? __ldg(row + X - 1) : 0u;     // bytes 4X-4 .. 4X-1
-        const uint32_t w1 = __ldg(row + X);                      // bytes 4X   .. 4X+3
-        px[c] = (w0 >> 24) | (w1 << 8);
+      // ages == NULL: the source is an already stacked observation tensor [n, 4, 84, 84] (host contract path)
+      const long long i = ages ? ((long long)(t + 3 - min(3 - c, age)) * B + b) : (r * 4 + c);
+      img[c] = planes + i * (W * W);
+    }
+    __nv_bfloat16* dst_sample = out + r * (long long)(G * G * 64);
+    for (int j = threadIdx.x; j < ITEMS; j += 256) {
+      const int dy = j & 3, p = j >> 2, Y = p / G, X = p - Y * G;
+      const int y = 4 * Y + dy - 1;
+      uint32_t px[4];                           // per channel: the 4 bytes at x = 4X-1 .. 4X+2
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        px[c] = 0u;
+        if (y >= 0) {
+          const uint32_t* row = reinterpret_cast<const uint32_t*>(img[c] + y * W);
+          const uint32_t w0 = X > 0 ? __ldg(row + X - 1) : 0u;     // bytes 4X-4 .. 4X-1
+          const uint32_t w1 = __ldg(row + X);                      // bytes 4X   .. 4X+3
+          px[c] = (w0 >> 24) | (w1 << 8);
+        }
       }
-    }
-    uint32_t pk[8];
+      uint32_t pk[8];
 #pragma unroll
-    for (int dx = 0; dx < 4; ++dx) {
-      float v[4];
+      for (int dx = 0; dx < 4; ++dx) {
+        float v[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) v[c] = (float)((px[c] >> (8 * dx)) & 0xffu) * scale;
-      __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
-      pk[dx * 2] = *reinterpret_cast<uint32_t*>(&lo), pk[dx * 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
+        for (int c = 0; c < 4; ++c) v[c] = (float)((px[c] >> (8 * dx)) & 0xffu) * scale;
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+        pk[dx * 2] = *reinterpret_cast<uint32_t*>(&lo), pk[dx * 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
+      }
+      uint4* dst = reinterpret_cast<uint4*>(dst_sample + p * 64 + dy * 16);
+      dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
-    uint4* dst = reinterpret_cast<uint4*>(out + ((r * G + Y) * G + X) * 64 + dy * 16);
-    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
   }
 }
 
@@ -509,9 +513,8 @@ extern "C" int rl_obs_stack_gather(const uint8_t* planes, const uint8_t* ages, i
         planes, ages, B, HW, t_begin, t_count, em, scale, (__nv_bfloat16*)out);
   } else if (out_dtype == 3) {
     RL_CHECK_ARG(HW == 84 * 84, "obs_stack_gather: the space-to-depth layout is defined for 84x84 frames");
-    const long long tot3 = (long long)t_count * B * 21 * 21 * 4;
-    long long b3 = (tot3 + 255) / 256;
-    if (b3 > 148LL * 32) b3 = 148LL * 32;
+    long long b3 = (long long)t_count * B;              // one CTA per sample, grid-stride beyond 8 CTAs per SM
+    if (b3 > 148LL * 8) b3 = 148LL * 8;
     obs_stack_gather_s2d_bf16_kernel<<<(unsigned)b3, 256, 0, (cudaStream_t)stream>>>(
         planes, ages, B, t_begin, t_count, em, scale, (__nv_bfloat16*)out);
   } else {

@@ -183,9 +183,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tn_kernel(const __g
         }
         if (g.mask) {
           const __nv_bfloat16* mrow = g.mask + (size_t)row * g.ldm + col;
+          if (col + 16 <= g.N && (g.ldm & 7) == 0 && (reinterpret_cast<uintptr_t>(g.mask) & 15u) == 0) {
+            // two 16-byte loads; keep where the saved activation is > 0 (bf16: sign clear and magnitude non-zero)
+            const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(mrow)), m1 = __ldg(reinterpret_cast<const uint4*>(mrow) + 1);
+            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (col + i < g.N && !(__bfloat162float(mrow[i]) > 0.f)) v[i] = 0.f;
+            for (int i = 0; i < 8; ++i) {
+              if ((mw[i] & 0x7fffu) == 0u || (mw[i] & 0x8000u)) v[2 * i] = 0.f;
+              if ((mw[i] & 0x7fff0000u) == 0u || (mw[i] & 0x80000000u)) v[2 * i + 1] = 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (col + i < g.N && !(__bfloat162float(mrow[i]) > 0.f)) v[i] = 0.f;
+          }
         }
         if (g.out_f32) {
           float* dst = reinterpret_cast<float*>(g.C) + (size_t)row * g.ldc + col;
@@ -276,9 +287,11 @@ static int gemm_launch(const void* A, const void* B, const float* bias, void* C,
   RL_CHECK_ARG(lda >= K && ldb >= K && ldc >= N && (lda % 8) == 0 && (ldb % 8) == 0,
                "gemm_bf16_tn: lda/ldb must be >= K and multiples of 8 elements (TMA row pitch)");
   int BN = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
-  // small problems: prefer more, narrower tiles so that the grid covers the 148 SMs
+  // small problems: prefer narrower tiles until the grid covers about two thirds of the 148 SMs — but no further:
+  // one thread issues every tcgen05.mma at ~50 cycles each, so an N = 64 tile (32 tensor-core cycles per
+  // instruction) is issue-bound while N = 128 is not (measured: 4096 x 512 x 5184 at BN 64 = two waves, 31 us)
   const long long mt = (M + kGemmBM - 1) / kGemmBM;
-  while (BN > 64 && mt * ((N + BN - 1) / BN) < 148) BN >>= 1;
+  while (BN > 64 && mt * ((N + BN - 1) / BN) < 100) BN >>= 1;
   alignas(64) CUtensorMap ma, mb;
   if (make_tensor_map_bf16_sw128(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kGemmBM) ||
       make_tensor_map_bf16_sw128(&mb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, (uint32_t)BN)) {

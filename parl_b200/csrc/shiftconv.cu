@@ -100,7 +100,23 @@ struct ShiftConvArgs {
   const __nv_bfloat16* mask;       // optional activation on the accumulator grid [Q, COUT]: out *= (mask > 0)
 };
 
-template <int COUT, int CBLK, int KS>
+// fp32 pair -> packed bf16x2 (lo = first argument), round-to-nearest-even; the ReLU form clamps in the same instruction
+__device__ __forceinline__ uint32_t s_pack_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t s_pack_relu_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+// MODE 0: forward  (out = act(acc + bias), ReLU optional)     MODE 1: data gradient (out = acc * (mask > 0), mask optional)
+// The epilogue is the instruction-issue hot spot of these kernels (ncu round 1: ~85 % of the issue slots of the
+// data-gradient kernel), so it is kept to: tcgen05.ld, 4 LDS.128 of bias + 16 FADD or one HSET2 mask per pair,
+// one cvt(.relu).bf16x2 per pair, two 16-byte stores — no per-element branches.
+template <int COUT, int CBLK, int KS, int MODE>
 __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __grid_constant__ CUtensorMap map_in,
                                                                       const __grid_constant__ CUtensorMap map_w,
                                                                       const ShiftConvArgs g) {
@@ -115,8 +131,10 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
   __shared__ __align__(8) unsigned long long full_bar[kScMaxStages], empty_bar[kScMaxStages], w_bar, tmem_full[kScAcc], tmem_empty[kScAcc];
   const uint32_t nstages = (uint32_t)g.stages;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_bias[COUT];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (MODE == 0 && threadIdx.x < COUT) s_bias[threadIdx.x] = g.bias[threadIdx.x];
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_in);
     tma_prefetch_desc(&map_w);
@@ -207,8 +225,9 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
       const int q = tile * kScBM + qd * 32 + lane;
       // ReLU mask of this row (accumulator grid [Q, COUT]): issued BEFORE waiting for the accumulator so that the
       // global-memory latency overlaps the MMAs of this tile
+      const bool has_mask = MODE == 1 && g.mask != nullptr;
       uint4 mk[COUT / 8];
-      if (g.mask && q < g.Q) {
+      if (has_mask && q < g.Q) {
         const uint4* mp = reinterpret_cast<const uint4*>(g.mask + (size_t)q * COUT);
 #pragma unroll
         for (int i = 0; i < COUT / 8; ++i) mk[i] = __ldg(mp + i);
@@ -228,6 +247,7 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
         obase = (((size_t)n * 12 + (yp >> 1)) * 12 + (xp >> 1)) * (4 * COUT) + (size_t)(((yp & 1) * 2 + (xp & 1)) * COUT);
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + buf * COUT;
+      const bool relu = g.relu != 0;
 #pragma unroll
       for (int c0 = 0; c0 < COUT; c0 += 16) {
         float v[16];
@@ -242,20 +262,30 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
         }
         if (ok) {
           uint32_t pk[8];
-          const uint4 mk0 = mk[c0 / 8], mk1 = mk[c0 / 8 + 1];
-          const uint32_t mw[8] = {mk0.x, mk0.y, mk0.z, mk0.w, mk1.x, mk1.y, mk1.z, mk1.w};
+          if (MODE == 0) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float x0 = v[2 * i], x1 = v[2 * i + 1];
-            if (g.bias) x0 += __ldg(g.bias + c0 + 2 * i), x1 += __ldg(g.bias + c0 + 2 * i + 1);
-            if (g.relu) x0 = fmaxf(x0, 0.f), x1 = fmaxf(x1, 0.f);
-            // ReLU backward: keep the gradient where the saved post-ReLU activation is positive (bf16 sign/zero test)
-            if (g.mask) {
-              if ((mw[i] & 0x7fffu) == 0u || (mw[i] & 0x8000u)) x0 = 0.f;
-              if ((mw[i] & 0x7fff0000u) == 0u || (mw[i] & 0x80000000u)) x1 = 0.f;
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * i]);      // broadcast LDS.128
+              v[4 * i] += b4.x, v[4 * i + 1] += b4.y, v[4 * i + 2] += b4.z, v[4 * i + 3] += b4.w;
             }
-            __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+            if (relu) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pk[i] = s_pack_relu_bf16x2(v[2 * i], v[2 * i + 1]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pk[i] = s_pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[i] = s_pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            if (has_mask) {
+              // ReLU backward: keep the gradient where the saved activation is > 0 — one packed bf16x2 compare per pair
+              const uint4 mk0 = mk[c0 / 8], mk1 = mk[c0 / 8 + 1];
+              const uint32_t mw[8] = {mk0.x, mk0.y, mk0.z, mk0.w, mk1.x, mk1.y, mk1.z, mk1.w};
+              const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pk[i] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&mw[i]), zero2);
+            }
           }
           uint4* dst = reinterpret_cast<uint4*>(g.out + dst_off);
           dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -293,14 +323,14 @@ static int sc_make_map(CUtensorMap* map, const void* base, uint64_t cols, uint64
              : -2;
 }
 
-template <int COUT, int CBLK, int KS>
+template <int COUT, int CBLK, int KS, int MODE>
 static void launch_shiftconv(const CUtensorMap& mi, const CUtensorMap& mw, const ShiftConvArgs& g, int num_kb, int sms,
                              cudaStream_t st) {
   const size_t win = (size_t)((g.wrows * 128 + 1023) & ~1023);
   const size_t smem = (size_t)((num_kb * COUT * 128 + 1023) & ~1023) + (size_t)g.stages * CBLK * win + 1024;
-  RL_SMEM_OPTIN(shiftconv_fwd_kernel<COUT, CBLK, KS>);
+  RL_SMEM_OPTIN(shiftconv_fwd_kernel<COUT, CBLK, KS, MODE>);
   const int grid = g.num_tiles < sms ? g.num_tiles : sms;
-  shiftconv_fwd_kernel<COUT, CBLK, KS><<<grid, kScThreads, smem, st>>>(mi, mw, g);
+  shiftconv_fwd_kernel<COUT, CBLK, KS, MODE><<<grid, kScThreads, smem, st>>>(mi, mw, g);
 }
 
 }  // namespace rl
@@ -357,17 +387,17 @@ static int shiftconv_launch(const void* in, const void* weight, const float* bia
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaStream_t st = (cudaStream_t)stream;
   // instantiations: the layers of the Atari actor-critic and their data gradients (2x2 and 3x3 filters)
-  const int key = Cout * 100 + cblk * 10 + KH;
+  const int key = (transposed ? 100000 : 0) + Cout * 100 + cblk * 10 + KH;
   switch (key) {
-    case 3212: launch_shiftconv<32, 1, 2>(mi, mw, g, num_kb, sms, st); break;     // conv1 fwd
-    case 6422: launch_shiftconv<64, 2, 2>(mi, mw, g, num_kb, sms, st); break;     // conv2 fwd
-    case 6413: launch_shiftconv<64, 1, 3>(mi, mw, g, num_kb, sms, st); break;     // conv3 fwd / dgrad
-    case 12812: launch_shiftconv<128, 1, 2>(mi, mw, g, num_kb, sms, st); break;   // conv2 dgrad
-    case 6412: launch_shiftconv<64, 1, 2>(mi, mw, g, num_kb, sms, st); break;
-    case 3213: launch_shiftconv<32, 1, 3>(mi, mw, g, num_kb, sms, st); break;
-    case 6423: launch_shiftconv<64, 2, 3>(mi, mw, g, num_kb, sms, st); break;
-    case 12813: launch_shiftconv<128, 1, 3>(mi, mw, g, num_kb, sms, st); break;
-    case 12822: launch_shiftconv<128, 2, 2>(mi, mw, g, num_kb, sms, st); break;
+    case 3212: launch_shiftconv<32, 1, 2, 0>(mi, mw, g, num_kb, sms, st); break;          // conv1 fwd
+    case 6422: launch_shiftconv<64, 2, 2, 0>(mi, mw, g, num_kb, sms, st); break;          // conv2 fwd
+    case 6413: launch_shiftconv<64, 1, 3, 0>(mi, mw, g, num_kb, sms, st); break;          // conv3 fwd
+    case 6412: launch_shiftconv<64, 1, 2, 0>(mi, mw, g, num_kb, sms, st); break;
+    case 6423: launch_shiftconv<64, 2, 3, 0>(mi, mw, g, num_kb, sms, st); break;
+    case 106413: launch_shiftconv<64, 1, 3, 1>(mi, mw, g, num_kb, sms, st); break;        // conv3 dgrad
+    case 112812: launch_shiftconv<128, 1, 2, 1>(mi, mw, g, num_kb, sms, st); break;       // conv2 dgrad
+    case 106412: launch_shiftconv<64, 1, 2, 1>(mi, mw, g, num_kb, sms, st); break;
+    case 112813: launch_shiftconv<128, 1, 3, 1>(mi, mw, g, num_kb, sms, st); break;
     default:
       set_error("%s: no instantiation for Cout=%d Cin=%d %dx%d", name, Cout, Cin, KH, KW);
       return RL_ERR_BAD_ARG;

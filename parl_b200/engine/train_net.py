@@ -49,7 +49,7 @@ class AtariTrainNet(object):
         self.dw1 = torch.empty((32, 256), dtype=f32, device=dev)
         self.dw2 = torch.empty((64, 512), dtype=f32, device=dev)
         self.dw3 = torch.empty((64, 576), dtype=f32, device=dev)
-        self.db = torch.empty(64, dtype=f32, device=dev)
+        self.dbs = [torch.empty(n, dtype=f32, device=dev) for n in (512, 64, 64, 32)]     # bias-gradient scratch
         # the two big fc contractions (K=5184 / N=5184 over all samples): our single-tile tcgen05 GEMM is L2-bound
         # at this size, so by default they go to the library GEMM with our fused epilogue kernels around it
         self.fc_library = fc_backend == 'library' or (fc_backend == 'auto' and N > 16384)
@@ -105,6 +105,11 @@ class AtariTrainNet(object):
         return self.logits, self.values
 
     # ------------------------------------------------------------------ backward
+    def _bias_grad(self, grid, scratch, param):
+        """param.grad = column sums of a gradient grid (a side stream was tried in round 1: the column sums then
+        merely share HBM bandwidth with the tensor-core kernels, no net gain)."""
+        param.grad.copy_(K.colsum_bf16(grid, out=scratch))
+
     @torch.no_grad()
     def backward(self, d_logits, d_values):
         """d_logits [N,A] f32, d_values [N] f32 -> fills ``p.grad`` of every model parameter."""
@@ -123,7 +128,7 @@ class AtariTrainNet(object):
         a3f = self.a3.view(N, 5184)
         dwfc = (self.dh.t() @ a3f).float()                                                   # [512, 5184] (h,w,c) cols
         m.fc.weight.grad.copy_(dwfc.view(512, 9, 9, 64).permute(0, 3, 1, 2).reshape(512, 5184))
-        m.fc.bias.grad.copy_(K.colsum_bf16(self.dh))
+        self._bias_grad(self.dh, self.dbs[0], m.fc.bias)
         if self.fc_library:
             torch.matmul(self.dh, self.wfc, out=self.da3c)                                   # [N, 5184] compact
             K.mask_scatter_grid_bf16(self.da3c, self.a3, self.da3g, N, 9, 9, 11, 11, 64)    # ReLU mask + 11x11 grid
@@ -133,16 +138,16 @@ class AtariTrainNet(object):
                 K.gemm_bf16_tn_masked(self.dh, self.wfcT[y * 576:(y + 1) * 576], a3f[:, y * 576:(y + 1) * 576],
                                       da3[:, y * 704:y * 704 + 576])
         # conv3
+        self._bias_grad(self.da3g, self.dbs[1], m.conv3.bias)
         K.conv2d_s1_nhwc_bf16_wgrad(self.da3g, self.a2, 3, 3, dw_krsc=self.dw3)
         m.conv3.weight.grad.copy_(self.dw3.view(64, 3, 3, 64).permute(0, 3, 1, 2))
-        m.conv3.bias.grad.copy_(K.colsum_bf16(self.da3g, out=self.db))
         K.conv2d_s1_nhwc_bf16_dgrad(self.da3g, self.w3T, 3, 3, self.da2g, act_mask=self.a2)   # onto the 12x12 grid
         # conv2 (2x2 block form)
+        self._bias_grad(self.da2g, self.dbs[2], m.conv2.bias)
         K.conv2d_s1_nhwc_bf16_wgrad(self.da2g, self.a1, 2, 2, dw_krsc=self.dw2)
         m.conv2.weight.grad.copy_(self.dw2.view(64, 2, 2, 2, 2, 32).permute(0, 5, 1, 3, 2, 4).reshape(64, 32, 4, 4))
-        m.conv2.bias.grad.copy_(K.colsum_bf16(self.da2g, out=self.db))
         K.conv2d_s1_nhwc_bf16_dgrad(self.da2g, self.w2T, 2, 2, self.da1g, act_mask=self.a1, out_mode=2)
         # conv1 (4x4 block form): 64-byte gradient rows -> role-swapped weight-gradient kernel (SWIZZLE_64B operand)
+        self._bias_grad(self.da1g, self.dbs[3], m.conv1.bias)
         K.conv2d_s1_nhwc_bf16_wgrad(self.da1g, self._x0_in, 2, 2, dw_krsc=self.dw1)
         m.conv1.weight.grad.copy_(self.dw1.view(32, 2, 2, 4, 4, 4).permute(0, 5, 1, 3, 2, 4).reshape(32, 4, 8, 8))
-        m.conv1.bias.grad.copy_(K.colsum_bf16(self.da1g, out=self.db[:32]))
