@@ -242,15 +242,19 @@ __global__ void __launch_bounds__(256) obs_stack_gather_nhwc_bf16_kernel(const u
 // pad 1 on 84x84x4 (benchmark/torch/a2c/atari_model.py:26-27); it never reads the last image row/column, so it
 // equals a 2x2 / stride 1 conv on a 21x21 grid of 4x4 pixel blocks with 64 channels:
 //   out[sample, Y, X, (dy*4+dx)*4 + c] = scale * frame_c[4Y+dy-1][4X+dx-1]      (zero outside the image)
-// bf16, 128 contiguous bytes per block -> tensor-core friendly NHWC input.  One CTA walks whole samples (the
-// (t,b) / plane lookups are per-sample scalars, all per-item index math is 32-bit with constant divisors: the
-// first version spent most of its time in 64-bit div/mod); one thread = one (Y,X,dy) item = 32 output bytes.
+// bf16, 128 contiguous bytes per block -> tensor-core friendly NHWC input.  One CTA walks whole samples: the four
+// source frames (4 x 7056 B) are staged in shared memory with coalesced 16-byte cp.async (the first version issued
+// eight 4-byte global loads per thread and sat in long-scoreboard stalls, ncu round 1), then one thread = one
+// (Y,X,dy) item = 32 output bytes.  u8 -> float goes through the 2^23 magic number on the FMA pipe:
+// fma(as_float(0x4B000000 | byte), scale, -2^23 * scale) == float(byte) * scale bit for bit (one rounding).
 __global__ void __launch_bounds__(256) obs_stack_gather_s2d_bf16_kernel(const uint8_t* __restrict__ planes,
                                                                         const uint8_t* __restrict__ ages, int B,
                                                                         int t_begin, int t_count, int env_major,
                                                                         float scale, __nv_bfloat16* __restrict__ out) {
-  constexpr int W = 84, G = 21, ITEMS = G * G * 4;
+  constexpr int W = 84, G = 21, ITEMS = G * G * 4, FRAME = W * W, CHUNKS = FRAME / 16;     // 7056 B = 441 x 16
+  __shared__ __align__(16) uint8_t sfr[4][FRAME];
   const long long nsamples = (long long)t_count * B;
+  const float bias = -8388608.0f * scale;
   for (long long r = blockIdx.x; r < nsamples; r += gridDim.x) {      // sample index in output order
     int t, b;
     if (env_major) {
@@ -260,13 +264,15 @@ __global__ void __launch_bounds__(256) obs_stack_gather_s2d_bf16_kernel(const ui
     }
     t += t_begin;
     const int age = ages ? ages[(long long)t * B + b] : 0;
-    const uint8_t* img[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int i = threadIdx.x; i < 4 * CHUNKS; i += 256) {
+      const int c = i / CHUNKS, k = i - c * CHUNKS;
       // ages == NULL: the source is an already stacked observation tensor [n, 4, 84, 84] (host contract path)
-      const long long i = ages ? ((long long)(t + 3 - min(3 - c, age)) * B + b) : (r * 4 + c);
-      img[c] = planes + i * (W * W);
+      const long long img = ages ? ((long long)(t + 3 - min(3 - c, age)) * B + b) : (r * 4 + c);
+      cp_async16(&sfr[c][k * 16], planes + img * FRAME + k * 16);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
     __nv_bfloat16* dst_sample = out + r * (long long)(G * G * 64);
     for (int j = threadIdx.x; j < ITEMS; j += 256) {
       const int dy = j & 3, p = j >> 2, Y = p / G, X = p - Y * G;
@@ -276,9 +282,9 @@ __global__ void __launch_bounds__(256) obs_stack_gather_s2d_bf16_kernel(const ui
       for (int c = 0; c < 4; ++c) {
         px[c] = 0u;
         if (y >= 0) {
-          const uint32_t* row = reinterpret_cast<const uint32_t*>(img[c] + y * W);
-          const uint32_t w0 = X > 0 ? __ldg(row + X - 1) : 0u;     // bytes 4X-4 .. 4X-1
-          const uint32_t w1 = __ldg(row + X);                      // bytes 4X   .. 4X+3
+          const uint32_t* row = reinterpret_cast<const uint32_t*>(&sfr[c][0]) + y * (W / 4);
+          const uint32_t w0 = X > 0 ? row[X - 1] : 0u;             // bytes 4X-4 .. 4X-1
+          const uint32_t w1 = row[X];                              // bytes 4X   .. 4X+3
           px[c] = (w0 >> 24) | (w1 << 8);
         }
       }
@@ -287,7 +293,8 @@ __global__ void __launch_bounds__(256) obs_stack_gather_s2d_bf16_kernel(const ui
       for (int dx = 0; dx < 4; ++dx) {
         float v[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) v[c] = (float)((px[c] >> (8 * dx)) & 0xffu) * scale;
+        for (int c = 0; c < 4; ++c)
+          v[c] = fmaf(__uint_as_float(__byte_perm(px[c], 0x4B000000u, 0x7540u | dx)), scale, bias);
         __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
         pk[dx * 2] = *reinterpret_cast<uint32_t*>(&lo), pk[dx * 2 + 1] = *reinterpret_cast<uint32_t*>(&hi);
       }
@@ -295,6 +302,7 @@ __global__ void __launch_bounds__(256) obs_stack_gather_s2d_bf16_kernel(const ui
       dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
+    __syncthreads();                            // the next sample overwrites the staged frames
   }
 }
 
@@ -513,8 +521,9 @@ extern "C" int rl_obs_stack_gather(const uint8_t* planes, const uint8_t* ages, i
         planes, ages, B, HW, t_begin, t_count, em, scale, (__nv_bfloat16*)out);
   } else if (out_dtype == 3) {
     RL_CHECK_ARG(HW == 84 * 84, "obs_stack_gather: the space-to-depth layout is defined for 84x84 frames");
+    RL_CHECK_ARG(aligned16(planes) && aligned16(out), "obs_stack_gather: 16-byte alignment required (cp.async staging)");
     long long b3 = (long long)t_count * B;              // one CTA per sample, grid-stride beyond 8 CTAs per SM
-    if (b3 > 148LL * 8) b3 = 148LL * 8;
+    if (b3 > 148LL * 7) b3 = 148LL * 7;                 // 28 KB of staged frames per CTA: 7 CTAs per SM
     obs_stack_gather_s2d_bf16_kernel<<<(unsigned)b3, 256, 0, (cudaStream_t)stream>>>(
         planes, ages, B, t_begin, t_count, em, scale, (__nv_bfloat16*)out);
   } else {

@@ -324,6 +324,148 @@ __global__ void __launch_bounds__(256) wgrad_reduce_n32_kernel(const float* __re
   dw[idx] = accumulate ? dw[idx] + acc : acc;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Paired-tap form (default).  Roles swapped — A = input window (MN-major, SWIZZLE_128B), B = dout tile (MN-major;
+// SWIZZLE_128B for 64 output channels, SWIZZLE_64B for 32) — and TWO filter taps share one instruction: an
+// MN-major operand's second 64-element block lies LBO bytes after the first, and the windows of two taps are the
+// same rows shifted by (off_{t+1} - off_t) * 128 bytes, so LBO = that shift gives an M = 128 tile
+//     D[(tap_lo | tap_hi, ci), co] += in[q + off, ci]^T dout[q, co]
+// at the tensor-core cost of one M = 64 tile.  Half the instructions, all 128 TMEM lanes used, so every tap of a
+// 3x3 / 64-channel layer fits the 512 columns at once (5 pairs x 64) and no position tile is read by two CTA groups
+// (the M = 64 form read conv3's operands twice: ncu round 1, 11.9 GB for 6.3 GB of unique data).  An odd last tap
+// is paired with the window one row further down; its upper 64 lanes are never read back.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWgSlotsPerIssuer = 3;      // (pair, channel-block) accumulators per issuing warp
+
+struct WgradPairArgs {
+  float* partials;                    // [gridDim.x][128 lanes][ncols] raw TMEM dumps
+  int W, KW, ntaps;
+  int wrows, num_tiles, stages;
+  int npairs, ncols;                  // ncols = npairs * CBLK * COUT
+};
+
+template <int COUT, int CBLK>
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_pair_kernel(const __grid_constant__ CUtensorMap map_dout,
+                                                                   const __grid_constant__ CUtensorMap map_x,
+                                                                   const WgradPairArgs g) {
+  constexpr int DOUT_BYTES = kWgBM * COUT * 2;                        // 16 KB (SW128) or 8 KB (SW64)
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const int win_bytes = (g.wrows * 128 + 1023) & ~1023;
+  const int stage_bytes = CBLK * win_bytes + DOUT_BYTES;              // windows first (1024-byte aligned), then dout
+  __shared__ __align__(8) unsigned long long full_bar[kWgMaxStages], empty_bar[kWgMaxStages], done_bar;
+  __shared__ uint32_t tmem_base_smem;
+  const uint32_t nstages = (uint32_t)g.stages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)g.ncols) tmem_cols <<= 1;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_dout);
+    tma_prefetch_desc(&map_x);
+    for (int s = 0; s < kWgMaxStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 2);          // both issuers commit
+    }
+    mbar_init(&done_bar, 2);
+    fence_mbar_init();
+  }
+  if (warp == 1) w_tmem_alloc(&tmem_base_smem, tmem_cols);
+  w_fence_before();
+  __syncthreads();
+  w_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t s = 0, par = 1;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        mbar_wait(&empty_bar[s], par);
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(DOUT_BYTES + CBLK * g.wrows * 128));
+        unsigned char* st = smem + s * stage_bytes;
+#pragma unroll
+        for (int cb = 0; cb < CBLK; ++cb) tma_load_2d(st + cb * win_bytes, &map_x, cb * 64, tile * kWgBM, &full_bar[s]);
+        tma_load_2d(st + CBLK * win_bytes, &map_dout, 0, tile * kWgBM, &full_bar[s]);
+        if (++s == nstages) s = 0, par ^= 1u;
+      }
+    }
+  } else if (warp == 1 || warp == 6) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = w_idesc_bf16_mn(128, COUT);
+      constexpr uint32_t hiB = COUT == 64 ? kWgHiSw128 : kWgHiSw64;
+      constexpr uint32_t kstepB = COUT == 64 ? 128u : 64u;             // 16 positions of dout rows, 16-byte units
+      // this issuer's accumulator slots: slot = pair * CBLK + cb, local indices [j0, j0 + nmine)
+      const int nslots = g.npairs * CBLK, half = (nslots + 1) >> 1;
+      const int j0 = warp == 1 ? 0 : half, nmine = warp == 1 ? half : nslots - half;
+      uint32_t a_off[kWgSlotsPerIssuer];      // (window shift of the pair's first tap + channel block) | LBO << 16
+#pragma unroll
+      for (int j = 0; j < kWgSlotsPerIssuer; ++j) {
+        const int slot = j0 + j, pair = slot / CBLK, cb = slot - pair * CBLK;
+        const int t0 = 2 * pair, t1 = min(2 * pair + 1, g.ntaps - 1);
+        const int r0 = t0 / g.KW, r1 = t1 / g.KW;
+        const int o0 = r0 * g.W + t0 - r0 * g.KW, o1 = r1 * g.W + t1 - r1 * g.KW;
+        const int delta = o1 > o0 ? o1 - o0 : 1;                       // odd last tap: dummy partner one row down
+        a_off[j] = (uint32_t)(o0 * 8 + cb * (win_bytes >> 4)) + ((uint32_t)(delta * 8) << 16);
+      }
+      const uint32_t lo0 = smem_u32(smem) >> 4, stage16 = (uint32_t)stage_bytes >> 4;
+      uint32_t s = 0, par = 0, acc0 = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        mbar_wait(&full_bar[s], par);
+        w_fence_after();
+        const uint32_t x_lo = lo0 + s * stage16;
+        const uint32_t b_lo = x_lo + (uint32_t)((CBLK * win_bytes) >> 4) + kWgLoLbo1;
+#pragma unroll
+        for (int j = 0; j < kWgSlotsPerIssuer; ++j) {
+          if (j < nmine) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)((j0 + j) * COUT);
+            const uint32_t a_lo = x_lo + a_off[j];
+#pragma unroll
+            for (int kk = 0; kk < kWgBM / 16; ++kk)       // 16 positions = 16 window rows (128 units) per K step
+              w_umma(d_tmem, w_desc(kWgHiSw128, a_lo + kk * 128u), w_desc(hiB, b_lo + kk * kstepB), idesc,
+                     kk == 0 ? acc0 : 1u);
+          }
+        }
+        w_commit(&empty_bar[s]);
+        acc0 = 1u;
+        if (++s == nstages) s = 0, par ^= 1u;
+      }
+      w_commit(&done_bar);
+    }
+  } else if (warp < 6) {
+    // ===== dump the TMEM accumulators once: [128 lanes][ncols] =====
+    const int qd = warp & 3;
+    mbar_wait(&done_bar, 0);
+    w_fence_after();
+    float* dst = g.partials + ((size_t)blockIdx.x * 128 + qd * 32 + lane) * g.ncols;
+    const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
+    for (int c0 = 0; c0 < g.ncols; c0 += 16) {
+      float v[16];
+      w_tmem_ld16(taddr + (uint32_t)c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+  }
+  w_fence_before();
+  __syncthreads();
+  if (warp == 1) w_tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// dW[co][(tap, cb, ci)] from the [lane = (tap & 1) * 64 + ci][col = ((tap >> 1) * cblk + cb) * cout + co] partials,
+// summed over the CTAs in index order (deterministic)
+__global__ void __launch_bounds__(256) wgrad_pair_reduce_kernel(const float* __restrict__ partials, int nctas, int ntaps,
+                                                                int cblk, int cout, int ncols, float* __restrict__ dw,
+                                                                int accumulate) {
+  const int K = ntaps * cblk * 64;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cout * K) return;
+  const int co = idx / K, k = idx - co * K;
+  const int tap = k / (cblk * 64), within = k - tap * cblk * 64, cb = within >> 6, ci = within & 63;
+  const int ln = (tap & 1) * 64 + ci, col = ((tap >> 1) * cblk + cb) * cout + co;
+  float acc = 0.f;
+  for (int c = 0; c < nctas; ++c) acc += partials[((size_t)c * 128 + ln) * ncols + col];
+  dw[idx] = accumulate ? dw[idx] + acc : acc;
+}
+
 // column sums of a [rows, C] bf16 matrix (bias gradients): deterministic two-stage, 16-byte loads.
 // A thread owns 8 adjacent columns (one uint4) and walks the rows of its block's chunk with stride
 // (256 / (C/8)) so that a warp reads whole 128-byte lines.
@@ -405,6 +547,9 @@ static int wg_make_map(CUtensorMap* map, const void* base, uint64_t cols, uint64
 
 using namespace rl;
 
+// bit 0: legacy M = 64 kernels read accumulator row i from TMEM lane i (wrong on B200; the measured map is
+// 32*(i/16) + i%16) — triage only.  bit 1: use the legacy one-tap-per-instruction (M = 64) kernels instead of the
+// paired-tap form.
 static int g_wg_lane_map = 0;
 extern "C" int rl_debug_set_wgrad_lane_map(int mode) {
   g_wg_lane_map = mode;
@@ -434,6 +579,51 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
   g.wrows = kWgBM + (KH - 1) * W + (KW - 1);
   RL_CHECK_ARG(g.wrows <= 256, "conv2d_s1_wgrad: window too tall");
   g.num_tiles = (int)((Q + kWgBM - 1) / kWgBM);
+  const int npairs = (ntaps + 1) / 2;
+  if (!(g_wg_lane_map & 2) && npairs * cblk <= 2 * kWgSlotsPerIssuer && npairs * cblk * Cout <= 512) {
+    // ---- paired-tap form (default) ----
+    WgradPairArgs a;
+    a.partials = reinterpret_cast<float*>(workspace);
+    a.W = W, a.KW = KW, a.ntaps = ntaps, a.wrows = g.wrows + 1;       // + the dummy partner row of an odd last tap
+    a.num_tiles = g.num_tiles, a.npairs = npairs, a.ncols = npairs * cblk * Cout;
+    RL_CHECK_ARG(a.wrows <= 256, "conv2d_s1_wgrad: window too tall");
+    int devp = 0, smsp = 148;
+    cudaGetDevice(&devp);
+    cudaDeviceGetAttribute(&smsp, cudaDevAttrMultiProcessorCount, devp);
+    const int gridp = smsp < a.num_tiles ? smsp : a.num_tiles;
+    if (workspace_bytes < (size_t)gridp * 128 * a.ncols * sizeof(float)) {
+      set_error("conv2d_s1_wgrad: workspace too small");
+      return RL_ERR_WORKSPACE;
+    }
+    alignas(64) CUtensorMap mdp, mxp;
+    if (wg_make_map(&mdp, dout_grid, (uint64_t)Cout, (uint64_t)Q, kWgBM, (uint32_t)Cout,
+                    Cout == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B) ||
+        wg_make_map(&mxp, in, (uint64_t)Cin, (uint64_t)Q, (uint32_t)a.wrows)) {
+      set_error("conv2d_s1_wgrad: cuTensorMapEncodeTiled failed");
+      return RL_ERR_CUDA;
+    }
+    const size_t winp = (size_t)((a.wrows * 128 + 1023) & ~1023);
+    const size_t stagep = (size_t)cblk * winp + (size_t)kWgBM * Cout * 2;
+    long long nstp = (long long)((218 * 1024) / stagep);
+    a.stages = (int)(nstp > kWgMaxStages ? kWgMaxStages : (nstp < 2 ? 2 : nstp));
+    const size_t smemp = (size_t)a.stages * stagep + 1024;
+    cudaStream_t stp = (cudaStream_t)stream;
+    if (Cout == 64 && cblk == 1) {
+      RL_SMEM_OPTIN(wgrad_pair_kernel<64, 1>);
+      wgrad_pair_kernel<64, 1><<<gridp, kWgThreads, smemp, stp>>>(mdp, mxp, a);
+    } else if (Cout == 64) {
+      RL_SMEM_OPTIN(wgrad_pair_kernel<64, 2>);
+      wgrad_pair_kernel<64, 2><<<gridp, kWgThreads, smemp, stp>>>(mdp, mxp, a);
+    } else {
+      RL_SMEM_OPTIN(wgrad_pair_kernel<32, 1>);
+      wgrad_pair_kernel<32, 1><<<gridp, kWgThreads, smemp, stp>>>(mdp, mxp, a);
+    }
+    const int Kp = ntaps * cblk * 64;
+    wgrad_pair_reduce_kernel<<<(Cout * Kp + 255) / 256, 256, 0, stp>>>(a.partials, gridp, ntaps, cblk, Cout, a.ncols,
+                                                                      dw_krsc, accumulate);
+    RL_CHECK_LAUNCH("rl_conv2d_s1_nhwc_bf16_wgrad");
+    return RL_OK;
+  }
   if (Cout == 32) {
     // swapped-role variant: D[ci, co], dout rows are 64 bytes (SWIZZLE_64B operand)
     RL_CHECK_ARG(ntaps <= 2 * kWgTapsPerIssuer, "conv2d_s1_wgrad: too many taps for Cout = 32");
@@ -499,7 +689,7 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
   }
   const int K = ntaps * cblk * 64;
   wgrad_reduce_kernel<<<(64 * K + 255) / 256, 256, 0, st>>>(g.partials, grid, g.ngroups, g.taps_per_group, ntaps, cblk,
-                                                           g.ncols_max, g_wg_lane_map, dw_krsc, accumulate);
+                                                           g.ncols_max, g_wg_lane_map & 1, dw_krsc, accumulate);
   RL_CHECK_LAUNCH("rl_conv2d_s1_nhwc_bf16_wgrad");
   return RL_OK;
 }

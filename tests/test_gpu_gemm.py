@@ -152,10 +152,20 @@ def test_conv2d_s1_dgrad_tma_window_form(N, H, Cin, Cout, k):
 
 @pytest.mark.parametrize('N,H,Cin,Cout,k', [(5, 11, 64, 64, 3), (150, 11, 64, 64, 3), (9, 12, 128, 64, 2),
                                             (7, 21, 64, 32, 2), (160, 21, 64, 32, 2)])
-def test_conv2d_s1_wgrad_tma_window_form(N, H, Cin, Cout, k):
-    """Window-form weight gradient (positions as the GEMM K dimension, MN-major tcgen05 operands; the Cout=32
-    case uses the role-swapped SWIZZLE_64B variant) against torch autograd on the same bf16 operands."""
-    from parl_b200 import kernels as K_
+@pytest.mark.parametrize('legacy', [0, 2])
+def test_conv2d_s1_wgrad_tma_window_form(N, H, Cin, Cout, k, legacy):
+    """Window-form weight gradient (positions as the GEMM K dimension, MN-major tcgen05 operands) against torch
+    autograd on the same bf16 operands.  legacy=0: paired-tap M=128 form (two taps per instruction through the
+    descriptor's leading byte offset); legacy=2: one tap per M=64 instruction (Cout=32: role-swapped SWIZZLE_64B)."""
+    from parl_b200 import kernels as K_, _lib
+    _lib.load().rl_debug_set_wgrad_lane_map(legacy)
+    try:
+        _wgrad_case(K_, N, H, Cin, Cout, k)
+    finally:
+        _lib.load().rl_debug_set_wgrad_lane_map(0)
+
+
+def _wgrad_case(K_, N, H, Cin, Cout, k):
     g = torch.Generator(device=DEV).manual_seed(N + H + Cout)
     Ho = H - k + 1
     x = torch.randn(N, H, H, Cin, device=DEV, generator=g).to(torch.bfloat16)
