@@ -317,9 +317,11 @@ int rl_conv2d_s1_nhwc_bf16_dgrad(const void* dout_grid, const void* weight_t_krs
  * accumulators resident in TMEM over the CTA's whole position range, deterministic two-stage reduction).
  * dout_grid [N,H,W,Cout] on the input grid (zeros at invalid positions), in [N,H,W,Cin], dw_krsc [Cout, KH*KW*Cin]
  * float32 (accumulate=1 adds to it).  (Cout, Cin) = (64, 64|128), or (32, 64) where the 64-byte dout rows are the
- * SWIZZLE_64B N-operand of a role-swapped product.  Workspace: rl_conv_wgrad_workspace_bytes. */
+ * SWIZZLE_64B N-operand of a role-swapped product.  db (optional, [Cout] float32) receives the bias gradient
+ * sum_q dout_grid[q, :] from the same pass (one extra tcgen05.mma per K step against a tile of ones).
+ * Workspace: rl_conv_wgrad_workspace_bytes. */
 size_t rl_conv_wgrad_workspace_bytes(int KH, int KW, int Cin);
-int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* in, float* dw_krsc, int N, int H, int W,
+int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* in, float* dw_krsc, float* db, int N, int H, int W,
                                  int Cin, int Cout, int KH, int KW, int accumulate,
                                  void* workspace, size_t workspace_bytes, rl_stream_t stream);
 int rl_debug_set_wgrad_lane_map(int mode);

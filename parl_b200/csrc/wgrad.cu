@@ -335,6 +335,9 @@ __global__ void __launch_bounds__(256) wgrad_reduce_n32_kernel(const float* __re
 // 3x3 / 64-channel layer fits the 512 columns at once (5 pairs x 64) and no position tile is read by two CTA groups
 // (the M = 64 form read conv3's operands twice: ncu round 1, 11.9 GB for 6.3 GB of unique data).  An odd last tap
 // is paired with the window one row further down; its upper 64 lanes are never read back.
+// The bias gradient rides along: one more M = 64 instruction per K step whose A operand is a constant tile of ones,
+//     D_b[m, co] += sum_q 1 * dout[q, co]        (every row m holds the column sums; lane 0 is read back)
+// so the gradient grid is not streamed from HBM a second time by a column-sum kernel.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kWgSlotsPerIssuer = 3;      // (pair, channel-block) accumulators per issuing warp
 
@@ -342,7 +345,8 @@ struct WgradPairArgs {
   float* partials;                    // [gridDim.x][128 lanes][ncols] raw TMEM dumps
   int W, KW, ntaps;
   int wrows, num_tiles, stages;
-  int npairs, ncols;                  // ncols = npairs * CBLK * COUT
+  int npairs, ncols;                  // ncols = npairs * CBLK * COUT (+ 2 * COUT bias-gradient columns)
+  int bias;                           // 1: also accumulate the column sums of dout (bias gradient) in TMEM
 };
 
 template <int COUT, int CBLK>
@@ -371,6 +375,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_pair_kernel(const __grid_
     fence_mbar_init();
   }
   if (warp == 1) w_tmem_alloc(&tmem_base_smem, tmem_cols);
+  // constant A operand of the bias-gradient instruction: 16 K-rows x 64 bf16 ones, after the stage ring
+  unsigned char* s_ones = smem + nstages * stage_bytes;
+  if (g.bias) {
+    for (int i = threadIdx.x; i < 512; i += kWgThreads) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3F803F80u;
+    fence_proxy_async_smem();               // generic-proxy stores -> visible to the tensor core's async proxy
+  }
   w_fence_before();
   __syncthreads();
   w_fence_after();
@@ -408,6 +418,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_pair_kernel(const __grid_
         a_off[j] = (uint32_t)(o0 * 8 + cb * (win_bytes >> 4)) + ((uint32_t)(delta * 8) << 16);
       }
       const uint32_t lo0 = smem_u32(smem) >> 4, stage16 = (uint32_t)stage_bytes >> 4;
+      constexpr uint32_t idesc_bias = w_idesc_bf16_mn(64, COUT);
+      // bias gradient: each issuer takes every other K step into its OWN accumulator (no ordering between issuers)
+      const bool do_bias = g.bias != 0;
+      const uint32_t issuer = warp == 1 ? 0u : 1u;
+      const uint32_t ones_lo = (smem_u32(s_ones) >> 4) + kWgLoLbo1;
+      const uint32_t d_bias = tmem_base + (uint32_t)(nslots * COUT) + issuer * COUT;
       uint32_t s = 0, par = 0, acc0 = 0;
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
         mbar_wait(&full_bar[s], par);
@@ -424,6 +440,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_pair_kernel(const __grid_
               w_umma(d_tmem, w_desc(kWgHiSw128, a_lo + kk * 128u), w_desc(hiB, b_lo + kk * kstepB), idesc,
                      kk == 0 ? acc0 : 1u);
           }
+        }
+        if (do_bias) {
+#pragma unroll
+          for (int k2 = 0; k2 < kWgBM / 32; ++k2)
+            w_umma(d_bias, w_desc(kWgHiSw128, ones_lo), w_desc(hiB, b_lo + (2u * k2 + issuer) * kstepB), idesc_bias,
+                   k2 == 0 ? acc0 : 1u);
         }
         w_commit(&empty_bar[s]);
         acc0 = 1u;
@@ -451,13 +473,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_pair_kernel(const __grid_
 }
 
 // dW[co][(tap, cb, ci)] from the [lane = (tap & 1) * 64 + ci][col = ((tap >> 1) * cblk + cb) * cout + co] partials,
-// summed over the CTAs in index order (deterministic)
+// summed over the CTAs in index order (deterministic); db[co] from lane 0 of the bias-gradient columns
 __global__ void __launch_bounds__(256) wgrad_pair_reduce_kernel(const float* __restrict__ partials, int nctas, int ntaps,
                                                                 int cblk, int cout, int ncols, float* __restrict__ dw,
-                                                                int accumulate) {
+                                                                float* __restrict__ db, int accumulate) {
   const int K = ntaps * cblk * 64;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= cout * K) return;
+  if (idx >= cout * K) {
+    const int co = idx - cout * K;
+    if (db && co < cout) {
+      const int col = ((ntaps + 1) / 2) * cblk * cout + co;          // two accumulators (one per issuer): col, col + cout
+      float acc = 0.f;
+      for (int c = 0; c < nctas; ++c) acc += partials[(size_t)c * 128 * ncols + col] + partials[(size_t)c * 128 * ncols + col + cout];
+      db[co] = accumulate ? db[co] + acc : acc;
+    }
+    return;
+  }
   const int co = idx / K, k = idx - co * K;
   const int tap = k / (cblk * 64), within = k - tap * cblk * 64, cb = within >> 6, ci = within & 63;
   const int ln = (tap & 1) * 64 + ci, col = ((tap >> 1) * cblk + cb) * cout + co;
@@ -563,9 +594,16 @@ extern "C" size_t rl_conv_wgrad_workspace_bytes(int KH, int KW, int Cin) {
   return (size_t)160 * 128 * (size_t)(per * cblk * 64) * sizeof(float) + 4096;
 }
 
-extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* in, float* dw_krsc, int N, int H, int W,
-                                            int Cin, int Cout, int KH, int KW, int accumulate, void* workspace,
-                                            size_t workspace_bytes, rl_stream_t stream) {
+static int wgrad_legacy_bias(const void* dout_grid, long long Q, int Cout, float* db, int accumulate, void* workspace,
+                             size_t workspace_bytes, rl_stream_t stream) {
+  if (!db) return RL_OK;
+  RL_CHECK_ARG(!accumulate, "conv2d_s1_wgrad: accumulate with a bias gradient needs the paired-tap form");
+  return rl_colsum_bf16(dout_grid, Q, Cout, db, workspace, workspace_bytes, stream);
+}
+
+extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* in, float* dw_krsc, float* db, int N,
+                                            int H, int W, int Cin, int Cout, int KH, int KW, int accumulate,
+                                            void* workspace, size_t workspace_bytes, rl_stream_t stream) {
   RL_CHECK_ARG(dout_grid && in && dw_krsc && workspace && N > 0, "conv2d_s1_wgrad: bad argument");
   RL_CHECK_ARG(aligned16(dout_grid) && aligned16(in) && aligned16(workspace), "conv2d_s1_wgrad: alignment");
   RL_CHECK_ARG((Cout == 64 && (Cin == 64 || Cin == 128)) || (Cout == 32 && Cin == 64),
@@ -585,7 +623,9 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
     WgradPairArgs a;
     a.partials = reinterpret_cast<float*>(workspace);
     a.W = W, a.KW = KW, a.ntaps = ntaps, a.wrows = g.wrows + 1;       // + the dummy partner row of an odd last tap
-    a.num_tiles = g.num_tiles, a.npairs = npairs, a.ncols = npairs * cblk * Cout;
+    a.num_tiles = g.num_tiles, a.npairs = npairs, a.bias = db ? 1 : 0;
+    a.ncols = npairs * cblk * Cout + (db ? 2 * Cout : 0);            // + one bias accumulator per issuer
+    RL_CHECK_ARG(a.ncols <= 512, "conv2d_s1_wgrad: accumulators exceed the 512 TMEM columns");
     RL_CHECK_ARG(a.wrows <= 256, "conv2d_s1_wgrad: window too tall");
     int devp = 0, smsp = 148;
     cudaGetDevice(&devp);
@@ -604,9 +644,9 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
     }
     const size_t winp = (size_t)((a.wrows * 128 + 1023) & ~1023);
     const size_t stagep = (size_t)cblk * winp + (size_t)kWgBM * Cout * 2;
-    long long nstp = (long long)((218 * 1024) / stagep);
+    long long nstp = (long long)((216 * 1024) / stagep);
     a.stages = (int)(nstp > kWgMaxStages ? kWgMaxStages : (nstp < 2 ? 2 : nstp));
-    const size_t smemp = (size_t)a.stages * stagep + 1024;
+    const size_t smemp = (size_t)a.stages * stagep + 2048 + 1024;      // + the 2 KB tile of ones
     cudaStream_t stp = (cudaStream_t)stream;
     if (Cout == 64 && cblk == 1) {
       RL_SMEM_OPTIN(wgrad_pair_kernel<64, 1>);
@@ -619,8 +659,8 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
       wgrad_pair_kernel<32, 1><<<gridp, kWgThreads, smemp, stp>>>(mdp, mxp, a);
     }
     const int Kp = ntaps * cblk * 64;
-    wgrad_pair_reduce_kernel<<<(Cout * Kp + 255) / 256, 256, 0, stp>>>(a.partials, gridp, ntaps, cblk, Cout, a.ncols,
-                                                                      dw_krsc, accumulate);
+    wgrad_pair_reduce_kernel<<<(Cout * Kp + Cout + 255) / 256, 256, 0, stp>>>(a.partials, gridp, ntaps, cblk, Cout,
+                                                                             a.ncols, dw_krsc, db, accumulate);
     RL_CHECK_LAUNCH("rl_conv2d_s1_nhwc_bf16_wgrad");
     return RL_OK;
   }
@@ -651,7 +691,7 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
     wgrad_reduce_n32_kernel<<<(32 * ntaps * 64 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
         g.partials, grid32, ntaps, g.ncols_max, dw_krsc, accumulate);
     RL_CHECK_LAUNCH("rl_conv2d_s1_nhwc_bf16_wgrad");
-    return RL_OK;
+    return wgrad_legacy_bias(dout_grid, Q, Cout, db, accumulate, workspace, workspace_bytes, stream);
   }
   int cap = 512 / (cblk * 64);                       // taps whose accumulators fit the 512 TMEM columns
   if (cap > ntaps) cap = ntaps;
@@ -691,7 +731,7 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
   wgrad_reduce_kernel<<<(64 * K + 255) / 256, 256, 0, st>>>(g.partials, grid, g.ngroups, g.taps_per_group, ntaps, cblk,
                                                            g.ncols_max, g_wg_lane_map & 1, dw_krsc, accumulate);
   RL_CHECK_LAUNCH("rl_conv2d_s1_nhwc_bf16_wgrad");
-  return RL_OK;
+  return wgrad_legacy_bias(dout_grid, Q, Cout, db, accumulate, workspace, workspace_bytes, stream);
 }
 
 extern "C" int rl_colsum_bf16(const void* x, long long rows, int C, float* out, void* workspace, size_t workspace_bytes,

@@ -8,7 +8,7 @@ Backward (after the fused loss kernel delivered d_logits / d_values):
     heads/fc data gradients : rl_gemm_bf16_tn_masked (ReLU masks fused in the epilogue)
     conv data gradients     : rl_conv2d_s1_nhwc_bf16_dgrad (same windows, flipped taps, ReLU mask fused)
     conv weight gradients   : rl_conv2d_s1_nhwc_bf16_wgrad (positions as the GEMM K dimension, TMEM-resident)
-    bias gradients          : rl_colsum_bf16
+    bias gradients          : from the weight-gradient pass (one extra tcgen05.mma per K step against ones); fc: rl_colsum_bf16
     fc / head weight gradients: two plain library GEMMs (torch.matmul -> cuBLAS), the only library calls left
 Activations for the whole learner batch stay resident in HBM (about 120 KB per sample in bf16).
 Gradients are written into the parameters' ``.grad`` views of the FlatAdam buffer in the reference layouts.
@@ -138,16 +138,16 @@ class AtariTrainNet(object):
                 K.gemm_bf16_tn_masked(self.dh, self.wfcT[y * 576:(y + 1) * 576], a3f[:, y * 576:(y + 1) * 576],
                                       da3[:, y * 704:y * 704 + 576])
         # conv3
-        self._bias_grad(self.da3g, self.dbs[1], m.conv3.bias)
-        K.conv2d_s1_nhwc_bf16_wgrad(self.da3g, self.a2, 3, 3, dw_krsc=self.dw3)
+        K.conv2d_s1_nhwc_bf16_wgrad(self.da3g, self.a2, 3, 3, dw_krsc=self.dw3, db=self.dbs[1])
         m.conv3.weight.grad.copy_(self.dw3.view(64, 3, 3, 64).permute(0, 3, 1, 2))
+        m.conv3.bias.grad.copy_(self.dbs[1])
         K.conv2d_s1_nhwc_bf16_dgrad(self.da3g, self.w3T, 3, 3, self.da2g, act_mask=self.a2)   # onto the 12x12 grid
         # conv2 (2x2 block form)
-        self._bias_grad(self.da2g, self.dbs[2], m.conv2.bias)
-        K.conv2d_s1_nhwc_bf16_wgrad(self.da2g, self.a1, 2, 2, dw_krsc=self.dw2)
+        K.conv2d_s1_nhwc_bf16_wgrad(self.da2g, self.a1, 2, 2, dw_krsc=self.dw2, db=self.dbs[2])
         m.conv2.weight.grad.copy_(self.dw2.view(64, 2, 2, 2, 2, 32).permute(0, 5, 1, 3, 2, 4).reshape(64, 32, 4, 4))
+        m.conv2.bias.grad.copy_(self.dbs[2])
         K.conv2d_s1_nhwc_bf16_dgrad(self.da2g, self.w2T, 2, 2, self.da1g, act_mask=self.a1, out_mode=2)
         # conv1 (4x4 block form): 64-byte gradient rows -> role-swapped weight-gradient kernel (SWIZZLE_64B operand)
-        self._bias_grad(self.da1g, self.dbs[3], m.conv1.bias)
-        K.conv2d_s1_nhwc_bf16_wgrad(self.da1g, self._x0_in, 2, 2, dw_krsc=self.dw1)
+        K.conv2d_s1_nhwc_bf16_wgrad(self.da1g, self._x0_in, 2, 2, dw_krsc=self.dw1, db=self.dbs[3])
         m.conv1.weight.grad.copy_(self.dw1.view(32, 2, 2, 4, 4, 4).permute(0, 5, 1, 3, 2, 4).reshape(32, 4, 8, 8))
+        m.conv1.bias.grad.copy_(self.dbs[3])

@@ -441,16 +441,17 @@ def _raw_ws(device, nbytes, key):
     return ws
 
 
-def conv2d_s1_nhwc_bf16_wgrad(dout_grid, x, KH, KW, dw_krsc=None, accumulate=False):
-    """Weight gradient of the TMA-window conv (rl_conv2d_s1_nhwc_bf16_wgrad) -> dw [Cout, KH*KW*Cin] float32."""
-    require_cuda(dout_grid, x, dw_krsc)
+def conv2d_s1_nhwc_bf16_wgrad(dout_grid, x, KH, KW, dw_krsc=None, accumulate=False, db=None):
+    """Weight gradient of the TMA-window conv (rl_conv2d_s1_nhwc_bf16_wgrad) -> dw [Cout, KH*KW*Cin] float32;
+    db (optional [Cout] float32) receives the bias gradient from the same pass."""
+    require_cuda(dout_grid, x, dw_krsc, db)
     N, H, W, Cout = dout_grid.shape
     Cin = x.shape[-1]
     assert x.shape[:3] == dout_grid.shape[:3]
     if dw_krsc is None:
         dw_krsc = torch.empty((Cout, KH * KW * Cin), dtype=torch.float32, device=x.device)
     ws = _raw_ws(x.device, _lib.load().rl_conv_wgrad_workspace_bytes(KH, KW, Cin), 'wgrad')
-    check(_lib.load().rl_conv2d_s1_nhwc_bf16_wgrad(ptr(dout_grid), ptr(x), ptr(dw_krsc), N, H, W, Cin, Cout, KH, KW,
+    check(_lib.load().rl_conv2d_s1_nhwc_bf16_wgrad(ptr(dout_grid), ptr(x), ptr(dw_krsc), ptr(db), N, H, W, Cin, Cout, KH, KW,
                                                    1 if accumulate else 0, ptr(ws), ws.numel(), stream()),
           'conv2d_s1_nhwc_bf16_wgrad')
     return dw_krsc

@@ -175,8 +175,11 @@ def _wgrad_case(K_, N, H, Cin, Cout, k):
     ref = w.grad.permute(0, 2, 3, 1).reshape(Cout, -1)
     dgrid = torch.zeros(N, H, H, Cout, device=DEV, dtype=torch.bfloat16)
     dgrid[:, :Ho, :Ho] = dout
-    dw = K_.conv2d_s1_nhwc_bf16_wgrad(dgrid, x, k, k)
+    dbf = torch.empty(Cout, device=DEV)
+    dw = K_.conv2d_s1_nhwc_bf16_wgrad(dgrid, x, k, k, db=dbf)
     torch.cuda.synchronize()
     assert (dw - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
     db = K_.colsum_bf16(dgrid)
-    assert (db - dgrid.float().sum((0, 1, 2))).abs().max().item() < 1e-2
+    ref_db = dgrid.float().sum((0, 1, 2))
+    assert (db - ref_db).abs().max().item() < 1e-2
+    assert (dbf - ref_db).abs().max().item() < 1e-3 * max(1.0, ref_db.abs().max().item())   # fused bias gradient
