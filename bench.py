@@ -233,6 +233,17 @@ def main():
     net_roof = dict(bound='tensor', what='policy/value network (tcgen05 conv/GEMM kernels), per GPU', achieved=ach_tf,
                     peak=tpeak, unit='TFLOP/s', frac=ach_tf / tpeak, peak_source=tsrc)
 
+    # HBM view of the whole step: with the convolutions at 2x2/3x3 filters on 32..128 channels the network kernels are
+    # bound by ACTIVATION traffic, not by the tensor pipe.  Algorithmic bytes per env-step of the dataflow as designed
+    # (bf16 activations, every tensor read/written once per kernel that needs it):
+    #   rollout 264 KB (gather 84.7, conv1 82.0, conv2 52.4, conv3 25.9, fc+heads 12.4, env frame 7.1)
+    #   learner 538 KB (forward 172.7, mask/scatter + fc products 61.1, dgrad 132.9, wgrad 170.9)
+    step_bytes = (264.5e3 + 537.6e3) * T_STEPS * B
+    ach_hbm = step_bytes * args.steps / elapsed / 1e9
+    step_roof = dict(bound='hbm', what='whole step: activation traffic of the network kernels, per GPU',
+                     achieved=ach_hbm, peak=peak, unit='GB/s', frac=ach_hbm / peak, peak_source=peak_src,
+                     algorithmic_bytes_per_env_step=802.1e3) if eng.train_net is not None else None
+
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(eng, args, world, dev)
@@ -257,9 +268,12 @@ def main():
                                 else 'sequential',
                                 network='hand-written tcgen05 kernels (actor fwd; learner fwd+dgrad+wgrad)' if
                                 eng.train_net is not None else 'torch',
-                                l2_policy='per-step working set (obs ring %.1f GB/GPU) >> 126 MB L2' %
-                                          ((T_STEPS + 4) * B * 7056 / 1e9)),
-                    gpu_launches=launches, clocks=clocks, roofline=roof, roofline_network=net_roof, e2e=e2e,
+                                l2_policy='per-step working set (frame ring %.1f GB + observation plane %.1f GB + '
+                                          'activations %.1f GB per GPU) >> 126 MB L2; K1 timed alone with L2 flushed' %
+                                          ((T_STEPS + 4) * B * 7056 / 1e9, T_STEPS * B * 56448 / 1e9,
+                                           T_STEPS * B * 120e3 / 1e9)),
+                    gpu_launches=launches, clocks=clocks, roofline=roof, roofline_network=net_roof, roofline_step=step_roof,
+                    e2e=e2e,
                     cpu_baseline=cpu,
                     learner_losses=[float(x) for x in losses[:5].tolist()])
         print(json.dumps(line))
