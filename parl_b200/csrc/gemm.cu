@@ -289,7 +289,9 @@ static int gemm_launch(const void* A, const void* B, const float* bias, void* C,
   int BN = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
   // small problems: prefer narrower tiles until the grid covers about two thirds of the 148 SMs — but no further:
   // one thread issues every tcgen05.mma at ~50 cycles each, so an N = 64 tile (32 tensor-core cycles per
-  // instruction) is issue-bound while N = 128 is not (measured: 4096 x 512 x 5184 at BN 64 = two waves, 31 us)
+  // instruction) is issue-bound while N = 128 is not.  Measured for 4096 x 512 x 5184 (the actor's fc layer): BN 64
+  // = 256 CTAs 30.8 us, BN 128 = 128 CTAs 32.4 us, BN 256 = 64 CTAs 40.0 us — all L2-bandwidth bound (340 MB of
+  // operand re-reads per call); the fix is a 2-CTA cluster with TMA multicast, not the tile shape.
   const long long mt = (M + kGemmBM - 1) / kGemmBM;
   while (BN > 64 && mt * ((N + BN - 1) / BN) < 100) BN >>= 1;
   alignas(64) CUtensorMap ma, mb;

@@ -183,3 +183,36 @@ def _wgrad_case(K_, N, H, Cin, Cout, k):
     ref_db = dgrid.float().sum((0, 1, 2))
     assert (db - ref_db).abs().max().item() < 1e-2
     assert (dbf - ref_db).abs().max().item() < 1e-3 * max(1.0, ref_db.abs().max().item())   # fused bias gradient
+
+
+def test_conv2d_s1_wgrad_accumulate_and_bias():
+    """accumulate=1 adds the weight AND the fused bias gradient to what is already there (paired-tap form)."""
+    from parl_b200 import kernels as K_
+    g = torch.Generator(device=DEV).manual_seed(11)
+    N, H, Cin, Cout, k = 20, 12, 128, 64, 2
+    x = torch.randn(N, H, H, Cin, device=DEV, generator=g).to(torch.bfloat16)
+    dgrid = torch.zeros(N, H, H, Cout, device=DEV, dtype=torch.bfloat16)
+    dgrid[:, :H - k + 1, :H - k + 1] = torch.randn(N, H - k + 1, H - k + 1, Cout, device=DEV, generator=g).to(torch.bfloat16)
+    db1 = torch.empty(Cout, device=DEV)
+    dw1 = K_.conv2d_s1_nhwc_bf16_wgrad(dgrid, x, k, k, db=db1).clone()
+    dw2, db2 = dw1.clone(), db1.clone()
+    K_.conv2d_s1_nhwc_bf16_wgrad(dgrid, x, k, k, dw_krsc=dw2, accumulate=True, db=db2)
+    torch.cuda.synchronize()
+    assert torch.equal(dw2, dw1 + dw1) and torch.equal(db2, db1 + db1)       # deterministic: exactly twice
+    assert (db1 - dgrid.float().sum((0, 1, 2))).abs().max().item() < 1e-3 * max(1.0, db1.abs().max().item())
+
+
+def test_obs_gather_s2d_matches_reference_layout():
+    """rl_obs_stack_gather out_dtype 3 (smem-staged, magic-number u8->float) against a torch restatement:
+    out[n,Y,X,(dy*4+dx)*4+c] = bf16(frame_c[4Y+dy-1, 4X+dx-1] / 255), zero outside the image."""
+    from parl_b200 import kernels as K_
+    g = torch.Generator(device=DEV).manual_seed(5)
+    n = 37
+    obs = torch.randint(0, 256, (n, 4, 84, 84), device=DEV, generator=g, dtype=torch.uint8)
+    out = torch.empty((n, 21, 21, 64), device=DEV, dtype=torch.bfloat16)
+    K_.obs_stack_gather(obs, None, 0, 1, out, scale=1.0 / 255.0, s2d=True)
+    pad = torch.zeros((n, 4, 88, 88), device=DEV)
+    pad[:, :, 1:85, 1:85] = obs.float()
+    ref = (pad[:, :, :84, :84] * (1.0 / 255.0)).view(n, 4, 21, 4, 21, 4).permute(0, 2, 4, 3, 5, 1).reshape(n, 21, 21, 64)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref.to(torch.bfloat16))
