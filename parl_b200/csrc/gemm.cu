@@ -94,6 +94,10 @@ struct GemmArgs {
   int relu, out_f32;
   const __nv_bfloat16* mask;   // optional [M, ldm] saved post-ReLU activation: C *= (mask > 0)  (ReLU backward)
   int ldm;
+  // split-K (few output tiles, long K — the actor's fc layer at small batch): blockIdx.z owns kb_per_split k-blocks
+  // and dumps its raw fp32 accumulator tile to partial[z][row][col]; gemm_splitk_reduce_kernel finishes the epilogue
+  float* partial;              // NULL: no split
+  int kb_per_split, ldp, mpad;
 };
 
 template <int BN>
@@ -113,7 +117,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tn_kernel(const __g
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * BN;
-  const int num_kb = (g.K + kGemmBK - 1) / kGemmBK;
+  const int num_kb_all = (g.K + kGemmBK - 1) / kGemmBK;
+  const int kb0 = g.partial ? (int)blockIdx.z * g.kb_per_split : 0;
+  const int num_kb = g.partial ? min(g.kb_per_split, num_kb_all - kb0) : num_kb_all;     // this CTA's k-blocks
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -139,8 +145,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tn_kernel(const __g
         const uint32_t ph = (kb / kGemmStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1u);                                  // slot free (first pass: immediately)
         mbar_arrive_expect_tx(&full_bar[s], A_STAGE + B_STAGE);
-        tma_load_2d(sA + s * A_STAGE, &map_a, kb * kGemmBK, m0, &full_bar[s]);
-        tma_load_2d(sB + s * B_STAGE, &map_b, kb * kGemmBK, n0, &full_bar[s]);
+        tma_load_2d(sA + s * A_STAGE, &map_a, (kb0 + kb) * kGemmBK, m0, &full_bar[s]);
+        tma_load_2d(sB + s * B_STAGE, &map_b, (kb0 + kb) * kGemmBK, n0, &full_bar[s]);
       }
     }
   } else if (warp == 1) {
@@ -174,6 +180,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tn_kernel(const __g
     for (int c0 = 0; c0 < BN; c0 += 16) {
       float v[16];
       tmem_ld16(tlane + (uint32_t)c0, v);
+      if (g.partial) {
+        // raw accumulator dump (padded tile grid: no bounds), finished by gemm_splitk_reduce_kernel
+        float* dst = g.partial + ((size_t)blockIdx.z * g.mpad + row) * g.ldp + n0 + c0;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        continue;
+      }
       if (row < g.M) {
         const int col = n0 + c0;
 #pragma unroll
@@ -229,6 +242,29 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tn_kernel(const __g
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// C[row, col] = act(sum_z partial[z][row][col] + bias[col]) in split order (deterministic)
+__global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(const float* __restrict__ partial, int splits, int mpad,
+                                                                 int ldp, const GemmArgs g) {
+  const int n4 = (g.N + 3) >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)g.M * n4) return;
+  const int row = (int)(idx / n4), col = (int)(idx - (long long)row * n4) * 4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < splits; ++z) {
+    const float4 p = *reinterpret_cast<const float4*>(partial + ((size_t)z * mpad + row) * ldp + col);
+    a.x += p.x, a.y += p.y, a.z += p.z, a.w += p.w;
+  }
+  float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (col + i >= g.N) break;
+    float x = v[i] + (g.bias ? g.bias[col + i] : 0.f);
+    x = g.relu ? fmaxf(x, 0.f) : x;
+    if (g.out_f32) reinterpret_cast<float*>(g.C)[(size_t)row * g.ldc + col + i] = x;
+    else reinterpret_cast<__nv_bfloat16*>(g.C)[(size_t)row * g.ldc + col + i] = __float2bfloat16(x);
+  }
+}
+
 // rank-2 bf16 tensor map {K (contiguous), rows}, box {64, box_rows}, SWIZZLE_128B
 static int make_tensor_map_bf16_sw128(CUtensorMap* map, const void* base, uint64_t K, uint64_t rows, uint64_t pitch_bytes,
                                       uint32_t box_rows) {
@@ -254,10 +290,10 @@ static int make_tensor_map_bf16_sw128(CUtensorMap* map, const void* base, uint64
 }
 
 template <int BN>
-static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, int splits, cudaStream_t st) {
   const size_t smem = (size_t)kGemmStages * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 1024;
   RL_SMEM_OPTIN(gemm_bf16_tn_kernel<BN>);
-  dim3 grid((g.M + kGemmBM - 1) / kGemmBM, (g.N + BN - 1) / BN);
+  dim3 grid((g.M + kGemmBM - 1) / kGemmBM, (g.N + BN - 1) / BN, splits);
   gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, smem, st>>>(ma, mb, g);
   return 0;
 }
@@ -267,21 +303,30 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmA
 using namespace rl;
 
 static int gemm_launch(const void* A, const void* B, const float* bias, void* C, int M, int N, int K, int lda, int ldb,
-                       int ldc, int relu, int out_f32, const void* mask, int ldm, rl_stream_t stream);
+                       int ldc, int relu, int out_f32, const void* mask, int ldm, void* workspace, size_t workspace_bytes,
+                       rl_stream_t stream);
 
 extern "C" int rl_gemm_bf16_tn(const void* A, const void* B, const float* bias, void* C, int M, int N, int K, int lda,
                                int ldb, int ldc, int relu, int out_f32, rl_stream_t stream) {
-  return gemm_launch(A, B, bias, C, M, N, K, lda, ldb, ldc, relu, out_f32, nullptr, 0, stream);
+  return gemm_launch(A, B, bias, C, M, N, K, lda, ldb, ldc, relu, out_f32, nullptr, 0, nullptr, 0, stream);
+}
+
+extern "C" int rl_gemm_bf16_tn_splitk(const void* A, const void* B, const float* bias, void* C, int M, int N, int K,
+                                      int lda, int ldb, int ldc, int relu, int out_f32, void* workspace,
+                                      size_t workspace_bytes, rl_stream_t stream) {
+  RL_CHECK_ARG(!workspace || aligned16(workspace), "gemm_bf16_tn_splitk: workspace must be 16-byte aligned");
+  return gemm_launch(A, B, bias, C, M, N, K, lda, ldb, ldc, relu, out_f32, nullptr, 0, workspace, workspace_bytes, stream);
 }
 
 extern "C" int rl_gemm_bf16_tn_masked(const void* A, const void* B, void* C, const void* mask, int M, int N, int K,
                                       int lda, int ldb, int ldc, int ldm, int out_f32, rl_stream_t stream) {
   RL_CHECK_ARG(mask && ldm >= N, "gemm_bf16_tn_masked: mask required, ldm >= N");
-  return gemm_launch(A, B, nullptr, C, M, N, K, lda, ldb, ldc, 0, out_f32, mask, ldm, stream);
+  return gemm_launch(A, B, nullptr, C, M, N, K, lda, ldb, ldc, 0, out_f32, mask, ldm, nullptr, 0, stream);
 }
 
 static int gemm_launch(const void* A, const void* B, const float* bias, void* C, int M, int N, int K, int lda, int ldb,
-                       int ldc, int relu, int out_f32, const void* mask, int ldm, rl_stream_t stream) {
+                       int ldc, int relu, int out_f32, const void* mask, int ldm, void* workspace, size_t workspace_bytes,
+                       rl_stream_t stream) {
   RL_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "gemm_bf16_tn: bad argument");
   RL_CHECK_ARG(aligned16(A) && aligned16(B) && aligned16(C), "gemm_bf16_tn: pointers must be 16-byte aligned");
   RL_CHECK_ARG(lda >= K && ldb >= K && ldc >= N && (lda % 8) == 0 && (ldb % 8) == 0,
@@ -303,12 +348,32 @@ static int gemm_launch(const void* A, const void* B, const float* bias, void* C,
   GemmArgs g;
   g.bias = bias, g.C = C, g.M = M, g.N = N, g.K = K, g.ldc = ldc, g.relu = relu, g.out_f32 = out_f32;
   g.mask = (const __nv_bfloat16*)mask, g.ldm = ldm;
+  g.partial = nullptr, g.kb_per_split = 0, g.ldp = 0, g.mpad = 0;
+  // split-K: fewer output tiles than half the SMs and a long reduction (one CTA would walk >= 16 k-blocks alone)
+  const int nt = (N + BN - 1) / BN, num_kb = (K + kGemmBK - 1) / kGemmBK;
+  int splits = 1;
+  if (workspace && !mask && mt * nt * 2 <= 148 && num_kb >= 16) {
+    int want = (int)(148 / (mt * nt));
+    if (want > num_kb / 8) want = num_kb / 8;
+    if (want > 8) want = 8;
+    const int per = (num_kb + want - 1) / want;
+    want = (num_kb + per - 1) / per;                                  // no empty split
+    const size_t need = (size_t)want * (size_t)(mt * kGemmBM) * (size_t)(nt * BN) * sizeof(float);
+    if (want > 1 && need <= workspace_bytes) {
+      splits = want;
+      g.partial = reinterpret_cast<float*>(workspace), g.kb_per_split = per, g.ldp = nt * BN, g.mpad = (int)mt * kGemmBM;
+    }
+  }
   cudaStream_t st = (cudaStream_t)stream;
   switch (BN) {
-    case 256: launch_gemm<256>(ma, mb, g, st); break;
-    case 128: launch_gemm<128>(ma, mb, g, st); break;
-    case 64: launch_gemm<64>(ma, mb, g, st); break;
-    default: launch_gemm<32>(ma, mb, g, st); break;
+    case 256: launch_gemm<256>(ma, mb, g, splits, st); break;
+    case 128: launch_gemm<128>(ma, mb, g, splits, st); break;
+    case 64: launch_gemm<64>(ma, mb, g, splits, st); break;
+    default: launch_gemm<32>(ma, mb, g, splits, st); break;
+  }
+  if (splits > 1) {
+    const long long items = (long long)M * ((N + 3) / 4);
+    gemm_splitk_reduce_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(g.partial, splits, g.mpad, g.ldp, g);
   }
   RL_CHECK_LAUNCH("rl_gemm_bf16_tn");
   return RL_OK;

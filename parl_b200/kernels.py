@@ -385,6 +385,15 @@ def gemm_bf16_tn(a, b, bias=None, relu=False, out_dtype=torch.bfloat16, out=None
     if out is None:
         out = torch.empty((M, N), dtype=out_dtype, device=a.device)
     assert out.dtype in (torch.bfloat16, torch.float32)
+    if M <= 2048 and K >= 1024:
+        # few output tiles, long reduction (the actor's fc layer at small per-GPU batch): split-K with a per-stream
+        # workspace (two streams never share partials)
+        ws = _raw_ws(a.device, 8 << 20, 'gemm_splitk_%d' % torch.cuda.current_stream(a.device).cuda_stream)
+        check(_lib.load().rl_gemm_bf16_tn_splitk(ptr(a), ptr(b), ptr(bias), ptr(out), M, N, K, a.stride(0), b.stride(0),
+                                                 out.stride(0), 1 if relu else 0,
+                                                 1 if out.dtype == torch.float32 else 0, ptr(ws), ws.numel(), stream()),
+              'gemm_bf16_tn_splitk')
+        return out
     check(_lib.load().rl_gemm_bf16_tn(ptr(a), ptr(b), ptr(bias), ptr(out), M, N, K, a.stride(0), b.stride(0),
                                       out.stride(0), 1 if relu else 0, 1 if out.dtype == torch.float32 else 0,
                                       stream()), 'gemm_bf16_tn')
