@@ -1,6 +1,6 @@
-"""TimeStat context manager (parl/utils/time_stat.py:21-52): windowed mean of wall-clock spans,
-e.g. ``with learn_time_stat: agent.learn(...)`` -> ``learn_time_s`` metric."""
-import time
+"""``with stat: ...`` wall-clock spans with sliding-window statistics — same surface as
+parl/utils/time_stat.py:21-52 (e.g. ``with learn_time_stat: agent.learn(...)`` -> the ``learn_time_s`` metric)."""
+from time import perf_counter
 
 from .window_stat import WindowStat
 
@@ -10,22 +10,17 @@ __all__ = ['TimeStat']
 class TimeStat(object):
     def __init__(self, window_size=1):
         self.time_samples = WindowStat(window_size)
-        self._start_time = None
+        self._t0 = None
 
     def __enter__(self):
-        self._start_time = time.time()
+        self._t0 = perf_counter()
+        return self
 
     def __exit__(self, exc_type, exc, tb):
-        self.time_samples.add(time.time() - self._start_time)
+        self.time_samples.add(perf_counter() - self._t0)
+        return False
 
-    @property
-    def mean(self):
-        return self.time_samples.mean
-
-    @property
-    def min(self):
-        return self.time_samples.min
-
-    @property
-    def max(self):
-        return self.time_samples.max
+    def __getattr__(self, name):                           # mean / min / max of the recorded spans
+        if name in ('mean', 'min', 'max'):
+            return getattr(self.time_samples, name)
+        raise AttributeError(name)

@@ -1,31 +1,25 @@
-"""WindowStat (parl/utils/window_stat.py:20-54): mean/min/max over the last ``window_size`` samples."""
-import numpy as np
+"""Sliding-window statistics of scalar samples — same surface as parl/utils/window_stat.py:20-54
+(``add``, ``mean``, ``min``, ``max``, ``count``; the three statistics are ``None`` before the first sample)."""
+from collections import deque
 
 __all__ = ['WindowStat']
 
 
+def _stat(reduce_fn):
+    def getter(self):
+        return float(reduce_fn(self._window)) if self._window else None
+    return property(getter)
+
+
 class WindowStat(object):
     def __init__(self, window_size):
-        self.items = [None] * window_size
-        self.idx = 0
-        self.count = 0
+        self._window = deque(maxlen=int(window_size))     # the deque drops the oldest sample by itself
+        self.count = 0                                     # samples ever added
 
     def add(self, obj):
-        self.items[self.idx] = obj
-        self.idx = (self.idx + 1) % len(self.items)
+        self._window.append(float(obj))
         self.count += 1
 
-    def _valid(self):
-        return self.items[:min(self.count, len(self.items))]
-
-    @property
-    def mean(self):
-        return float(np.mean(self._valid())) if self.count > 0 else None
-
-    @property
-    def min(self):
-        return float(np.min(self._valid())) if self.count > 0 else None
-
-    @property
-    def max(self):
-        return float(np.max(self._valid())) if self.count > 0 else None
+    mean = _stat(lambda w: sum(w) / len(w))
+    min = _stat(min)
+    max = _stat(max)

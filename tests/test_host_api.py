@@ -184,6 +184,8 @@ def test_schedulers_and_stats():
     from parl_b200.utils import PiecewiseScheduler, LinearDecayScheduler, WindowStat, TimeStat
     s = PiecewiseScheduler([(0, 0.001), (20000, 0.0005), (40000, 0.0001)])     # impala_config.py:36
     assert s.step(1000) == 0.001 and s.step(19000) == 0.0005 and s.step(30000) == 0.0001
+    s2 = PiecewiseScheduler([(0, 1.0), (10, 2.0), (20, 3.0)])
+    assert s2.step(25) == 2.0 and s2.step(1) == 3.0        # the reference moves one segment per call (scheduler.py:52-60)
     ld = LinearDecayScheduler(0.001, 100)
     assert abs(ld.step(50) - 0.0005) < 1e-12 and ld.step(100) == 0.0
     w = WindowStat(3)
