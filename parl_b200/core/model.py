@@ -5,6 +5,8 @@ reference's numpy-dict contract (one entry per ``state_dict`` key, in order) and
 ``sync_weights_to`` keeps ``target = decay*target + (1-decay)*self``
 (behaviours pinned by parl/core/torch/tests/model_base_test_torch.py:53-335).
 """
+from collections import OrderedDict
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -23,15 +25,14 @@ class Model(nn.Module):
         with torch.no_grad():
             for name, src in self.named_parameters():
                 dst = targets[name]
-                if decay == 0.0:
-                    dst.copy_(src)
-                else:
-                    dst.mul_(decay).add_(src.detach().to(dst.device), alpha=1.0 - decay)
+                # same three roundings as the reference expression (model.py:110-112): two products, one sum
+                dst.copy_(decay * dst + (1 - decay) * src.detach().to(dst.device))
 
     def get_weights(self):
-        return {k: v.detach().cpu().numpy() for k, v in self.state_dict().items()}
+        # an OrderedDict in state_dict order, like the reference (model.py:115-123 fills state_dict() in place)
+        return OrderedDict((k, v.detach().cpu().numpy()) for k, v in self.state_dict().items())
 
     def set_weights(self, weights):
-        if not isinstance(weights, dict):
-            raise TypeError('set_weights expects the dict returned by get_weights(), got %s' % type(weights).__name__)
-        self.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()})
+        # like the reference (model.py:126-134): anything without .keys() fails with AttributeError, a wrong
+        # shape with load_state_dict's RuntimeError
+        self.load_state_dict({k: torch.from_numpy(np.asarray(weights[k])) for k in weights.keys()})

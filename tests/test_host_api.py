@@ -31,7 +31,7 @@ def test_model_get_set_weights_and_sync():
     b.set_weights(w)
     x = torch.randn(3, 4)
     assert torch.equal(a(x), b(x))
-    with pytest.raises(TypeError):
+    with pytest.raises(AttributeError):                    # like the reference: no .keys() on a list (model.py:131)
         b.set_weights(list(w.values()))
     bad = dict(w)
     bad['fc1.weight'] = np.zeros((3, 3), np.float32)
