@@ -277,15 +277,16 @@ int rl_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, l
  * ---------------------------------------------------------------------- */
 int rl_gemm_bf16_tn(const void* A, const void* B, const float* bias, void* C, int M, int N, int K,
                     int lda, int ldb, int ldc, int relu, int out_f32, rl_stream_t stream);
-/* Backward-through-ReLU form: C[M,N] = (A . B^T) * (mask > 0), mask [M, ldm] bf16 = the saved post-ReLU activation
- * of the layer whose input gradient is being formed (dX = dY . W, B = W^T stored [N, K]). */
-/* rl_gemm_bf16_tn with an optional split-K workspace (>= splits * ceil(M/128)*128 * ceil(N/BN)*BN * 4 bytes; 8 MB
+/* rl_gemm_bf16_tn with an optional split-K workspace — the actor-side nn.Linear (atari_model.py:46-49 evaluated on
+ *  the 5-env batch of examples/IMPALA/actor.py:60-62; here 512..4096 envs per GPU).  Workspace (>= splits * ceil(M/128)*128 * ceil(N/BN)*BN * 4 bytes; 8 MB
  * covers every shape that splits): when the output has fewer tiles than half the SMs and K >= 1024, the reduction is
  * split over up to 8 CTAs per tile (fp32 partials, fixed-order second pass with the bias/ReLU epilogue).  Same
  * result contract as rl_gemm_bf16_tn; workspace NULL = never split. */
 int rl_gemm_bf16_tn_splitk(const void* A, const void* B, const float* bias, void* C, int M, int N, int K,
                            int lda, int ldb, int ldc, int relu, int out_f32, void* workspace, size_t workspace_bytes,
                            rl_stream_t stream);
+/* Backward-through-ReLU form: C[M,N] = (A . B^T) * (mask > 0), mask [M, ldm] bf16 = the saved post-ReLU activation
+ * of the layer whose input gradient is being formed (dX = dY . W, B = W^T stored [N, K]). */
 int rl_gemm_bf16_tn_masked(const void* A, const void* B, void* C, const void* mask, int M, int N, int K,
                            int lda, int ldb, int ldc, int ldm, int out_f32, rl_stream_t stream);
 
