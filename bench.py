@@ -213,8 +213,9 @@ def main():
     if k1_s:
         ach = alg_bytes / k1_s / 1e9
         # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch at B=4096 from the committed
-        # `ncu --set full` capture (profiles/r01_k1_vtrace_loss_*.txt); the gradient tile stays in L2 past the launch
-        traffic = 42.9e6 if B == 4096 else None
+        # `ncu --set full` capture of this kernel version (profiles/r01_k1_vtrace_loss_v4.txt: 32.18 MB read +
+        # 0.06 MB written — the 15.3 MB gradient tile is still in the 126 MB L2 when the launch ends)
+        traffic = 32.24e6 if B == 4096 else None
         roof = dict(bound='hbm', kernel='vtrace_loss_kernel (rl_vtrace_loss_fwd_bwd)', achieved=ach, peak=peak,
                     unit='GB/s', frac=ach / peak, traffic=traffic, peak_source=peak_src,
                     algorithmic_bytes_per_launch=alg_bytes, us_per_launch=k1_s * 1e6,
