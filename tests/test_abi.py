@@ -38,3 +38,25 @@ def test_cpu_tensor_is_rejected_loudly():
     x = torch.zeros(4, 3)
     with pytest.raises(RuntimeError):
         kernels.sample_categorical(x, 0, 0)
+
+
+def test_product_path_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under parl_b200/ may import it (static scan of every module)."""
+    import ast
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'parl_b200')
+    offenders = []
+    for d, _, files in os.walk(root):
+        for f in files:
+            if not f.endswith('.py'):
+                continue
+            tree = ast.parse(open(os.path.join(d, f)).read())
+            for node in ast.walk(tree):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or '']
+                if any(n == 'oracle' or n.startswith('oracle.') for n in names):
+                    offenders.append(os.path.join(d, f))
+    assert not offenders, offenders
