@@ -221,6 +221,15 @@ def main():
                     algorithmic_bytes_per_launch=alg_bytes, us_per_launch=k1_s * 1e6,
                     us_per_launch_in_pipelined_step=k1_in_step_us, l2='flushed before every timed launch')
 
+    # the kernel with the largest share of the step (profiles/r01_bench_launches_final.txt: 15 %): conv1 forward in
+    # TMA-window form, timed here live at the learner's batch on the step's own buffers (11.6 GB in, 7.5 GB out: far
+    # beyond L2, nothing to flush), CUDA events on the launching stream, nothing else in flight
+    dom = None
+    try:
+        dom = measure_dominant_kernel(eng, kernels, torch, B, peak, peak_src)
+    except Exception as e:                       # never lose the bench line over the extra measurement
+        sys.stderr.write('dominant-kernel roofline skipped: %r\n' % (e, ))
+
     # tensor-pipe view of the whole step: policy/value network FLOPs (actor forward + learner forward/backward
     # = 4 x 25.8 MFLOP per env-step) over the step time, against the measured sustained bf16 peak
     net_roof = None
@@ -273,13 +282,44 @@ def main():
                                           'activations %.1f GB per GPU) >> 126 MB L2; K1 timed alone with L2 flushed' %
                                           ((T_STEPS + 4) * B * 7056 / 1e9, T_STEPS * B * 56448 / 1e9,
                                            T_STEPS * B * 120e3 / 1e9)),
-                    gpu_launches=launches, clocks=clocks, roofline=roof, roofline_network=net_roof, roofline_step=step_roof,
+                    gpu_launches=launches, clocks=clocks, roofline=dom if dom is not None else roof, roofline_k1=roof,
+                    roofline_network=net_roof, roofline_step=step_roof,
                     e2e=e2e,
                     cpu_baseline=cpu,
                     learner_losses=[float(x) for x in losses[:5].tolist()])
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_dominant_kernel(eng, kernels, torch, B, peak, peak_src):
+    """Roofline entry of the step's dominant kernel, shiftconv_fwd_kernel<32,1,2,0> (conv1 forward): algorithmic bytes
+    per launch = samples x (21*21*64*2 B of space-to-depth input read + 20*20*32*2 B of outputs written)."""
+    net = eng.train_net
+    if net is None:
+        return None
+    n = T_STEPS * B
+    x0 = eng.x0.view(n, 21, 21, 64) if eng.share_obs else net.x0
+    spans = []
+    for _ in range(6):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        kernels.conv2d_s1_nhwc_bf16_fwd(x0, net.w1, net.b1, 2, 2, relu=True, out=net.a1, out_mode=1)
+        b.record()
+        spans.append((a, b))
+    torch.cuda.synchronize()
+    ms = sorted(x.elapsed_time(y) for x, y in spans[1:])
+    sec = sum(ms) / len(ms) * 1e-3
+    alg_bytes = n * (21 * 21 * 64 * 2 + 20 * 20 * 32 * 2)
+    ach = alg_bytes / sec / 1e9
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel in the committed `ncu --set full` capture
+    # (profiles/r01_learner_kernels_final.txt: 2.948 GB + 1.282 GB at 51 200 samples), scaled to this launch's samples
+    traffic = (2.947656e9 + 1.281806e9) * n / 51200.0
+    return dict(bound='hbm', kernel='shiftconv_fwd_kernel<32,1,2,0> (rl_conv2d_s1_nhwc_bf16_fwd, conv1 forward at the '
+                                    'learner batch): largest share of the step (15 % of kernel time)',
+                achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=traffic, peak_source=peak_src,
+                algorithmic_bytes_per_launch=alg_bytes, us_per_launch=sec * 1e6, samples_per_launch=n,
+                l2='operands (11.6 GB + 7.5 GB at 204 800 samples) far beyond the 126 MB L2')
 
 
 def run_e2e(eng, args, world, dev):
