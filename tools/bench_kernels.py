@@ -1,5 +1,5 @@
 """Micro-benchmarks of individual kernels (CUDA events, rotating >L2 buffers).
-    python tools/bench_kernels.py [vtrace|env|all]
+    python tools/bench_kernels.py [vtrace|env|losses|all]
 """
 import json
 import sys
@@ -66,6 +66,74 @@ def bench_env(B=4096, HW=84 * 84, nplanes=16, iters=64):
                 env_steps_per_s=B / sec)
 
 
+def bench_a2c(N=256 * 20, A=2, nbuf=32):
+    """K2 at configs[1]: 256 CartPole envs x 20 steps per update; algorithmic bytes 8A+17 per row."""
+    dev = 'cuda:0'
+    g = torch.Generator(device=dev).manual_seed(0)
+    bufs = [(torch.randn(N, A, device=dev, generator=g), torch.randn(N, device=dev, generator=g),
+             torch.randint(0, A, (N,), device=dev, dtype=torch.int32, generator=g),
+             torch.randn(N, device=dev, generator=g), torch.randn(N, device=dev, generator=g)) for _ in range(nbuf)]
+    sec = time_fn(lambda i: K.a2c_loss_fwd_bwd(*bufs[i % nbuf], 0.5, -0.01))
+    alg = N * (8 * A + 17)
+    return dict(kernel='a2c_loss_fwd_bwd', N=N, A=A, us=sec * 1e6, alg_bytes=alg, gbps=alg / sec / 1e9)
+
+
+def bench_gae(T=2048, B=2048, segments=False, iters=20):
+    """K3 at configs[3]: 2048 envs x 2048 steps; 17 B per (t,b) (read r, V, done; write adv, ret)."""
+    dev = 'cuda:0'
+    g = torch.Generator(device=dev).manual_seed(1)
+    r, v = torch.randn(T, B, device=dev, generator=g), torch.randn(T, B, device=dev, generator=g)
+    d = (torch.rand(T, B, device=dev, generator=g) < 0.01)
+    lv = torch.randn(B, device=dev, generator=g)
+    if segments:
+        sec = time_fn(lambda i: K.gae_scan_segments(r, v, d.to(torch.uint8), lv, 0.99, 0.95), iters=iters)
+    else:
+        df, ld = d.float(), torch.zeros(B, device=dev)
+        sec = time_fn(lambda i: K.gae_scan(r, v, df, lv, ld, 0.99, 0.95), iters=iters)
+    alg = T * B * 17
+    return dict(kernel='gae_scan_segments' if segments else 'gae_scan', T=T, B=B, us=sec * 1e6, alg_bytes=alg,
+                gbps=alg / sec / 1e9)
+
+
+def bench_ppo(N=2048 * 64, D=6, iters=30):
+    """K3 loss at configs[3]: Gaussian minibatch (obs 17, act 6); 12D+24 B per row."""
+    dev = 'cuda:0'
+    g = torch.Generator(device=dev).manual_seed(2)
+    rn = lambda *s: torch.randn(*s, device=dev, generator=g)
+    vals, act, bv, br, blp, adv = rn(N), rn(N, D), rn(N), rn(N), rn(N), rn(N)
+    mean, logstd = rn(N, D), torch.zeros(D, device=dev)
+    sec = time_fn(lambda i: K.ppo_loss_fwd_bwd(vals, act, bv, br, blp, adv, mean=mean, logstd=logstd), iters=iters)
+    alg = N * (12 * D + 24)
+    return dict(kernel='ppo_loss_fwd_bwd(gaussian)+adv_stats', N=N, D=D, us=sec * 1e6, alg_bytes=alg,
+                gbps=alg / sec / 1e9)
+
+
+def bench_td(M=4096, A=18, double_q=True):
+    """K4: TD loss of a replay batch; (8..12)A+17 B per sample."""
+    dev = 'cuda:0'
+    g = torch.Generator(device=dev).manual_seed(3)
+    q, qt, qo = (torch.randn(M, A, device=dev, generator=g) for _ in range(3))
+    a = torch.randint(0, A, (M,), device=dev, dtype=torch.int32, generator=g)
+    r, term = torch.randn(M, device=dev, generator=g), (torch.rand(M, device=dev, generator=g) < 0.05).float()
+    sec = time_fn(lambda i: K.td_loss_fwd_bwd(q, qt, a, r, term, 0.99, q_online_next=qo if double_q else None))
+    alg = M * ((12 if double_q else 8) * A + 17)
+    return dict(kernel='td_loss_fwd_bwd', M=M, A=A, double_q=double_q, us=sec * 1e6, alg_bytes=alg,
+                gbps=alg / sec / 1e9)
+
+
+def bench_per(capacity=1 << 20, batch=4096):
+    """C5: priority sample + update on a 1M-leaf fp64 sum tree (latency-bound: tree depth 20)."""
+    dev = 'cuda:0'
+    tree = K.DeviceSumTree(capacity, dev)
+    tree.store(0, capacity, 0.6, 0.01)
+    pri = torch.rand(batch, device=dev)
+    out = {}
+    sec = time_fn(lambda i: out.__setitem__('s', tree.sample(batch, 0.4, float(capacity), seed=7, draw=i)))
+    sec_u = time_fn(lambda i: tree.update(out['s'][0], pri, 0.6, 0.01))
+    return dict(kernel='per_sample / per_update', capacity=capacity, batch=batch, sample_us=sec * 1e6,
+                update_us=sec_u * 1e6, samples_per_s=batch / sec)
+
+
 if __name__ == '__main__':
     which = sys.argv[1] if len(sys.argv) > 1 else 'all'
     if which == 'vtrace_cpasync':
@@ -83,3 +151,10 @@ if __name__ == '__main__':
     if which in ('env', 'all'):
         print(json.dumps(bench_env()))
         print(json.dumps(bench_env(B=512)))
+    if which in ('losses', 'all'):
+        # K2-K4 at the BASELINE.json configs[1], [3], [4] shapes (not yet captured under ncu: next round)
+        for fn in (bench_a2c, bench_gae, lambda: bench_gae(T=20, B=256, segments=True), bench_ppo, bench_td, bench_per):
+            try:
+                print(json.dumps(fn()))
+            except Exception as e:      # a tool, not a test: report and carry on
+                print(json.dumps(dict(error=repr(e))))
