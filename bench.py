@@ -38,7 +38,11 @@ def parse():
     ap.add_argument('--envs', type=int, default=TOTAL_ENVS, help='total env instances over all GPUs')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--cpu-seconds', type=float, default=15.0)
+    ap.add_argument('--cpu-seconds', type=float, default=16.0, help='timed CPU-baseline sample of our arm')
+    ap.add_argument('--ref-seconds', type=float, default=90.0, help='--impl reference: timed steady state in total')
+    ap.add_argument('--ref-warmup-seconds', type=float, default=20.0)
+    ap.add_argument('--ref-deepmind-seconds', type=float, default=20.0,
+                    help='--impl reference: extra run of the full wrap_deepmind pipeline flavour (0 = skip)')
     ap.add_argument('--no-pipeline', action='store_true', help='strictly sequential rollout -> learn')
     return ap.parse_args()
 
@@ -92,31 +96,84 @@ def measured_peaks():
 
 
 def run_reference(args, rank, world):
-    """Reference arm: the reference's CPU actor-learner path (oracle port; the Python reference itself
-    cannot travel to the GPU box) on all host cores; each step = a bounded wall-clock sample."""
+    """Reference arm: the reference's CPU actor-learner path (examples/IMPALA/train.py + actor.py; oracle port —
+    the Python reference itself cannot travel to the GPU box) on all host cores, learner on one B200 through torch
+    eager as BASELINE.md section 3 asks.  ONE long-lived actor pool for the whole arm; a "step" is a wall-clock
+    window over which sample_total_steps / elapsed is read exactly as the reference logs it (train.py:93,227,243).
+    Under torchrun only rank 0 measures; the other ranks exit 0 without work."""
     if rank != 0:
         return
-    from oracle.actor_learner import run_cpu_impala
-    per = max(4.0, min(20.0, 100.0 / max(args.steps + args.warmup, 1)))
-    res = None
-    vals = []
-    for i in range(args.warmup + args.steps):
-        res = run_cpu_impala(seconds=per, seed=i)
-        if i >= args.warmup:
-            vals.append(res['env_steps_per_s'])
-    v = sum(vals) / len(vals)
-    sample = ('%d actor processes x %d envs x T=%d (lean 84x84 synthetic env + FrameStack4, torch-CPU 84x84 '
-              'actor-critic, numpy V-trace), %.0f s wall clock per step' % (res['actors'], res['env_num'], T_STEPS, per))
+    from oracle.actor_learner import CpuImpalaCluster
+    t_arm = time.time()
+    total = args.ref_seconds                                   # timed steady state (>= 60 s by default)
+    per = max(1.0, total / max(args.steps, 1))
+    warm_per = max(per, args.ref_warmup_seconds / max(args.warmup, 1))
+    cl = CpuImpalaCluster(flavour='lean', seed=0)
+    try:
+        for _ in range(max(args.warmup, 1)):
+            cl.window(warm_per)
+        wins = [cl.window(per) for _ in range(args.steps)]
+        info = cl.info()
+    finally:
+        cl.close()
+    steps_done = sum(w['sample_steps'] for w in wins)
+    elapsed = sum(w['elapsed_s'] for w in wins)
+    v = steps_done / elapsed
+    ls = sum(w['learn_steps'] for w in wins)
+    lms = (sum((w['learn_ms_per_batch'] or 0.0) * w['learn_steps'] for w in wins) / ls) if ls else None
+    # Appendix-C flavour (i): mock Pong through the whole wrap_deepmind chain, a shorter second run
+    dm = None
+    if args.ref_deepmind_seconds > 0:
+        cl2 = CpuImpalaCluster(flavour='deepmind', seed=1)
+        try:
+            cl2.window(min(20.0, max(8.0, args.ref_deepmind_seconds * 0.5)))
+            w2 = cl2.window(args.ref_deepmind_seconds)
+            dm = dict(value=w2['env_steps_per_s'], unit=UNIT, seconds=w2['elapsed_s'],
+                      what='mock PongNoFrameskip-v4 (210x160x3) -> wrap_deepmind(dim=84) chain (SURVEY.md Appendix C '
+                           'flavour i)', learner_ms_per_batch=w2['learn_ms_per_batch'])
+        finally:
+            cl2.close()
+    sample = ('%d actor processes (1 core each) x %d envs x T=%d, lean 84x84 synthetic env + FrameStack4 (SURVEY.md '
+              'Appendix C flavour ii, the most favourable for the CPU side), torch-CPU fp32 84x84 actor-critic per '
+              'actor, pickle-over-pipe sample dicts, learner torch eager fp32 on %s (train batch %d); %d windows of '
+              '%.1f s after %.0f s warm-up' % (info['actors'], info['env_num'], T_STEPS, info['learner_device'],
+                                                info['train_batch_size'], args.steps, per,
+                                                warm_per * max(args.warmup, 1)))
     line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=per * 1e3, higher_is_better=True, scaling='strong', vs_baseline=None, dtype='f32',
                 data='synthetic', impl='reference',
                 config=dict(workload='IMPALA synthetic Atari-shaped 84x84x4->18, CPU actor pool (oracle port of '
-                                     'examples/IMPALA on host cores)', total_envs=res['actors'] * res['env_num'],
-                            T=T_STEPS, train_batch_size=res['train_batch_size']),
-                cpu_baseline=dict(value=v, unit=UNIT, cores=res['cores'], kind='port', sample=sample,
-                                  learner_ms_per_batch=res['learn_ms_per_batch']),
-                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+                                     'examples/IMPALA on the host cores; one host cannot hold 4096 xparl jobs, so '
+                                     'actors = cores - 2, reported as is)',
+                            total_envs=info['actors'] * info['env_num'], T=T_STEPS,
+                            train_batch_size=info['train_batch_size'], host_cores=info['cores'],
+                            learner_device=info['learner_device']),
+                cpu_baseline=dict(value=v, unit=UNIT, cores=info['cores'], kind='port', sample=sample,
+                                  learner_ms_per_batch=lms, learner_device=info['learner_device'],
+                                  deepmind_pipeline=dm),
+                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                arm_wall_s=time.time() - t_arm)
     print(json.dumps(line))
+    sys.stdout.flush()
+
+
+def cpu_baseline_subprocess(args):
+    """cpu_baseline leg of our arm: the reference arm as a child process (its actor pool must be forked from a
+    process that has not initialised CUDA), bounded to about half a minute."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '4', '--warmup', '2',
+           '--ref-seconds', str(args.cpu_seconds), '--ref-warmup-seconds', '8', '--ref-deepmind-seconds', '0']
+    env = dict(os.environ)
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'):
+        env.pop(k, None)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=args.cpu_seconds + 120, env=env)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith('{'):
+                return json.loads(ln)['cpu_baseline']
+        sys.stderr.write('cpu_baseline: no line from the child (rc %d)\n%s\n' % (r.returncode, r.stderr[-2000:]))
+    except Exception as e:
+        sys.stderr.write('cpu_baseline failed: %r\n' % (e, ))
+    return None
 
 
 def main():
@@ -259,12 +316,7 @@ def main():
         e2e = run_e2e(eng, args, world, dev)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle.actor_learner import run_cpu_impala
-        r = run_cpu_impala(seconds=args.cpu_seconds)
-        cpu = dict(value=r['env_steps_per_s'], unit=UNIT, cores=r['cores'], kind='port',
-                   sample='%d actor processes x %d envs x T=%d lean synthetic 84x84 env, torch-CPU model, %.0f s'
-                          % (r['actors'], r['env_num'], T_STEPS, r['elapsed_s']),
-                   learner_ms_per_batch=r['learn_ms_per_batch'])
+        cpu = cpu_baseline_subprocess(args)
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=elapsed * 1e3 / args.steps, higher_is_better=True, scaling='strong', vs_baseline=None,
