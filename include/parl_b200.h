@@ -52,6 +52,10 @@ size_t rl_loss_workspace_bytes(int n_cols);
 /* Triage hook: 1 forces the cp.async tile path of rl_vtrace_loss_fwd_bwd, 0 (default) lets the
  * TMA tensor-map path run when the layout allows it. */
 int rl_debug_set_tma(int disable);
+/* Triage hook for rl_vtrace_loss_fwd_bwd: 0 = automatic (the warp-streaming kernel, 4 env columns per warp,
+ * whenever the layout is time-major and TMA-able), 1 = always the general CTA-per-4-columns kernel,
+ * 2 / 8 = warp-streaming kernel with 2 / 8 columns per warp. */
+int rl_debug_set_vtrace_path(int mode);
 
 /* ------------------------------------------------------------------------
  * a1  V-trace returns.
@@ -345,6 +349,30 @@ int rl_colsum_bf16(const void* x, long long rows, int C, float* out, void* works
 int rl_bias_act_bf16(void* x, const float* bias, long long M, int N, int relu, rl_stream_t stream);
 int rl_mask_scatter_grid_bf16(const void* src, const void* act, void* dst, long long N, int PH, int PW, int GH, int GW,
                               int C, rl_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * a13  K6 for the MLP model family: whole-network forward / backward in ONE launch, fp32 on the CUDA cores.
+ * Replaces the torch/paddle eager execution of benchmark/torch/ppo/mujoco_model.py:27-53 (17-64-64 tanh ->
+ * {mean 6, value 1}), benchmark/torch/QuickStart/cartpole_model.py:21-38 (4-20 tanh -> 2),
+ * examples/DQN/cartpole_model.py:21-41 (4-128-128 relu -> 2).
+ *   n_layers (1..4) linear layers; dims[n_layers+1] = {in, h1, ..., out} (each 1..128); hidden layers use
+ *   `act` (0 relu, 1 tanh, 2 none), the last layer is linear.  Parameters are handed over as n_seg row
+ *   SEGMENTS in torch nn.Linear layout: segment s holds rows [.., +seg_rows[s]) of layer seg_layer[s]
+ *   (segments of one layer are stacked in the order given — e.g. the policy and value heads of an
+ *   actor-critic are two segments of the last layer), seg_w[s] [rows, in] float32, seg_b[s] [rows] or NULL.
+ *   dims, seg_layer, seg_rows, seg_w, seg_b, seg_dw, seg_db are HOST arrays (of device pointers where typed so).
+ * rl_mlp_fwd: x [n, in] -> out [n, out].
+ * rl_mlp_bwd: recomputes the hidden activations from x, back-propagates d_out [n, out] and writes
+ *   (accumulate=0) or adds (1) the parameter gradients into seg_dw[s] / seg_db[s] (same shapes as the
+ *   parameters); deterministic two-stage reduction through `workspace` (rl_mlp_workspace_bytes). */
+size_t rl_mlp_workspace_bytes(int n_layers, const int* dims);
+int rl_mlp_fwd(const float* x, int n, int n_layers, const int* dims, int n_seg, const int* seg_layer,
+               const int* seg_rows, const float* const* seg_w, const float* const* seg_b, int act, float* out,
+               rl_stream_t stream);
+int rl_mlp_bwd(const float* x, int n, int n_layers, const int* dims, int n_seg, const int* seg_layer,
+               const int* seg_rows, const float* const* seg_w, const float* const* seg_b, int act,
+               const float* d_out, float* const* seg_dw, float* const* seg_db, int accumulate,
+               void* workspace, size_t workspace_bytes, rl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -30,6 +30,7 @@ SIGNATURES = {
     'rl_device_sm_count': (c_i, [c_i]),
     'rl_loss_workspace_bytes': (c_sz, [c_i]),
     'rl_debug_set_tma': (c_i, [c_i]),
+    'rl_debug_set_vtrace_path': (c_i, [c_i]),
     'rl_vtrace_from_importance_weights': (c_i, [c_p] * 6 + [c_i, c_i, c_f, c_f, c_p, c_p, c_p]),
     'rl_vtrace_loss_fwd_bwd': (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_i,
                                      c_f, c_f, c_f, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
@@ -74,6 +75,9 @@ SIGNATURES = {
     'rl_colsum_bf16': (c_i, [c_p, ctypes.c_longlong, c_i, c_p, c_p, c_sz, c_p]),
     'rl_gemm_bf16_tn_masked': (c_i, [c_p, c_p, c_p, c_p] + [c_i] * 8 + [c_p]),
     'rl_bias_act_bf16': (c_i, [c_p, c_p, ctypes.c_longlong, c_i, c_i, c_p]),
+    'rl_mlp_workspace_bytes': (c_sz, [c_i, c_p]),
+    'rl_mlp_fwd': (c_i, [c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p]),
+    'rl_mlp_bwd': (c_i, [c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_p, c_sz, c_p]),
     'rl_mask_scatter_grid_bf16': (c_i, [c_p, c_p, c_p, ctypes.c_longlong, c_i, c_i, c_i, c_i, c_i, c_p]),
 }
 
@@ -104,6 +108,8 @@ def ptr(t):
 
 
 def stream():
+    """cudaStream_t of torch's current stream on the current device.  Launches are made on the current device:
+    ``require_cuda`` rejects tensors that live on another GPU (one process drives one GPU)."""
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -124,3 +130,8 @@ def require_cuda(*tensors):
             raise RuntimeError('parl_b200 kernels need CUDA tensors (no CPU fallback); got a %s tensor' % t.device)
         if t is not None and not t.is_contiguous():
             raise RuntimeError('parl_b200 kernels need contiguous tensors')
+        if t is not None and t.device.index != torch.cuda.current_device():
+            # launches go to the current device's current stream; a tensor of another GPU would be dereferenced
+            # from the wrong context: make the owner set the device (torch.cuda.set_device / device guard)
+            raise RuntimeError('parl_b200: tensor on cuda:%d but the current device is cuda:%d — wrap the call in '
+                               'torch.cuda.device(tensor.device)' % (t.device.index, torch.cuda.current_device()))

@@ -66,6 +66,7 @@ class PPO(Algorithm):
                   use_clipped_value_loss=self.use_clipped_value_loss, norm_adv=self.norm_adv, stats=stats)
         if self.continuous_action:
             mean, std = self.model.policy(obs)
+            self._check_state_independent_std(std)
             act = to_device_tensor(batch_action, dev, f32)
             std_row = std.detach().float().reshape(-1, std.shape[-1])[0].contiguous()
             logstd = torch.log(std_row)
@@ -92,6 +93,18 @@ class PPO(Algorithm):
         L = res['losses'].tolist()          # the reference returns Python floats (.item(), ppo.py:149)
         return L[0], L[1], L[2]
 
+    def _check_state_independent_std(self, std):
+        """The fused Gaussian loss / sampler take ONE log-std vector [D] (the reference models' ``fc_pi_std``
+        parameter expanded over the batch, benchmark/torch/ppo/mujoco_model.py:46-53).  A model whose std
+        depends on the state would silently get wrong log-probs: checked once, loudly."""
+        if getattr(self, '_std_checked', False):
+            return
+        s2 = std.detach().reshape(-1, std.shape[-1])
+        if s2.shape[0] > 1 and not bool((s2 == s2[0:1]).all()):
+            raise ValueError('PPO(continuous_action=True): model.policy() returned a state-dependent std; '
+                             'parl_b200 supports the reference form std = exp(logstd parameter) only')
+        self._std_checked = True
+
     def sample(self, obs):
         """ppo.py:151-179 -> (value, action, action_log_probs, action_entropy)."""
         with torch.no_grad():
@@ -101,6 +114,7 @@ class PPO(Algorithm):
             self._sample_step += 1
             if self.continuous_action:
                 mean, std = self.model.policy(obs)
+                self._check_state_independent_std(std)
                 logstd = torch.log(std.float().reshape(-1, std.shape[-1])[0]).contiguous()
                 action, logp = kernels.sample_gaussian(mean.float().contiguous(), logstd, self.seed, step)
                 entropy = (0.5 + 0.5 * 1.8378770664093453 + logstd).sum().expand(mean.shape[0])

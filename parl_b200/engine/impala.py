@@ -13,6 +13,9 @@ CUDA graph (step counter resident on the device) and replayed.  ``learn`` runs t
 T*B observations, the fused V-trace loss kernel, backward, (NCCL all-reduce of the flat gradient),
 clip + Adam.
 """
+import copy
+import os
+
 import torch
 
 from .. import kernels
@@ -81,6 +84,13 @@ class ImpalaEngine(object):
         # written straight into row t of a (T,B) plane of the rollout buffer set and the learner's conv1 forward /
         # weight gradient read it from there — the learner never re-gathers the frame ring.  11.6 GB per set at
         # T*B = 204 800: HBM is spent (180 GB) to save one full pass over the observations per update.
+        # Pipelined engines whose actor runs the user's torch Model (no native actor net): the actor stream must not
+        # read the fp32 master weights while the learner stream's Adam step overwrites them, so the
+        # rollout runs on a SNAPSHOT copy of the model that is refreshed on the actor stream before each rollout.
+        self._actor_model = copy.deepcopy(self.model) if (self.pipeline and self.actor_net is None) else None
+        if self._actor_model is not None:
+            for q in self._actor_model.parameters():
+                q.requires_grad_(False)
         self.share_obs = self.actor_net is not None and self.train_net is not None
         if self.share_obs:
             for st in self._sets:
@@ -128,7 +138,8 @@ class ImpalaEngine(object):
                 if self.actor_net is not None:
                     self.actor_net.policy(obs_t, self.beh_logits[t])
                 else:
-                    self.beh_logits[t].copy_(self.model.policy(obs_t))
+                    pol = self._actor_model if self._actor_model is not None else self.model
+                    self.beh_logits[t].copy_(pol.policy(obs_t))
                 kernels.env_atari_synth_step(self.planes[t + 4], self.rewards[t], self.dones[t], self.ages[t],
                                              self.ages[t + 1], self.stats, self.seed, 0, p_done=self.p_done,
                                              env_offset=self.env_offset, logits=self.beh_logits[t],
@@ -179,8 +190,7 @@ class ImpalaEngine(object):
         with torch.cuda.stream(self.actor_stream):
             if self._learn_done[nxt] is not None:          # update k-1 finished: its weights are final, set nxt is free
                 self.actor_stream.wait_event(self._learn_done[nxt])
-            if self.actor_net is not None:
-                self.actor_net.pack()
+            self._snapshot_actor_weights()
             self._ev_pack.record(self.actor_stream)
             self._run_rollout(nxt)
             self._roll_done[nxt].record(self.actor_stream)
@@ -193,6 +203,48 @@ class ImpalaEngine(object):
         self._learn_done[cur] = ev
         self._k += 1
         return losses
+
+    def _snapshot_actor_weights(self):
+        """Actor-side copy of the current weights, taken on the actor stream (bf16 operand copies of the native
+        actor net, or the snapshot model of a torch actor)."""
+        if self.actor_net is not None:
+            self.actor_net.pack()
+        elif self._actor_model is not None:
+            with torch.no_grad():
+                for q, p in zip(self._actor_model.parameters(), self.model.parameters()):
+                    q.copy_(p)
+                for q, p in zip(self._actor_model.buffers(), self.model.buffers()):
+                    q.copy_(p)
+
+    # ------------------------------------------------------------------ weights / checkpoints
+    def repack(self):
+        """Refresh every packed operand copy from the fp32 master weights.  Call after ANY external change of the
+        model's parameters (set_weights, load_state_dict, Agent.restore, sync_weights_to into this model)."""
+        if self.train_net is not None:
+            self.train_net.pack()
+        self._snapshot_actor_weights()
+
+    def get_weights(self):
+        return self.alg.get_weights()
+
+    def set_weights(self, weights):
+        self.alg.set_weights(weights)
+        self.repack()
+
+    def save(self, path):
+        """Model weights + optimiser moments + step counters (torch.save)."""
+        d = os.path.dirname(path)
+        if d and not os.path.exists(d):
+            os.makedirs(d)
+        torch.save(dict(model=self.model.state_dict(), optimizer=self.alg.optimizer.state_dict(),
+                        sample_steps=self.sample_steps), path)
+
+    def restore(self, path, map_location=None):
+        ck = torch.load(path, map_location=map_location)
+        self.model.load_state_dict(ck['model'])
+        self.alg.optimizer.load_state_dict(ck['optimizer'])
+        self.sample_steps = int(ck.get('sample_steps', 0))
+        self.repack()
 
     # ------------------------------------------------------------------ learner side
     def learn(self, learning_rate=0.001, entropy_coeff=-0.01):
@@ -234,7 +286,7 @@ class ImpalaEngine(object):
         self.alg.optimizer.step(lr=learning_rate)
         if self.actor_net is not None and not self.pipeline:
             self.actor_net.pack()              # refresh the actor's bf16 operand copies (weights never leave HBM)
-        return res['losses']
+        return res['losses'].clone()
 
     def _learn_native(self, learning_rate, entropy_coeff):
         """learn() with the network forward/backward on the hand-written kernels (AtariTrainNet)."""
@@ -264,7 +316,7 @@ class ImpalaEngine(object):
         net.pack()
         if self.actor_net is not None and not self.pipeline:
             self.actor_net.pack()
-        return res['losses']
+        return res['losses'].clone()
 
     # ------------------------------------------------------------------ reference-facing host contract
     def make_host_sample_buffers(self):
@@ -319,8 +371,7 @@ class ImpalaEngine(object):
         with torch.cuda.stream(self.actor_stream):
             if self._learn_done[nxt] is not None:
                 self.actor_stream.wait_event(self._learn_done[nxt])
-            if self.actor_net is not None:
-                self.actor_net.pack()
+            self._snapshot_actor_weights()
             self._ev_pack.record(self.actor_stream)
             self._run_rollout(nxt)
             self._sample_dict_to_host(hosts[nxt])
@@ -383,7 +434,7 @@ class ImpalaEngine(object):
             self.train_net.pack()
         if self.actor_net is not None and not self.pipeline:
             self.actor_net.pack()
-        return res['losses']
+        return res['losses'].clone()
 
     # ------------------------------------------------------------------ metrics (Actor.get_metrics analogue)
     def get_metrics(self):

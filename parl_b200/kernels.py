@@ -101,6 +101,29 @@ def vtrace_loss_fwd_bwd(target_logits, behaviour_logits, actions, rewards, dones
     return dict(losses=losses, d_logits=d_logits, d_values=d_values, vs=vs, pg_advantages=pg)
 
 
+def _chk(name, t, dtype=None, numel=None, optional=False):
+    """dtype / element-count validation of one wrapper argument (the C ABI takes raw pointers)."""
+    if t is None:
+        if optional:
+            return
+        raise RuntimeError('parl_b200: %s is required' % name)
+    if dtype is not None:
+        dts = dtype if isinstance(dtype, (tuple, list)) else (dtype, )
+        if t.dtype not in dts:
+            raise RuntimeError('parl_b200: %s must be %s, got %s' % (name, ' or '.join(str(d) for d in dts), t.dtype))
+    if numel is not None and t.numel() != numel:
+        raise RuntimeError('parl_b200: %s must have %d elements, got %d' % (name, numel, t.numel()))
+
+
+def _as_u8(t):
+    """done / terminal flags as uint8 (bool is reinterpreted, float is converted)."""
+    if t.dtype == torch.bool:
+        return t.view(torch.uint8)
+    if t.dtype == torch.uint8:
+        return t
+    return (t != 0).to(torch.uint8)
+
+
 # --------------------------------------------------------------------------- envs / sampling
 class EpisodeStats(object):
     """Device-side episode bookkeeping shared by the env steppers."""
@@ -167,6 +190,7 @@ def env_cartpole_step(state, obs_out, reward_out, done_out, actions, stats, seed
 
 def sample_categorical(logits, seed, step, env_offset=0, want_logp=False):
     require_cuda(logits)
+    _chk('logits', logits, torch.float32)
     N, A = logits.shape
     actions = torch.empty(N, dtype=torch.int32, device=logits.device)
     logp = torch.empty(N, dtype=torch.float32, device=logits.device) if want_logp else None
@@ -178,6 +202,8 @@ def sample_categorical(logits, seed, step, env_offset=0, want_logp=False):
 def sample_gaussian(mean, logstd, seed, step, env_offset=0):
     require_cuda(mean, logstd)
     N, D = mean.shape
+    _chk('mean', mean, torch.float32)
+    _chk('logstd', logstd, torch.float32, D)
     action = torch.empty_like(mean)
     logp = torch.empty(N, dtype=torch.float32, device=mean.device)
     check(_lib.load().rl_sample_gaussian(ptr(mean), ptr(logstd), N, D, int(seed), int(step), int(env_offset),
@@ -205,6 +231,11 @@ def a2c_loss_fwd_bwd(logits, values, actions, advantages, target_values, vf_loss
     """parl/algorithms/torch/a2c.py:40-60 -> dict(losses[4]={total,pi,vf,entropy}, d_logits, d_values)."""
     require_cuda(logits, values, actions, advantages, target_values)
     N, A = logits.shape
+    _chk('logits', logits, torch.float32)
+    _chk('values', values, torch.float32, N)
+    _chk('actions', actions, (torch.int32, torch.int64), N)
+    _chk('advantages', advantages, torch.float32, N)
+    _chk('target_values', target_values, torch.float32, N)
     dev = logits.device
     losses = torch.empty(4, dtype=torch.float32, device=dev)
     d_logits, d_values = torch.empty_like(logits), torch.empty_like(values)
@@ -219,9 +250,12 @@ def a2c_loss_fwd_bwd(logits, values, actions, advantages, target_values, vf_loss
 def gae_scan_segments(rewards, values, dones, bootstrap_value, gamma, lam):
     """calc_gae per episode segment (rl_utils.py:34-51, a2c/actor.py:82-102) on [T,B] -> (adv, target_values)."""
     require_cuda(rewards, values, dones, bootstrap_value)
-    if dones.dtype == torch.bool:
-        dones = dones.view(torch.uint8)
+    dones = _as_u8(dones)
     T, B = rewards.shape
+    _chk('rewards', rewards, torch.float32)
+    _chk('values', values, torch.float32, T * B)
+    _chk('dones', dones, torch.uint8, T * B)
+    _chk('bootstrap_value', bootstrap_value, torch.float32, B)
     adv, tv = torch.empty_like(rewards), torch.empty_like(rewards)
     check(_lib.load().rl_gae_scan_segments(ptr(rewards), ptr(values), ptr(dones), ptr(bootstrap_value), T, B,
                                            float(gamma), float(lam), ptr(adv), ptr(tv), stream()), 'gae_scan_segments')
@@ -232,6 +266,16 @@ def gae_scan(rewards, values, dones, last_value, last_done, gamma=0.99, gae_lamb
     """RolloutStorage.compute_returns (benchmark/torch/ppo/storage.py:45-64) -> (advantages, returns)."""
     require_cuda(rewards, values, dones, last_value, last_done)
     T, B = rewards.shape
+    # the kernel reads the done flags as float32 (RolloutStorage keeps them as float, storage.py:31)
+    if dones.dtype != torch.float32:
+        dones = dones.float()
+    if last_done.dtype != torch.float32:
+        last_done = last_done.float()
+    _chk('rewards', rewards, torch.float32)
+    _chk('values', values, torch.float32, T * B)
+    _chk('dones', dones, torch.float32, T * B)
+    _chk('last_value', last_value, torch.float32, B)
+    _chk('last_done', last_done, torch.float32, B)
     adv, ret = torch.empty_like(rewards), torch.empty_like(rewards)
     check(_lib.load().rl_gae_scan(ptr(rewards), ptr(values), ptr(dones), ptr(last_value), ptr(last_done), T, B,
                                   float(gamma), float(gae_lambda), ptr(adv), ptr(ret), stream()), 'gae_scan')
@@ -240,6 +284,7 @@ def gae_scan(rewards, values, dones, last_value, last_done, gamma=0.99, gae_lamb
 
 def adv_stats(adv):
     require_cuda(adv)
+    _chk('adv', adv, torch.float32)
     stats = torch.empty(2, dtype=torch.float32, device=adv.device)
     check(_lib.load().rl_adv_stats(ptr(adv), adv.numel(), ptr(stats), stream()), 'adv_stats')
     return stats
@@ -252,6 +297,17 @@ def ppo_loss_fwd_bwd(values, batch_action, batch_value, batch_return, batch_logp
     require_cuda(values, batch_action, batch_value, batch_return, batch_logprob, batch_adv, logits, mean, logstd)
     dev = values.device
     N = values.numel()
+    for nm, t in (('values', values), ('batch_value', batch_value), ('batch_return', batch_return),
+                  ('batch_logprob', batch_logprob), ('batch_adv', batch_adv)):
+        _chk(nm, t, torch.float32, N)
+    if logits is not None:
+        _chk('logits', logits, torch.float32, N * logits.shape[-1])
+        _chk('batch_action', batch_action, (torch.int32, torch.int64), N)
+    else:
+        _chk('mean', mean, torch.float32, N * mean.shape[-1])
+        _chk('logstd', logstd, torch.float32, mean.shape[-1])
+        _chk('batch_action', batch_action, torch.float32, mean.numel())
+    _chk('stats', stats, torch.float32, 2, optional=True)
     if norm_adv and stats is None:
         stats = adv_stats(batch_adv)
     if not norm_adv:
@@ -285,6 +341,13 @@ def td_loss_fwd_bwd(q, q_target_next, action, reward, terminal, gamma, q_online_
     require_cuda(q, q_target_next, action, reward, terminal, q_online_next, weights)
     M, A = q.shape
     dev = q.device
+    _chk('q', q, torch.float32)
+    _chk('q_target_next', q_target_next, torch.float32, M * A)
+    _chk('q_online_next', q_online_next, torch.float32, M * A, optional=True)
+    _chk('action', action, (torch.int32, torch.int64), M)
+    _chk('reward', reward, torch.float32, M)
+    _chk('terminal', terminal, torch.float32, M)
+    _chk('weights', weights, torch.float32, M, optional=True)
     losses = torch.empty(1, dtype=torch.float32, device=dev)
     d_q = torch.empty_like(q)
     td = torch.empty(M, dtype=torch.float32, device=dev) if want_td_abs else None
@@ -299,6 +362,9 @@ def pg_loss_fwd_bwd(prob, action, reward):
     """policy_gradient.py:54-75 -> dict(losses[1], d_prob)."""
     require_cuda(prob, action, reward)
     N, A = prob.shape
+    _chk('prob', prob, torch.float32)
+    _chk('action', action, (torch.int32, torch.int64), N)
+    _chk('reward', reward, torch.float32, N)
     losses = torch.empty(1, dtype=torch.float32, device=prob.device)
     d_prob = torch.empty_like(prob)
     ws = _flat_ws(prob.device, N)
@@ -317,16 +383,19 @@ class DeviceSumTree(object):
         self.state = torch.tensor([10.0, 1.0], dtype=torch.float64, device=device)   # _min, _max_priority
 
     def store(self, write_pos, n, alpha, eps, delta=None):
+        _chk('delta', delta, torch.float32, int(n), optional=True)
         check(_lib.load().rl_per_store(ptr(self.tree), ptr(self.state), self.capacity, int(write_pos), int(n),
                                        ptr(delta), float(alpha), float(eps), stream()), 'per_store')
 
     def update(self, tree_idx, priorities, alpha, eps):
-        assert tree_idx.dtype == torch.int32 and priorities.dtype == torch.float32
+        _chk('tree_idx', tree_idx, torch.int32)
+        _chk('priorities', priorities, torch.float32, tree_idx.numel())
         check(_lib.load().rl_per_update(ptr(self.tree), ptr(self.state), self.capacity, ptr(tree_idx), ptr(priorities),
                                         tree_idx.numel(), float(alpha), float(eps), stream()), 'per_update')
 
     def sample(self, seg_num, beta, size, u=None, seed=0, draw=0):
         dev = self.tree.device
+        _chk('u', u, torch.float32, int(seg_num), optional=True)
         tidx = torch.empty(seg_num, dtype=torch.int32, device=dev)
         eidx = torch.empty(seg_num, dtype=torch.int32, device=dev)
         w = torch.empty(seg_num, dtype=torch.float32, device=dev)
@@ -341,9 +410,11 @@ def replay_gather_frames(frames, is_over, idx, curr_size, context_len):
     require_cuda(frames, is_over, idx)
     HW = frames[0].numel()
     n = idx.numel()
+    _chk('frames', frames, torch.uint8)
+    _chk('idx', idx, torch.int32)
     out = torch.empty((n, context_len + 1, HW), dtype=torch.uint8, device=frames.device)
-    if is_over.dtype == torch.bool:
-        is_over = is_over.view(torch.uint8)
+    is_over = _as_u8(is_over)
+    _chk('is_over', is_over, torch.uint8, frames.shape[0])
     check(_lib.load().rl_replay_gather_frames(ptr(frames), ptr(is_over), ptr(idx), n, int(curr_size), int(context_len),
                                               HW, ptr(out), stream()), 'replay_gather_frames')
     return out
@@ -361,6 +432,8 @@ def gather_rows(src, idx):
 
 # --------------------------------------------------------------------------- optimizer
 def grad_global_norm(grad_flat, out_norm):
+    _chk('grad', grad_flat, torch.float32)
+    _chk('norm', out_norm, torch.float32, 1)
     ws = _flat_ws(grad_flat.device, 1)
     check(_lib.load().rl_grad_global_norm(ptr(grad_flat), grad_flat.numel(), ptr(out_norm), ptr(ws), ws.numel(),
                                           stream()), 'grad_global_norm')
@@ -369,6 +442,11 @@ def grad_global_norm(grad_flat, out_norm):
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_div=1.0, grad_norm=None,
               max_norm=0.0, clip_mode=0, zero_grad=True, lr_device=None):
+    n = param.numel()
+    for nm, t in (('param', param), ('grad', grad), ('exp_avg', exp_avg), ('exp_avg_sq', exp_avg_sq)):
+        _chk(nm, t, torch.float32, n)
+    _chk('grad_norm', grad_norm, torch.float32, 1, optional=True)
+    _chk('lr_device', lr_device, torch.float32, 1, optional=True)
     check(_lib.load().rl_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), ptr(lr_device),
                                    float(lr), float(beta1), float(beta2), float(eps), int(step), float(grad_div),
                                    ptr(grad_norm), float(max_norm), int(clip_mode), 1 if zero_grad else 0, stream()),
@@ -504,3 +582,81 @@ def mask_scatter_grid_bf16(src, act, dst, n, PH, PW, GH, GW, C):
     check(_lib.load().rl_mask_scatter_grid_bf16(ptr(src), ptr(act), ptr(dst), int(n), PH, PW, GH, GW, C, stream()),
           'mask_scatter_grid_bf16')
     return dst
+
+
+# --------------------------------------------------------------------------- fused fp32 MLP (K6, MLP model family)
+ACT_RELU, ACT_TANH, ACT_NONE = 0, 1, 2
+
+
+class MlpPlan(object):
+    """Shape + parameter-pointer tables of one MLP for rl_mlp_fwd / rl_mlp_bwd.
+
+    ``layers`` is a list (one entry per linear layer) of lists of (weight, bias) tensors — the row segments of that
+    layer in torch nn.Linear layout; the last layer's segments are the heads (outputs concatenated).  Pointers are
+    taken once: parameters re-homed into a FlatAdam buffer keep their addresses, so build the plan AFTER the
+    optimiser.  ``grads`` may be given as matching (dweight, dbias) tensors (default: the parameters' .grad)."""
+
+    def __init__(self, layers, act):
+        import ctypes
+        self.act = int(act)
+        segs = []
+        dims = [layers[0][0][0].shape[1]]
+        for li, seg_list in enumerate(layers):
+            rows = 0
+            for (w, b) in seg_list:
+                require_cuda(w, b)
+                assert w.dtype == torch.float32 and w.dim() == 2 and w.shape[1] == dims[li], 'layer %d weight' % li
+                assert b is None or (b.dtype == torch.float32 and b.numel() == w.shape[0])
+                segs.append((li, w, b))
+                rows += w.shape[0]
+            dims.append(rows)
+        self.dims_list = dims
+        self.n_layers = len(layers)
+        self.segs = segs
+        self.device = segs[0][1].device
+        n = len(segs)
+        IntA, PtrA = ctypes.c_int * n, ctypes.c_void_p * n
+        self.c_dims = (ctypes.c_int * len(dims))(*dims)
+        self.c_layer = IntA(*[s[0] for s in segs])
+        self.c_rows = IntA(*[s[1].shape[0] for s in segs])
+        self.c_w = PtrA(*[s[1].data_ptr() for s in segs])
+        self.c_b = PtrA(*[(s[2].data_ptr() if s[2] is not None else None) for s in segs])
+        self._PtrA = PtrA
+        self._grad_tabs = None
+        self.ws = torch.empty(int(_lib.load().rl_mlp_workspace_bytes(self.n_layers, self.c_dims)), dtype=torch.uint8,
+                              device=self.device)
+
+    @property
+    def out_dim(self):
+        return self.dims_list[-1]
+
+    def forward(self, x, out=None):
+        require_cuda(x)
+        assert x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] == self.dims_list[0]
+        n = x.shape[0]
+        if out is None:
+            out = torch.empty((n, self.out_dim), dtype=torch.float32, device=x.device)
+        assert out.dtype == torch.float32 and out.numel() == n * self.out_dim and out.is_contiguous()
+        check(_lib.load().rl_mlp_fwd(ptr(x), n, self.n_layers, self.c_dims, len(self.segs), self.c_layer, self.c_rows,
+                                     self.c_w, self.c_b, self.act, ptr(out), stream()), 'mlp_fwd')
+        return out
+
+    def backward(self, x, d_out, grads=None, accumulate=False):
+        """Parameter gradients of sum(out * d_out) into ``grads`` [(dw, db), ...] (default: each parameter's .grad)."""
+        require_cuda(x, d_out)
+        n = x.shape[0]
+        assert x.dtype == torch.float32 and d_out.dtype == torch.float32 and d_out.numel() == n * self.out_dim
+        if grads is None:
+            if self._grad_tabs is None:
+                gw = [s[1].grad for s in self.segs]
+                gb = [(s[2].grad if s[2] is not None else None) for s in self.segs]
+                assert all(g is not None for g in gw), 'parameters have no .grad buffers (build a FlatAdam first)'
+                self._grad_tabs = (self._PtrA(*[g.data_ptr() for g in gw]),
+                                   self._PtrA(*[(g.data_ptr() if g is not None else None) for g in gb]), gw, gb)
+            c_dw, c_db = self._grad_tabs[0], self._grad_tabs[1]
+        else:
+            c_dw = self._PtrA(*[g[0].data_ptr() for g in grads])
+            c_db = self._PtrA(*[(g[1].data_ptr() if g[1] is not None else None) for g in grads])
+        check(_lib.load().rl_mlp_bwd(ptr(x), n, self.n_layers, self.c_dims, len(self.segs), self.c_layer, self.c_rows,
+                                     self.c_w, self.c_b, self.act, ptr(d_out), c_dw, c_db, 1 if accumulate else 0,
+                                     ptr(self.ws), self.ws.numel(), stream()), 'mlp_bwd')

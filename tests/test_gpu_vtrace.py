@@ -137,21 +137,34 @@ def test_vtrace_loss_full_size_properties():
 
 
 def test_tma_and_cpasync_tile_paths_agree():
-    """The TMA tensor-map tile path and the cp.async path of the fused kernel are the same arithmetic."""
+    """The TMA tensor-map tile path and the cp.async path of the general (v4) kernel are the same arithmetic, and
+    the warp-streaming kernel (v5; 2, 4 or 8 env columns per warp) agrees with both to float32 round-off."""
     from parl_b200 import kernels, _lib
     lib = _lib.load()
-    for (T, B, A) in [(50, 512, 18), (50, 7 * 4, 6), (130, 64, 18), (20, 256, 2)]:
+    for (T, B, A) in [(50, 512, 18), (50, 7 * 4, 6), (130, 64, 18), (20, 256, 2), (50, 4096, 18), (7, 8, 18),
+                      (64, 40, 4), (33, 16, 18)]:
         tl, bl, acts, rew, dones, vals = make_rollout(T, B, A, 11)
         args = [_cuda(tl).reshape(T * B, A), _cuda(bl).reshape(T * B, A), _cuda(acts).reshape(-1),
                 _cuda(rew).reshape(-1), _cuda(dones).reshape(-1), _cuda(vals).reshape(-1)]
         try:
+            lib.rl_debug_set_vtrace_path(1)
             lib.rl_debug_set_tma(1)
             r0 = kernels.vtrace_loss_fwd_bwd(*args, T, B, 0.99, 0.5, -0.01, want_returns=True)
             torch.cuda.synchronize()
+            lib.rl_debug_set_tma(0)
+            r1 = kernels.vtrace_loss_fwd_bwd(*args, T, B, 0.99, 0.5, -0.01, want_returns=True)
+            torch.cuda.synchronize()
+            for k in ('d_logits', 'd_values', 'vs', 'pg_advantages'):
+                assert torch.equal(r0[k], r1[k]), (k, T, B, A)
+            assert torch.equal(r0['losses'][:5], r1['losses'][:5])
+            for mode in (0, 2, 8):
+                lib.rl_debug_set_vtrace_path(mode)
+                r5 = kernels.vtrace_loss_fwd_bwd(*args, T, B, 0.99, 0.5, -0.01, want_returns=True)
+                torch.cuda.synchronize()
+                for k in ('d_logits', 'd_values', 'vs', 'pg_advantages'):
+                    assert torch.allclose(r5[k], r1[k], rtol=2e-5, atol=2e-5), (k, T, B, A, mode,
+                                                                               (r5[k] - r1[k]).abs().max().item())
+                assert torch.allclose(r5['losses'][:5], r1['losses'][:5], rtol=1e-5, atol=1e-4), (T, B, A, mode)
         finally:
             lib.rl_debug_set_tma(0)
-        r1 = kernels.vtrace_loss_fwd_bwd(*args, T, B, 0.99, 0.5, -0.01, want_returns=True)
-        torch.cuda.synchronize()
-        for k in ('d_logits', 'd_values', 'vs', 'pg_advantages'):
-            assert torch.equal(r0[k], r1[k]), (k, T, B, A)
-        assert torch.equal(r0['losses'][:5], r1['losses'][:5])
+            lib.rl_debug_set_vtrace_path(0)
