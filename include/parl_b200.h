@@ -251,8 +251,14 @@ int rl_per_update(double* tree, double* state, int capacity, const int32_t* tree
 int rl_per_sample(const double* tree, const double* state, int capacity, int seg_num, const float* u,
                   uint64_t seed, uint32_t draw, double beta, double size,
                   int32_t* tree_idx, int32_t* elem_idx, float* weights, rl_stream_t stream);
+/* Frame-ring gather (benchmark/torch/dqn/replay_memory.py:59-85): for every start index the n_out (<= ctx+1) frames
+ * start .. start+n_out-1 (positions modulo curr_size), frames at or before the last episode end among the first
+ * ctx-1 positions zeroed.  `lanes` interleaved transition streams (one per lock-stepped env): position q of lane l
+ * is row q*lanes + l and a start index encodes (q0, l) as q0*lanes + l; lanes = 1 is the reference's single ring.
+ * n_out = ctx+1: the learner's (obs, next_obs) window; n_out = ctx: the actor's current stacked observation. */
 int rl_replay_gather_frames(const uint8_t* frames, const uint8_t* is_over, const int32_t* idx, int n,
-                            int curr_size, int context_len, int HW, uint8_t* out, rl_stream_t stream);
+                            int curr_size, int context_len, int HW, int lanes, int n_out, uint8_t* out,
+                            rl_stream_t stream);
 int rl_gather_rows(const void* src, const int32_t* idx, long long n, int row_bytes, void* out, rl_stream_t stream);
 
 /* ------------------------------------------------------------------------
@@ -361,18 +367,41 @@ int rl_mask_scatter_grid_bf16(const void* src, const void* act, void* dst, long 
  *   (segments of one layer are stacked in the order given — e.g. the policy and value heads of an
  *   actor-critic are two segments of the last layer), seg_w[s] [rows, in] float32, seg_b[s] [rows] or NULL.
  *   dims, seg_layer, seg_rows, seg_w, seg_b, seg_dw, seg_db are HOST arrays (of device pointers where typed so).
- * rl_mlp_fwd: x [n, in] -> out [n, out].
+ * rl_mlp_fwd: x [n, in] -> out [n, out]; with out2 != NULL the output columns are delivered as two dense
+ *   tensors, out [n, split] and out2 [n, out-split] (policy head / value head).  rl_mlp_bwd takes d_out /
+ *   d_out2 the same way.
  * rl_mlp_bwd: recomputes the hidden activations from x, back-propagates d_out [n, out] and writes
  *   (accumulate=0) or adds (1) the parameter gradients into seg_dw[s] / seg_db[s] (same shapes as the
  *   parameters); deterministic two-stage reduction through `workspace` (rl_mlp_workspace_bytes). */
 size_t rl_mlp_workspace_bytes(int n_layers, const int* dims);
 int rl_mlp_fwd(const float* x, int n, int n_layers, const int* dims, int n_seg, const int* seg_layer,
                const int* seg_rows, const float* const* seg_w, const float* const* seg_b, int act, float* out,
-               rl_stream_t stream);
+               float* out2, int split, rl_stream_t stream);
 int rl_mlp_bwd(const float* x, int n, int n_layers, const int* dims, int n_seg, const int* seg_layer,
                const int* seg_rows, const float* const* seg_w, const float* const* seg_b, int act,
-               const float* d_out, float* const* seg_dw, float* const* seg_db, int accumulate,
-               void* workspace, size_t workspace_bytes, rl_stream_t stream);
+               const float* d_out, const float* d_out2, int split, float* const* seg_dw, float* const* seg_db,
+               int accumulate, void* workspace, size_t workspace_bytes, rl_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * a10 + a11 + a13  Fused on-device actor pool for MLP policies: ONE launch runs T lock-step steps of all B envs
+ * — policy/value forward (network as in rl_mlp_fwd; outputs = [action_dim policy outputs | value if has_value]),
+ * action sampling (policy_kind 0: categorical, exact inverse CDF; 1: diagonal Gaussian with logstd [action_dim]),
+ * env step (env_kind 0: MuJoCo-shaped synthetic env of rl_env_mujoco_synth_step; 1: CartPole physics of
+ * rl_env_cartpole_step), auto-reset, episode bookkeeping — and writes the trajectory time-major.
+ * Replaces per step: agent.sample -> envs.step -> rollout.append (benchmark/torch/ppo/train.py:91-101,
+ * benchmark/torch/a2c/actor.py:56-80) and its RPC.  Bit-identical to stepping the stand-alone kernels.
+ *   obs_cur [B, obs_dim] in/out: the observation every env is in (initialise with the env's reset kernel);
+ *   global step index of row t = step0 + t (RNG counter);
+ *   outputs: obs_out [T,B,obs_dim], act_out [T,B] int32 | [T,B,action_dim] f32, logp_out [T,B] (opt),
+ *   val_out [T+1,B] (opt; row T = value of the observation after the last step), logits_out [T,B,action_dim]
+ *   (opt, categorical), rew_out [T,B] f32, done_out [T,B] u8. */
+int rl_rollout_mlp(int n_layers, const int* dims, int n_seg, const int* seg_layer, const int* seg_rows,
+                   const float* const* seg_w, const float* const* seg_b, int act, int env_kind, int policy_kind,
+                   int T, int B, int action_dim, int has_value, const float* logstd, float* obs_cur,
+                   float* ep_ret, int32_t* ep_len, float* totals, float* ring_ret, int32_t* ring_len,
+                   uint32_t* ring_head, int ring_cap, uint64_t seed, uint32_t step0, uint32_t env_offset,
+                   float p_done, int max_episode_steps, float* obs_out, void* act_out, float* logp_out,
+                   float* val_out, float* logits_out, float* rew_out, uint8_t* done_out, rl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -58,7 +58,7 @@ SIGNATURES = {
     'rl_per_update': (c_i, [c_p, c_p, c_i, c_p, c_p, c_i, ctypes.c_double, ctypes.c_double, c_p]),
     'rl_per_sample': (c_i, [c_p, c_p, c_i, c_i, c_p, c_u64, c_u32, ctypes.c_double, ctypes.c_double, c_p, c_p,
                             c_p, c_p]),
-    'rl_replay_gather_frames': (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p]),
+    'rl_replay_gather_frames': (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     'rl_gather_rows': (c_i, [c_p, c_p, ctypes.c_longlong, c_i, c_p, c_p]),
     'rl_grad_global_norm': (c_i, [c_p, ctypes.c_longlong, c_p, c_p, c_sz, c_p]),
     'rl_adam_step': (c_i, [c_p, c_p, c_p, c_p, ctypes.c_longlong, c_p, c_f, c_f, c_f, c_f, c_i, c_f, c_p, c_f, c_i,
@@ -76,8 +76,11 @@ SIGNATURES = {
     'rl_gemm_bf16_tn_masked': (c_i, [c_p, c_p, c_p, c_p] + [c_i] * 8 + [c_p]),
     'rl_bias_act_bf16': (c_i, [c_p, c_p, ctypes.c_longlong, c_i, c_i, c_p]),
     'rl_mlp_workspace_bytes': (c_sz, [c_i, c_p]),
-    'rl_mlp_fwd': (c_i, [c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p]),
-    'rl_mlp_bwd': (c_i, [c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_p, c_sz, c_p]),
+    'rl_mlp_fwd': (c_i, [c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_p]),
+    'rl_mlp_bwd': (c_i, [c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_sz, c_p]),
+    'rl_rollout_mlp': (c_i, [c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p,
+                             c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_u64, c_u32, c_u32, c_f, c_i, c_p, c_p, c_p, c_p, c_p,
+                             c_p, c_p, c_p]),
     'rl_mask_scatter_grid_bf16': (c_i, [c_p, c_p, c_p, ctypes.c_longlong, c_i, c_i, c_i, c_i, c_i, c_p]),
 }
 

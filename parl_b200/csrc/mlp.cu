@@ -19,6 +19,7 @@
 //                      per-CTA partial sums live in an L2-resident workspace, a second kernel adds them up in a
 //                      fixed order (deterministic)
 #include "common.cuh"
+#include "env_common.cuh"
 
 namespace rl {
 
@@ -41,6 +42,9 @@ struct MlpArgs {
   const float* x;        // [n, dims[0]]
   float* out;            // [n, dims[L]]
   const float* d_out;    // [n, dims[L]]
+  float* out2;           // optional second output: columns [split, dims[L]) go to out2 [n, dims[L]-split],
+  const float* d_out2;   //   columns [0, split) to out [n, split]  (heads of an actor-critic as separate tensors)
+  int split;
   float* partial;        // [grid, np_pad]  backward: per-CTA partial gradients (padded layout)
   int n, L, n_seg, act, accumulate;
   int dims[kMaxLayers + 1];
@@ -243,9 +247,14 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_fwd_kernel(const MlpArgs p) {
       float* t = cur;
       cur = nxt, nxt = t;
     }
+    const int S = p.out2 ? p.split : O;
     for (int i = threadIdx.x; i < kTN * O; i += kMlpThreads) {
       const int nn = i / O, o = i - nn * O;
-      if (n0 + nn < p.n) p.out[(size_t)(n0 + nn) * O + o] = cur[o * kTS + nn];
+      if (n0 + nn < p.n) {
+        const float v = cur[o * kTS + nn];
+        if (o < S) p.out[(size_t)(n0 + nn) * S + o] = v;
+        else p.out2[(size_t)(n0 + nn) * (O - S) + (o - S)] = v;
+      }
     }
     __syncthreads();
   }
@@ -266,10 +275,12 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_bwd_kernel(const MlpArgs p) {
     const int n0 = tile * kTN;
     load_input_tile(p, n0, s_act + p.a_off[0]);
     // d_out tile -> s_d0[o][n]   (zero beyond n / beyond O)
+    const int S = p.d_out2 ? p.split : O;
     for (int i = threadIdx.x; i < Op * kTN; i += kMlpThreads) {
       const int nn = i / Op, o = i - nn * Op;
       float v = 0.f;
-      if (o < O && n0 + nn < p.n) v = p.d_out[(size_t)(n0 + nn) * O + o];
+      if (o < O && n0 + nn < p.n)
+        v = o < S ? p.d_out[(size_t)(n0 + nn) * S + o] : p.d_out2[(size_t)(n0 + nn) * (O - S) + (o - S)];
       s_d0[o * kTS + nn] = v;
     }
     __syncthreads();
@@ -319,6 +330,158 @@ __global__ void __launch_bounds__(256) mlp_grad_reduce_kernel(const MlpArgs p, i
       for (int c = 0; c < nparts; ++c) a += p.partial[(size_t)c * p.np_pad + off];
       *dst = p.accumulate ? *dst + a : a;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Fused on-device actor pool for MLP policies: ONE launch runs all T lock-step steps of a tile of 64 envs —
+// policy/value forward (weights resident in shared memory), action sampling, env step, episode bookkeeping — and
+// writes the trajectory straight into the time-major (T,B) rollout buffers.  Replaces, per step and per env, the
+// reference's agent.sample -> env.step -> rollout.append round trip (benchmark/torch/ppo/train.py:91-101,
+// benchmark/torch/a2c/actor.py:56-80) and its xparl RPC (parl/remote/remote_wrapper.py:178-227).
+// Arithmetic is the same device code as the stand-alone kernels (rl_mlp_fwd, rl_sample_*, rl_env_*_step), so a
+// fused rollout is bit-identical to stepping those kernels one at a time (tests/test_gpu_rollout.py).
+// ---------------------------------------------------------------------------
+struct RolloutArgs {
+  int env_kind;        // 0 MuJoCo-shaped synthetic (obs ~ N(0,1)^D), 1 CartPole physics
+  int policy_kind;     // 0 categorical over AD actions, 1 diagonal Gaussian with AD dimensions
+  int T, B, AD, has_value, max_steps;
+  const float* logstd; // [AD] (Gaussian)
+  float* obs_cur;      // [B, D]  observation each env is in (in: before step 0, out: after step T-1)
+  EpisodeStats st;
+  uint32_t k0, k1, step0, env_offset, done_thr;
+  float* obs_out;      // [T, B, D]
+  void* act_out;       // [T, B] int32 (categorical) or [T, B, AD] float32 (Gaussian)
+  float* logp_out;     // [T, B] or NULL
+  float* val_out;      // [T+1, B] (row T: value of the observation after the last step) or NULL
+  float* logits_out;   // [T, B, AD] or NULL (categorical: behaviour logits for off-policy corrections)
+  float* rew_out;      // [T, B]
+  uint8_t* done_out;   // [T, B]
+};
+
+// sample_categorical_exact (philox.cuh) over a strided row — same operations in the same order
+__device__ __forceinline__ int sample_categorical_exact_strided(const float* __restrict__ lg, int stride, int A, float u) {
+  float m = lg[0];
+  for (int j = 1; j < A; ++j) m = fmaxf(m, lg[j * stride]);
+  float total = 0.f;
+  for (int j = 0; j < A; ++j) total = __fadd_rn(total, exp_exact(__fsub_rn(lg[j * stride], m)));
+  const float thr = __fmul_rn(u, total);
+  float acc = 0.f;
+  int a = 0;
+  for (int j = 0; j < A; ++j) {
+    acc = __fadd_rn(acc, exp_exact(__fsub_rn(lg[j * stride], m)));
+    a += (acc <= thr) ? 1 : 0;
+  }
+  return min(a, A - 1);
+}
+
+__global__ void __launch_bounds__(kMlpThreads) rollout_mlp_kernel(const MlpArgs p, const RolloutArgs r) {
+  extern __shared__ __align__(16) float smem_f[];
+  float* s_par = smem_f;
+  float* s_x = smem_f + ((p.np_pad + 3) & ~3);            // observation tile [pd[0]][kTS]
+  float* s_a = s_x + kMaxWidth * kTS;                      // ping
+  float* s_b = s_a + kMaxWidth * kTS;                      // pong
+  load_params(p, s_par);
+  const int n0 = blockIdx.x * kTN;
+  const int D = p.dims[0], Dp = p.pd[0], B = r.B;
+  const int tid = threadIdx.x;
+  // the envs' current observations -> s_x[k][n]
+  for (int i = tid; i < Dp * kTN; i += kMlpThreads) {
+    const int nn = i / Dp, k = i - nn * Dp;
+    float v = 0.f;
+    if (k < D && n0 + nn < B) v = r.obs_cur[(size_t)(n0 + nn) * D + k];
+    s_x[k * kTS + nn] = v;
+  }
+  __syncthreads();
+  for (int t = 0; t <= r.T; ++t) {
+    if (t == r.T && !(r.has_value && r.val_out)) break;
+    if (t < r.T) {
+      for (int i = tid; i < D * kTN; i += kMlpThreads) {     // trajectory: observation of step t
+        const int nn = i / D, k = i - nn * D;
+        if (n0 + nn < B) r.obs_out[((size_t)t * B + n0 + nn) * D + k] = s_x[k * kTS + nn];
+      }
+    }
+    const float* cur = s_x;
+    float* nxt = s_a;
+    for (int l = 0; l < p.L; ++l) {
+      layer_fwd_any(s_par + p.w_off[l], s_par + p.b_off[l], cur, nxt, p.pd[l], p.pd[l + 1], l + 1 < p.L ? p.act : 2);
+      __syncthreads();
+      cur = nxt;
+      nxt = (nxt == s_a) ? s_b : s_a;
+    }
+    // one thread per env: value, action, env step (two full warps: the episode bookkeeping is warp-synchronous)
+    if (tid < kTN) {
+      const int b = n0 + tid;
+      const bool valid = b < B;
+      const uint32_t env = r.env_offset + (uint32_t)b;
+      const uint32_t step = r.step0 + (uint32_t)t;
+      const float* o = cur + tid;                            // output j of this env: o[j * kTS]
+      if (valid && r.has_value && r.val_out) r.val_out[(size_t)t * B + b] = o[r.AD * kTS];
+      float reward = 0.f;
+      bool done = false;
+      if (t < r.T) {
+        int a_cat = 0;
+        if (valid) {
+          const size_t tb = (size_t)t * B + b;
+          if (r.policy_kind == 0) {
+            const uint4 ua = philox4x32_10(env, step, 0u, STREAM_ACTION, r.k0, r.k1);
+            a_cat = sample_categorical_exact_strided(o, kTS, r.AD, u01_24(ua.x));
+            reinterpret_cast<int*>(r.act_out)[tb] = a_cat;
+            if (r.logp_out) {
+              float m = o[0];
+              for (int j = 1; j < r.AD; ++j) m = fmaxf(m, o[j * kTS]);
+              float S = 0.f;
+              for (int j = 0; j < r.AD; ++j) S += expf(o[j * kTS] - m);
+              r.logp_out[tb] = o[a_cat * kTS] - m - logf(S);
+            }
+            if (r.logits_out)
+              for (int j = 0; j < r.AD; ++j) r.logits_out[tb * r.AD + j] = o[j * kTS];
+          } else {
+            float lp = 0.f;
+            float* ao = reinterpret_cast<float*>(r.act_out) + tb * r.AD;
+            for (int blk = 0; blk * 4 < r.AD; ++blk) {
+              float z[4];
+              gauss_block(env, step, (uint32_t)blk, STREAM_GAUSS, r.k0, r.k1, z);
+              for (int k = 0; k < 4 && blk * 4 + k < r.AD; ++k) {
+                const int d = blk * 4 + k;
+                const float ls = r.logstd[d], sd = expf(ls);
+                ao[d] = fmaf(sd, z[k], o[d * kTS]);
+                lp += -0.5f * z[k] * z[k] - ls - 0.9189385332046727f;
+              }
+            }
+            if (r.logp_out) r.logp_out[tb] = lp;
+          }
+          // ---- env step (same draws / physics as rl_env_mujoco_synth_step / rl_env_cartpole_step)
+          if (r.env_kind == 0) {
+            const uint4 x = philox4x32_10(env, step, 0u, STREAM_REWDONE, r.k0, r.k1);
+            reward = (float)(x.x & 1u);
+            done = x.y < r.done_thr;
+            if (r.max_steps > 0 && r.st.ep_len[b] + 1 >= r.max_steps) done = true;
+            for (int blk = 0; blk * 4 < D; ++blk) {
+              float z[4];
+              gauss_block(env, step + 1u, (uint32_t)blk, STREAM_OBS, r.k0, r.k1, z);
+              for (int k = 0; k < 4 && blk * 4 + k < D; ++k) s_x[(blk * 4 + k) * kTS + tid] = z[k];
+            }
+          } else {
+            float4 s = make_float4(s_x[tid], s_x[kTS + tid], s_x[2 * kTS + tid], s_x[3 * kTS + tid]);
+            done = cartpole_physics(s, a_cat);
+            reward = 1.0f;
+            if (r.max_steps > 0 && r.st.ep_len[b] + 1 >= r.max_steps) done = true;
+            if (done) s = cartpole_reset_state(env, step + 1u, r.k0, r.k1);
+            s_x[tid] = s.x, s_x[kTS + tid] = s.y, s_x[2 * kTS + tid] = s.z, s_x[3 * kTS + tid] = s.w;
+          }
+          r.rew_out[tb] = reward;
+          r.done_out[tb] = done ? 1 : 0;
+        }
+        episode_update(r.st, b, valid, reward, done);
+      }
+    }
+    __syncthreads();
+  }
+  // carry the envs' observations to the next rollout
+  for (int i = tid; i < D * kTN; i += kMlpThreads) {
+    const int nn = i / D, k = i - nn * D;
+    if (n0 + nn < B) r.obs_cur[(size_t)(n0 + nn) * D + k] = s_x[k * kTS + nn];
   }
 }
 
@@ -376,13 +539,15 @@ extern "C" size_t rl_mlp_workspace_bytes(int n_layers, const int* dims) {
 
 extern "C" int rl_mlp_fwd(const float* x, int n, int n_layers, const int* dims, int n_seg, const int* seg_layer,
                           const int* seg_rows, const float* const* seg_w, const float* const* seg_b, int act, float* out,
-                          rl_stream_t stream) {
+                          float* out2, int split, rl_stream_t stream) {
   using namespace rl;
   RL_CHECK_ARG(x && out && dims && seg_layer && seg_rows && seg_w, "mlp_fwd: null pointer");
   MlpArgs a;
   const int rc = mlp_shape(a, n, n_layers, dims, n_seg, seg_layer, seg_rows, seg_w, seg_b, act);
   if (rc != RL_OK) return rc;
+  RL_CHECK_ARG(!out2 || (split >= 1 && split < dims[n_layers]), "mlp_fwd: split %d outside 1..%d", split, dims[n_layers] - 1);
   a.x = x, a.out = out, a.d_out = nullptr, a.partial = nullptr, a.accumulate = 0;
+  a.out2 = out2, a.d_out2 = nullptr, a.split = split;
   const size_t smem = (((size_t)a.np_pad + 3) & ~(size_t)3) * 4 + 2 * (size_t)kMaxWidth * kTS * 4;
   RL_CHECK_ARG(smem <= 220 * 1024, "mlp_fwd: network too large for shared memory (%zu B)", smem);
   int dev = 0, nsm = 148;
@@ -398,8 +563,9 @@ extern "C" int rl_mlp_fwd(const float* x, int n, int n_layers, const int* dims, 
 
 extern "C" int rl_mlp_bwd(const float* x, int n, int n_layers, const int* dims, int n_seg, const int* seg_layer,
                           const int* seg_rows, const float* const* seg_w, const float* const* seg_b, int act,
-                          const float* d_out, float* const* seg_dw, float* const* seg_db, int accumulate,
-                          void* workspace, size_t workspace_bytes, rl_stream_t stream) {
+                          const float* d_out, const float* d_out2, int split, float* const* seg_dw,
+                          float* const* seg_db, int accumulate, void* workspace, size_t workspace_bytes,
+                          rl_stream_t stream) {
   using namespace rl;
   RL_CHECK_ARG(x && d_out && dims && seg_layer && seg_rows && seg_w && seg_dw && workspace, "mlp_bwd: null pointer");
   MlpArgs a;
@@ -410,7 +576,9 @@ extern "C" int rl_mlp_bwd(const float* x, int n, int n_layers, const int* dims, 
     a.seg[s].dw = seg_dw[s];
     a.seg[s].db = seg_db ? seg_db[s] : nullptr;
   }
+  RL_CHECK_ARG(!d_out2 || (split >= 1 && split < dims[n_layers]), "mlp_bwd: split %d outside 1..%d", split, dims[n_layers] - 1);
   a.x = x, a.out = nullptr, a.d_out = d_out, a.accumulate = accumulate;
+  a.out2 = nullptr, a.d_out2 = d_out2, a.split = split;
   const size_t smem = (((size_t)a.np_pad + 3) & ~(size_t)3) * 4 + (size_t)a.a_off[a.L] * 4 + 2 * (size_t)kMaxWidth * kTS * 4;
   RL_CHECK_ARG(smem <= 220 * 1024, "mlp_bwd: network too large for shared memory (%zu B)", smem);
   int dev = 0, nsm = 148;
@@ -430,5 +598,47 @@ extern "C" int rl_mlp_bwd(const float* x, int n, int n_layers, const int* dims, 
   RL_CHECK_LAUNCH("rl_mlp_bwd");
   mlp_grad_reduce_kernel<<<(a.np_pad + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a, grid);
   RL_CHECK_LAUNCH("rl_mlp_bwd(reduce)");
+  return RL_OK;
+}
+
+extern "C" int rl_rollout_mlp(int n_layers, const int* dims, int n_seg, const int* seg_layer, const int* seg_rows,
+                              const float* const* seg_w, const float* const* seg_b, int act, int env_kind,
+                              int policy_kind, int T, int B, int action_dim, int has_value, const float* logstd,
+                              float* obs_cur, float* ep_ret, int32_t* ep_len, float* totals, float* ring_ret,
+                              int32_t* ring_len, uint32_t* ring_head, int ring_cap, uint64_t seed, uint32_t step0,
+                              uint32_t env_offset, float p_done, int max_episode_steps, float* obs_out, void* act_out,
+                              float* logp_out, float* val_out, float* logits_out, float* rew_out, uint8_t* done_out,
+                              rl_stream_t stream) {
+  using namespace rl;
+  RL_CHECK_ARG(dims && seg_layer && seg_rows && seg_w && obs_cur && ep_ret && ep_len && totals && obs_out && act_out &&
+                   rew_out && done_out,
+               "rollout_mlp: null pointer");
+  RL_CHECK_ARG(env_kind == 0 || env_kind == 1, "rollout_mlp: env_kind %d not in {0 mujoco-synth, 1 cartpole}", env_kind);
+  RL_CHECK_ARG(policy_kind == 0 || policy_kind == 1, "rollout_mlp: policy_kind %d not in {0 categorical, 1 gaussian}", policy_kind);
+  RL_CHECK_ARG(T >= 1 && B >= 1 && action_dim >= 1, "rollout_mlp: T=%d B=%d action_dim=%d", T, B, action_dim);
+  MlpArgs a;
+  const int rc = mlp_shape(a, B, n_layers, dims, n_seg, seg_layer, seg_rows, seg_w, seg_b, act);
+  if (rc != RL_OK) return rc;
+  RL_CHECK_ARG(dims[n_layers] == action_dim + (has_value ? 1 : 0),
+               "rollout_mlp: network has %d outputs, expected action_dim %d + value %d", dims[n_layers], action_dim,
+               has_value ? 1 : 0);
+  RL_CHECK_ARG(env_kind != 1 || (dims[0] == 4 && policy_kind == 0 && action_dim == 2),
+               "rollout_mlp: CartPole needs obs dim 4 and a 2-way categorical policy");
+  RL_CHECK_ARG(policy_kind != 1 || logstd, "rollout_mlp: Gaussian policy without logstd");
+  a.x = nullptr, a.out = nullptr, a.d_out = nullptr, a.out2 = nullptr, a.d_out2 = nullptr, a.split = 0;
+  a.partial = nullptr, a.accumulate = 0;
+  RolloutArgs r;
+  r.env_kind = env_kind, r.policy_kind = policy_kind, r.T = T, r.B = B, r.AD = action_dim, r.has_value = has_value;
+  r.max_steps = max_episode_steps, r.logstd = logstd, r.obs_cur = obs_cur;
+  r.st = make_episode_stats(ep_ret, ep_len, totals, ring_ret, ring_len, ring_head, ring_cap);
+  r.k0 = (uint32_t)seed, r.k1 = (uint32_t)(seed >> 32), r.step0 = step0, r.env_offset = env_offset;
+  r.done_thr = prob_threshold(p_done);
+  r.obs_out = obs_out, r.act_out = act_out, r.logp_out = logp_out, r.val_out = val_out, r.logits_out = logits_out;
+  r.rew_out = rew_out, r.done_out = done_out;
+  const size_t smem = (((size_t)a.np_pad + 3) & ~(size_t)3) * 4 + 3 * (size_t)kMaxWidth * kTS * 4;
+  RL_CHECK_ARG(smem <= 220 * 1024, "rollout_mlp: network too large for shared memory (%zu B)", smem);
+  RL_SMEM_OPTIN(rollout_mlp_kernel);
+  rollout_mlp_kernel<<<(B + kTN - 1) / kTN, kMlpThreads, smem, (cudaStream_t)stream>>>(a, r);
+  RL_CHECK_LAUNCH("rl_rollout_mlp");
   return RL_OK;
 }

@@ -124,25 +124,31 @@ __global__ void __launch_bounds__(128) per_sample_kernel(const double* __restric
 __global__ void __launch_bounds__(256) replay_gather_frames_kernel(const uint8_t* __restrict__ frames,
                                                                    const uint8_t* __restrict__ is_over,
                                                                    const int* __restrict__ idx, int n, int curr_size,
-                                                                   int ctx, int HW, uint8_t* __restrict__ out) {
+                                                                   int ctx, int HW, int lanes, int n_out,
+                                                                   uint8_t* __restrict__ out) {
+  // Ring of `lanes` interleaved transition streams (one per env, stepped in lock-step): stream position q of lane l
+  // is row q*lanes + l, so the plane of one position is a dense [lanes, HW] block the env kernel writes in place.
+  // A start index encodes (q0, l) as q0*lanes + l; lanes == 1 is the reference's single ring.
   const int nblk = HW >> 4;
-  const long long total = (long long)n * (ctx + 1) * nblk;
+  const long long total = (long long)n * n_out * nblk;
   const long long gstride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gstride) {
     const int blk = (int)(i % nblk);
     const long long r = i / nblk;
-    const int j = (int)(r % (ctx + 1));
-    const int s = (int)(r / (ctx + 1));
+    const int j = (int)(r % n_out);
+    const int s = (int)(r / n_out);
     const int start = idx[s];
+    const int q0 = start / lanes, lane = start - q0 * lanes;
     int cut = -1;
     for (int k = ctx - 2; k >= 0; --k) {
-      if (is_over[(start + k) % curr_size]) {
+      if (is_over[(long long)((q0 + k) % curr_size) * lanes + lane]) {
         cut = k;
         break;
       }
     }
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (j > cut) v = __ldg(reinterpret_cast<const uint4*>(frames + (long long)((start + j) % curr_size) * HW) + blk);
+    if (j > cut)
+      v = __ldg(reinterpret_cast<const uint4*>(frames + ((long long)((q0 + j) % curr_size) * lanes + lane) * HW) + blk);
     reinterpret_cast<uint4*>(out + r * HW)[blk] = v;
   }
 }
@@ -201,15 +207,17 @@ extern "C" int rl_per_sample(const double* tree, const double* state, int capaci
 }
 
 extern "C" int rl_replay_gather_frames(const uint8_t* frames, const uint8_t* is_over, const int32_t* idx, int n,
-                                       int curr_size, int context_len, int HW, uint8_t* out, rl_stream_t stream) {
+                                       int curr_size, int context_len, int HW, int lanes, int n_out, uint8_t* out,
+                                       rl_stream_t stream) {
   RL_CHECK_ARG(frames && is_over && idx && out, "replay_gather_frames: null pointer");
   RL_CHECK_ARG(n >= 1 && curr_size >= 1 && context_len >= 1 && HW % 16 == 0 && aligned16(frames) && aligned16(out),
                "replay_gather_frames: bad shape / alignment");
-  const long long total = (long long)n * (context_len + 1) * (HW / 16);
+  RL_CHECK_ARG(lanes >= 1 && n_out >= 1 && n_out <= context_len + 1, "replay_gather_frames: lanes=%d n_out=%d", lanes, n_out);
+  const long long total = (long long)n * n_out * (HW / 16);
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
   replay_gather_frames_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(frames, is_over, idx, n, curr_size,
-                                                                                 context_len, HW, out);
+                                                                                 context_len, HW, lanes, n_out, out);
   RL_CHECK_LAUNCH("rl_replay_gather_frames");
   return RL_OK;
 }

@@ -72,26 +72,57 @@ class AtariActorCritic(Model):
         return logits, values
 
 
+def _dim(space_or_int):
+    """The reference models take gym spaces (``MujocoModel(obs_space, act_space)``); plain ints work too."""
+    if hasattr(space_or_int, 'shape'):
+        shp = tuple(space_or_int.shape)
+        n = 1
+        for d in shp:
+            n *= int(d)
+        return n
+    return int(space_or_int)
+
+
+def _orthogonal(layer, std=2 ** 0.5, bias_const=0.0):
+    nn.init.orthogonal_(layer.weight, std)
+    nn.init.constant_(layer.bias, bias_const)
+    return layer
+
+
 class MujocoModel(Model):
-    def __init__(self, obs_dim=17, act_dim=6):
+    """benchmark/torch/ppo/mujoco_model.py:27-53: shared 64-64 tanh trunk, value head, policy-mean head,
+    state-independent log-std parameter; orthogonal init (std sqrt2 / 1.0 / 0.01)."""
+
+    def __init__(self, obs_space=17, act_space=6):
         super(MujocoModel, self).__init__()
-        self.fc_v1, self.fc_v2, self.fc_v3 = nn.Linear(obs_dim, 64), nn.Linear(64, 64), nn.Linear(64, 1)
-        self.fc_pi1, self.fc_pi2, self.fc_pi3 = nn.Linear(obs_dim, 64), nn.Linear(64, 64), nn.Linear(64, act_dim)
+        obs_dim, act_dim = _dim(obs_space), _dim(act_space)
+        self.fc1 = _orthogonal(nn.Linear(obs_dim, 64))
+        self.fc2 = _orthogonal(nn.Linear(64, 64))
+        self.fc_value = _orthogonal(nn.Linear(64, 1), std=1.0)
+        self.fc_policy = _orthogonal(nn.Linear(64, act_dim), std=0.01)
         self.fc_pi_std = nn.Parameter(torch.zeros(1, act_dim))
 
+    def _trunk(self, obs):
+        return torch.tanh(self.fc2(torch.tanh(self.fc1(obs))))
+
     def value(self, obs):
-        x = torch.tanh(self.fc_v1(obs))
-        x = torch.tanh(self.fc_v2(x))
-        return self.fc_v3(x)
+        return self.fc_value(self._trunk(obs))
 
     def policy(self, obs):
-        x = torch.tanh(self.fc_pi1(obs))
-        x = torch.tanh(self.fc_pi2(x))
-        mean = self.fc_pi3(x)
+        mean = self.fc_policy(self._trunk(obs))
         return mean, torch.exp(self.fc_pi_std.expand_as(mean))
+
+    def native_layers(self):
+        """Row segments per linear layer for rl_mlp_fwd/bwd: outputs = [mean (act_dim) | value (1)]."""
+        from ..kernels import ACT_TANH
+        return [[(self.fc1.weight, self.fc1.bias)], [(self.fc2.weight, self.fc2.bias)],
+                [(self.fc_policy.weight, self.fc_policy.bias), (self.fc_value.weight, self.fc_value.bias)]], ACT_TANH
 
 
 class CartPoleActorCritic(Model):
+    """Actor-critic MLP for A2C on CartPole (BASELINE configs[1]); the reference ships no CartPole A2C model, the
+    layout follows its Atari actor-critic (shared trunk, policy + value heads, benchmark/torch/a2c/atari_model.py)."""
+
     def __init__(self, obs_dim=4, act_dim=2, hidden=64):
         super(CartPoleActorCritic, self).__init__()
         self.fc1, self.fc2 = nn.Linear(obs_dim, hidden), nn.Linear(hidden, hidden)
@@ -110,6 +141,11 @@ class CartPoleActorCritic(Model):
         h = self._trunk(x)
         return self.fc_pi(h), self.fc_v(h).squeeze(1)
 
+    def native_layers(self):
+        from ..kernels import ACT_TANH
+        return [[(self.fc1.weight, self.fc1.bias)], [(self.fc2.weight, self.fc2.bias)],
+                [(self.fc_pi.weight, self.fc_pi.bias), (self.fc_v.weight, self.fc_v.bias)]], ACT_TANH
+
 
 class CartPolePolicy(Model):
     """benchmark/torch/QuickStart/cartpole_model.py:21-38: forward returns action probabilities."""
@@ -121,3 +157,59 @@ class CartPolePolicy(Model):
 
     def forward(self, x):
         return F.softmax(self.fc2(torch.tanh(self.fc1(x))), dim=-1)
+
+    def native_layers(self):
+        """Logits (the softmax is applied by the consumer)."""
+        from ..kernels import ACT_TANH
+        return [[(self.fc1.weight, self.fc1.bias)], [(self.fc2.weight, self.fc2.bias)]], ACT_TANH
+
+
+class CartPoleQModel(Model):
+    """examples/DQN/cartpole_model.py:21-41: 128-128 ReLU MLP -> Q values."""
+
+    def __init__(self, obs_dim=4, act_dim=2, hidden=128):
+        super(CartPoleQModel, self).__init__()
+        self.fc1, self.fc2, self.fc3 = nn.Linear(obs_dim, hidden), nn.Linear(hidden, hidden), nn.Linear(hidden, act_dim)
+
+    def forward(self, obs):
+        return self.fc3(F.relu(self.fc2(F.relu(self.fc1(obs)))))
+
+    def native_layers(self):
+        from ..kernels import ACT_RELU
+        return [[(self.fc1.weight, self.fc1.bias)], [(self.fc2.weight, self.fc2.bias)],
+                [(self.fc3.weight, self.fc3.bias)]], ACT_RELU
+
+
+class AtariQModel(Model):
+    """benchmark/torch/dqn/model.py:19-95: conv 5x5/p2 -> pool -> conv 5x5/p2 -> pool -> conv 4x4/p1 -> pool ->
+    conv 3x3/p1 -> flatten 6400 -> linear (or the dueling pair of 512-unit streams), kaiming-normal fan-out init,
+    ``obs / 255`` inside the model."""
+
+    def __init__(self, act_dim, dueling=False):
+        super(AtariQModel, self).__init__()
+        self.conv1 = nn.Conv2d(4, 32, kernel_size=5, stride=1, padding=2)
+        self.conv2 = nn.Conv2d(32, 32, kernel_size=5, stride=1, padding=2)
+        self.conv3 = nn.Conv2d(32, 64, kernel_size=4, stride=1, padding=1)
+        self.conv4 = nn.Conv2d(64, 64, kernel_size=3, stride=1, padding=1)
+        self.dueling = dueling
+        if dueling:
+            self.linear_1_adv, self.linear_2_adv = nn.Linear(6400, 512), nn.Linear(512, act_dim)
+            self.linear_1_val, self.linear_2_val = nn.Linear(6400, 512), nn.Linear(512, 1)
+        else:
+            self.linear_1 = nn.Linear(6400, act_dim)
+        for m in self.modules():
+            if isinstance(m, (nn.Linear, nn.Conv2d)):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+                nn.init.zeros_(m.bias)
+
+    def forward(self, obs):
+        x = obs.float() / 255.0
+        x = F.max_pool2d(F.relu(self.conv1(x)), 2, 2)
+        x = F.max_pool2d(F.relu(self.conv2(x)), 2, 2)
+        x = F.max_pool2d(F.relu(self.conv3(x)), 2, 2)
+        x = F.relu(self.conv4(x)).flatten(1)
+        if self.dueling:
+            a = self.linear_2_adv(F.relu(self.linear_1_adv(x)))
+            v = self.linear_2_val(F.relu(self.linear_1_val(x)))
+            return a + (v - a.mean(dim=1, keepdim=True))
+        return self.linear_1(x)

@@ -405,18 +405,22 @@ class DeviceSumTree(object):
         return tidx, eidx, w
 
 
-def replay_gather_frames(frames, is_over, idx, curr_size, context_len):
-    """benchmark/torch/dqn/replay_memory.py:59-85 for a batch of start indices -> [n, ctx+1, HW] uint8."""
+def replay_gather_frames(frames, is_over, idx, curr_size, context_len, lanes=1, n_out=None, out=None):
+    """benchmark/torch/dqn/replay_memory.py:59-85 for a batch of start indices -> [n, n_out (default ctx+1), HW]
+    uint8; ``lanes`` interleaved per-env streams (row = position*lanes + lane), see include/parl_b200.h."""
     require_cuda(frames, is_over, idx)
     HW = frames[0].numel()
     n = idx.numel()
     _chk('frames', frames, torch.uint8)
     _chk('idx', idx, torch.int32)
-    out = torch.empty((n, context_len + 1, HW), dtype=torch.uint8, device=frames.device)
+    n_out = context_len + 1 if n_out is None else int(n_out)
+    if out is None:
+        out = torch.empty((n, n_out, HW), dtype=torch.uint8, device=frames.device)
+    _chk('out', out, torch.uint8, n * n_out * HW)
     is_over = _as_u8(is_over)
-    _chk('is_over', is_over, torch.uint8, frames.shape[0])
+    _chk('is_over', is_over, torch.uint8, frames.numel() // HW)
     check(_lib.load().rl_replay_gather_frames(ptr(frames), ptr(is_over), ptr(idx), n, int(curr_size), int(context_len),
-                                              HW, ptr(out), stream()), 'replay_gather_frames')
+                                              HW, int(lanes), n_out, ptr(out), stream()), 'replay_gather_frames')
     return out
 
 
@@ -630,22 +634,33 @@ class MlpPlan(object):
     def out_dim(self):
         return self.dims_list[-1]
 
-    def forward(self, x, out=None):
-        require_cuda(x)
+    def forward(self, x, out=None, out2=None, split=0):
+        """x [n, in] -> out [n, out_dim]; with ``split`` the output columns are delivered as two dense tensors
+        (out [n, split], out2 [n, out_dim - split]) — e.g. the policy head and the value head."""
+        require_cuda(x, out, out2)
         assert x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] == self.dims_list[0]
         n = x.shape[0]
+        first = split if split else self.out_dim
         if out is None:
-            out = torch.empty((n, self.out_dim), dtype=torch.float32, device=x.device)
-        assert out.dtype == torch.float32 and out.numel() == n * self.out_dim and out.is_contiguous()
+            out = torch.empty((n, first), dtype=torch.float32, device=x.device)
+        _chk('out', out, torch.float32, n * first)
+        if split:
+            if out2 is None:
+                out2 = torch.empty((n, self.out_dim - split), dtype=torch.float32, device=x.device)
+            _chk('out2', out2, torch.float32, n * (self.out_dim - split))
         check(_lib.load().rl_mlp_fwd(ptr(x), n, self.n_layers, self.c_dims, len(self.segs), self.c_layer, self.c_rows,
-                                     self.c_w, self.c_b, self.act, ptr(out), stream()), 'mlp_fwd')
-        return out
+                                     self.c_w, self.c_b, self.act, ptr(out), ptr(out2) if split else None, int(split),
+                                     stream()), 'mlp_fwd')
+        return (out, out2) if split else out
 
-    def backward(self, x, d_out, grads=None, accumulate=False):
+    def backward(self, x, d_out, grads=None, accumulate=False, d_out2=None, split=0):
         """Parameter gradients of sum(out * d_out) into ``grads`` [(dw, db), ...] (default: each parameter's .grad)."""
-        require_cuda(x, d_out)
+        require_cuda(x, d_out, d_out2)
         n = x.shape[0]
-        assert x.dtype == torch.float32 and d_out.dtype == torch.float32 and d_out.numel() == n * self.out_dim
+        _chk('x', x, torch.float32, n * self.dims_list[0])
+        _chk('d_out', d_out, torch.float32, n * (split if split else self.out_dim))
+        if split:
+            _chk('d_out2', d_out2, torch.float32, n * (self.out_dim - split))
         if grads is None:
             if self._grad_tabs is None:
                 gw = [s[1].grad for s in self.segs]
@@ -658,5 +673,33 @@ class MlpPlan(object):
             c_dw = self._PtrA(*[g[0].data_ptr() for g in grads])
             c_db = self._PtrA(*[(g[1].data_ptr() if g[1] is not None else None) for g in grads])
         check(_lib.load().rl_mlp_bwd(ptr(x), n, self.n_layers, self.c_dims, len(self.segs), self.c_layer, self.c_rows,
-                                     self.c_w, self.c_b, self.act, ptr(d_out), c_dw, c_db, 1 if accumulate else 0,
-                                     ptr(self.ws), self.ws.numel(), stream()), 'mlp_bwd')
+                                     self.c_w, self.c_b, self.act, ptr(d_out), ptr(d_out2) if split else None,
+                                     int(split), c_dw, c_db, 1 if accumulate else 0, ptr(self.ws), self.ws.numel(),
+                                     stream()), 'mlp_bwd')
+
+    def rollout(self, env_kind, policy_kind, T, obs_cur, stats, seed, step0, obs_out, act_out, rew_out, done_out,
+                logp_out=None, val_out=None, logits_out=None, logstd=None, has_value=True, env_offset=0, p_done=0.01,
+                max_episode_steps=0):
+        """rl_rollout_mlp: T lock-step steps of all envs in ONE launch (policy forward + sampling + env step)."""
+        require_cuda(obs_cur, obs_out, act_out, rew_out, done_out, logp_out, val_out, logits_out, logstd)
+        B, D = obs_cur.shape
+        AD = self.out_dim - (1 if has_value else 0)
+        _chk('obs_cur', obs_cur, torch.float32, B * self.dims_list[0])
+        _chk('obs_out', obs_out, torch.float32, T * B * D)
+        _chk('act_out', act_out, torch.int32 if policy_kind == 0 else torch.float32, T * B * (1 if policy_kind == 0 else AD))
+        _chk('rew_out', rew_out, torch.float32, T * B)
+        _chk('done_out', done_out, torch.uint8, T * B)
+        _chk('logp_out', logp_out, torch.float32, T * B, optional=True)
+        _chk('val_out', val_out, torch.float32, (T + 1) * B, optional=True)
+        _chk('logits_out', logits_out, torch.float32, T * B * AD, optional=True)
+        _chk('logstd', logstd, torch.float32, AD, optional=policy_kind == 0)
+        check(_lib.load().rl_rollout_mlp(self.n_layers, self.c_dims, len(self.segs), self.c_layer, self.c_rows, self.c_w,
+                                         self.c_b, self.act, int(env_kind), int(policy_kind), int(T), B, AD,
+                                         1 if has_value else 0, ptr(logstd), ptr(obs_cur), *stats.args(), int(seed),
+                                         int(step0), int(env_offset), float(p_done), int(max_episode_steps),
+                                         ptr(obs_out), ptr(act_out), ptr(logp_out), ptr(val_out), ptr(logits_out),
+                                         ptr(rew_out), ptr(done_out), stream()), 'rollout_mlp')
+
+
+ENV_MUJOCO_SYNTH, ENV_CARTPOLE = 0, 1
+POLICY_CATEGORICAL, POLICY_GAUSSIAN = 0, 1
