@@ -161,6 +161,22 @@ int rl_env_cartpole_step(
     int B, int max_episode_steps, uint64_t seed, uint32_t step, uint32_t env_offset, int reset,
     rl_stream_t stream);
 
+/* VecNormalizeEnv on the device (f2; parl/env/mujoco_wrappers.py:95-168 as benchmark/torch/ppo/env_utils.py uses it:
+ * one wrapper — one set of running statistics — PER ENV, fed one sample per step, float64).  State arrays (caller
+ * owned, initialise mean 0 / var 1 / count 1e-4 / ret 0): ob_mean, ob_var [B,D], ob_count, ret, ret_mean, ret_var,
+ * ret_count [B].
+ *   reward_step = 1: VecNormalizeEnv.step — ret = ret*gamma + reward; (term_obs != NULL and done: the finished
+ *     episode's terminal observation updates the observation statistics first); reward <- clip(reward /
+ *     sqrt(ret_var + eps), +-cliprew) IN PLACE; ret = 0 where done; then the observation handed on (obs_in; the reset
+ *     observation where done) is filtered: statistics update (if `update`) and clip((x-mean)/sqrt(var+eps), +-clipob).
+ *   reward_step = 0: VecNormalizeEnv.reset — only the observation filter.
+ * obs_out may alias obs_in. */
+int rl_vecnormalize_step(const float* obs_in, const float* term_obs, float* obs_out, float* reward,
+                         const uint8_t* done, double* ob_mean, double* ob_var, double* ob_count, double* ret,
+                         double* ret_mean, double* ret_var, double* ret_count, int B, int D, int update,
+                         int norm_ob, int norm_ret, int reward_step, double clipob, double cliprew,
+                         double gamma, double eps, rl_stream_t stream);
+
 /* Standalone samplers.  logp_out may be NULL. */
 int rl_sample_categorical(
     const float* logits, int N, int A, uint64_t seed, uint32_t step, uint32_t env_offset,
@@ -394,14 +410,20 @@ int rl_mlp_bwd(const float* x, int n, int n_layers, const int* dims, int n_seg, 
  *   global step index of row t = step0 + t (RNG counter);
  *   outputs: obs_out [T,B,obs_dim], act_out [T,B] int32 | [T,B,action_dim] f32, logp_out [T,B] (opt),
  *   val_out [T+1,B] (opt; row T = value of the observation after the last step), logits_out [T,B,action_dim]
- *   (opt, categorical), rew_out [T,B] f32, done_out [T,B] u8. */
+ *   (opt, categorical), rew_out [T,B] f32, done_out [T,B] u8.
+ *   vecnorm_state (optional; host array of the 7 device state arrays of rl_vecnormalize_step in its order
+ *   {ob_mean, ob_var, ob_count, ret, ret_mean, ret_var, ret_count}), vecnorm_cfg host {clipob, cliprew, gamma, eps},
+ *   vecnorm_flags bit0 update | bit1 normalise observations | bit2 normalise rewards: a VecNormalizeEnv per env
+ *   between the env and the policy (obs_cur / obs_out / rew_out then hold NORMALISED values; episode statistics
+ *   keep raw rewards, as MonitorEnv sits below VecNormalizeEnv in wrap_rms). */
 int rl_rollout_mlp(int n_layers, const int* dims, int n_seg, const int* seg_layer, const int* seg_rows,
                    const float* const* seg_w, const float* const* seg_b, int act, int env_kind, int policy_kind,
                    int T, int B, int action_dim, int has_value, const float* logstd, float* obs_cur,
                    float* ep_ret, int32_t* ep_len, float* totals, float* ring_ret, int32_t* ring_len,
                    uint32_t* ring_head, int ring_cap, uint64_t seed, uint32_t step0, uint32_t env_offset,
                    float p_done, int max_episode_steps, float* obs_out, void* act_out, float* logp_out,
-                   float* val_out, float* logits_out, float* rew_out, uint8_t* done_out, rl_stream_t stream);
+                   float* val_out, float* logits_out, float* rew_out, uint8_t* done_out,
+                   double* const* vecnorm_state, const double* vecnorm_cfg, int vecnorm_flags, rl_stream_t stream);
 
 #ifdef __cplusplus
 }

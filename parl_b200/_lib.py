@@ -41,6 +41,7 @@ SIGNATURES = {
                                        c_u64, c_u32, c_u32, c_f, c_i, c_p]),
     'rl_env_cartpole_step': (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i,
                                    c_u64, c_u32, c_u32, c_i, c_p]),
+    'rl_vecnormalize_step': (c_i, [c_p] * 12 + [c_i] * 6 + [ctypes.c_double] * 4 + [c_p]),
     'rl_sample_categorical': (c_i, [c_p, c_i, c_i, c_u64, c_u32, c_u32, c_p, c_p, c_p]),
     'rl_sample_gaussian': (c_i, [c_p, c_p, c_i, c_i, c_u64, c_u32, c_u32, c_p, c_p, c_p]),
     'rl_flat_workspace_bytes': (c_sz, [ctypes.c_longlong, c_i]),
@@ -80,7 +81,7 @@ SIGNATURES = {
     'rl_mlp_bwd': (c_i, [c_p, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_sz, c_p]),
     'rl_rollout_mlp': (c_i, [c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p,
                              c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_u64, c_u32, c_u32, c_f, c_i, c_p, c_p, c_p, c_p, c_p,
-                             c_p, c_p, c_p]),
+                             c_p, c_p, c_p, c_p, c_i, c_p]),
     'rl_mask_scatter_grid_bf16': (c_i, [c_p, c_p, c_p, ctypes.c_longlong, c_i, c_i, c_i, c_i, c_i, c_p]),
 }
 

@@ -339,6 +339,27 @@ __global__ void __launch_bounds__(128) cartpole_step_kernel(const VecStepArgs p)
 }
 
 // ---------------------------------------------------------------------------
+// VecNormalizeEnv as a stand-alone kernel (one lane per env); the fused rollout applies the same device functions.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) vecnormalize_step_kernel(const VecNormState v, const float* __restrict__ obs_in,
+                                                                const float* __restrict__ term_obs,
+                                                                float* __restrict__ obs_out, float* __restrict__ reward,
+                                                                const uint8_t* __restrict__ done, int B, int D,
+                                                                int reward_step) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (reward_step) {
+    const bool dn = done[b] != 0;
+    if (term_obs && dn) vecnorm_obs_absorb(v, b, D, term_obs + (size_t)b * D, 1);
+    reward[b] = vecnorm_reward(v, b, reward[b], dn);
+  }
+  float* o = obs_out + (size_t)b * D;
+  if (obs_out != obs_in)
+    for (int d = 0; d < D; ++d) o[d] = obs_in[(size_t)b * D + d];
+  vecnorm_obs_filter(v, b, D, o, 1);
+}
+
+// ---------------------------------------------------------------------------
 // K7 standalone samplers.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) sample_categorical_kernel(const float* __restrict__ logits, int N, int A,
@@ -500,6 +521,25 @@ extern "C" int rl_env_cartpole_step(float* state, float* obs_out, float* reward_
   vec_step(true, obs_out, reward_out, done_out, state, actions, ep_ret, ep_len, totals, ring_ret, ring_len, ring_head,
            ring_cap, B, 4, max_episode_steps, seed, step, env_offset, 0.f, reset, stream);
   RL_CHECK_LAUNCH("rl_env_cartpole_step");
+  return RL_OK;
+}
+
+extern "C" int rl_vecnormalize_step(const float* obs_in, const float* term_obs, float* obs_out, float* reward,
+                                    const uint8_t* done, double* ob_mean, double* ob_var, double* ob_count, double* ret,
+                                    double* ret_mean, double* ret_var, double* ret_count, int B, int D, int update,
+                                    int norm_ob, int norm_ret, int reward_step, double clipob, double cliprew,
+                                    double gamma, double eps, rl_stream_t stream) {
+  RL_CHECK_ARG(obs_in && obs_out && ob_mean && ob_var && ob_count && ret && ret_mean && ret_var && ret_count,
+               "vecnormalize_step: null pointer");
+  RL_CHECK_ARG(!reward_step || (reward && done), "vecnormalize_step: a reward step needs reward and done");
+  RL_CHECK_ARG(B > 0 && D > 0, "vecnormalize_step: bad shape");
+  VecNormState v;
+  v.ob_mean = ob_mean, v.ob_var = ob_var, v.ob_count = ob_count, v.ret = ret, v.ret_mean = ret_mean;
+  v.ret_var = ret_var, v.ret_count = ret_count, v.clipob = clipob, v.cliprew = cliprew, v.gamma = gamma, v.eps = eps;
+  v.update = update, v.norm_ob = norm_ob, v.norm_ret = norm_ret;
+  vecnormalize_step_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(v, obs_in, term_obs, obs_out, reward, done,
+                                                                             B, D, reward_step);
+  RL_CHECK_LAUNCH("rl_vecnormalize_step");
   return RL_OK;
 }
 

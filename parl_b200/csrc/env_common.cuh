@@ -76,6 +76,78 @@ inline uint32_t prob_threshold(float p) {
   return (uint32_t)v;
 }
 
+// ---------------------------------------------------------------------------
+// VecNormalizeEnv on the device (parl/env/mujoco_wrappers.py:95-168): every env keeps ITS OWN running statistics
+// (benchmark/torch/ppo/env_utils.py wraps each env separately) fed one sample per step, float64 like the reference.
+//   update_from_moments with batch (x, var 0, count 1)                      (:74-92, :191-217)
+// ---------------------------------------------------------------------------
+struct VecNormState {
+  double* ob_mean;     // [B, D]
+  double* ob_var;      // [B, D]
+  double* ob_count;    // [B]
+  double* ret;         // [B] discounted return accumulator
+  double* ret_mean;    // [B]
+  double* ret_var;     // [B]
+  double* ret_count;   // [B]
+  double clipob, cliprew, gamma, eps;
+  int update;          // training: observation statistics follow the data (env.train() / env.eval())
+  int norm_ob, norm_ret;
+};
+
+__device__ __forceinline__ void rms_update1(double& mean, double& var, double count, double x) {
+  const double delta = x - mean;
+  const double tot = count + 1.0;
+  mean = mean + delta * 1.0 / tot;
+  const double m2 = var * count + 0.0 + delta * delta * count * 1.0 / tot;
+  var = m2 / tot;
+}
+
+// reward side of VecNormalizeEnv.step for env b: ret = ret*gamma + rew; ret_rms.update(ret);
+// rew / sqrt(var + eps) clipped; ret = 0 when the episode ended.  Returns the normalised reward.
+__device__ __forceinline__ float vecnorm_reward(const VecNormState& v, int b, float rew, bool done) {
+  double ret = v.ret[b] * v.gamma + (double)rew;
+  double out = (double)rew;
+  if (v.norm_ret) {
+    double m = v.ret_mean[b], s = v.ret_var[b];
+    const double c = v.ret_count[b];
+    rms_update1(m, s, c, ret);
+    v.ret_mean[b] = m, v.ret_var[b] = s, v.ret_count[b] = c + 1.0;
+    out = fmin(fmax(out / sqrt(s + v.eps), -v.cliprew), v.cliprew);
+  }
+  v.ret[b] = done ? 0.0 : ret;
+  return (float)out;
+}
+
+// statistics-only pass over one observation of env b (the terminal observation of a finished episode)
+__device__ __forceinline__ void vecnorm_obs_absorb(const VecNormState& v, int b, int D, const float* __restrict__ x,
+                                                   int x_stride) {
+  if (!(v.norm_ob && v.update)) return;
+  const double c = v.ob_count[b];
+  for (int d = 0; d < D; ++d) {
+    double m = v.ob_mean[(size_t)b * D + d], s = v.ob_var[(size_t)b * D + d];
+    rms_update1(m, s, c, (double)x[d * x_stride]);
+    v.ob_mean[(size_t)b * D + d] = m, v.ob_var[(size_t)b * D + d] = s;
+  }
+  v.ob_count[b] = c + 1.0;
+}
+
+// _obfilt of one observation of env b, in place on x (stride x_stride between its D components)
+__device__ __forceinline__ void vecnorm_obs_filter(const VecNormState& v, int b, int D, float* __restrict__ x, int x_stride) {
+  if (!v.norm_ob) return;
+  const double c = v.ob_count[b];
+  const bool upd = v.update != 0;
+  for (int d = 0; d < D; ++d) {
+    double m = v.ob_mean[(size_t)b * D + d], s = v.ob_var[(size_t)b * D + d];
+    const double xv = (double)x[d * x_stride];
+    if (upd) {
+      rms_update1(m, s, c, xv);
+      v.ob_mean[(size_t)b * D + d] = m, v.ob_var[(size_t)b * D + d] = s;
+    }
+    x[d * x_stride] = (float)fmin(fmax((xv - m) / sqrt(s + v.eps), -v.clipob), v.clipob);
+  }
+  if (upd) v.ob_count[b] = c + 1.0;
+}
+
 // gym classic_control/cartpole.py (third party, restated: SURVEY.md 8c item 4): one Euler step of the state
 // s = (x, x_dot, theta, theta_dot) under action a; returns done.
 __device__ __forceinline__ bool cartpole_physics(float4& s, int a) {

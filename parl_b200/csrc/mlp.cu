@@ -18,6 +18,8 @@
 //                      the sample axis (conflict-free: consecutive lanes = consecutive rows), 64 FMA per 8 LDS.128;
 //                      per-CTA partial sums live in an L2-resident workspace, a second kernel adds them up in a
 //                      fixed order (deterministic)
+#include <string.h>
+
 #include "common.cuh"
 #include "env_common.cuh"
 
@@ -357,6 +359,8 @@ struct RolloutArgs {
   float* logits_out;   // [T, B, AD] or NULL (categorical: behaviour logits for off-policy corrections)
   float* rew_out;      // [T, B]
   uint8_t* done_out;   // [T, B]
+  int use_vn;          // VecNormalizeEnv between the env and the policy (per-env running statistics)
+  VecNormState vn;
 };
 
 // sample_categorical_exact (philox.cuh) over a strided row — same operations in the same order
@@ -470,7 +474,12 @@ __global__ void __launch_bounds__(kMlpThreads) rollout_mlp_kernel(const MlpArgs 
             if (done) s = cartpole_reset_state(env, step + 1u, r.k0, r.k1);
             s_x[tid] = s.x, s_x[kTS + tid] = s.y, s_x[2 * kTS + tid] = s.z, s_x[3 * kTS + tid] = s.w;
           }
-          r.rew_out[tb] = reward;
+          float rew_seen = reward;           // what the agent sees; the episode statistics keep the raw reward
+          if (r.use_vn) {                    // VecNormalizeEnv.step, then (where done) .reset, of env b
+            rew_seen = vecnorm_reward(r.vn, b, reward, done);
+            vecnorm_obs_filter(r.vn, b, D, s_x + tid, kTS);
+          }
+          r.rew_out[tb] = rew_seen;
           r.done_out[tb] = done ? 1 : 0;
         }
         episode_update(r.st, b, valid, reward, done);
@@ -608,6 +617,7 @@ extern "C" int rl_rollout_mlp(int n_layers, const int* dims, int n_seg, const in
                               int32_t* ring_len, uint32_t* ring_head, int ring_cap, uint64_t seed, uint32_t step0,
                               uint32_t env_offset, float p_done, int max_episode_steps, float* obs_out, void* act_out,
                               float* logp_out, float* val_out, float* logits_out, float* rew_out, uint8_t* done_out,
+                              double* const* vecnorm_state, const double* vecnorm_cfg, int vecnorm_flags,
                               rl_stream_t stream) {
   using namespace rl;
   RL_CHECK_ARG(dims && seg_layer && seg_rows && seg_w && obs_cur && ep_ret && ep_len && totals && obs_out && act_out &&
@@ -635,6 +645,17 @@ extern "C" int rl_rollout_mlp(int n_layers, const int* dims, int n_seg, const in
   r.done_thr = prob_threshold(p_done);
   r.obs_out = obs_out, r.act_out = act_out, r.logp_out = logp_out, r.val_out = val_out, r.logits_out = logits_out;
   r.rew_out = rew_out, r.done_out = done_out;
+  r.use_vn = vecnorm_state != nullptr;
+  memset(&r.vn, 0, sizeof(r.vn));
+  if (r.use_vn) {
+    RL_CHECK_ARG(vecnorm_cfg, "rollout_mlp: vecnorm_state without vecnorm_cfg");
+    for (int i = 0; i < 7; ++i) RL_CHECK_ARG(vecnorm_state[i], "rollout_mlp: vecnorm_state[%d] is NULL", i);
+    r.vn.ob_mean = vecnorm_state[0], r.vn.ob_var = vecnorm_state[1], r.vn.ob_count = vecnorm_state[2];
+    r.vn.ret = vecnorm_state[3], r.vn.ret_mean = vecnorm_state[4], r.vn.ret_var = vecnorm_state[5];
+    r.vn.ret_count = vecnorm_state[6];
+    r.vn.clipob = vecnorm_cfg[0], r.vn.cliprew = vecnorm_cfg[1], r.vn.gamma = vecnorm_cfg[2], r.vn.eps = vecnorm_cfg[3];
+    r.vn.update = vecnorm_flags & 1, r.vn.norm_ob = (vecnorm_flags >> 1) & 1, r.vn.norm_ret = (vecnorm_flags >> 2) & 1;
+  }
   const size_t smem = (((size_t)a.np_pad + 3) & ~(size_t)3) * 4 + 3 * (size_t)kMaxWidth * kTS * 4;
   RL_CHECK_ARG(smem <= 220 * 1024, "rollout_mlp: network too large for shared memory (%zu B)", smem);
   RL_SMEM_OPTIN(rollout_mlp_kernel);

@@ -24,7 +24,7 @@ class PPOEngine(object):
     def __init__(self, num_envs=2048, step_nums=2048, obs_dim=17, act_dim=6, num_minibatches=32, update_epochs=10,
                  gamma=0.99, gae_lambda=0.95, clip_param=0.2, value_loss_coef=0.5, entropy_coef=0.0, initial_lr=3e-4,
                  lr_decay=True, num_updates=1000, seed=0, device=None, env_offset=0, p_done=0.01, max_episode_steps=1000,
-                 model=None):
+                 model=None, vec_normalize=False):
         if device is None:
             device = torch.device('cuda', torch.cuda.current_device())
         self.device = dev = torch.device(device)
@@ -45,6 +45,8 @@ class PPOEngine(object):
         assert N % self.num_minibatches == 0
         self.M = N // self.num_minibatches
         self.stats = kernels.EpisodeStats(B, dev)
+        # wrap_rms(env, gamma): a VecNormalizeEnv per env (benchmark/torch/ppo/env_utils.py:121-133), on the device
+        self.vn = kernels.VecNormalize(B, self.D, dev, gamma=self.gamma) if vec_normalize else None
         self.obs_cur = torch.zeros((B, self.D), dtype=f32, device=dev)
         self.obs = torch.empty((T, B, self.D), dtype=f32, device=dev)
         self.actions = torch.empty((T, B, self.AD), dtype=f32, device=dev)
@@ -64,6 +66,8 @@ class PPOEngine(object):
     def reset(self):
         kernels.env_mujoco_synth_step(self.obs_cur, None, None, self.stats, self.seed, 0, env_offset=self.env_offset,
                                       reset=True)
+        if self.vn is not None:
+            self.vn.reset(self.obs_cur)
         self.env_steps = 0
         self.last_done.zero_()
 
@@ -75,7 +79,8 @@ class PPOEngine(object):
         self.plan.rollout(kernels.ENV_MUJOCO_SYNTH, kernels.POLICY_GAUSSIAN, T, self.obs_cur, self.stats, self.seed,
                           self.env_steps, self.obs, self.actions, self.rewards, self.step_dones,
                           logp_out=self.logprobs, val_out=self.values, logstd=self._logstd(), has_value=True,
-                          env_offset=self.env_offset, p_done=self.p_done, max_episode_steps=self.max_episode_steps)
+                          env_offset=self.env_offset, p_done=self.p_done, max_episode_steps=self.max_episode_steps,
+                          vecnorm=self.vn)
         # storage.append(obs, action, logprob, reward, done, value) stores the done flag carried INTO step t
         self.dones[0].copy_(self.last_done)
         if T > 1:
@@ -128,6 +133,14 @@ class PPOEngine(object):
         self.rollout()
         self.compute_returns()
         return self.learn()
+
+    def get_ob_rms(self, env_index=0):
+        """(mean, var, count) of one env's observation statistics — what ParallelEnv.eval_ob_rms hands to the
+        evaluation env (benchmark/torch/ppo/env_utils.py:100-103, train.py:117-120)."""
+        if self.vn is None:
+            return None
+        return (self.vn.ob_mean[env_index].cpu().numpy(), self.vn.ob_var[env_index].cpu().numpy(),
+                float(self.vn.ob_count[env_index].item()))
 
     def get_metrics(self):
         tot = self.stats.totals.tolist()

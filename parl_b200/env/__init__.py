@@ -2,5 +2,8 @@
 envs, and the device-resident vector envs that replace it on the B200."""
 from .vector_env import VectorEnv
 from .device_envs import AtariSynthVectorEnv, MujocoSynthVectorEnv, CartPoleVectorEnv
+from .compat_wrappers import CompatWrapper
+from . import atari_wrappers, mujoco_wrappers, compat_wrappers
 
-__all__ = ['VectorEnv', 'AtariSynthVectorEnv', 'MujocoSynthVectorEnv', 'CartPoleVectorEnv']
+__all__ = ['VectorEnv', 'CompatWrapper', 'AtariSynthVectorEnv', 'MujocoSynthVectorEnv', 'CartPoleVectorEnv',
+           'atari_wrappers', 'mujoco_wrappers', 'compat_wrappers']

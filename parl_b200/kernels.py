@@ -679,7 +679,7 @@ class MlpPlan(object):
 
     def rollout(self, env_kind, policy_kind, T, obs_cur, stats, seed, step0, obs_out, act_out, rew_out, done_out,
                 logp_out=None, val_out=None, logits_out=None, logstd=None, has_value=True, env_offset=0, p_done=0.01,
-                max_episode_steps=0):
+                max_episode_steps=0, vecnorm=None):
         """rl_rollout_mlp: T lock-step steps of all envs in ONE launch (policy forward + sampling + env step)."""
         require_cuda(obs_cur, obs_out, act_out, rew_out, done_out, logp_out, val_out, logits_out, logstd)
         B, D = obs_cur.shape
@@ -698,8 +698,66 @@ class MlpPlan(object):
                                          1 if has_value else 0, ptr(logstd), ptr(obs_cur), *stats.args(), int(seed),
                                          int(step0), int(env_offset), float(p_done), int(max_episode_steps),
                                          ptr(obs_out), ptr(act_out), ptr(logp_out), ptr(val_out), ptr(logits_out),
-                                         ptr(rew_out), ptr(done_out), stream()), 'rollout_mlp')
+                                         ptr(rew_out), ptr(done_out),
+                                         vecnorm.c_state if vecnorm is not None else None,
+                                         vecnorm.c_cfg if vecnorm is not None else None,
+                                         vecnorm.flags if vecnorm is not None else 0, stream()), 'rollout_mlp')
 
 
 ENV_MUJOCO_SYNTH, ENV_CARTPOLE = 0, 1
 POLICY_CATEGORICAL, POLICY_GAUSSIAN = 0, 1
+
+
+class VecNormalize(object):
+    """Device VecNormalizeEnv state for B envs of obs dim D (rl_vecnormalize_step / the fused rollout):
+    per-env running observation statistics and return statistics in float64 (parl/env/mujoco_wrappers.py:95-168)."""
+
+    def __init__(self, B, D, device, ob=True, ret=True, clipob=10.0, cliprew=10.0, gamma=0.99, epsilon=1e-8):
+        import ctypes
+        f64 = torch.float64
+        self.B, self.D = int(B), int(D)
+        self.ob_mean = torch.zeros((B, D), dtype=f64, device=device)
+        self.ob_var = torch.ones((B, D), dtype=f64, device=device)
+        self.ob_count = torch.full((B, ), 1e-4, dtype=f64, device=device)
+        self.ret = torch.zeros(B, dtype=f64, device=device)
+        self.ret_mean = torch.zeros(B, dtype=f64, device=device)
+        self.ret_var = torch.ones(B, dtype=f64, device=device)
+        self.ret_count = torch.full((B, ), 1e-4, dtype=f64, device=device)
+        self.ob, self.norm_ret, self.training = bool(ob), bool(ret), True
+        self.clipob, self.cliprew, self.gamma, self.epsilon = float(clipob), float(cliprew), float(gamma), float(epsilon)
+        self._state = [self.ob_mean, self.ob_var, self.ob_count, self.ret, self.ret_mean, self.ret_var, self.ret_count]
+        self.c_state = (ctypes.c_void_p * 7)(*[t.data_ptr() for t in self._state])
+        self.c_cfg = (ctypes.c_double * 4)(self.clipob, self.cliprew, self.gamma, self.epsilon)
+
+    @property
+    def flags(self):
+        return (1 if self.training else 0) | (2 if self.ob else 0) | (4 if self.norm_ret else 0)
+
+    def train(self):
+        self.training = True
+
+    def eval(self):
+        self.training = False
+
+    def _call(self, obs_in, obs_out, reward, done, term_obs, reward_step):
+        require_cuda(obs_in, obs_out, reward, done, term_obs)
+        _chk('obs', obs_in, torch.float32, self.B * self.D)
+        _chk('obs_out', obs_out, torch.float32, self.B * self.D)
+        _chk('reward', reward, torch.float32, self.B, optional=not reward_step)
+        _chk('done', done, torch.uint8, self.B, optional=not reward_step)
+        _chk('terminal_obs', term_obs, torch.float32, self.B * self.D, optional=True)
+        check(_lib.load().rl_vecnormalize_step(ptr(obs_in), ptr(term_obs), ptr(obs_out), ptr(reward), ptr(done),
+                                               *[ptr(t) for t in self._state], self.B, self.D,
+                                               1 if self.training else 0, 1 if self.ob else 0,
+                                               1 if self.norm_ret else 0, 1 if reward_step else 0, self.clipob,
+                                               self.cliprew, self.gamma, self.epsilon, stream()), 'vecnormalize_step')
+        return obs_out
+
+    def reset(self, obs, out=None):
+        """VecNormalizeEnv.reset(): filter the first observations ([B, D] float32; in place unless ``out``)."""
+        self.ret.zero_()
+        return self._call(obs, obs if out is None else out, None, None, None, False)
+
+    def step(self, obs, reward, done, terminal_obs=None, out=None):
+        """VecNormalizeEnv.step() (+ reset where done): reward is normalised IN PLACE, returns filtered obs."""
+        return self._call(obs, obs if out is None else out, reward, _as_u8(done), terminal_obs, True)

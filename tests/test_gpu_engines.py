@@ -235,3 +235,60 @@ def test_dqn_engine_runs_and_priorities_follow_td(prioritized, double_q):
         assert 0.5 < eng.beta <= 1.0
     m = eng.get_metrics()
     assert m['learn_steps'] == 6 and m['sample_steps'] == (12 + 12) * 64
+
+
+def test_device_vecnormalize_matches_reference_trace(golden):
+    """rl_vecnormalize_step vs the trace recorded from parl.env.mujoco_wrappers.VecNormalizeEnv (float32 I/O)."""
+    from parl_b200 import kernels as K
+    g = golden('vecnormalize')
+    T, B, D = g['term_seq'].shape
+    vn = K.VecNormalize(B, D, DEV)
+    f32 = lambda x: torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).to(DEV)
+    ob0 = vn.reset(f32(g['obs_seq'][0]))
+    np.testing.assert_allclose(ob0.cpu().numpy(), g['ob0'], rtol=2e-6, atol=2e-6)
+    for t in range(T):
+        rew = f32(g['rew_seq'][t])
+        done = torch.as_tensor(g['done_seq'][t].astype(np.uint8)).to(DEV)
+        ob = vn.step(f32(g['obs_seq'][t + 1]), rew, done, terminal_obs=f32(g['term_seq'][t]))
+        np.testing.assert_allclose(ob.cpu().numpy(), g['ob_out'][t], rtol=1e-5, atol=1e-5, err_msg='t=%d' % t)
+        np.testing.assert_allclose(rew.cpu().numpy(), g['rew_out'][t], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(vn.ob_count.cpu().numpy(), g['ob_count'], rtol=1e-12)
+    np.testing.assert_allclose(vn.ob_var.cpu().numpy(), g['ob_var'], rtol=1e-5)        # float32 inputs
+    np.testing.assert_allclose(vn.ret_var.cpu().numpy(), g['ret_var'], rtol=1e-5)
+
+
+def test_fused_rollout_with_vecnormalize_equals_unfused_kernels():
+    from parl_b200 import kernels as K
+    from parl_b200.engine.nets import MujocoModel
+    torch.manual_seed(6)
+    B, T, seed = 70, 30, 4
+    model = MujocoModel(17, 6).to(DEV)
+    layers, act = model.native_layers()
+    plan = K.MlpPlan([[(w.detach(), b.detach()) for (w, b) in seg] for seg in layers], act)
+    logstd = model.fc_pi_std.detach().reshape(-1).contiguous()
+    st_f, st_u = K.EpisodeStats(B, DEV), K.EpisodeStats(B, DEV)
+    vn_f, vn_u = K.VecNormalize(B, 17, DEV), K.VecNormalize(B, 17, DEV)
+    obs_cur = torch.zeros((B, 17), device=DEV)
+    K.env_mujoco_synth_step(obs_cur, None, None, st_f, seed, 0, reset=True)
+    vn_f.reset(obs_cur)
+    f = dict(obs=torch.empty((T, B, 17), device=DEV), act=torch.empty((T, B, 6), device=DEV),
+             rew=torch.empty((T, B), device=DEV), done=torch.empty((T, B), dtype=torch.uint8, device=DEV),
+             val=torch.empty((T + 1, B), device=DEV))
+    plan.rollout(K.ENV_MUJOCO_SYNTH, K.POLICY_GAUSSIAN, T, obs_cur, st_f, seed, 0, f['obs'], f['act'], f['rew'],
+                 f['done'], val_out=f['val'], logstd=logstd, p_done=0.1, vecnorm=vn_f)
+    obs = torch.zeros((B, 17), device=DEV)
+    K.env_mujoco_synth_step(obs, None, None, st_u, seed, 0, reset=True)
+    vn_u.reset(obs)
+    rew, done = torch.zeros(B, device=DEV), torch.zeros(B, dtype=torch.uint8, device=DEV)
+    for t in range(T):
+        assert torch.equal(f['obs'][t], obs), t
+        mean, _ = plan.forward(obs.clone(), split=6)
+        a, _ = K.sample_gaussian(mean, logstd, seed, t)
+        assert torch.equal(f['act'][t], a), t
+        K.env_mujoco_synth_step(obs, rew, done, st_u, seed, t, p_done=0.1)
+        vn_u.step(obs, rew, done)
+        assert torch.equal(f['rew'][t], rew) and torch.equal(f['done'][t], done), t
+    assert torch.equal(obs_cur, obs)
+    for a, b in zip(vn_f._state, vn_u._state):
+        assert torch.equal(a, b)
+    assert torch.equal(st_f.totals, st_u.totals)           # raw rewards in the episode statistics
