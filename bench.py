@@ -374,48 +374,101 @@ def measure_dominant_kernel(eng, kernels, torch, B, peak, peak_src):
                 l2='operands (11.6 GB + 7.5 GB at 204 800 samples) far beyond the 126 MB L2')
 
 
+def numa_pin(gpu_index):
+    """Bind this process to the CPUs nearest to its GPU before the pinned staging buffers are allocated
+    (first-touch places them on the local NUMA node).  Best effort: returns a description or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return 'cpus %d' % len(os.sched_getaffinity(0))
+    except Exception as e:
+        return 'unpinned (%s)' % type(e).__name__
+
+
+def copy_bandwidth(torch, dev, nbytes=1 << 30):
+    """Measured pinned H2D / D2H copy bandwidth (GB/s) — the ceiling of the host-contract path."""
+    h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = {}
+    for name, (dst, src) in (('h2d', (d, h)), ('d2h', (h, d))):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            dst.copy_(src, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize()
+        out[name] = 3 * nbytes / (a.elapsed_time(b) * 1e-3) / 1e9
+    return out
+
+
 def run_e2e(eng, args, world, dev):
-    """The same metric through the reference-facing contract with HOST buffers: per step the rollout is
-    handed to the host as the numpy dict Actor.sample() returns (D2H into pinned memory) and
-    agent.learn() is fed from those host arrays (H2D) — copies inside the timed region."""
+    """The same metric END TO END through the reference-facing surface with HOST buffers, exactly the Learner loop of
+    examples/IMPALA/train.py:165-194: a ``@parl.remote_class(wait=False)`` Actor (the device actor pool) whose
+    ``sample()`` returns the numpy sample dict (uint8 stacked obs, env-major; D2H into pinned memory inside the
+    timed region), ``actor.set_weights(agent.get_weights())`` with numpy weight dicts, and ``agent.learn(numpy...)``
+    (H2D inside the timed region).  The next sample is produced while the learner trains on the current one, as
+    the reference's sampling threads do."""
     import torch
     import torch.distributed as dist
-    steps = max(2, min(args.steps, 4))
-    if eng.pipeline:
-        hosts = [eng.make_host_sample_buffers() for _ in range(2)]
-        host = hosts[0]
-        eng._k = 0                                        # restart the pipeline on the host path
-        eng._learn_done = [None, None]
-        for _ in range(2):                                # warm-up (prologue + one steady-state iteration)
-            eng.step_host(hosts, 0.001, -0.01)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.time()
-        for _ in range(steps):
-            losses = eng.step_host(hosts, 0.001, -0.01)
-            _ = losses[:5].cpu()                          # D2H read of the step's result
-    else:
-        host = eng.make_host_sample_buffers()
-        eng.sample_to_host(host)
-        eng.learn_from_host(host, 0.001, -0.01)           # warm-up
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.time()
-        for _ in range(steps):
-            eng.sample_to_host(host)
-            losses = eng.learn_from_host(host, 0.001, -0.01)
-            _ = losses[:5].cpu()                          # D2H read of the step's result
+    import parl_b200 as parl
+    from parl_b200.engine.impala_host import DeviceImpalaActor, AtariAgent
+    rank = int(os.environ.get('RANK', 0))
+    B = args.envs // world
+    pin = numa_pin(dev.index)
+    parl.connect('localhost:8010')
+    Actor = parl.remote_class(wait=False)(DeviceImpalaActor)
+    cfg = dict(env_num=B, sample_batch_steps=T_STEPS, act_dim=ACT_DIM, seed=1234, env_offset=rank * B)
+    torch.manual_seed(0)
+    agent = AtariAgent(cfg, device=dev)
+    if world > 1:
+        agent.alg.grad_sync = lambda g: dist.all_reduce(g, op=dist.ReduceOp.SUM)
+    actor = Actor(cfg, device=dev)
+    steps = max(10, min(args.steps, 20))
+    actor.set_weights(agent.get_weights()).get()
+    fut = actor.sample()
+
+    def one_step(fut):
+        batch = fut.get()
+        actor.set_weights(agent.get_weights())            # queued on the actor's worker: applies before its next sample
+        nxt = actor.sample()
+        losses = agent.learn(batch['obs'], batch['actions'], batch['behaviour_logits'], batch['rewards'],
+                             batch['dones'], 0.001, -0.01)  # returns Python floats: a D2H read of the step's result
+        return nxt, losses, batch
+
+    for _ in range(3):                                    # warm-up (graph capture, allocator, both host buffer sets)
+        fut, losses, batch = one_step(fut)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.time()
+    for _ in range(steps):
+        fut, losses, batch = one_step(fut)
     torch.cuda.synchronize()
     el = torch.tensor([time.time() - t0], device=dev)
     if world > 1:
         dist.barrier()
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
-    nbytes = sum(v.numel() * v.element_size() for v in host.values())
-    return dict(value=steps * T_STEPS * args.envs / el.item(), unit=UNIT, h2d_bytes_per_step=nbytes,
-                d2h_bytes_per_step=nbytes + 20, steps=steps,
-                path='Actor.sample() numpy dict (uint8 obs) -> pinned host -> Agent.learn(numpy)')
+    fut.get()
+    nbytes = sum(v.nbytes for v in batch.values())
+    wbytes = sum(v.nbytes for v in agent.get_weights().values())
+    bw = copy_bandwidth(torch, dev) if rank == 0 else None
+    actor.destroy()
+    value = steps * T_STEPS * args.envs / el.item()
+    ceiling = None
+    if bw:
+        # both directions run concurrently (full-duplex PCIe): the slower one bounds a step
+        ceiling = T_STEPS * B * world / (nbytes / (min(bw['h2d'], bw['d2h']) * 1e9))
+    return dict(value=value, unit=UNIT, h2d_bytes_per_step=nbytes + wbytes, d2h_bytes_per_step=nbytes + wbytes + 40,
+                steps=steps, ms_per_step=el.item() * 1e3 / steps,
+                path='@parl.remote_class(wait=False) Actor.sample() -> numpy dict (uint8 stacked obs, env-major, pinned) '
+                     '-> AtariAgent.learn(numpy) ; actor.set_weights(agent.get_weights()) numpy weight dicts '
+                     '(examples/IMPALA/train.py:165-194)',
+                host_buffers=pin, copy_bandwidth_gbs=bw, pcie_ceiling_env_steps_per_s=ceiling,
+                sample_dict_bytes=nbytes, last_losses=[float(x) for x in losses])
 
 
 if __name__ == '__main__':

@@ -29,10 +29,17 @@ class ImpalaEngine(object):
     def __init__(self, num_envs=4096, sample_batch_steps=50, act_dim=18, frame_hw=(84, 84), seed=0, device=None,
                  env_offset=0, gamma=0.99, vf_loss_coeff=0.5, clip_rho_threshold=1.0, clip_pg_rho_threshold=1.0,
                  p_done=0.1, model=None, learn_chunk_rows=5, use_graph=True, actor_kernels='auto',
-                 learner_kernels='auto', pipeline=False):
+                 learner_kernels='auto', pipeline=False, role='both'):
         if device is None:
             device = torch.device('cuda', torch.cuda.current_device())
         self.device = torch.device(device)
+        assert role in ('both', 'actor', 'learner')
+        # role 'actor': only the actor pool (envs, rollout buffers, packed actor network) — what a remote Actor hosts;
+        # role 'learner': only the learner (train network, loss buffers) — what the Learner's Agent hosts.  The two
+        # halves then talk through the reference's host contract (numpy sample dicts, numpy weight dicts).
+        self.role = role
+        if role != 'both':
+            assert not pipeline, 'actor-only / learner-only engines are driven through the host contract'
         self.B, self.T, self.A = int(num_envs), int(sample_batch_steps), int(act_dim)
         self.h, self.w = frame_hw
         self.hw = self.h * self.w
@@ -42,7 +49,7 @@ class ImpalaEngine(object):
         # rollout buffer sets: one, or two when actor and learner are pipelined (double buffering)
         self.pipeline = bool(pipeline)
         self._sets = []
-        for _ in range(2 if self.pipeline else 1):
+        for _ in range(0 if role == 'learner' else (2 if self.pipeline else 1)):
             self._sets.append(dict(
                 planes=torch.zeros((T + 4, B, self.hw), dtype=torch.uint8, device=dev),
                 ages=torch.zeros((T + 1, B), dtype=torch.uint8, device=dev),
@@ -50,7 +57,8 @@ class ImpalaEngine(object):
                 actions=torch.zeros((T, B), dtype=torch.int32, device=dev),
                 rewards=torch.zeros((T, B), dtype=torch.float32, device=dev),
                 dones=torch.zeros((T, B), dtype=torch.uint8, device=dev)))
-        self._bind(0)
+        if self._sets:
+            self._bind(0)
         self.stats = kernels.EpisodeStats(B, dev)
         self.s2d = (self.h, self.w) == (84, 84)              # conv1 space-to-depth input [N,21,21,64]
         obs_shape = (21, 21, 64) if self.s2d else (self.h, self.w, 4)
@@ -63,22 +71,23 @@ class ImpalaEngine(object):
                           clip_rho_threshold=clip_rho_threshold, clip_pg_rho_threshold=clip_pg_rho_threshold)
         self.learn_chunk_rows = int(learn_chunk_rows)
         native_ok = (self.h, self.w) == (84, 84) and isinstance(self.model, AtariActorCritic)
-        use_native_learner = learner_kernels is True or (learner_kernels == 'auto' and native_ok)
+        use_native_learner = role != 'actor' and (learner_kernels is True or (learner_kernels == 'auto' and native_ok))
         # learner forward+backward on hand-written tcgen05 kernels (no autograd) when the model is the Atari net
         self.train_net = AtariTrainNet(self.model, T * B, dev) if use_native_learner else None
         # learner inputs: one pre-scaled bf16 NHWC buffer per chunk (each is saved by autograd for conv1's
         # weight gradient, so chunks must not share storage): T*B*56 KB in total
-        self.obs_chunks = [] if self.train_net is not None else [
+        self.obs_chunks = [] if (self.train_net is not None or role == 'actor') else [
             torch.empty((min(self.learn_chunk_rows, T - t0) * B, ) + obs_shape, dtype=torch.bfloat16, device=dev)
             for t0 in range(0, T, self.learn_chunk_rows)]
-        self.tgt_logits = torch.empty((T, B, A), dtype=torch.float32, device=dev)
-        self.values = torch.empty((T, B), dtype=torch.float32, device=dev)
-        self.loss_out = dict(losses=torch.zeros(8, device=dev), d_logits=torch.empty((T * B, A), device=dev),
-                             d_values=torch.empty(T * B, device=dev))
+        if role != 'actor':
+            self.tgt_logits = torch.empty((T, B, A), dtype=torch.float32, device=dev)
+            self.values = torch.empty((T, B), dtype=torch.float32, device=dev)
+            self.loss_out = dict(losses=torch.zeros(8, device=dev), d_logits=torch.empty((T * B, A), device=dev),
+                                 d_values=torch.empty(T * B, device=dev))
         # actor-side policy forward: hand-written tcgen05 conv/GEMM kernels when the model is the Atari
         # actor-critic on 84x84 frames ('auto'), else the user's torch Model
-        use_native = actor_kernels is True or (actor_kernels == 'auto' and self.s2d and
-                                               isinstance(self.model, AtariActorCritic))
+        use_native = role != 'learner' and (actor_kernels is True or (actor_kernels == 'auto' and self.s2d and
+                                                                     isinstance(self.model, AtariActorCritic)))
         self.actor_net = AtariActorNet(self.model, B, dev) if use_native else None
         # Shared observation plane: the actor's per-step conv1 input (space-to-depth bf16, 56 KB per env step) is
         # written straight into row t of a (T,B) plane of the rollout buffer set and the learner's conv1 forward /
@@ -106,7 +115,8 @@ class ImpalaEngine(object):
             self._roll_done = [torch.cuda.Event() for _ in range(2)]
             self._learn_done = [None, None]
             self._ev_pack = torch.cuda.Event()
-        self.reset()
+        if role != 'learner':
+            self.reset()
 
     def _bind(self, i):
         """Make buffer set i the one the attribute names (planes, ages, beh_logits, ...) refer to."""

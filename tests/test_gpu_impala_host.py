@@ -1,0 +1,57 @@
+"""GPU test of the IMPALA example's host contract on the device actor pool: a ``@parl.remote_class`` Actor with
+sample() / set_weights() / get_metrics() and ``AtariAgent.learn(numpy...)`` driven exactly like the Learner loop of
+examples/IMPALA/train.py:165-194 (keys, dtypes and env-major order of examples/IMPALA/actor.py:79-91)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device('cuda:0')
+
+
+def test_remote_actor_and_agent_learn_through_numpy_contract():
+    import parl_b200 as parl
+    from parl_b200.engine.impala_host import DeviceImpalaActor, AtariAgent
+    from oracle import envs as oenv
+    torch.manual_seed(0)
+    B, T, A, seed = 64, 8, 18, 77
+    cfg = dict(env_num=B, sample_batch_steps=T, act_dim=A, seed=seed)
+    parl.connect('localhost:8010')
+    agent = AtariAgent(cfg, device=DEV)
+    Actor = parl.remote_class(wait=False)(DeviceImpalaActor)
+    actor = Actor(cfg, device=DEV)
+    actor.set_weights(agent.get_weights()).get()
+    batch = actor.sample().get()
+    assert set(batch) == {'obs', 'actions', 'behaviour_logits', 'rewards', 'dones'}
+    assert batch['obs'].shape == (B * T, 4, 84, 84) and batch['obs'].dtype == np.uint8
+    assert batch['actions'].dtype == np.int64 and batch['behaviour_logits'].shape == (B * T, A)
+    assert batch['rewards'].dtype == np.float32 and batch['dones'].dtype == np.bool_
+    # env-major order + the env twin: row b*T + t is env b at step t (actor.py:79-89)
+    ref = oenv.AtariSynthVec(B, seed, p_done=0.1)
+    ref.reset()
+    obs_em = batch['obs'].reshape(B, T, 4, 84 * 84)
+    rew_em, done_em = batch['rewards'].reshape(B, T), batch['dones'].reshape(B, T)
+    for t in range(T):
+        assert np.array_equal(obs_em[:, t], ref.obs())
+        _, r, d = ref.step()
+        assert np.array_equal(rew_em[:, t], r) and np.array_equal(done_em[:, t], d)
+    # the actor really runs the learner's weights: its behaviour logits == the agent model's policy on the same obs
+    with torch.no_grad():
+        lg = agent.alg.model.policy(torch.from_numpy(batch['obs'][:256]).to(DEV)).float().cpu().numpy()
+    assert np.abs(lg - batch['behaviour_logits'][:256]).max() < 0.05 * max(1.0, np.abs(lg).max())
+    # Learner loop, future mode: the next sample is produced while the agent learns
+    w0 = {k: v.copy() for k, v in agent.get_weights().items()}
+    fut = actor.sample()
+    for _ in range(3):
+        out = agent.learn(batch['obs'], batch['actions'], batch['behaviour_logits'], batch['rewards'], batch['dones'],
+                          0.001, -0.01)
+        assert len(out) == 5 and all(np.isfinite(x) for x in out)
+        batch = fut.get()
+        actor.set_weights(agent.get_weights())
+        fut = actor.sample()
+    fut.get()
+    w1 = agent.get_weights()
+    assert any(not np.array_equal(w0[k], w1[k]) for k in w0)
+    m = actor.get_metrics().get()
+    assert set(m) == {'episode_rewards', 'episode_steps'} and len(m['episode_rewards']) == len(m['episode_steps']) > 0
+    actor.destroy()
