@@ -8,7 +8,9 @@ from .window_stat import WindowStat
 from .misc import check_model_method, get_gpu_count, is_gpu_available
 from .rl_utils import calc_gae, calc_discount_sum_rewards
 from .replay_memory import ReplayMemory
+from .rollout_storage import RolloutStorage
+from . import atari_replay_memory
 
 __all__ = ['logger', 'summary', 'PiecewiseScheduler', 'LinearDecayScheduler', 'TimeStat', 'WindowStat',
            'check_model_method', 'get_gpu_count', 'is_gpu_available', 'calc_gae', 'calc_discount_sum_rewards',
-           'ReplayMemory']
+           'ReplayMemory', 'RolloutStorage', 'atari_replay_memory']

@@ -292,3 +292,93 @@ def test_fused_rollout_with_vecnormalize_equals_unfused_kernels():
     for a, b in zip(vn_f._state, vn_u._state):
         assert torch.equal(a, b)
     assert torch.equal(st_f.totals, st_u.totals)           # raw rewards in the episode statistics
+
+
+def test_rollout_storage_facade_matches_reference_fixture(golden):
+    """parl_b200.utils.RolloutStorage (append / compute_returns / sample_batch) on the reference-recorded
+    compute_returns fixture (tests/golden/ppo_returns.npz, from benchmark/torch/ppo/storage.py, gamma .99 / lambda .95)."""
+    from parl_b200.utils import RolloutStorage
+    g = golden('ppo_returns')
+    for c in range(int(g['n_cases'])):
+        pre = 'c%d_' % c
+        rew, val, don = g[pre + 'rewards'], g[pre + 'values'], g[pre + 'dones']
+        T, B = rew.shape
+        st = RolloutStorage(T, B, 17, 6, device=DEV)
+        rng = np.random.RandomState(c)
+        obs, act = rng.randn(T, B, 17).astype(np.float32), rng.randn(T, B, 6).astype(np.float32)
+        lp = rng.randn(T, B).astype(np.float32)
+        for t in range(T):
+            st.append(obs[t], act[t], lp[t], rew[t], don[t], val[t])
+        adv, ret = st.compute_returns(g[pre + 'value'], g[pre + 'done'])
+        assert np.array_equal(adv.cpu().numpy(), g[pre + 'adv']) and np.array_equal(ret.cpu().numpy(), g[pre + 'ret'])
+        idx = rng.permutation(T * B)[:min(37, T * B)]
+        o, a, l, ad, r, v = st.sample_batch(idx, as_numpy=True)
+        assert np.array_equal(o, obs.reshape(T * B, 17)[idx]) and np.array_equal(a, act.reshape(T * B, 6)[idx])
+        assert np.array_equal(l, lp.reshape(-1)[idx]) and np.array_equal(ad, g[pre + 'adv'].reshape(-1)[idx])
+        assert np.array_equal(r, g[pre + 'ret'].reshape(-1)[idx]) and np.array_equal(v, val.reshape(-1)[idx])
+
+
+def test_atari_replay_memory_facade_matches_reference_fixture(golden):
+    """parl_b200.utils.atari_replay_memory.ReplayMemory vs the reference-recorded sample() stacking."""
+    from parl_b200.utils.atari_replay_memory import ReplayMemory, Experience
+    g = golden('atari_replay')
+    size, ctx = int(g['size']), int(g['ctx'])
+    shp = tuple(g['frames'].shape[1:])
+    # frames of the fixture are 3x2 bytes: widen to 16 bytes per frame (the device gather's alignment contract)
+    rpm = ReplayMemory(size, (4, 4), ctx, device=DEV)
+    ref_ctx = []
+    for f, a, r, o in zip(g['frames'], g['actions'], g['rewards'], g['overs']):
+        wide = np.zeros((4, 4), np.uint8)
+        wide.reshape(-1)[:f.size] = f.reshape(-1)
+        rpm.append(Experience(wide, int(a), float(r), bool(o)))
+    assert rpm.size() == min(len(g['frames']), size)
+    ref = orp.AtariReplay(size, shp, ctx)
+    for f, a, r, o in zip(g['frames'], g['actions'], g['rewards'], g['overs']):
+        ref.append(f, a, r, o)
+    idx = ref.batch_indices(g['raw'])
+    obs, act, rew, over = rpm.sample_batch_by_index(idx)
+    got = obs.reshape(len(idx), ctx + 1, 16)[:, :, :g['frames'][0].size].reshape((len(idx), ctx + 1) + shp)
+    np.testing.assert_array_equal(got, g['obs'])
+    np.testing.assert_array_equal(act.astype(np.int32), g['action'])
+    assert len(rpm.recent_obs()) == ctx - 1
+
+
+def test_policy_gradient_engine_matches_algorithm_and_learns_cartpole():
+    """QuickStart on the device: one update equals parl.algorithms.PolicyGradient.learn on the same batch, and a
+    short training run raises the mean CartPole episode length (benchmark/torch/QuickStart/train.py)."""
+    from parl_b200 import kernels as K
+    from parl_b200.algorithms import PolicyGradient
+    from parl_b200.engine.pg import PolicyGradientEngine
+    from parl_b200.engine.nets import CartPolePolicy
+    torch.manual_seed(0)
+    eng = PolicyGradientEngine(num_envs=128, rollout_steps=64, lr=1e-3, seed=3, device=DEV)
+    ref_model = CartPolePolicy(4, 2).to(DEV)
+    ref_model.load_state_dict(eng.model.state_dict())
+    ref = PolicyGradient(ref_model, lr=1e-3)
+    eng.rollout()
+    T, B = eng.T, eng.B
+    togo, _ = K.gae_scan_segments(eng.rewards, eng.zeros_tb, eng.dones, eng.zeros_b, 1.0, 1.0)
+    # reward-to-go of CartPole (reward 1 per step) inside a segment = number of remaining steps of the segment
+    d = eng.dones.cpu().numpy()
+    tg = togo.cpu().numpy()
+    for b in range(0, B, 17):
+        cnt = 0.0
+        for t in range(T - 1, -1, -1):
+            cnt = 1.0 if d[t, b] else cnt + 1.0
+            assert tg[t, b] == cnt
+    loss = eng.learn().item()
+    rloss = float(ref.learn(eng.obs.view(T * B, 4), eng.actions.view(-1), togo.view(-1)))
+    assert abs(loss - rloss) <= 1e-4 * max(1.0, abs(rloss))
+    for (n, p), (_, q) in zip(eng.model.named_parameters(), ref_model.named_parameters()):
+        assert torch.allclose(p, q, rtol=1e-4, atol=1e-5), n
+    eng2 = PolicyGradientEngine(num_envs=256, rollout_steps=200, lr=5e-3, seed=1, device=DEV)
+    eng2.rollout()
+    first = eng2.get_metrics()['mean_episode_steps']
+    for _ in range(60):
+        eng2.step()
+    m = eng2.get_metrics()
+    eng2.stats.totals.zero_()
+    for _ in range(3):
+        eng2.rollout()
+    last = eng2.get_metrics()['mean_episode_steps']
+    assert last > 1.5 * first and last > 40, (first, last)
