@@ -52,9 +52,9 @@ size_t rl_loss_workspace_bytes(int n_cols);
 /* Triage hook: 1 forces the cp.async tile path of rl_vtrace_loss_fwd_bwd, 0 (default) lets the
  * TMA tensor-map path run when the layout allows it. */
 int rl_debug_set_tma(int disable);
-/* Triage hook for rl_vtrace_loss_fwd_bwd: 0 = automatic (the warp-streaming kernel, 4 env columns per warp,
- * whenever the layout is time-major and TMA-able), 1 = always the general CTA-per-4-columns kernel,
- * 2 / 8 = warp-streaming kernel with 2 / 8 columns per warp. */
+/* Triage hook for rl_vtrace_loss_fwd_bwd: 0 = automatic (v6: CTA per 4-column block, one 8-row TMA chunk per warp,
+ * whenever the layout is time-major, TMA-able and T <= 56), 1 = always the general v4 kernel,
+ * 2 / 4 / 8 = v5 (warp-autonomous streaming kernel) with 2 / 4 / 8 columns per warp. */
 int rl_debug_set_vtrace_path(int mode);
 
 /* ------------------------------------------------------------------------
@@ -286,14 +286,15 @@ int rl_gather_rows(const void* src, const int32_t* idx, long long n, int row_byt
  * rl_adam_step: grad is first divided by grad_div (e.g. world size for MEAN losses), then scaled by
  *   clip_mode 0: 1 ; 1 (torch): min(1, max_norm/(norm+1e-6)) ; 2 (paddle): max_norm/max(norm, max_norm)
  *   where norm = grad_norm[0]/grad_div; lr from lr_device[0] if non-NULL else `lr`;
- *   step = 1-based update count (bias correction); zero_grad=1 clears grad in the same pass.
+ *   step = 1-based update count (bias correction), read from step_device[0] instead when that is non-NULL (an
+ *   int32 on the device: lets a captured CUDA graph of the update be replayed); zero_grad=1 clears grad in the same pass.
  * ---------------------------------------------------------------------- */
 int rl_grad_global_norm(const float* grad, long long n, float* out_norm, void* workspace, size_t workspace_bytes,
                         rl_stream_t stream);
 int rl_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                  const float* lr_device, float lr, float beta1, float beta2, float eps, int step,
                  float grad_div, const float* grad_norm, float max_norm, int clip_mode, int zero_grad,
-                 rl_stream_t stream);
+                 const int32_t* step_device, rl_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * a13 / K6  Dense contraction on the tcgen05 tensor cores (TMA-staged tiles, fp32 accumulation in TMEM):

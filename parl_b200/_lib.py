@@ -63,7 +63,7 @@ SIGNATURES = {
     'rl_gather_rows': (c_i, [c_p, c_p, ctypes.c_longlong, c_i, c_p, c_p]),
     'rl_grad_global_norm': (c_i, [c_p, ctypes.c_longlong, c_p, c_p, c_sz, c_p]),
     'rl_adam_step': (c_i, [c_p, c_p, c_p, c_p, ctypes.c_longlong, c_p, c_f, c_f, c_f, c_f, c_i, c_f, c_p, c_f, c_i,
-                           c_i, c_p]),
+                           c_i, c_p, c_p]),
     'rl_gemm_bf16_tn': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
     'rl_gemm_bf16_tn_splitk': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_sz, c_p]),
     'rl_conv2d_nhwc_bf16_fwd': (c_i, [c_p, c_p, c_p, c_p] + [c_i] * 10 + [c_p]),

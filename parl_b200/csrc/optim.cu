@@ -43,7 +43,13 @@ __global__ void __launch_bounds__(kOT) adam_step_kernel(float* __restrict__ p, c
                                                         const float* __restrict__ lr_ptr, float lr, float b1, float b2,
                                                         float eps, float bc1, float bc2_sqrt, float grad_div,
                                                         const float* __restrict__ norm, float max_norm, int clip_mode,
-                                                        int zero_grad, float* __restrict__ g_mut) {
+                                                        int zero_grad, float* __restrict__ g_mut,
+                                                        const int* __restrict__ step_ptr) {
+  if (step_ptr) {                      // update count resident on the device (CUDA-graph replay): same fp64 formula
+    const double st = (double)step_ptr[0];
+    bc1 = (float)(1.0 - pow((double)b1, st));
+    bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, st));
+  }
   float scale = 1.0f / grad_div;
   if (clip_mode != 0) {
     const float nrm = norm[0] / grad_div;
@@ -88,8 +94,9 @@ extern "C" int rl_grad_global_norm(const float* grad, long long n, float* out_no
 extern "C" int rl_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                             const float* lr_device, float lr, float beta1, float beta2, float eps, int step,
                             float grad_div, const float* grad_norm, float max_norm, int clip_mode, int zero_grad,
-                            rl_stream_t stream) {
-  RL_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step: bad argument");
+                            const int32_t* step_device, rl_stream_t stream) {
+  RL_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && (step >= 1 || step_device), "adam_step: bad argument");
+  if (step < 1) step = 1;
   RL_CHECK_ARG(clip_mode == 0 || grad_norm, "adam_step: clip_mode %d needs grad_norm", clip_mode);
   RL_CHECK_ARG(grad_div > 0.f, "adam_step: grad_div must be positive");
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
@@ -98,7 +105,7 @@ extern "C" int rl_adam_step(float* param, float* grad, float* exp_avg, float* ex
   if (blocks > 148 * 8) blocks = 148 * 8;
   adam_step_kernel<<<(unsigned)blocks, kOT, 0, (cudaStream_t)stream>>>(
       param, grad, exp_avg, exp_avg_sq, n, lr_device, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), grad_div,
-      grad_norm, max_norm, clip_mode, zero_grad, grad);
+      grad_norm, max_norm, clip_mode, zero_grad, grad, step_device);
   RL_CHECK_LAUNCH("rl_adam_step");
   return RL_OK;
 }

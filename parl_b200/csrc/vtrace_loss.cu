@@ -723,9 +723,261 @@ __global__ void __launch_bounds__(kMaxWarpsV5 * 32, 1)
   }
 }
 
+// ---------------------------------------------------------------------------
+// v6: CTA per 4-column block, ONE 8-row pass per warp (the default fast path).  v5 showed that a warp walking
+// all of T alone is bound by its own instruction latency (7 warps per SM cannot hide LDS -> MUFU -> FADD chains),
+// so the rows of a column block are spread over ceil(T/8) warps: every warp waits only for ITS 8-row TMA chunk,
+// computes the softmax statistics of its 32 elements (two register-light sweeps: 7 CTAs = 49 warps stay resident
+// per SM), reduces its rows to one affine map per column (3 shuffle steps), and after the CTA's single
+// __syncthreads composes the maps of the later warps (<= 6 FMAs) to get its incoming accumulator.  The gradient
+// rows are recomputed in place and each warp TMA-stores its own chunk at once.
+// ---------------------------------------------------------------------------
+constexpr int kV6Rows = 8;                 // rows per warp / per TMA chunk
+constexpr int kV6MaxWarps = 7;             // T <= 56
+
+template <int A_>
+__global__ void __maxnreg__(40)          // 7 CTAs x 7 warps x 40 registers fit the 64 K register file
+    vtrace_loss_cta_kernel(const VtraceLossArgs p, const __grid_constant__ CUtensorMap map_tl,
+                           const __grid_constant__ CUtensorMap map_bl, const __grid_constant__ CUtensorMap map_dl,
+                           const __grid_constant__ CUtensorMap map_tl_tail, const __grid_constant__ CUtensorMap map_bl_tail,
+                           const __grid_constant__ CUtensorMap map_dl_tail) {
+  static_assert(A_ >= 2 && (A_ & 1) == 0, "v6 needs an even compile-time A");
+  constexpr int CW = 4, R = kV6Rows;
+  constexpr uint32_t FULL = 0xffffffffu;
+  constexpr int kChunkBytes = R * CW * A_ * 4;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long s_bar[kV6MaxWarps];
+  __shared__ float2 s_comp[kV6MaxWarps][CW];
+  __shared__ float s_red[4][kV6MaxWarps];
+  __shared__ bool s_last;
+  const int T = p.T, B = p.B;
+  const int P = (T + R - 1) / R, nfull = T / R, tail_rows = T - nfull * R;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b0 = blockIdx.x * CW;
+  unsigned char* s_tl = smem_raw;
+  unsigned char* s_bl = smem_raw + (((size_t)T * CW * A_ * 4 + 127) & ~(size_t)127);   // TMA tiles: 128-byte aligned
+
+  if (tid == 0) {
+    for (int c = 0; c < P; ++c) mbar_init(&s_bar[c], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int c = P - 1; c >= 0; --c) {                  // latest rows first: they head the dependency chain
+      const bool full = c < nfull;
+      const uint32_t bytes = (uint32_t)((full ? R : tail_rows) * CW * A_ * 4);
+      mbar_arrive_expect_tx(&s_bar[c], 2u * bytes);
+      tma_load_2d(s_tl + c * kChunkBytes, full ? &map_tl : &map_tl_tail, b0 * A_, c * R, &s_bar[c]);
+      tma_load_2d(s_bl + c * kChunkBytes, full ? &map_bl : &map_bl_tail, b0 * A_, c * R, &s_bar[c]);
+    }
+  }
+  // ---- this lane's element: (t, b) = (warp*8 + lane/4, b0 + lane%4); scalars straight from global
+  const int r = lane >> 2, c = lane & 3;
+  const int t = warp * R + r;
+  const bool valid = t < T;
+  const bool loss_row = t < T - 1;
+  const int g = t * B + b0 + c;
+  int act = 0;
+  float e_r = 0.f, e_v = 0.f, e_vn = 0.f, e_g = 0.f;
+  if (valid) {
+    act = p.act64 ? (int)reinterpret_cast<const long long*>(p.actions)[g] : reinterpret_cast<const int*>(p.actions)[g];
+    e_r = p.rewards[g];
+    e_v = p.values[g];
+    e_g = p.dones[g] ? 0.0f : p.gamma;                  // impala.py:59  (~dones) * discount
+    if (t + 1 < T) e_vn = p.values[g + B];
+  }
+  mbar_wait(&s_bar[warp], 0);
+
+  // ---- phase A: softmax statistics (two sweeps over the shared-memory row, registers hold scalars only)
+  float* pt = reinterpret_cast<float*>(s_tl) + (size_t)(t * CW + c) * A_;
+  const float* pb = reinterpret_cast<const float*>(s_bl) + (size_t)(t * CW + c) * A_;
+  float nm = 0.f, l2S = 0.f, inv = 0.f, la = 0.f, H = 0.f, D = 0.f, K = 0.f, rpg = 0.f;
+  float sum_pi = 0.f, sum_vf = 0.f, sum_ent = 0.f, sum_kl = 0.f;
+  if (valid) {
+    float m = -INFINITY, my = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < A_; j += 2) {
+      const float2 a = *reinterpret_cast<const float2*>(pt + j);
+      const float2 y = *reinterpret_cast<const float2*>(pb + j);
+      m = fmaxf(m, fmaxf(a.x, a.y));
+      my = fmaxf(my, fmaxf(y.x, y.y));
+    }
+    nm = -m * kL2E;
+    const float nmy = -my * kL2E;
+    float S0 = 0.f, S1 = 0.f, W0 = 0.f, W1 = 0.f, Y0 = 0.f, Y1 = 0.f, Sy0 = 0.f, Sy1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < A_; j += 2) {
+      const float2 a = *reinterpret_cast<const float2*>(pt + j);
+      const float2 y = *reinterpret_cast<const float2*>(pb + j);
+      const float xs0 = fmaf(a.x, kL2E, nm), xs1 = fmaf(a.y, kL2E, nm);
+      const float e0 = ex2_approx(xs0), e1 = ex2_approx(xs1);
+      S0 += e0, S1 += e1;
+      W0 = fmaf(e0, xs0, W0), W1 = fmaf(e1, xs1, W1);
+      Y0 = fmaf(e0, y.x, Y0), Y1 = fmaf(e1, y.y, Y1);
+      Sy0 += ex2_approx(fmaf(y.x, kL2E, nmy));
+      Sy1 += ex2_approx(fmaf(y.y, kL2E, nmy));
+    }
+    const float S = S0 + S1, Wt = W0 + W1, Y = Y0 + Y1, Sy = Sy0 + Sy1;
+    l2S = lg2_approx(S);
+    inv = __fdividef(1.0f, S);
+    const float logSy = lg2_approx(Sy) * kLN2;
+    const float Hn = (Wt * inv - l2S) * kLN2;              // sum_j p_j log p_j
+    H = -Hn;
+    sum_kl = Hn - Y * inv + my + logSy;                    // impala.py:160-162: every row
+    la = (fmaf(pt[act], kL2E, nm) - l2S) * kLN2;
+    const float lma = pb[act] - my - logSy;
+    if (loss_row) {
+      const float rho = expf(la - lma);                    // vtrace.py:101-103
+      const float rhoc = p.clip_rho >= 0.f ? fminf(rho, p.clip_rho) : rho;
+      const float cs = fminf(rho, 1.0f);                   // :109
+      rpg = p.clip_pg >= 0.f ? fminf(rho, p.clip_pg) : rho;
+      D = __fmul_rn(rhoc, __fsub_rn(__fadd_rn(e_r, __fmul_rn(e_g, e_vn)), e_v));     // :115
+      K = __fmul_rn(e_g, cs);
+      sum_ent = H;
+    }
+  }
+  // suffix scan of the affine maps acc -> D + K acc over the warp's 8 rows (later time = higher lane)
+#pragma unroll
+  for (int off = CW; off < 32; off <<= 1) {
+    const float Dn = __shfl_down_sync(FULL, D, off);
+    const float Kn = __shfl_down_sync(FULL, K, off);
+    if (lane + off < 32) {
+      D = fmaf(K, Dn, D);
+      K *= Kn;
+    }
+  }
+  if (lane < CW) s_comp[warp][lane] = make_float2(D, K);   // the whole pass as one map, per column
+  __syncthreads();
+  // ---- phase B: accumulator entering this warp's rows = later warps' maps applied to 0, latest first
+  float cin = 0.f;
+  for (int w2 = P - 1; w2 > warp; --w2) {
+    const float2 m2 = s_comp[w2][c];
+    cin = fmaf(m2.y, cin, m2.x);
+  }
+  const float acc = fmaf(K, cin, D);
+  float acc_n = __shfl_down_sync(FULL, acc, CW);
+  if (r == R - 1) acc_n = cin;
+  // ---- phase C: advantages, losses, gradient row recomputed over the target-logit row
+  if (valid) {
+    if (loss_row) {
+      const float vs = __fadd_rn(acc, e_v);                          // vtrace.py:125
+      const float vs_n = __fadd_rn(acc_n, e_vn);                     // :128-129 (bootstrap at the end)
+      const float adv = __fmul_rn(rpg, __fsub_rn(__fadd_rn(e_r, __fmul_rn(e_g, vs_n)), e_v));   // :136-137
+      const float dv = e_v - vs;
+      sum_pi = -la * adv;                                             // impala.py:67-68
+      sum_vf = 0.5f * dv * dv;                                        // :71-72
+      p.d_values[g] = p.vf_coeff * dv;
+      if (p.vs_out) p.vs_out[g] = vs;
+      if (p.pg_out) p.pg_out[g] = adv;
+      const float ce2 = p.ent_coeff * kLN2;
+      const float c0 = fmaf(ce2, l2S, adv - p.ent_coeff * H) * inv;  // folded with 1/S
+      const float c1 = -ce2 * inv;
+#pragma unroll
+      for (int j = 0; j < A_; j += 2) {
+        const float2 a = *reinterpret_cast<const float2*>(pt + j);
+        const float xs0 = fmaf(a.x, kL2E, nm), xs1 = fmaf(a.y, kL2E, nm);
+        const float d0 = ex2_approx(xs0) * fmaf(c1, xs0, c0), d1 = ex2_approx(xs1) * fmaf(c1, xs1, c0);
+        *reinterpret_cast<float2*>(pt + j) = make_float2(d0, d1);
+      }
+      pt[act] -= adv;
+    } else {
+      p.d_values[g] = 0.f;                                            // bootstrap row: no gradient
+#pragma unroll
+      for (int j = 0; j < A_; j += 2) *reinterpret_cast<float2*>(pt + j) = make_float2(0.f, 0.f);
+    }
+  }
+  fence_proxy_async_smem();              // generic-proxy writes of the gradient rows -> visible to the TMA engine
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(warp < nfull ? &map_dl : &map_dl_tail, b0 * A_, warp * R, s_tl + warp * kChunkBytes);
+    tma_store_commit();
+  }
+  // ---- loss reduction: warp -> CTA -> (last CTA) grid, fixed order, fp64 at the end
+  sum_pi = warp_sum(sum_pi), sum_vf = warp_sum(sum_vf), sum_ent = warp_sum(sum_ent), sum_kl = warp_sum(sum_kl);
+  if (lane == 0) {
+    s_red[0][warp] = sum_pi, s_red[1][warp] = sum_vf, s_red[2][warp] = sum_ent, s_red[3][warp] = sum_kl;
+    tma_store_wait_read();               // the shared-memory rows must outlive the bulk read
+  }
+  __syncthreads();
+  if (tid < 4) {
+    float a = 0.f;
+    for (int x = 0; x < P; ++x) a += s_red[tid][x];
+    p.partials[blockIdx.x * 4 + tid] = a;
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double accd[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = tid; i < (int)gridDim.x; i += blockDim.x) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) accd[q] += (double)__ldcg(p.partials + i * 4 + q);
+    }
+    __shared__ double s_dred[4][kV6MaxWarps];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double v = accd[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+      if (lane == 0) s_dred[q][warp] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double rr[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        rr[q] = 0.0;
+        for (int x = 0; x < P; ++x) rr[q] += s_dred[q][x];
+      }
+      const float pi = (float)rr[0], vf = (float)rr[1], ent = (float)rr[2];
+      p.losses[0] = pi + vf * p.vf_coeff + ent * p.ent_coeff;      // impala.py:78-79
+      p.losses[1] = pi;
+      p.losses[2] = vf;
+      p.losses[3] = ent;
+      p.losses[4] = (float)(rr[3] / ((double)T * (double)B));
+      *p.ticket = 0u;
+    }
+  }
+}
+
+template <int A_>
+static bool try_launch_v6(const VtraceLossArgs& a, const float* tl, const float* bl, float* dl, cudaStream_t st) {
+  if constexpr (A_ >= 2 && (A_ & 1) == 0 && A_ <= 64) {
+    constexpr int CW = 4, R = kV6Rows;
+    const int T = a.T, B = a.B;
+    if (B % CW != 0 || T > R * kV6MaxWarps || ((CW * A_ * 4) % 16) != 0 || CW * A_ > 256) return false;
+    if ((R * CW * A_ * 4) % 128 != 0) return false;          // every chunk starts 128-byte aligned in shared memory
+    const int P = (T + R - 1) / R, nfull = T / R, tail = T - nfull * R;
+    alignas(64) CUtensorMap maps[6];
+    const char* err = nullptr;
+    const uint64_t pitch = (uint64_t)B * A_ * sizeof(float);
+    const float* bases[3] = {tl, bl, dl};
+    for (int i = 0; i < 3; ++i) {
+      if (make_tensor_map_2d_f32(&maps[i], bases[i], (uint64_t)B * A_, (uint64_t)T, pitch, CW * A_, R, &err)) return false;
+      if (make_tensor_map_2d_f32(&maps[3 + i], bases[i], (uint64_t)B * A_, (uint64_t)T, pitch, CW * A_, tail > 0 ? tail : R,
+                                 &err))
+        return false;
+    }
+    const size_t smem = 2 * (((size_t)T * CW * A_ * 4 + 127) & ~(size_t)127);
+    if (smem > 200 * 1024) return false;
+    RL_SMEM_OPTIN(vtrace_loss_cta_kernel<A_>);
+    static bool carve = false;
+    if (!carve) {
+      cudaFuncSetAttribute(vtrace_loss_cta_kernel<A_>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
+      carve = true;
+    }
+    vtrace_loss_cta_kernel<A_><<<B / CW, P * 32, smem, st>>>(a, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5]);
+    return true;
+  }
+  return false;
+}
+
 // Host side of the v5 path: shape the per-warp shared-memory region and launch.  Returns false when the shape
 // does not fit (the caller then takes the general kernel).
-static int g_v5_cw = 4;          // columns per warp (2, 4 or 8); rl_debug_set_vtrace_path can change it
+static int g_v5_cw = 0;          // 0: automatic (v6 CTA-per-block kernel); 2 / 4 / 8: v5 with that many columns per warp
 static int g_v5_disable = 0;
 
 template <int A_, int CW>
@@ -783,9 +1035,10 @@ static bool try_launch_v5(const VtraceLossArgs& a, const float* tl, const float*
 template <int A_>
 static bool try_launch_v5_cw(const VtraceLossArgs& a, const float* tl, const float* bl, float* dl, cudaStream_t st) {
   if constexpr (A_ >= 2 && (A_ & 1) == 0 && A_ <= 32) {
+    if (g_v5_cw == 0) return try_launch_v6<A_>(a, tl, bl, dl, st);
     if (CW_OK(2, A_) && g_v5_cw == 2) return try_launch_v5<A_, 2>(a, tl, bl, dl, st);
     if (CW_OK(8, A_) && g_v5_cw == 8) return try_launch_v5<A_, 8>(a, tl, bl, dl, st);
-    if (CW_OK(4, A_)) return try_launch_v5<A_, 4>(a, tl, bl, dl, st);
+    if (CW_OK(4, A_) && g_v5_cw == 4) return try_launch_v5<A_, 4>(a, tl, bl, dl, st);
   }
   return false;
 }
@@ -817,15 +1070,15 @@ extern "C" int rl_debug_set_tma(int disable) {
   return RL_OK;
 }
 
-// Triage hook: 0 = automatic (v5 warp-streaming kernel with 4 columns per warp when the shape allows it),
-// 1 = always the general v4 kernel, 2 / 8 = v5 with 2 / 8 columns per warp.
+// Triage hook: 0 = automatic (v6: CTA per 4-column block, one 8-row pass per warp, when the shape allows it),
+// 1 = always the general v4 kernel, 2 / 4 / 8 = v5 (warp-autonomous streaming) with 2 / 4 / 8 columns per warp.
 extern "C" int rl_debug_set_vtrace_path(int mode) {
   if (mode != 0 && mode != 1 && mode != 2 && mode != 4 && mode != 8) {
     rl::set_error("rl_debug_set_vtrace_path: mode %d not in {0,1,2,4,8}", mode);
     return RL_ERR_BAD_ARG;
   }
   rl::g_v5_disable = mode == 1;
-  rl::g_v5_cw = (mode == 2 || mode == 8) ? mode : 4;
+  rl::g_v5_cw = (mode == 2 || mode == 4 || mode == 8) ? mode : 0;
   return RL_OK;
 }
 

@@ -41,19 +41,38 @@ class FlatAdam(object):
         self.lr, self.betas, self.eps = lr, betas, eps
         self.clip_mode, self.max_norm = _CLIP[clip], max_norm
         self.step_count = 0
+        self.step_dev = self.lr_dev = None          # device-resident update count / learning rate (graph replay)
+
+    def enable_device_state(self):
+        """Keep the update count and the learning rate on the device so that a captured CUDA graph of the whole
+        update (forward, loss, backward, clip, Adam) can be replayed: ``step()`` then increments the device counter
+        and the Adam kernel reads both scalars from memory.  Set the rate with ``set_lr`` (outside the graph)."""
+        if self.step_dev is None:
+            dev = self.flat.device
+            self.step_dev = torch.full((1, ), self.step_count, dtype=torch.int32, device=dev)
+            self.lr_dev = torch.full((1, ), float(self.lr), dtype=torch.float32, device=dev)
+        return self
+
+    def set_lr(self, lr):
+        self.lr = float(lr)
+        if self.lr_dev is not None:
+            self.lr_dev.fill_(self.lr)
 
     def zero_grad(self):
         self.grad.zero_()
 
     def step(self, lr=None, grad_div=1.0):
-        if lr is not None:
+        if lr is not None and self.lr_dev is None:
             self.lr = lr
         self.step_count += 1
+        if self.step_dev is not None:
+            self.step_dev.add_(1)
         if self.clip_mode:
             kernels.grad_global_norm(self.grad, self.norm)
         kernels.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
                           self.eps, self.step_count, grad_div=grad_div, grad_norm=self.norm if self.clip_mode else None,
-                          max_norm=self.max_norm, clip_mode=self.clip_mode, zero_grad=True)
+                          max_norm=self.max_norm, clip_mode=self.clip_mode, zero_grad=True, lr_device=self.lr_dev,
+                          step_device=self.step_dev)
 
     def state_dict(self):
         return dict(exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq, step=self.step_count, lr=self.lr)
@@ -62,3 +81,6 @@ class FlatAdam(object):
         self.exp_avg.copy_(sd['exp_avg'])
         self.exp_avg_sq.copy_(sd['exp_avg_sq'])
         self.step_count, self.lr = int(sd['step']), float(sd['lr'])
+        if self.step_dev is not None:
+            self.step_dev.fill_(self.step_count)
+            self.lr_dev.fill_(self.lr)

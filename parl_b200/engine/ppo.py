@@ -24,7 +24,7 @@ class PPOEngine(object):
     def __init__(self, num_envs=2048, step_nums=2048, obs_dim=17, act_dim=6, num_minibatches=32, update_epochs=10,
                  gamma=0.99, gae_lambda=0.95, clip_param=0.2, value_loss_coef=0.5, entropy_coef=0.0, initial_lr=3e-4,
                  lr_decay=True, num_updates=1000, seed=0, device=None, env_offset=0, p_done=0.01, max_episode_steps=1000,
-                 model=None, vec_normalize=False):
+                 model=None, vec_normalize=False, use_graph=True):
         if device is None:
             device = torch.device('cuda', torch.cuda.current_device())
         self.device = dev = torch.device(device)
@@ -58,6 +58,12 @@ class PPOEngine(object):
         self.values = torch.empty((T + 1, B), dtype=f32, device=dev)
         self.mean_mb = torch.empty((self.M, self.AD), dtype=f32, device=dev)
         self.val_mb = torch.empty((self.M, 1), dtype=f32, device=dev)
+        self.idx_buf = torch.zeros(self.M, dtype=torch.int32, device=dev)
+        self.alg.optimizer.enable_device_state()
+        self.use_graph = bool(use_graph)
+        self._graph, self._eager_calls, self._mb_losses = None, 0, None
+        self.advantages = torch.empty((T, B), dtype=f32, device=dev)
+        self.returns = torch.empty((T, B), dtype=f32, device=dev)
         self.env_steps = 0
         self.sample_steps = 0
         self.grad_world = 1            # multi-GPU: divide the all-reduced gradient by the world size (mean losses)
@@ -91,14 +97,15 @@ class PPOEngine(object):
 
     def compute_returns(self):
         """RolloutStorage.compute_returns(value, done) with value = V(obs after the last step), done = last done."""
-        self.advantages, self.returns = kernels.gae_scan(self.rewards, self.values[:self.T], self.dones,
-                                                         self.values[self.T], self.last_done, self.gamma,
-                                                         self.gae_lambda)
+        kernels.gae_scan(self.rewards, self.values[:self.T], self.dones, self.values[self.T], self.last_done,
+                         self.gamma, self.gae_lambda, out=(self.advantages, self.returns))
         return self.advantages, self.returns
 
-    def learn_minibatch(self, idx, lr):
-        """PPO.learn (parl/algorithms/torch/ppo.py:79-149) on the rows ``idx`` of the flattened rollout."""
-        alg, N = self.alg, self.N
+    def _minibatch_body(self):
+        """PPO.learn (parl/algorithms/torch/ppo.py:79-149) on the rows ``self.idx_buf`` of the flattened rollout;
+        every scalar that changes between calls (learning rate, Adam step count) lives on the device, so the whole
+        body — 6 gathers, forward, advantage statistics, loss, backward, clip, Adam — is one CUDA graph."""
+        alg, N, idx = self.alg, self.N, self.idx_buf
         obs = kernels.gather_rows(self.obs.view(N, self.D), idx)
         act = kernels.gather_rows(self.actions.view(N, self.AD), idx)
         gv = lambda x: kernels.gather_rows(x.reshape(N, 1), idx).view(-1)
@@ -116,8 +123,31 @@ class PPOEngine(object):
         self.model.fc_pi_std.grad.copy_(res['d_logstd'].view_as(self.model.fc_pi_std))
         if alg.grad_sync is not None:
             alg.grad_sync(alg.optimizer.grad)
-        alg.optimizer.step(lr=lr, grad_div=float(self.grad_world))
-        return res['losses']
+        alg.optimizer.step(grad_div=float(self.grad_world))
+        self._mb_losses = res['losses']
+
+    def learn_minibatch(self, idx, lr):
+        """One PPO minibatch update on the rows ``idx``; returns the device losses {value, action, entropy, total}.
+        The first call runs eagerly, the second captures the CUDA graph, later calls replay it."""
+        opt = self.alg.optimizer
+        if lr is not None:
+            opt.set_lr(lr)
+        self.idx_buf.copy_(idx)
+        if not self.use_graph or self._eager_calls == 0:
+            self._eager_calls += 1
+            self._minibatch_body()
+            return self._mb_losses
+        if self._graph is None:
+            count = opt.step_count
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._minibatch_body()
+            opt.step_count = count                      # capture is not execution
+            self._graph = g
+        self._graph.replay()
+        opt.step_count += 1
+        return self._mb_losses
 
     def learn(self):
         """PPOAgent.learn (benchmark/torch/ppo/agent.py:54-96): update_epochs shuffles x num_minibatches steps."""

@@ -262,7 +262,7 @@ def gae_scan_segments(rewards, values, dones, bootstrap_value, gamma, lam):
     return adv, tv
 
 
-def gae_scan(rewards, values, dones, last_value, last_done, gamma=0.99, gae_lambda=0.95):
+def gae_scan(rewards, values, dones, last_value, last_done, gamma=0.99, gae_lambda=0.95, out=None):
     """RolloutStorage.compute_returns (benchmark/torch/ppo/storage.py:45-64) -> (advantages, returns)."""
     require_cuda(rewards, values, dones, last_value, last_done)
     T, B = rewards.shape
@@ -276,7 +276,9 @@ def gae_scan(rewards, values, dones, last_value, last_done, gamma=0.99, gae_lamb
     _chk('dones', dones, torch.float32, T * B)
     _chk('last_value', last_value, torch.float32, B)
     _chk('last_done', last_done, torch.float32, B)
-    adv, ret = torch.empty_like(rewards), torch.empty_like(rewards)
+    adv, ret = out if out is not None else (torch.empty_like(rewards), torch.empty_like(rewards))
+    _chk('advantages', adv, torch.float32, T * B)
+    _chk('returns', ret, torch.float32, T * B)
     check(_lib.load().rl_gae_scan(ptr(rewards), ptr(values), ptr(dones), ptr(last_value), ptr(last_done), T, B,
                                   float(gamma), float(gae_lambda), ptr(adv), ptr(ret), stream()), 'gae_scan')
     return adv, ret
@@ -445,15 +447,17 @@ def grad_global_norm(grad_flat, out_norm):
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_div=1.0, grad_norm=None,
-              max_norm=0.0, clip_mode=0, zero_grad=True, lr_device=None):
+              max_norm=0.0, clip_mode=0, zero_grad=True, lr_device=None, step_device=None):
     n = param.numel()
     for nm, t in (('param', param), ('grad', grad), ('exp_avg', exp_avg), ('exp_avg_sq', exp_avg_sq)):
         _chk(nm, t, torch.float32, n)
     _chk('grad_norm', grad_norm, torch.float32, 1, optional=True)
     _chk('lr_device', lr_device, torch.float32, 1, optional=True)
+    _chk('step_device', step_device, torch.int32, 1, optional=True)
     check(_lib.load().rl_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), param.numel(), ptr(lr_device),
                                    float(lr), float(beta1), float(beta2), float(eps), int(step), float(grad_div),
-                                   ptr(grad_norm), float(max_norm), int(clip_mode), 1 if zero_grad else 0, stream()),
+                                   ptr(grad_norm), float(max_norm), int(clip_mode), 1 if zero_grad else 0,
+                                   ptr(step_device), stream()),
           'adam_step')
 
 
