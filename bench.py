@@ -295,7 +295,7 @@ def main():
         # `ncu --set full` capture of this kernel version (profiles/r02_k1_*.txt); the gradient tile (15.3 MB) is
         # mostly still in the 126 MB L2 when the launch ends, so the write half shows up only partly
         traffic = K1_NCU_TRAFFIC_BYTES if B == 4096 else None
-        roof = dict(bound='hbm', kernel='vtrace_loss_cta_kernel (rl_vtrace_loss_fwd_bwd)', achieved=ach, peak=peak,
+        roof = dict(bound='hbm', kernel='vtrace_loss_kernel (rl_vtrace_loss_fwd_bwd)', achieved=ach, peak=peak,
                     unit='GB/s', frac=ach / peak, traffic=traffic, peak_source=peak_src,
                     algorithmic_bytes_per_launch=alg_bytes, us_per_launch=k1_s * 1e6,
                     us_per_launch_l2_flushed_single_event_pair=k1_flushed_s * 1e6,

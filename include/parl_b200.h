@@ -52,9 +52,8 @@ size_t rl_loss_workspace_bytes(int n_cols);
 /* Triage hook: 1 forces the cp.async tile path of rl_vtrace_loss_fwd_bwd, 0 (default) lets the
  * TMA tensor-map path run when the layout allows it. */
 int rl_debug_set_tma(int disable);
-/* Triage hook for rl_vtrace_loss_fwd_bwd: 0 = automatic (v6: CTA per 4-column block, one 8-row TMA chunk per warp,
- * whenever the layout is time-major, TMA-able and T <= 56), 1 = always the general v4 kernel,
- * 2 / 4 / 8 = v5 (warp-autonomous streaming kernel) with 2 / 4 / 8 columns per warp. */
+/* Triage hook for rl_vtrace_loss_fwd_bwd: 0 = default kernel (v4), 6 = the v6 kernel (one 8-row TMA chunk per
+ * warp, single block sync; time-major, TMA-able shapes with T <= 56; slower than v4 at every measured shape). */
 int rl_debug_set_vtrace_path(int mode);
 
 /* ------------------------------------------------------------------------

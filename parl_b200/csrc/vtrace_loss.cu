@@ -9,19 +9,16 @@
 //
 // Layout in HBM: logits [T,B,A] f32, per-step scalars [T,B].  Two kernels:
 //
-//  * vtrace_loss_warp_kernel (v5, the fast path: time-major, TMA-able shapes, T*CW*A*8 B per warp in smem).
-//    A WARP owns CW adjacent env columns for all T rows; nothing is ever synchronised across warps.  Lane 0
-//    issues every TMA tile load of the warp's column block up front (2-D tensor maps, box = RB rows x CW*A
-//    floats, one mbarrier per row chunk, latest rows first) and the warp then walks backwards in time in
-//    passes of 32/CW rows x CW columns, one (t,b) element per lane: the 2x A logits go from shared memory to
-//    registers ONCE, softmax / entropy / KL / rho / delta are computed there, the recurrence
-//    acc_t = delta_t + k_t acc_{t+1} is a warp-shuffle segmented suffix scan inside the pass with the carry
-//    of the pass above in a register, the gradient overwrites the target-logit tile and each finished row
-//    chunk is TMA-stored immediately.  Loads of earlier rows, compute and stores of later rows overlap inside
-//    every warp, and 7 such warps per SM keep ~29 KB each in flight: the kernel is DRAM-streaming instead of
-//    one lock-step load -> compute -> store wave.
-//  * vtrace_loss_kernel (v4, general fallback: env-major layout, shapes the TMA path cannot take, long T):
-//    a CTA owns 4 columns, cp.async / TMA tile staging, block-level phases.
+//  * vtrace_loss_kernel (v4, the default): a CTA owns 4 adjacent env columns for ALL T rows (the scan never leaves
+//    the CTA); the logits tiles [T, 4*A] move by 2-D TMA tensor maps (cp.async for env-major / unaligned shapes),
+//    one (t,b) element per thread, array-free two-sweep softmax, warp-shuffle segmented suffix scan, gradient tile
+//    written in place and TMA-stored, deterministic loss reduction (CTA partials -> last CTA, fp64).
+//  * vtrace_loss_cta_kernel (v6, opt-in via rl_debug_set_vtrace_path(6)): same CTA shape, but every warp owns ONE
+//    8-row TMA chunk (own mbarrier, own store) and the scan is composed from per-warp affine maps after a single
+//    __syncthreads.  Round-2 measurements (profiles/r02_k1_*): 23.5 us vs 20.4 us for v4 at T=50, B=4096 — the
+//    instruction count per element did not drop (777 vs 815 warp-instructions per warp) and 40 registers round up
+//    to 6 CTAs per SM (1.15 waves); a warp-autonomous variant (v5: one warp per column block, 7 warps per SM) was
+//    latency-bound at 24.8 us and was removed.  DESIGN.md section 4 has the analysis.
 // Algorithmic traffic: (12A+17) bytes per kept (t,b) element.
 #include <stdarg.h>
 #include <string.h>
@@ -470,260 +467,6 @@ __global__ void __launch_bounds__(128) vtrace_returns_kernel(const float* __rest
 }
 
 // ---------------------------------------------------------------------------
-// v5: warp-autonomous streaming kernel (see the file header).  Time-major, A_ even and known at compile time.
-// ---------------------------------------------------------------------------
-struct WarpPathArgs {
-  int W;              // warps per CTA
-  int ntiles;         // column blocks of CW columns
-  int RB;             // rows per TMA box (divides T)
-  int nchunk;         // T / RB
-  int chunk_stride;   // bytes between row chunks in shared memory (RB * CW * A * 4 rounded up to 128)
-  int per_warp;       // bytes of shared memory per warp
-  int off_bl, off_rew, off_val, off_gam, off_act, off_bar;     // byte offsets inside the warp's region
-};
-
-constexpr int kMaxWarpsV5 = 16;
-
-template <int A_, int CW>
-__global__ void __launch_bounds__(kMaxWarpsV5 * 32, 1)
-    vtrace_loss_warp_kernel(const VtraceLossArgs p, const WarpPathArgs w, const __grid_constant__ CUtensorMap map_tl,
-                            const __grid_constant__ CUtensorMap map_bl, const __grid_constant__ CUtensorMap map_dl) {
-  static_assert(A_ >= 2 && (A_ & 1) == 0, "v5 needs an even compile-time A");
-  static_assert(CW == 2 || CW == 4 || CW == 8, "CW");
-  constexpr int R = 32 / CW;                   // rows per pass
-  constexpr uint32_t FULL = 0xffffffffu;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ bool s_last;
-  __shared__ double s_dred[4][kMaxWarpsV5];
-  const int T = p.T, B = p.B;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x * w.W + warp;
-  const bool active = tile < w.ntiles;
-  float sum_pi = 0.f, sum_vf = 0.f, sum_ent = 0.f, sum_kl = 0.f;
-
-  if (active) {
-    unsigned char* base = smem_raw + (size_t)warp * w.per_warp;
-    unsigned char* s_tl = base;
-    unsigned char* s_bl = base + w.off_bl;
-    float* s_rew = reinterpret_cast<float*>(base + w.off_rew);
-    float* s_val = reinterpret_cast<float*>(base + w.off_val);
-    float* s_gam = reinterpret_cast<float*>(base + w.off_gam);
-    int* s_act = reinterpret_cast<int*>(base + w.off_act);
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + w.off_bar);
-    const int b0 = tile * CW;
-    const int RB = w.RB, nchunk = w.nchunk;
-    const uint32_t chunk_bytes = (uint32_t)(RB * CW * A_ * 4);
-
-    if (lane == 0) {
-      for (int c = 0; c < nchunk; ++c) mbar_init(&bars[c], 1);
-      fence_mbar_init();
-      // every tile load of this warp, latest rows first (they are consumed first)
-      for (int c = nchunk - 1; c >= 0; --c) {
-        mbar_arrive_expect_tx(&bars[c], 2u * chunk_bytes);
-        tma_load_2d(s_tl + c * w.chunk_stride, &map_tl, b0 * A_, c * RB, &bars[c]);
-        tma_load_2d(s_bl + c * w.chunk_stride, &map_bl, b0 * A_, c * RB, &bars[c]);
-      }
-    }
-    // per-step scalars of the column block -> shared memory (overlaps the tile loads)
-    for (int e = lane; e < T * CW; e += 32) {
-      const int t = e / CW, c = e % CW;
-      const int g = t * B + b0 + c;
-      s_rew[e] = p.rewards[g];
-      s_val[e] = p.values[g];
-      s_gam[e] = p.dones[g] ? 0.0f : p.gamma;                 // impala.py:59  (~dones) * discount
-      s_act[e] = p.act64 ? (int)reinterpret_cast<const long long*>(p.actions)[g]
-                         : reinterpret_cast<const int*>(p.actions)[g];
-    }
-    __syncwarp();
-
-    const int r = lane / CW, c = lane % CW;
-    const int P = (T + R - 1) / R;
-    int wait_c = nchunk - 1, store_c = nchunk - 1;
-    float carry_acc = 0.f;
-    const float ce2 = p.ent_coeff * kLN2;
-
-    for (int ps = P - 1; ps >= 0; --ps) {
-      const int row0 = ps * R;
-      const int lo_chunk = row0 / RB;
-      while (wait_c >= lo_chunk) {
-        mbar_wait(&bars[wait_c], 0);
-        --wait_c;
-      }
-      const int t = row0 + r;
-      const bool valid = t < T;
-      const bool loss_row = t < T - 1;
-      float D = 0.f, K = 0.f, rpg = 0.f, la = 0.f, H = 0.f, l2S = 0.f, inv = 0.f;
-      float e_r = 0.f, e_v = 0.f, e_vn = 0.f, e_g = 0.f;
-      int act = 0;
-      float xs[A_], ex[A_];
-      float* pt = nullptr;
-      if (valid) {
-        const int ch = t / RB, tr = t - ch * RB;
-        const int eoff = ch * w.chunk_stride + (tr * CW + c) * A_ * 4;
-        pt = reinterpret_cast<float*>(s_tl + eoff);
-        const float* pb = reinterpret_cast<const float*>(s_bl + eoff);
-        const int e = t * CW + c;
-        act = s_act[e];
-        e_r = s_rew[e], e_v = s_val[e], e_g = s_gam[e];
-        if (t + 1 < T) e_vn = s_val[e + CW];
-        // ---- target logits: one shared-memory read into registers
-        float m = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < A_; j += 2) {
-          const float2 a = *reinterpret_cast<const float2*>(pt + j);
-          xs[j] = a.x, xs[j + 1] = a.y;
-          m = fmaxf(m, fmaxf(a.x, a.y));
-        }
-        const float x_act = pt[act];
-        const float nm = -m * kL2E;
-        float S0 = 0.f, S1 = 0.f, W0 = 0.f, W1 = 0.f;
-#pragma unroll
-        for (int j = 0; j < A_; j += 2) {
-          xs[j] = fmaf(xs[j], kL2E, nm), xs[j + 1] = fmaf(xs[j + 1], kL2E, nm);
-          ex[j] = ex2_approx(xs[j]), ex[j + 1] = ex2_approx(xs[j + 1]);
-          S0 += ex[j], S1 += ex[j + 1];
-          W0 = fmaf(ex[j], xs[j], W0), W1 = fmaf(ex[j + 1], xs[j + 1], W1);
-        }
-        // ---- behaviour logits: max, then log-sum-exp and sum_j p_j y_j
-        float my = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < A_; j += 2) {
-          const float2 y = *reinterpret_cast<const float2*>(pb + j);
-          my = fmaxf(my, fmaxf(y.x, y.y));
-        }
-        const float nmy = -my * kL2E;
-        float Y0 = 0.f, Y1 = 0.f, Sy0 = 0.f, Sy1 = 0.f;
-#pragma unroll
-        for (int j = 0; j < A_; j += 2) {
-          const float2 y = *reinterpret_cast<const float2*>(pb + j);
-          Y0 = fmaf(ex[j], y.x, Y0), Y1 = fmaf(ex[j + 1], y.y, Y1);
-          Sy0 += ex2_approx(fmaf(y.x, kL2E, nmy));
-          Sy1 += ex2_approx(fmaf(y.y, kL2E, nmy));
-        }
-        const float y_act = pb[act];
-        const float S = S0 + S1, Wt = W0 + W1, Y = Y0 + Y1, Sy = Sy0 + Sy1;
-        l2S = lg2_approx(S);
-        inv = __fdividef(1.0f, S);
-        const float logSy = lg2_approx(Sy) * kLN2;
-        const float Hn = (Wt * inv - l2S) * kLN2;            // sum_j p_j log p_j
-        H = -Hn;
-        sum_kl += Hn - Y * inv + my + logSy;                // impala.py:160-162: every row
-        la = (fmaf(x_act, kL2E, nm) - l2S) * kLN2;
-        const float lma = y_act - my - logSy;
-        if (loss_row) {
-          const float rho = expf(la - lma);                 // vtrace.py:101-103
-          const float rhoc = p.clip_rho >= 0.f ? fminf(rho, p.clip_rho) : rho;
-          const float cs = fminf(rho, 1.0f);                // :109
-          rpg = p.clip_pg >= 0.f ? fminf(rho, p.clip_pg) : rho;
-          // deltas = clipped_rhos * (rewards + discounts * values_t_plus_1 - values)   :115
-          D = __fmul_rn(rhoc, __fsub_rn(__fadd_rn(e_r, __fmul_rn(e_g, e_vn)), e_v));
-          K = __fmul_rn(e_g, cs);
-          sum_ent += H;
-        }
-      }
-      // ---- backward-in-time recurrence inside the pass: suffix scan of the affine maps acc -> D + K acc over
-      //      the R rows (lanes r*CW + c, later time = higher lane); rows >= T-1 carry (0, 0) so acc_{T-1} = 0
-#pragma unroll
-      for (int off = CW; off < 32; off <<= 1) {
-        const float Dn = __shfl_down_sync(FULL, D, off);
-        const float Kn = __shfl_down_sync(FULL, K, off);
-        if (lane + off < 32) {
-          D = fmaf(K, Dn, D);
-          K *= Kn;
-        }
-      }
-      const float cin = __shfl_sync(FULL, carry_acc, c);     // acc at the first row of the pass above, column c
-      const float acc = fmaf(K, cin, D);
-      float acc_n = __shfl_down_sync(FULL, acc, CW);
-      if (r == R - 1) acc_n = cin;
-      carry_acc = acc;
-      // ---- advantages, losses, gradient (written over the target-logit tile)
-      if (valid) {
-        const int g = t * B + b0 + c;
-        if (loss_row) {
-          const float vs = __fadd_rn(acc, e_v);                          // vtrace.py:125
-          const float vs_n = __fadd_rn(acc_n, e_vn);                     // :128-129 (bootstrap at the end)
-          const float adv = __fmul_rn(rpg, __fsub_rn(__fadd_rn(e_r, __fmul_rn(e_g, vs_n)), e_v));   // :136-137
-          const float dv = e_v - vs;
-          sum_pi -= la * adv;                                             // impala.py:67-68
-          sum_vf += 0.5f * dv * dv;                                       // :71-72
-          p.d_values[g] = p.vf_coeff * dv;
-          if (p.vs_out) p.vs_out[g] = vs;
-          if (p.pg_out) p.pg_out[g] = adv;
-          // dL/dz_j = p_j (adv - c_e (H + log p_j)) - adv [j == a],  log p_j = ln2 (xs_j - log2 S)
-          const float c0 = fmaf(ce2, l2S, adv - p.ent_coeff * H) * inv;  // folded with 1/S
-          const float c1 = -ce2 * inv;
-#pragma unroll
-          for (int j = 0; j < A_; j += 2) {
-            const float d0 = ex[j] * fmaf(c1, xs[j], c0), d1 = ex[j + 1] * fmaf(c1, xs[j + 1], c0);
-            *reinterpret_cast<float2*>(pt + j) = make_float2(d0, d1);
-          }
-          pt[act] -= adv;
-        } else {
-          p.d_values[g] = 0.f;                                            // bootstrap row: no gradient
-#pragma unroll
-          for (int j = 0; j < A_; j += 2) *reinterpret_cast<float2*>(pt + j) = make_float2(0.f, 0.f);
-        }
-      }
-      // ---- every row chunk that lies entirely at or above this pass's first row is final: store it
-      if (store_c >= 0 && store_c * RB >= row0) {
-        fence_proxy_async_smem();          // generic-proxy writes of the gradient rows -> visible to the TMA engine
-        __syncwarp();
-        while (store_c >= 0 && store_c * RB >= row0) {
-          if (lane == 0) {
-            tma_store_2d(&map_dl, b0 * A_, store_c * RB, s_tl + store_c * w.chunk_stride);
-            tma_store_commit();
-          }
-          --store_c;
-        }
-      }
-    }
-    if (lane == 0) tma_store_wait_read();  // the shared-memory tiles must outlive the bulk reads
-    sum_pi = warp_sum(sum_pi), sum_vf = warp_sum(sum_vf), sum_ent = warp_sum(sum_ent), sum_kl = warp_sum(sum_kl);
-    if (lane == 0) {
-      p.partials[tile * 4 + 0] = sum_pi, p.partials[tile * 4 + 1] = sum_vf;
-      p.partials[tile * 4 + 2] = sum_ent, p.partials[tile * 4 + 3] = sum_kl;
-      __threadfence();
-    }
-  }
-  // ---- loss reduction: per-warp partials -> (last CTA) fixed-order fp64 sum
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int i = threadIdx.x; i < w.ntiles; i += blockDim.x) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q] += (double)__ldcg(p.partials + i * 4 + q);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      double v = acc[q];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-      if (lane == 0) s_dred[q][warp] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double rr[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        rr[q] = 0.0;
-        for (int x = 0; x < w.W; ++x) rr[q] += s_dred[q][x];
-      }
-      const float pi = (float)rr[0], vf = (float)rr[1], ent = (float)rr[2];
-      p.losses[0] = pi + vf * p.vf_coeff + ent * p.ent_coeff;      // impala.py:78-79
-      p.losses[1] = pi;
-      p.losses[2] = vf;
-      p.losses[3] = ent;
-      p.losses[4] = (float)(rr[3] / ((double)T * (double)B));
-      *p.ticket = 0u;
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------
 // v6: CTA per 4-column block, ONE 8-row pass per warp (the default fast path).  v5 showed that a warp walking
 // all of T alone is bound by its own instruction latency (7 warps per SM cannot hide LDS -> MUFU -> FADD chains),
 // so the rows of a column block are spread over ceil(T/8) warps: every warp waits only for ITS 8-row TMA chunk,
@@ -975,73 +718,7 @@ static bool try_launch_v6(const VtraceLossArgs& a, const float* tl, const float*
   return false;
 }
 
-// Host side of the v5 path: shape the per-warp shared-memory region and launch.  Returns false when the shape
-// does not fit (the caller then takes the general kernel).
-static int g_v5_cw = 0;          // 0: automatic (v6 CTA-per-block kernel); 2 / 4 / 8: v5 with that many columns per warp
-static int g_v5_disable = 0;
-
-template <int A_, int CW>
-static bool try_launch_v5(const VtraceLossArgs& a, const float* tl, const float* bl, float* dl, cudaStream_t st) {
-  const int T = a.T, B = a.B;
-  if (B % CW != 0 || T > 256) return false;
-  const int rowb = CW * A_ * 4;
-  // rows per TMA box: T / nchunk for the smallest nchunk that divides T with at most 16 rows per box
-  int nchunk = 0;
-  for (int n = 1; n <= 32; ++n) {
-    if (T % n == 0 && T / n <= 16) {
-      nchunk = n;
-      break;
-    }
-  }
-  if (nchunk == 0) nchunk = 1;
-  WarpPathArgs w;
-  w.RB = T / nchunk, w.nchunk = nchunk;
-  w.chunk_stride = (w.RB * rowb + 127) & ~127;
-  const int tile_b = nchunk * w.chunk_stride;
-  const int scal_b = (T * CW * 4 + 15) & ~15;          // only the TMA tiles need 128-byte alignment
-  w.off_bl = tile_b, w.off_rew = 2 * tile_b, w.off_val = w.off_rew + scal_b, w.off_gam = w.off_val + scal_b;
-  w.off_act = w.off_gam + scal_b, w.off_bar = w.off_act + scal_b;
-  w.per_warp = (w.off_bar + nchunk * 8 + 127) & ~127;
-  w.ntiles = B / CW;
-  int dev = 0, optin = 0, nsm = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-  const int budget = optin - 1024;                       // static shared memory of the kernel
-  int wmax = budget / w.per_warp;
-  if (wmax < 1) return false;
-  if (wmax > kMaxWarpsV5) wmax = kMaxWarpsV5;
-  int W = (w.ntiles + nsm - 1) / nsm;                    // one wave when it fits: every tile in flight at once
-  if (W > wmax) {
-    // more tiles than one wave holds: two CTAs per SM so that one loads while the other computes / stores
-    W = wmax / 2 > 0 ? wmax / 2 : 1;
-  }
-  w.W = W;
-  const int grid = (w.ntiles + W - 1) / W;
-  alignas(64) CUtensorMap maps[3];
-  const char* err = nullptr;
-  const uint64_t pitch = (uint64_t)B * A_ * sizeof(float);
-  if (make_tensor_map_2d_f32(&maps[0], tl, (uint64_t)B * A_, (uint64_t)T, pitch, CW * A_, w.RB, &err) ||
-      make_tensor_map_2d_f32(&maps[1], bl, (uint64_t)B * A_, (uint64_t)T, pitch, CW * A_, w.RB, &err) ||
-      make_tensor_map_2d_f32(&maps[2], dl, (uint64_t)B * A_, (uint64_t)T, pitch, CW * A_, w.RB, &err))
-    return false;
-  RL_SMEM_OPTIN(vtrace_loss_warp_kernel<A_, CW>);
-  vtrace_loss_warp_kernel<A_, CW><<<grid, W * 32, (size_t)W * w.per_warp, st>>>(a, w, maps[0], maps[1], maps[2]);
-  return true;
-}
-
-// TMA box rows must be a multiple of 16 bytes and at most 256 elements wide
-#define CW_OK(cw, a) ((((cw) * (a) * 4) % 16 == 0) && ((cw) * (a) <= 256))
-template <int A_>
-static bool try_launch_v5_cw(const VtraceLossArgs& a, const float* tl, const float* bl, float* dl, cudaStream_t st) {
-  if constexpr (A_ >= 2 && (A_ & 1) == 0 && A_ <= 32) {
-    if (g_v5_cw == 0) return try_launch_v6<A_>(a, tl, bl, dl, st);
-    if (CW_OK(2, A_) && g_v5_cw == 2) return try_launch_v5<A_, 2>(a, tl, bl, dl, st);
-    if (CW_OK(8, A_) && g_v5_cw == 8) return try_launch_v5<A_, 8>(a, tl, bl, dl, st);
-    if (CW_OK(4, A_) && g_v5_cw == 4) return try_launch_v5<A_, 4>(a, tl, bl, dl, st);
-  }
-  return false;
-}
+static int g_v6_enable = 0;      // rl_debug_set_vtrace_path(6): opt in to the v6 kernel
 
 template <int A_>
 static int launch_vtrace_loss(const VtraceLossArgs& a, int layout, bool tma, const CUtensorMap* maps, int grid,
@@ -1070,15 +747,14 @@ extern "C" int rl_debug_set_tma(int disable) {
   return RL_OK;
 }
 
-// Triage hook: 0 = automatic (v6: CTA per 4-column block, one 8-row pass per warp, when the shape allows it),
-// 1 = always the general v4 kernel, 2 / 4 / 8 = v5 (warp-autonomous streaming) with 2 / 4 / 8 columns per warp.
+// Triage hook: 0 = default (the CTA-per-4-columns kernel with block-level phases, v4: the fastest measured path at
+// every shape, profiles/r02_k1_matrix_b.jsonl), 6 = the v6 kernel (one 8-row TMA chunk per warp, single block sync).
 extern "C" int rl_debug_set_vtrace_path(int mode) {
-  if (mode != 0 && mode != 1 && mode != 2 && mode != 4 && mode != 8) {
-    rl::set_error("rl_debug_set_vtrace_path: mode %d not in {0,1,2,4,8}", mode);
+  if (mode != 0 && mode != 6) {
+    rl::set_error("rl_debug_set_vtrace_path: mode %d not in {0, 6}", mode);
     return RL_ERR_BAD_ARG;
   }
-  rl::g_v5_disable = mode == 1;
-  rl::g_v5_cw = (mode == 2 || mode == 4 || mode == 8) ? mode : 0;
+  rl::g_v6_enable = mode == 6;
   return RL_OK;
 }
 
@@ -1155,11 +831,11 @@ extern "C" int rl_vtrace_loss_fwd_bwd(const float* target_logits, const float* b
     }
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const bool v5_ok = tma && !g_v5_disable;
+  const bool v6_ok = tma && g_v6_enable;
   switch (A) {
 #define RL_CASE(N)                                                                                     \
   case N:                                                                                              \
-    if (!(v5_ok && try_launch_v5_cw<N>(a, target_logits, behaviour_logits, d_logits, st)))              \
+    if (!(v6_ok && try_launch_v6<N>(a, target_logits, behaviour_logits, d_logits, st)))                 \
       launch_vtrace_loss<N>(a, layout, tma, maps, grid, smem, st);                                      \
     break;
     RL_CASE(2) RL_CASE(3) RL_CASE(4) RL_CASE(5) RL_CASE(6) RL_CASE(7) RL_CASE(8) RL_CASE(9) RL_CASE(10) RL_CASE(12)

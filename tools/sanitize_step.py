@@ -31,3 +31,22 @@ for _ in range(3):
     eng.step_host(hosts, 1e-3, -0.01)
 torch.cuda.synchronize()
 print('host-contract ok')
+
+# ---- the reference-facing host contract: remote Actor + AtariAgent.learn(numpy) (engine roles actor / learner)
+import parl_b200 as parl  # noqa
+from parl_b200.engine.impala_host import DeviceImpalaActor, AtariAgent  # noqa
+parl.connect('localhost:8010')
+cfg = dict(env_num=B, sample_batch_steps=T, act_dim=18, seed=4)
+agent = AtariAgent(cfg, device=dev)
+actor = parl.remote_class(wait=False)(DeviceImpalaActor)(cfg, device=dev)
+actor.set_weights(agent.get_weights()).get()
+fut = actor.sample()
+for _ in range(2):
+    batch = fut.get()
+    actor.set_weights(agent.get_weights())
+    fut = actor.sample()
+    agent.learn(batch['obs'], batch['actions'], batch['behaviour_logits'], batch['rewards'], batch['dones'], 1e-3, -0.01)
+fut.get()
+actor.destroy()
+torch.cuda.synchronize()
+print('remote actor / agent ok')
