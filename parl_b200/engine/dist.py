@@ -75,7 +75,8 @@ def global_adv_stats(local_adv, group=None):
     """{mean, 1/(std_unbiased + 1e-8)} of the advantages of ALL ranks' minibatch shards (float32 [2] on the
     advantages' device) — the stats tensor rl_ppo_loss_fwd_bwd takes."""
     a = local_adv.double().reshape(-1)
-    mom = torch.stack([a.sum(), (a * a).sum(), torch.tensor(float(a.numel()), dtype=torch.float64, device=a.device)])
+    # torch.full (a fill kernel), not torch.tensor (a pageable H2D copy): the call may sit inside a captured CUDA graph
+    mom = torch.stack([a.sum(), (a * a).sum(), torch.full((), float(a.numel()), dtype=torch.float64, device=a.device)])
     if world_size(group) > 1:
         dist.all_reduce(mom, op=dist.ReduceOp.SUM, group=group)
     n = mom[2]
