@@ -276,10 +276,27 @@ __global__ void __launch_bounds__(kFT) ppo_gaussian_loss_kernel(const GaussArgs 
     const float al = (float)(tot[0] / M), vl = (float)(tot[1] / M), el = (float)(tot[2] / M);
     p.losses[0] = vl, p.losses[1] = al, p.losses[2] = el;
     p.losses[3] = vl * p.vf_coeff + al - el * p.ent_coeff;
+  }
+  // d_logstd: the WHOLE last CTA adds up the [grid, D] partials (fixed order: strided per thread, shuffle tree, warps
+  // in order, fp64).  Round 2: a single thread walking grid*D dependent L2 loads cost 1 ms per 131 072-row minibatch.
+  __shared__ bool s_fin;
+  __shared__ double s_dd[kFT / 32];
+  if (tid == 0) s_fin = fin;
+  __syncthreads();
+  if (s_fin) {
     for (int d = 0; d < D; ++d) {
       double a = 0.0;
-      for (unsigned i = 0; i < gridDim.x; ++i) a += (double)__ldcg(part + (long long)i * D + d);
-      p.d_logstd[d] = (float)a - p.ent_coeff;                 // d(-c_e * mean_m sum_d (.. + logstd_d)) = -c_e
+      for (unsigned i = tid; i < gridDim.x; i += kFT) a += (double)__ldcg(part + (long long)i * D + d);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if ((tid & 31) == 0) s_dd[tid >> 5] = a;
+      __syncthreads();
+      if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kFT / 32; ++w) t += s_dd[w];
+        p.d_logstd[d] = (float)t - p.ent_coeff;               // d(-c_e * mean_m sum_d (.. + logstd_d)) = -c_e
+      }
+      __syncthreads();
     }
   }
 }
