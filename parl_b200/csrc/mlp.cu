@@ -311,13 +311,17 @@ __global__ void __launch_bounds__(kMlpThreads) mlp_bwd_kernel(const MlpArgs p) {
   }
 }
 
-// grads (true layout, per segment) (+)= sum over CTAs of the padded partials, fixed order
+// grads (true layout, per segment) (+)= sum over CTAs of the padded partials.  One WARP per parameter: lane l adds
+// parts l, l+32, ... (coalescing does not matter at 4 B per part; latency does), then a fixed xor-shuffle tree — the
+// order never changes between runs (deterministic).
 __global__ void __launch_bounds__(256) mlp_grad_reduce_kernel(const MlpArgs p, int nparts) {
+  const int lane = threadIdx.x & 31;
+  const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int s = 0; s < p.n_seg; ++s) {
     const MlpSeg& g = p.seg[s];
     const int in = p.dims[g.layer], inp = p.pd[g.layer];
     const int nw = g.rows * in;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nw + g.rows; i += gridDim.x * blockDim.x) {
+    for (int i = wglobal; i < nw + g.rows; i += nwarps) {
       int off;
       float* dst;
       if (i < nw) {
@@ -329,8 +333,10 @@ __global__ void __launch_bounds__(256) mlp_grad_reduce_kernel(const MlpArgs p, i
       }
       if (!dst) continue;
       float a = 0.f;
-      for (int c = 0; c < nparts; ++c) a += p.partial[(size_t)c * p.np_pad + off];
-      *dst = p.accumulate ? *dst + a : a;
+      for (int c = lane; c < nparts; c += 32) a += p.partial[(size_t)c * p.np_pad + off];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) *dst = p.accumulate ? *dst + a : a;
     }
   }
 }
@@ -605,7 +611,7 @@ extern "C" int rl_mlp_bwd(const float* x, int n, int n_layers, const int* dims, 
   RL_SMEM_OPTIN(mlp_bwd_kernel);
   mlp_bwd_kernel<<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(a);
   RL_CHECK_LAUNCH("rl_mlp_bwd");
-  mlp_grad_reduce_kernel<<<(a.np_pad + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a, grid);
+  mlp_grad_reduce_kernel<<<(a.np_pad + 7) / 8, 256, 0, (cudaStream_t)stream>>>(a, grid);
   RL_CHECK_LAUNCH("rl_mlp_bwd(reduce)");
   return RL_OK;
 }

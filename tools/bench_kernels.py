@@ -134,6 +134,41 @@ def bench_per(capacity=1 << 20, batch=4096):
                 update_us=sec_u * 1e6, samples_per_s=batch / sec)
 
 
+def bench_replay_gather(cap=1 << 17, lanes=8, batch=4096, ctx=4, HW=7056):
+    """C5: 5-frame window gather from the frame ring; 35 280 B read + 35 280 B written per sample."""
+    dev = 'cuda:0'
+    frames = torch.randint(0, 255, (cap, HW), device=dev, dtype=torch.uint8)
+    over = (torch.rand(cap, device=dev) < 0.05).to(torch.uint8)
+    g = torch.Generator(device=dev).manual_seed(5)
+    idx = [torch.randint(0, cap - 16 * lanes, (batch, ), device=dev, dtype=torch.int32, generator=g) for _ in range(8)]
+    out = torch.empty((batch, ctx + 1, HW), dtype=torch.uint8, device=dev)
+    sec = time_fn(lambda i: K.replay_gather_frames(frames, over, idx[i % 8], cap // lanes, ctx, lanes=lanes, out=out))
+    alg = batch * (ctx + 1) * HW * 2
+    return dict(kernel='replay_gather_frames', batch=batch, lanes=lanes, us=sec * 1e6, alg_bytes=alg,
+                gbps=alg / sec / 1e9)
+
+
+def bench_mlp(N=131072, dims=(17, 64, 64), heads=(6, 1)):
+    """K6 (MLP family) at the C4 minibatch: fp32 forward / backward of the MuJoCo actor-critic."""
+    dev = 'cuda:0'
+    import torch.nn as nn
+    torch.manual_seed(0)
+    layers = [nn.Linear(dims[i], dims[i + 1]).to(dev) for i in range(len(dims) - 1)]
+    hs = [nn.Linear(dims[-1], h).to(dev) for h in heads]
+    plan = K.MlpPlan([[(m.weight.detach(), m.bias.detach())] for m in layers] +
+                     [[(h.weight.detach(), h.bias.detach()) for h in hs]], K.ACT_TANH)
+    x = torch.randn(N, dims[0], device=dev)
+    out = torch.empty(N, sum(heads), device=dev)
+    d = torch.randn_like(out)
+    grads = [(torch.empty_like(m.weight), torch.empty_like(m.bias)) for m in layers + hs]
+    sf = time_fn(lambda i: plan.forward(x, out=out), iters=30)
+    sb = time_fn(lambda i: plan.backward(x, d, grads=grads), iters=30)
+    flop = 2.0 * N * (sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1)) + dims[-1] * sum(heads))
+    return dict(kernel='mlp_fwd / mlp_bwd', N=N, dims=list(dims), heads=list(heads), fwd_us=sf * 1e6, bwd_us=sb * 1e6,
+                fwd_tflops=flop / sf / 1e12, bwd_tflops=3 * flop / sb / 1e12,
+                fwd_gbps=N * (dims[0] + sum(heads)) * 4 / sf / 1e9)
+
+
 if __name__ == '__main__':
     which = sys.argv[1] if len(sys.argv) > 1 else 'all'
     if which == 'vtrace_cpasync':
@@ -153,7 +188,8 @@ if __name__ == '__main__':
         print(json.dumps(bench_env(B=512)))
     if which in ('losses', 'all'):
         # K2-K4 at the BASELINE.json configs[1], [3], [4] shapes (not yet captured under ncu: next round)
-        for fn in (bench_a2c, bench_gae, lambda: bench_gae(T=20, B=256, segments=True), bench_ppo, bench_td, bench_per):
+        for fn in (bench_a2c, bench_gae, lambda: bench_gae(T=20, B=256, segments=True), bench_ppo, bench_td, bench_per,
+                   bench_replay_gather, bench_mlp):
             try:
                 print(json.dumps(fn()))
             except Exception as e:      # a tool, not a test: report and carry on
