@@ -478,8 +478,52 @@ __global__ void __launch_bounds__(128) vtrace_returns_kernel(const float* __rest
 constexpr int kV6Rows = 8;                 // rows per warp / per TMA chunk
 constexpr int kV6MaxWarps = 7;             // T <= 56
 
+// packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2): two lanes of arithmetic per issue slot
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+// mbarrier wait that lets the hardware suspend the warp for up to ~1 ms per probe instead of spinning
+__device__ __forceinline__ void mbar_wait_suspend(void* mbar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT_S:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra LAB_DONE_S;\n"
+      "bra LAB_WAIT_S;\n"
+      "LAB_DONE_S:\n"
+      "}\n" ::"r"(smem_u32(mbar)),
+      "r"(parity), "r"(0x000f4240)
+      : "memory");
+}
+
 template <int A_>
-__global__ void __maxnreg__(40)          // 7 CTAs x 7 warps x 40 registers fit the 64 K register file
+__global__ void __maxnreg__(32)          // 7 CTAs x 7 warps x 32 registers: one wave of 1024 CTAs on 148 SMs
     vtrace_loss_cta_kernel(const VtraceLossArgs p, const __grid_constant__ CUtensorMap map_tl,
                            const __grid_constant__ CUtensorMap map_bl, const __grid_constant__ CUtensorMap map_dl,
                            const __grid_constant__ CUtensorMap map_tl_tail, const __grid_constant__ CUtensorMap map_bl_tail,
@@ -514,80 +558,75 @@ __global__ void __maxnreg__(40)          // 7 CTAs x 7 warps x 40 registers fit 
       tma_load_2d(s_bl + c * kChunkBytes, full ? &map_bl : &map_bl_tail, b0 * A_, c * R, &s_bar[c]);
     }
   }
-  // ---- this lane's element: (t, b) = (warp*8 + lane/4, b0 + lane%4); scalars straight from global
+  // ---- this lane's element: (t, b) = (warp*8 + lane/4, b0 + lane%4).  Lanes past the last row are CLAMPED onto
+  //      row T-1 (they read valid memory and compute throw-away values) so that the hot path has no branches;
+  //      fv / fl are the 0/1 masks "row exists" / "row carries a loss term".
   const int r = lane >> 2, c = lane & 3;
-  const int t = warp * R + r;
-  const bool valid = t < T;
-  const bool loss_row = t < T - 1;
+  const int t_raw = warp * R + r;
+  const int t = min(t_raw, T - 1);
+  const float fv = t_raw < T ? 1.f : 0.f;
+  const float fl = t_raw < T - 1 ? 1.f : 0.f;
   const int g = t * B + b0 + c;
-  int act = 0;
-  float e_r = 0.f, e_v = 0.f, e_vn = 0.f, e_g = 0.f;
-  if (valid) {
-    act = p.act64 ? (int)reinterpret_cast<const long long*>(p.actions)[g] : reinterpret_cast<const int*>(p.actions)[g];
-    e_r = p.rewards[g];
-    e_v = p.values[g];
-    e_g = p.dones[g] ? 0.0f : p.gamma;                  // impala.py:59  (~dones) * discount
-    if (t + 1 < T) e_vn = p.values[g + B];
-  }
-  mbar_wait(&s_bar[warp], 0);
+  const int act = p.act64 ? (int)reinterpret_cast<const long long*>(p.actions)[g] : reinterpret_cast<const int*>(p.actions)[g];
+  const float e_r = p.rewards[g];
+  const float e_v = p.values[g];
+  const float e_g = p.dones[g] ? 0.0f : p.gamma;          // impala.py:59  (~dones) * discount
+  const float e_vn = p.values[min(g + B, (T - 1) * B + b0 + c)];
+  mbar_wait_suspend(&s_bar[warp], 0);
 
-  // ---- phase A: softmax statistics (two sweeps over the shared-memory row, registers hold scalars only)
+  // ---- phase A: softmax statistics.  Sweep 1: maxima.  Sweep 2 (packed pairs): exponentials, S, W = sum e xs,
+  //      Y = sum e y, Sy; the target exponentials are parked over the (dead) behaviour logits for phase C.
   float* pt = reinterpret_cast<float*>(s_tl) + (size_t)(t * CW + c) * A_;
-  const float* pb = reinterpret_cast<const float*>(s_bl) + (size_t)(t * CW + c) * A_;
-  float nm = 0.f, l2S = 0.f, inv = 0.f, la = 0.f, H = 0.f, D = 0.f, K = 0.f, rpg = 0.f;
-  float sum_pi = 0.f, sum_vf = 0.f, sum_ent = 0.f, sum_kl = 0.f;
-  if (valid) {
-    float m = -INFINITY, my = -INFINITY;
+  float* pb = reinterpret_cast<float*>(s_bl) + (size_t)(t * CW + c) * A_;
+  float m = -INFINITY, my = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < A_; j += 2) {
-      const float2 a = *reinterpret_cast<const float2*>(pt + j);
-      const float2 y = *reinterpret_cast<const float2*>(pb + j);
-      m = fmaxf(m, fmaxf(a.x, a.y));
-      my = fmaxf(my, fmaxf(y.x, y.y));
-    }
-    nm = -m * kL2E;
-    const float nmy = -my * kL2E;
-    float S0 = 0.f, S1 = 0.f, W0 = 0.f, W1 = 0.f, Y0 = 0.f, Y1 = 0.f, Sy0 = 0.f, Sy1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < A_; j += 2) {
-      const float2 a = *reinterpret_cast<const float2*>(pt + j);
-      const float2 y = *reinterpret_cast<const float2*>(pb + j);
-      const float xs0 = fmaf(a.x, kL2E, nm), xs1 = fmaf(a.y, kL2E, nm);
-      const float e0 = ex2_approx(xs0), e1 = ex2_approx(xs1);
-      S0 += e0, S1 += e1;
-      W0 = fmaf(e0, xs0, W0), W1 = fmaf(e1, xs1, W1);
-      Y0 = fmaf(e0, y.x, Y0), Y1 = fmaf(e1, y.y, Y1);
-      Sy0 += ex2_approx(fmaf(y.x, kL2E, nmy));
-      Sy1 += ex2_approx(fmaf(y.y, kL2E, nmy));
-    }
-    const float S = S0 + S1, Wt = W0 + W1, Y = Y0 + Y1, Sy = Sy0 + Sy1;
-    l2S = lg2_approx(S);
-    inv = __fdividef(1.0f, S);
-    const float logSy = lg2_approx(Sy) * kLN2;
-    const float Hn = (Wt * inv - l2S) * kLN2;              // sum_j p_j log p_j
-    H = -Hn;
-    sum_kl = Hn - Y * inv + my + logSy;                    // impala.py:160-162: every row
-    la = (fmaf(pt[act], kL2E, nm) - l2S) * kLN2;
-    const float lma = pb[act] - my - logSy;
-    if (loss_row) {
-      const float rho = expf(la - lma);                    // vtrace.py:101-103
-      const float rhoc = p.clip_rho >= 0.f ? fminf(rho, p.clip_rho) : rho;
-      const float cs = fminf(rho, 1.0f);                   // :109
-      rpg = p.clip_pg >= 0.f ? fminf(rho, p.clip_pg) : rho;
-      D = __fmul_rn(rhoc, __fsub_rn(__fadd_rn(e_r, __fmul_rn(e_g, e_vn)), e_v));     // :115
-      K = __fmul_rn(e_g, cs);
-      sum_ent = H;
-    }
+  for (int j = 0; j < A_; j += 2) {
+    const float2 a = *reinterpret_cast<const float2*>(pt + j);
+    const float2 y = *reinterpret_cast<const float2*>(pb + j);
+    m = fmaxf(m, fmaxf(a.x, a.y));
+    my = fmaxf(my, fmaxf(y.x, y.y));
   }
+  const float nm = -m * kL2E, nmy = -my * kL2E;
+  const float x_act = pt[act], y_act = pb[act];
+  const float2 cL = make_float2(kL2E, kL2E), cnm = make_float2(nm, nm), cnmy = make_float2(nmy, nmy);
+  float2 S2 = make_float2(0.f, 0.f), W2 = S2, Y2 = S2, Sy2 = S2;
+#pragma unroll
+  for (int j = 0; j < A_; j += 2) {
+    const float2 a = *reinterpret_cast<const float2*>(pt + j);
+    const float2 y = *reinterpret_cast<const float2*>(pb + j);
+    const float2 xs = f2_fma(a, cL, cnm);
+    const float2 e = make_float2(ex2_approx(xs.x), ex2_approx(xs.y));
+    const float2 ys = f2_fma(y, cL, cnmy);
+    const float2 ey = make_float2(ex2_approx(ys.x), ex2_approx(ys.y));
+    S2 = f2_add(S2, e);
+    W2 = f2_fma(e, xs, W2);
+    Y2 = f2_fma(e, y, Y2);
+    Sy2 = f2_add(Sy2, ey);
+    *reinterpret_cast<float2*>(pb + j) = e;              // this lane's own row: no cross-lane hazard
+  }
+  const float S = S2.x + S2.y, Wt = W2.x + W2.y, Y = Y2.x + Y2.y, Sy = Sy2.x + Sy2.y;
+  const float l2S = lg2_approx(S);
+  const float inv = __fdividef(1.0f, S);
+  const float logSy = lg2_approx(Sy) * kLN2;
+  const float Hn = (Wt * inv - l2S) * kLN2;              // sum_j p_j log p_j
+  const float H = -Hn;
+  float sum_kl = fv * (Hn - Y * inv + my + logSy);       // impala.py:160-162: every row
+  const float la = (fmaf(x_act, kL2E, nm) - l2S) * kLN2;
+  const float lma = y_act - my - logSy;
+  const float rho = ex2_approx((la - lma) * kL2E);       // vtrace.py:101-103
+  const float rhoc = p.clip_rho >= 0.f ? fminf(rho, p.clip_rho) : rho;
+  const float rpg = p.clip_pg >= 0.f ? fminf(rho, p.clip_pg) : rho;
+  float D = fl * __fmul_rn(rhoc, __fsub_rn(__fadd_rn(e_r, __fmul_rn(e_g, e_vn)), e_v));     // :115 (0 past T-2)
+  float K = fl * __fmul_rn(e_g, fminf(rho, 1.0f));                                          // :109
+  float sum_ent = fl * H;
   // suffix scan of the affine maps acc -> D + K acc over the warp's 8 rows (later time = higher lane)
 #pragma unroll
   for (int off = CW; off < 32; off <<= 1) {
     const float Dn = __shfl_down_sync(FULL, D, off);
     const float Kn = __shfl_down_sync(FULL, K, off);
-    if (lane + off < 32) {
-      D = fmaf(K, Dn, D);
-      K *= Kn;
-    }
+    const bool in = lane + off < 32;
+    D = in ? fmaf(K, Dn, D) : D;
+    K = in ? K * Kn : K;
   }
   if (lane < CW) s_comp[warp][lane] = make_float2(D, K);   // the whole pass as one map, per column
   __syncthreads();
@@ -599,35 +638,32 @@ __global__ void __maxnreg__(40)          // 7 CTAs x 7 warps x 40 registers fit 
   }
   const float acc = fmaf(K, cin, D);
   float acc_n = __shfl_down_sync(FULL, acc, CW);
-  if (r == R - 1) acc_n = cin;
-  // ---- phase C: advantages, losses, gradient row recomputed over the target-logit row
-  if (valid) {
-    if (loss_row) {
-      const float vs = __fadd_rn(acc, e_v);                          // vtrace.py:125
-      const float vs_n = __fadd_rn(acc_n, e_vn);                     // :128-129 (bootstrap at the end)
-      const float adv = __fmul_rn(rpg, __fsub_rn(__fadd_rn(e_r, __fmul_rn(e_g, vs_n)), e_v));   // :136-137
-      const float dv = e_v - vs;
-      sum_pi = -la * adv;                                             // impala.py:67-68
-      sum_vf = 0.5f * dv * dv;                                        // :71-72
-      p.d_values[g] = p.vf_coeff * dv;
-      if (p.vs_out) p.vs_out[g] = vs;
-      if (p.pg_out) p.pg_out[g] = adv;
-      const float ce2 = p.ent_coeff * kLN2;
-      const float c0 = fmaf(ce2, l2S, adv - p.ent_coeff * H) * inv;  // folded with 1/S
-      const float c1 = -ce2 * inv;
+  acc_n = r == R - 1 ? cin : acc_n;
+  // ---- phase C: advantages, losses, gradient row (exponentials read back, no second MUFU pass)
+  const float vs = __fadd_rn(acc, e_v);                              // vtrace.py:125
+  const float vs_n = __fadd_rn(acc_n, e_vn);                         // :128-129 (bootstrap at the end)
+  const float adv = fl * __fmul_rn(rpg, __fsub_rn(__fadd_rn(e_r, __fmul_rn(e_g, vs_n)), e_v));   // :136-137
+  const float dv = fl * (e_v - vs);
+  float sum_pi = -la * adv;                                           // impala.py:67-68
+  float sum_vf = 0.5f * dv * dv;                                      // :71-72
+  if (fv != 0.f) {
+    p.d_values[g] = p.vf_coeff * dv;
+    if (p.vs_out) p.vs_out[g] = vs;
+    if (p.pg_out) p.pg_out[g] = adv;
+  }
+  {
+    const float ce2 = fl * p.ent_coeff * kLN2;
+    const float c0 = fmaf(ce2, l2S, adv - fl * p.ent_coeff * H) * inv;   // folded with 1/S; 0 on the bootstrap row
+    const float c1 = -ce2 * inv;
+    const float2 c02 = make_float2(c0, c0), c12 = make_float2(c1, c1);
 #pragma unroll
-      for (int j = 0; j < A_; j += 2) {
-        const float2 a = *reinterpret_cast<const float2*>(pt + j);
-        const float xs0 = fmaf(a.x, kL2E, nm), xs1 = fmaf(a.y, kL2E, nm);
-        const float d0 = ex2_approx(xs0) * fmaf(c1, xs0, c0), d1 = ex2_approx(xs1) * fmaf(c1, xs1, c0);
-        *reinterpret_cast<float2*>(pt + j) = make_float2(d0, d1);
-      }
-      pt[act] -= adv;
-    } else {
-      p.d_values[g] = 0.f;                                            // bootstrap row: no gradient
-#pragma unroll
-      for (int j = 0; j < A_; j += 2) *reinterpret_cast<float2*>(pt + j) = make_float2(0.f, 0.f);
+    for (int j = 0; j < A_; j += 2) {
+      const float2 a = *reinterpret_cast<const float2*>(pt + j);
+      const float2 e = *reinterpret_cast<const float2*>(pb + j);
+      const float2 xs = f2_fma(a, cL, cnm);
+      *reinterpret_cast<float2*>(pt + j) = f2_mul(e, f2_fma(c12, xs, c02));
     }
+    pt[act] -= adv;
   }
   fence_proxy_async_smem();              // generic-proxy writes of the gradient rows -> visible to the TMA engine
   __syncwarp();
