@@ -43,6 +43,11 @@ int rl_abi_version(void);
 const char* rl_last_error(void);
 /* Number of SMs / device name probe used by the host side for grid sizing. */
 int rl_device_sm_count(int device);
+/* Cap the CTA count of the persistent network kernels (conv forward / dgrad / wgrad) launched AFTER the call
+ * (0 = one CTA per SM).  A pipelined engine caps its actor-side and learner-side kernels so that both streams'
+ * grids are resident together instead of serialising; process-wide setting, read at launch (baked into a graph
+ * at capture). */
+int rl_set_sm_limit(int max_ctas);
 
 /* Bytes of zero-initialised scratch the loss kernels need for a problem with
  * `n_cols` independent columns (B) — partial sums + the last-block ticket.

@@ -28,6 +28,7 @@ SIGNATURES = {
     'rl_abi_version': (c_i, []),
     'rl_last_error': (ctypes.c_char_p, []),
     'rl_device_sm_count': (c_i, [c_i]),
+    'rl_set_sm_limit': (c_i, [c_i]),
     'rl_loss_workspace_bytes': (c_sz, [c_i]),
     'rl_debug_set_tma': (c_i, [c_i]),
     'rl_debug_set_vtrace_path': (c_i, [c_i]),

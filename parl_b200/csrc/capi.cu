@@ -12,7 +12,20 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+// Upper bound on the CTAs a persistent network kernel launches (0 = one per SM).  Two streams that both launch
+// whole-GPU persistent grids serialise; capping each side lets the actor's and the learner's kernels share the SMs.
+static int g_sm_limit = 0;
+int effective_sms(int sms) { return (g_sm_limit > 0 && g_sm_limit < sms) ? g_sm_limit : sms; }
 }  // namespace rl
+
+extern "C" int rl_set_sm_limit(int max_ctas) {
+  if (max_ctas < 0) {
+    rl::set_error("rl_set_sm_limit: %d < 0", max_ctas);
+    return RL_ERR_BAD_ARG;
+  }
+  rl::g_sm_limit = max_ctas;
+  return RL_OK;
+}
 
 extern "C" int rl_abi_version(void) { return 1; }
 extern "C" const char* rl_last_error(void) { return rl::g_err; }

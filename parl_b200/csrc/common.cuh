@@ -9,6 +9,7 @@
 namespace rl {
 
 void set_error(const char* fmt, ...);
+int effective_sms(int sms);          // SM count capped by rl_set_sm_limit
 
 #define RL_CHECK_ARG(cond, ...)            \
   do {                                     \

@@ -385,6 +385,7 @@ static int shiftconv_launch(const void* in, const void* weight, const float* bia
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  sms = effective_sms(sms);
   cudaStream_t st = (cudaStream_t)stream;
   // instantiations: the layers of the Atari actor-critic and their data gradients (2x2 and 3x3 filters)
   const int key = (transposed ? 100000 : 0) + Cout * 100 + cblk * 10 + KH;

@@ -630,6 +630,7 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
     int devp = 0, smsp = 148;
     cudaGetDevice(&devp);
     cudaDeviceGetAttribute(&smsp, cudaDevAttrMultiProcessorCount, devp);
+    smsp = effective_sms(smsp);
     const int gridp = smsp < a.num_tiles ? smsp : a.num_tiles;
     if (workspace_bytes < (size_t)gridp * 128 * a.ncols * sizeof(float)) {
       set_error("conv2d_s1_wgrad: workspace too small");
@@ -671,6 +672,7 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
     int dev32 = 0, sms32 = 148;
     cudaGetDevice(&dev32);
     cudaDeviceGetAttribute(&sms32, cudaDevAttrMultiProcessorCount, dev32);
+    sms32 = effective_sms(sms32);
     int grid32 = sms32 < g.num_tiles ? sms32 : g.num_tiles;
     if (workspace_bytes < (size_t)grid32 * 128 * g.ncols_max * sizeof(float)) {
       set_error("conv2d_s1_wgrad: workspace too small");
@@ -702,6 +704,7 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  sms = effective_sms(sms);
   int grid = sms;
   if (grid > g.num_tiles * g.ngroups) grid = g.num_tiles * g.ngroups;
   if (grid < g.ngroups) grid = g.ngroups;

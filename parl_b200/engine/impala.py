@@ -29,7 +29,7 @@ class ImpalaEngine(object):
     def __init__(self, num_envs=4096, sample_batch_steps=50, act_dim=18, frame_hw=(84, 84), seed=0, device=None,
                  env_offset=0, gamma=0.99, vf_loss_coeff=0.5, clip_rho_threshold=1.0, clip_pg_rho_threshold=1.0,
                  p_done=0.1, model=None, learn_chunk_rows=5, use_graph=True, actor_kernels='auto',
-                 learner_kernels='auto', pipeline=False, role='both'):
+                 learner_kernels='auto', pipeline=False, role='both', actor_sms=None, learner_sms=None):
         if device is None:
             device = torch.device('cuda', torch.cuda.current_device())
         self.device = torch.device(device)
@@ -38,6 +38,11 @@ class ImpalaEngine(object):
         # role 'learner': only the learner (train network, loss buffers) — what the Learner's Agent hosts.  The two
         # halves then talk through the reference's host contract (numpy sample dicts, numpy weight dicts).
         self.role = role
+        # pipelined engines: CTA caps of the persistent network kernels of the two streams (None = one CTA per SM).
+        # With both at the SM count the actor's and the learner's whole-GPU grids serialise; capped, they co-reside.
+        env_a, env_l = os.environ.get('PARL_B200_ACTOR_SMS'), os.environ.get('PARL_B200_LEARNER_SMS')
+        self.actor_sms = int(env_a) if env_a else (actor_sms or 0)
+        self.learner_sms = int(env_l) if env_l else (learner_sms or 0)
         if role != 'both':
             assert not pipeline, 'actor-only / learner-only engines are driven through the host contract'
         self.B, self.T, self.A = int(num_envs), int(sample_batch_steps), int(act_dim)
@@ -158,6 +163,16 @@ class ImpalaEngine(object):
     def _run_rollout(self, i):
         """Rollout into buffer set i on the current stream (graph replay after the first, eager, run)."""
         self._bind(i)
+        if self.actor_sms or self.learner_sms:
+            kernels.set_sm_limit(self.actor_sms)          # read at launch: baked into the rollout graph at capture
+            try:
+                self._run_rollout_inner(i)
+            finally:
+                kernels.set_sm_limit(self.learner_sms)    # the learner's eager launches that follow
+            return
+        self._run_rollout_inner(i)
+
+    def _run_rollout_inner(self, i):
         if self.use_graph:
             if self._graphs[i] is None:
                 self._rollout_body()                      # eager once (allocator / autotune warm-up), then capture

@@ -31,6 +31,12 @@ def add_graph_launches(n):
     _graph_launches += int(n)
 
 
+def set_sm_limit(max_ctas):
+    """Cap the CTAs of the persistent network kernels launched from now on (0 = one per SM)."""
+    check(_lib.load().rl_set_sm_limit(int(max_ctas)), 'set_sm_limit')
+    _lib.launches -= 1
+
+
 def loss_workspace(device, n_cols):
     """Zero-initialised scratch for the loss kernels (partials + ticket), cached per device."""
     need = _lib.load().rl_loss_workspace_bytes(int(n_cols))
