@@ -131,6 +131,18 @@ __device__ __forceinline__ void vecnorm_obs_absorb(const VecNormState& v, int b,
   v.ob_count[b] = c + 1.0;
 }
 
+// one component of _obfilt: statistics update of dimension d with sample xv given the count BEFORE this observation,
+// returns the filtered value.  (The caller bumps ob_count[b] once per observation.)
+__device__ __forceinline__ float vecnorm_obs_dim(const VecNormState& v, int b, int D, int d, double count_old, float x) {
+  double m = v.ob_mean[(size_t)b * D + d], s = v.ob_var[(size_t)b * D + d];
+  const double xv = (double)x;
+  if (v.update) {
+    rms_update1(m, s, count_old, xv);
+    v.ob_mean[(size_t)b * D + d] = m, v.ob_var[(size_t)b * D + d] = s;
+  }
+  return (float)fmin(fmax((xv - m) / sqrt(s + v.eps), -v.clipob), v.clipob);
+}
+
 // _obfilt of one observation of env b, in place on x (stride x_stride between its D components)
 __device__ __forceinline__ void vecnorm_obs_filter(const VecNormState& v, int b, int D, float* __restrict__ x, int x_stride) {
   if (!v.norm_ob) return;

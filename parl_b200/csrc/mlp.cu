@@ -391,6 +391,7 @@ __global__ void __launch_bounds__(kMlpThreads) rollout_mlp_kernel(const MlpArgs 
   float* s_x = smem_f + ((p.np_pad + 3) & ~3);            // observation tile [pd[0]][kTS]
   float* s_a = s_x + kMaxWidth * kTS;                      // ping
   float* s_b = s_a + kMaxWidth * kTS;                      // pong
+  __shared__ double s_cnt[kTN];                            // VecNormalize: observation count before this step
   load_params(p, s_par);
   const int n0 = blockIdx.x * kTN;
   const int D = p.dims[0], Dp = p.pd[0], B = r.B;
@@ -461,17 +462,13 @@ __global__ void __launch_bounds__(kMlpThreads) rollout_mlp_kernel(const MlpArgs 
             }
             if (r.logp_out) r.logp_out[tb] = lp;
           }
-          // ---- env step (same draws / physics as rl_env_mujoco_synth_step / rl_env_cartpole_step)
+          // ---- env step (same draws / physics as rl_env_mujoco_synth_step / rl_env_cartpole_step); the MuJoCo-shaped
+          //      env's next observation is produced by ALL threads of the CTA after this block (stage 2)
           if (r.env_kind == 0) {
             const uint4 x = philox4x32_10(env, step, 0u, STREAM_REWDONE, r.k0, r.k1);
             reward = (float)(x.x & 1u);
             done = x.y < r.done_thr;
             if (r.max_steps > 0 && r.st.ep_len[b] + 1 >= r.max_steps) done = true;
-            for (int blk = 0; blk * 4 < D; ++blk) {
-              float z[4];
-              gauss_block(env, step + 1u, (uint32_t)blk, STREAM_OBS, r.k0, r.k1, z);
-              for (int k = 0; k < 4 && blk * 4 + k < D; ++k) s_x[(blk * 4 + k) * kTS + tid] = z[k];
-            }
           } else {
             float4 s = make_float4(s_x[tid], s_x[kTS + tid], s_x[2 * kTS + tid], s_x[3 * kTS + tid]);
             done = cartpole_physics(s, a_cat);
@@ -481,9 +478,10 @@ __global__ void __launch_bounds__(kMlpThreads) rollout_mlp_kernel(const MlpArgs 
             s_x[tid] = s.x, s_x[kTS + tid] = s.y, s_x[2 * kTS + tid] = s.z, s_x[3 * kTS + tid] = s.w;
           }
           float rew_seen = reward;           // what the agent sees; the episode statistics keep the raw reward
-          if (r.use_vn) {                    // VecNormalizeEnv.step, then (where done) .reset, of env b
+          if (r.use_vn) {                    // VecNormalizeEnv.step (reward side) of env b
             rew_seen = vecnorm_reward(r.vn, b, reward, done);
-            vecnorm_obs_filter(r.vn, b, D, s_x + tid, kTS);
+            if (r.env_kind == 0) s_cnt[tid] = r.vn.ob_count[b];
+            else vecnorm_obs_filter(r.vn, b, D, s_x + tid, kTS);
           }
           r.rew_out[tb] = rew_seen;
           r.done_out[tb] = done ? 1 : 0;
@@ -492,6 +490,27 @@ __global__ void __launch_bounds__(kMlpThreads) rollout_mlp_kernel(const MlpArgs 
       }
     }
     __syncthreads();
+    // ---- stage 2 (MuJoCo-shaped env): next observation of every env, one Box-Muller block (4 components) per
+    //      task over all 256 threads; with VecNormalize each component is filtered where it is produced
+    if (t < r.T && r.env_kind == 0) {
+      const int nblk = (D + 3) >> 2;
+      const uint32_t step = r.step0 + (uint32_t)t;
+      const bool filt = r.use_vn && r.vn.norm_ob;
+      for (int task = tid; task < kTN * nblk; task += kMlpThreads) {
+        const int blk = task / kTN, n = task - blk * kTN;           // consecutive threads = consecutive envs
+        const int b = n0 + n;
+        if (b >= B) continue;
+        float z[4];
+        gauss_block(r.env_offset + (uint32_t)b, step + 1u, (uint32_t)blk, STREAM_OBS, r.k0, r.k1, z);
+        const double cnt = filt ? s_cnt[n] : 0.0;
+        for (int k = 0; k < 4 && blk * 4 + k < D; ++k) {
+          const int d = blk * 4 + k;
+          s_x[d * kTS + n] = filt ? vecnorm_obs_dim(r.vn, b, D, d, cnt, z[k]) : z[k];
+        }
+      }
+      if (filt && r.vn.update && tid < kTN && n0 + tid < B) r.vn.ob_count[n0 + tid] = s_cnt[tid] + 1.0;
+      __syncthreads();
+    }
   }
   // carry the envs' observations to the next rollout
   for (int i = tid; i < D * kTN; i += kMlpThreads) {
