@@ -15,11 +15,12 @@ pytestmark = pytest.mark.gpu
 DEV = torch.device('cuda:0')
 
 
-def test_fused_rollout_cartpole_equals_unfused_kernels():
+@pytest.mark.parametrize('B,T', [(200, 37), (9600, 6)])       # 16-env latency tiles / 64-env throughput tiles
+def test_fused_rollout_cartpole_equals_unfused_kernels(B, T):
     from parl_b200 import kernels as K
     from parl_b200.engine.nets import CartPoleActorCritic
     torch.manual_seed(3)
-    B, T, seed, off = 200, 37, 11, 5
+    seed, off = 11, 5
     model = CartPoleActorCritic(4, 2).to(DEV)
     layers, act = model.native_layers()
     plan = K.MlpPlan([[(w.detach(), b.detach()) for (w, b) in seg] for seg in layers], act)
