@@ -54,7 +54,7 @@ def test_fused_rollout_cartpole_equals_unfused_kernels(B, T):
     _, val = plan.forward(obs.clone(), split=2)
     assert torch.equal(f['val'][T], val.view(-1))
     assert torch.equal(st_f.totals, st_u.totals) and torch.equal(st_f.ep_len, st_u.ep_len)
-    assert f['done'].sum().item() > 0                     # episodes did end (30-step limit / pole falls)
+    assert T < 30 or f['done'].sum().item() > 0           # episodes did end (30-step limit / pole falls)
 
 
 def test_fused_rollout_mujoco_gaussian_equals_unfused_kernels():
