@@ -141,7 +141,11 @@ int rl_env_atari_synth_step(
  * out_dtype 2 = bfloat16 [n,HW,4] (NHWC, value * scale) — the network input transform fused in;
  * out_dtype 3 = bfloat16 [n,21,21,64]: conv1's space-to-depth form (8x8/4/pad-1 conv == 2x2/1 conv over 4x4
  *               pixel blocks, channel = (dy*4+dx)*4+c, zero outside the image), 84x84 frames only; with
- *               ages == NULL `planes` is an already stacked uint8 tensor [t_count*B, 4, 84, 84]. */
+ *               ages == NULL `planes` is an already stacked uint8 tensor [t_count*B, 4, 84, 84];
+ * out_dtype 4 = uint8   [n,21,21,64]: the same space-to-depth layout with the bytes untouched (scale unused) — the
+ *               input of rl_conv2d_s1_u8in_bf16_{fwd,wgrad}, which apply the /255 of the reference model
+ *               (benchmark/torch/a2c/atari_model.py:41, examples/IMPALA/atari_model.py) while widening to bf16
+ *               in shared memory. */
 int rl_obs_stack_gather(
     const uint8_t* planes, const uint8_t* ages, int B, int HW, int t_begin, int t_count,
     int out_layout, int out_dtype, float scale, void* out, rl_stream_t stream);
@@ -340,6 +344,13 @@ int rl_conv2d_s1_nhwc_bf16_fwd(const void* in, const void* weight_krsc, const fl
                                int N, int H, int W, int Cin, int Cout, int KH, int KW, int relu, int out_mode,
                                rl_stream_t stream);
 int rl_debug_set_shiftconv_base_offset(int enable);
+/* The same forward for conv1 of the Atari models on the uint8 observation: in_u8 [N,H,W,64] uint8 (space-to-depth,
+ * rl_obs_stack_gather out_dtype 4); operand = bf16(byte * in_scale), converted in shared memory by four extra warps,
+ * bit-identical to feeding rl_conv2d_s1_nhwc_bf16_fwd the out_dtype-3 tensor at half the input traffic.
+ * Built for KH = KW = 2, Cin = 64, Cout = 32. */
+int rl_conv2d_s1_u8in_bf16_fwd(const void* in_u8, float in_scale, const void* weight_krsc, const float* bias, void* out,
+                               int N, int H, int W, int Cout, int KH, int KW, int relu, int out_mode,
+                               rl_stream_t stream);
 
 /* Data gradient of rl_conv2d_s1_nhwc_bf16_fwd in the same TMA-window form (transposed conv = shifted GEMMs run
  * backwards).  dout_grid [N,H,W,Cout] is the output gradient ON THE INPUT GRID (zeros where y>=H-KH+1 or
@@ -362,6 +373,10 @@ int rl_conv2d_s1_nhwc_bf16_dgrad(const void* dout_grid, const void* weight_t_krs
 size_t rl_conv_wgrad_workspace_bytes(int KH, int KW, int Cin);
 int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* in, float* dw_krsc, float* db, int N, int H, int W,
                                  int Cin, int Cout, int KH, int KW, int accumulate,
+                                 void* workspace, size_t workspace_bytes, rl_stream_t stream);
+/* Weight (+ bias) gradient of rl_conv2d_s1_u8in_bf16_fwd: `in_u8` [N,H,W,64] uint8, same workspace rule (Cin = 64). */
+int rl_conv2d_s1_u8in_bf16_wgrad(const void* dout_grid, const void* in_u8, float in_scale, float* dw_krsc, float* db,
+                                 int N, int H, int W, int Cout, int KH, int KW, int accumulate,
                                  void* workspace, size_t workspace_bytes, rl_stream_t stream);
 int rl_debug_set_wgrad_lane_map(int mode);
 /* out[c] = sum_r x[r,c] for a [rows, C] bf16 matrix (bias gradients); C a multiple of 8 with C/8 dividing 256;

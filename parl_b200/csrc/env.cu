@@ -205,10 +205,13 @@ __global__ void __launch_bounds__(256) obs_stack_gather_nhwc_bf16_kernel(const u
 // eight 4-byte global loads per thread and sat in long-scoreboard stalls, ncu round 1), then one thread = one
 // (Y,X,dy) item = 32 output bytes.  u8 -> float goes through the 2^23 magic number on the FMA pipe:
 // fma(as_float(0x4B000000 | byte), scale, -2^23 * scale) == float(byte) * scale bit for bit (one rounding).
-__global__ void __launch_bounds__(256) obs_stack_gather_s2d_bf16_kernel(const uint8_t* __restrict__ planes,
-                                                                        const uint8_t* __restrict__ ages, int B,
-                                                                        int t_begin, int t_count, int env_major,
-                                                                        float scale, __nv_bfloat16* __restrict__ out) {
+// U8OUT (out_dtype 4): the same layout with the bytes left as they are, 64 B per block — half the traffic; the
+// conv1 kernels widen it to bf16 in shared memory (rl_conv2d_s1_u8in_bf16_{fwd,wgrad}, u8win.cuh).
+template <bool U8OUT>
+__global__ void __launch_bounds__(256) obs_stack_gather_s2d_kernel(const uint8_t* __restrict__ planes,
+                                                                   const uint8_t* __restrict__ ages, int B, int t_begin,
+                                                                   int t_count, int env_major, float scale,
+                                                                   void* __restrict__ out_v) {
   constexpr int W = 84, G = 21, ITEMS = G * G * 4, FRAME = W * W, CHUNKS = FRAME / 16;     // 7056 B = 441 x 16
   __shared__ __align__(16) uint8_t sfr[4][FRAME];
   const long long nsamples = (long long)t_count * B;
@@ -231,7 +234,8 @@ __global__ void __launch_bounds__(256) obs_stack_gather_s2d_bf16_kernel(const ui
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    __nv_bfloat16* dst_sample = out + r * (long long)(G * G * 64);
+    __nv_bfloat16* dst_sample = reinterpret_cast<__nv_bfloat16*>(out_v) + r * (long long)(G * G * 64);
+    uint8_t* dst_sample_u8 = reinterpret_cast<uint8_t*>(out_v) + r * (long long)(G * G * 64);
     for (int j = threadIdx.x; j < ITEMS; j += 256) {
       const int dy = j & 3, p = j >> 2, Y = p / G, X = p - Y * G;
       const int y = 4 * Y + dy - 1;
@@ -245,6 +249,17 @@ __global__ void __launch_bounds__(256) obs_stack_gather_s2d_bf16_kernel(const ui
           const uint32_t w1 = row[X];                              // bytes 4X   .. 4X+3
           px[c] = (w0 >> 24) | (w1 << 8);
         }
+      }
+      if (U8OUT) {
+        // 4x4 byte transpose: word dx = {px[0].b[dx], px[1].b[dx], px[2].b[dx], px[3].b[dx]}
+        uint32_t wd[4];
+#pragma unroll
+        for (int dx = 0; dx < 4; ++dx) {
+          const uint32_t sel = (uint32_t)dx | ((uint32_t)(4 + dx) << 4);
+          wd[dx] = __byte_perm(__byte_perm(px[0], px[1], sel), __byte_perm(px[2], px[3], sel), 0x5410u);
+        }
+        *reinterpret_cast<uint4*>(dst_sample_u8 + p * 64 + dy * 16) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        continue;
       }
       uint32_t pk[8];
 #pragma unroll
@@ -445,7 +460,7 @@ extern "C" int rl_env_atari_synth_step(uint8_t* frame_out, float* reward_out, ui
 
 extern "C" int rl_obs_stack_gather(const uint8_t* planes, const uint8_t* ages, int B, int HW, int t_begin, int t_count,
                                    int out_layout, int out_dtype, float scale, void* out, rl_stream_t stream) {
-  RL_CHECK_ARG(planes && out && (ages || out_dtype == 3), "obs_stack_gather: null pointer");
+  RL_CHECK_ARG(planes && out && (ages || out_dtype == 3 || out_dtype == 4), "obs_stack_gather: null pointer");
   RL_CHECK_ARG(B > 0 && HW > 0 && HW % 16 == 0 && t_count > 0 && t_begin >= 0, "obs_stack_gather: bad shape");
   RL_CHECK_ARG(aligned16(planes) && aligned16(out), "obs_stack_gather: 16-byte alignment required");
   const long long total = (long long)t_count * B * 4 * (HW / 16);
@@ -464,15 +479,20 @@ extern "C" int rl_obs_stack_gather(const uint8_t* planes, const uint8_t* ages, i
     if (b2 > 148LL * 32) b2 = 148LL * 32;
     obs_stack_gather_nhwc_bf16_kernel<<<(unsigned)b2, 256, 0, (cudaStream_t)stream>>>(
         planes, ages, B, HW, t_begin, t_count, em, scale, (__nv_bfloat16*)out);
-  } else if (out_dtype == 3) {
+  } else if (out_dtype == 3 || out_dtype == 4) {
     RL_CHECK_ARG(HW == 84 * 84, "obs_stack_gather: the space-to-depth layout is defined for 84x84 frames");
     RL_CHECK_ARG(aligned16(planes) && aligned16(out), "obs_stack_gather: 16-byte alignment required (cp.async staging)");
     long long b3 = (long long)t_count * B;              // one CTA per sample, grid-stride beyond 8 CTAs per SM
     if (b3 > 148LL * 7) b3 = 148LL * 7;                 // 28 KB of staged frames per CTA: 7 CTAs per SM
-    obs_stack_gather_s2d_bf16_kernel<<<(unsigned)b3, 256, 0, (cudaStream_t)stream>>>(
-        planes, ages, B, t_begin, t_count, em, scale, (__nv_bfloat16*)out);
+    if (out_dtype == 3)
+      obs_stack_gather_s2d_kernel<false><<<(unsigned)b3, 256, 0, (cudaStream_t)stream>>>(planes, ages, B, t_begin, t_count,
+                                                                                         em, scale, out);
+    else
+      obs_stack_gather_s2d_kernel<true><<<(unsigned)b3, 256, 0, (cudaStream_t)stream>>>(planes, ages, B, t_begin, t_count,
+                                                                                        em, scale, out);
   } else {
-    set_error("obs_stack_gather: out_dtype %d unsupported (0=u8, 1=f32, 2=bf16 NHWC, 3=bf16 space-to-depth)", out_dtype);
+    set_error("obs_stack_gather: out_dtype %d unsupported (0=u8, 1=f32, 2=bf16 NHWC, 3=bf16 space-to-depth, 4=u8 space-to-depth)",
+              out_dtype);
     return RL_ERR_UNSUPPORTED;
   }
   RL_CHECK_LAUNCH("rl_obs_stack_gather");

@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "tma.cuh"
+#include "u8win.cuh"
 
 namespace rl {
 
@@ -98,6 +99,7 @@ struct ShiftConvArgs {
   int row_shift;                   // TMA row coordinate of a tile = tile*128 + row_shift (dgrad: -((KH-1)*W+KW-1))
   int flip;                        // 1: tap (r,s) reads window row (KH-1-r)*W + (KW-1-s)  (transposed conv)
   const __nv_bfloat16* mask;       // optional activation on the accumulator grid [Q, COUT]: out *= (mask > 0)
+  float in_scale;                  // U8IN: operand = bf16(byte * in_scale)
 };
 
 // fp32 pair -> packed bf16x2 (lo = first argument), round-to-nearest-even; the ReLU form clamps in the same instruction
@@ -116,10 +118,13 @@ __device__ __forceinline__ uint32_t s_pack_relu_bf16x2(float lo, float hi) {
 // The epilogue is the instruction-issue hot spot of these kernels (ncu round 1: ~85 % of the issue slots of the
 // data-gradient kernel), so it is kept to: tcgen05.ld, 4 LDS.128 of bias + 16 FADD or one HSET2 mask per pair,
 // one cvt(.relu).bf16x2 per pair, two 16-byte stores — no per-element branches.
-template <int COUT, int CBLK, int KS, int MODE>
-__global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __grid_constant__ CUtensorMap map_in,
-                                                                      const __grid_constant__ CUtensorMap map_w,
-                                                                      const ShiftConvArgs g) {
+// U8IN (conv1 on the uint8 observation): map_in is the uint8 [Q][64] matrix, the producer fills a dense staging
+// ring and four more warps (11-14) convert each window into the bf16 SWIZZLE_128B ring (u8win.cuh).
+template <int COUT, int CBLK, int KS, int MODE, bool U8IN = false>
+__global__ void __launch_bounds__(U8IN ? kScThreads + kU8Threads : kScThreads, 1)
+    shiftconv_fwd_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
+                         const ShiftConvArgs g) {
+  static_assert(!U8IN || CBLK == 1, "the uint8 window is one 64-channel block");
   constexpr int W_KB = COUT * 128;                        // one 64-wide weight k-block
   constexpr int TMEM_COLS = kScAcc * COUT;                // 128 / 256 / 512: powers of two
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
@@ -129,7 +134,9 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
   unsigned char* sW = smem;                               // [num_kb][COUT][128 B]
   unsigned char* sWin = smem + ((num_kb * W_KB + 1023) & ~1023);   // [stages][CBLK][wrows][128 B]
   __shared__ __align__(8) unsigned long long full_bar[kScMaxStages], empty_bar[kScMaxStages], w_bar, tmem_full[kScAcc], tmem_empty[kScAcc];
+  __shared__ __align__(8) unsigned long long u8_full[kU8Stages], u8_empty[kU8Stages];
   const uint32_t nstages = (uint32_t)g.stages;
+  unsigned char* sStage = sWin + nstages * CBLK * win_bytes;       // U8IN: [kU8Stages][wrows][64 B]
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_bias[COUT];
 
@@ -139,8 +146,12 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
     tma_prefetch_desc(&map_in);
     tma_prefetch_desc(&map_w);
     for (int s = 0; s < kScMaxStages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], U8IN ? kU8Threads : 1);
       mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kU8Stages; ++s) {
+      mbar_init(&u8_full[s], 1);
+      mbar_init(&u8_empty[s], kU8Threads);
     }
     mbar_init(&w_bar, 1);
     for (int b = 0; b < kScAcc; ++b) {
@@ -159,14 +170,41 @@ __global__ void __launch_bounds__(kScThreads, 1) shiftconv_fwd_kernel(const __gr
     // ===== TMA producer: one window (CBLK column blocks) per tile =====
     if (lane == 0) {
       uint32_t s = 0, par = 1;
-      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-        mbar_wait(&empty_bar[s], par);
-        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(CBLK * g.wrows * 128));
+      if (U8IN) {
+        const int sbytes = u8_stage_bytes(g.wrows);
+        for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+          mbar_wait(&u8_empty[s], par);
+          mbar_arrive_expect_tx(&u8_full[s], (uint32_t)(g.wrows * 64));
+          tma_load_2d(sStage + s * sbytes, &map_in, 0, tile * kScBM + g.row_shift, &u8_full[s]);
+          if (++s == kU8Stages) s = 0, par ^= 1u;
+        }
+      } else {
+        for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+          mbar_wait(&empty_bar[s], par);
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(CBLK * g.wrows * 128));
 #pragma unroll
-        for (int cb = 0; cb < CBLK; ++cb)
-          tma_load_2d(sWin + (s * CBLK + cb) * win_bytes, &map_in, cb * 64, tile * kScBM + g.row_shift, &full_bar[s]);
-        if (++s == nstages) s = 0, par ^= 1u;
+          for (int cb = 0; cb < CBLK; ++cb)
+            tma_load_2d(sWin + (s * CBLK + cb) * win_bytes, &map_in, cb * 64, tile * kScBM + g.row_shift, &full_bar[s]);
+          if (++s == nstages) s = 0, par ^= 1u;
+        }
       }
+    }
+  } else if (U8IN && warp > kScIssuer2) {
+    // ===== uint8 -> bf16 window converters =====
+    const int ct = threadIdx.x - kScThreads;
+    const int sbytes = u8_stage_bytes(g.wrows);
+    const float bias = -8388608.0f * g.in_scale;
+    uint32_t s = 0, epar = 1, ss = 0, fpar = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      mbar_wait(&u8_full[ss], fpar);
+      mbar_wait(&empty_bar[s], epar);              // the MMAs that read this window slot have completed
+      s_fence_after();
+      u8_window_to_bf16_sw128(sStage + ss * sbytes, sWin + s * win_bytes, g.wrows, ct, g.in_scale, bias);
+      fence_proxy_async_smem();                    // generic-proxy stores -> visible to the tensor core's async proxy
+      s_mbar_arrive(&full_bar[s]);
+      s_mbar_arrive(&u8_empty[ss]);
+      if (++s == nstages) s = 0, epar ^= 1u;
+      if (++ss == kU8Stages) ss = 0, fpar ^= 1u;
     }
   } else if (warp == 1 || warp == kScIssuer2) {
     // ===== resident weights + MMA issue (issuer 0: even tiles of this CTA, issuer 1: odd tiles) =====
@@ -323,14 +361,18 @@ static int sc_make_map(CUtensorMap* map, const void* base, uint64_t cols, uint64
              : -2;
 }
 
-template <int COUT, int CBLK, int KS, int MODE>
+static size_t u8_ring_bytes(int wrows) { return (size_t)kU8Stages * (size_t)((wrows * 64 + 1023) & ~1023); }
+
+template <int COUT, int CBLK, int KS, int MODE, bool U8IN = false>
 static void launch_shiftconv(const CUtensorMap& mi, const CUtensorMap& mw, const ShiftConvArgs& g, int num_kb, int sms,
                              cudaStream_t st) {
   const size_t win = (size_t)((g.wrows * 128 + 1023) & ~1023);
-  const size_t smem = (size_t)((num_kb * COUT * 128 + 1023) & ~1023) + (size_t)g.stages * CBLK * win + 1024;
-  RL_SMEM_OPTIN(shiftconv_fwd_kernel<COUT, CBLK, KS, MODE>);
+  const size_t smem = (size_t)((num_kb * COUT * 128 + 1023) & ~1023) + (size_t)g.stages * CBLK * win + 1024 +
+                      (U8IN ? u8_ring_bytes(g.wrows) : 0);
+  auto kern = shiftconv_fwd_kernel<COUT, CBLK, KS, MODE, U8IN>;
+  RL_SMEM_OPTIN(kern);
   const int grid = g.num_tiles < sms ? g.num_tiles : sms;
-  shiftconv_fwd_kernel<COUT, CBLK, KS, MODE><<<grid, kScThreads, smem, st>>>(mi, mw, g);
+  kern<<<grid, U8IN ? kScThreads + kU8Threads : kScThreads, smem, st>>>(mi, mw, g);
 }
 
 }  // namespace rl
@@ -348,7 +390,8 @@ extern "C" int rl_debug_set_shiftconv_base_offset(int enable) {
 
 static int shiftconv_launch(const void* in, const void* weight, const float* bias, void* out, int N, int H, int W,
                             int Cin, int Cout, int KH, int KW, int relu, int out_mode, int Hout, int Wout, int OGH, int OGW,
-                            int transposed, const void* mask, rl_stream_t stream, const char* name) {
+                            int transposed, const void* mask, rl_stream_t stream, const char* name, int u8in = 0,
+                            float in_scale = 1.f) {
   RL_CHECK_ARG(in && weight && out && N > 0, "%s: bad argument", name);
   RL_CHECK_ARG(aligned16(in) && aligned16(weight) && aligned16(out) && (!mask || aligned16(mask)),
                "%s: 16-byte alignment required", name);
@@ -362,13 +405,13 @@ static int shiftconv_launch(const void* in, const void* weight, const float* bia
   RL_CHECK_ARG(Q < (1LL << 31), "%s: too many positions", name);
   g.Q = (int)Q, g.wrows = kScBM + (KH - 1) * W + (KW - 1), g.relu = relu, g.out_mode = out_mode;
   g.row_shift = transposed ? -((KH - 1) * W + (KW - 1)) : 0, g.flip = transposed;
-  g.mask = (const __nv_bfloat16*)mask;
+  g.mask = (const __nv_bfloat16*)mask, g.in_scale = in_scale;
   RL_CHECK_ARG(g.wrows <= 256, "%s: window of %d rows exceeds the TMA box limit", name, g.wrows);
   g.num_tiles = (int)((Q + kScBM - 1) / kScBM);
   const int cblk = Cin / 64, num_kb = KH * KW * cblk;
   const size_t win = (size_t)((g.wrows * 128 + 1023) & ~1023);
   {
-    const size_t budget = 220 * 1024 - ((size_t)num_kb * Cout * 128 + 2048);
+    const size_t budget = 220 * 1024 - ((size_t)num_kb * Cout * 128 + 2048) - (u8in ? u8_ring_bytes(g.wrows) : 0);
     long long st = (long long)(budget / ((size_t)cblk * win));
     if (st > kScMaxStages) st = kScMaxStages;
     // the dgrad epilogue reads the ReLU mask through L1: leave the unified L1/shared array some cache
@@ -377,7 +420,8 @@ static int shiftconv_launch(const void* in, const void* weight, const float* bia
     g.stages = (int)st;
   }
   alignas(64) CUtensorMap mi, mw;
-  if (sc_make_map(&mi, in, (uint64_t)Cin, (uint64_t)Q, (uint32_t)g.wrows) ||
+  if ((u8in ? make_tensor_map_u8_rows64(&mi, in, (uint64_t)Q, (uint32_t)g.wrows)
+            : sc_make_map(&mi, in, (uint64_t)Cin, (uint64_t)Q, (uint32_t)g.wrows)) ||
       sc_make_map(&mw, weight, (uint64_t)KH * KW * Cin, (uint64_t)Cout, (uint32_t)Cout)) {
     set_error("%s: cuTensorMapEncodeTiled failed", name);
     return RL_ERR_CUDA;
@@ -388,8 +432,9 @@ static int shiftconv_launch(const void* in, const void* weight, const float* bia
   sms = effective_sms(sms);
   cudaStream_t st = (cudaStream_t)stream;
   // instantiations: the layers of the Atari actor-critic and their data gradients (2x2 and 3x3 filters)
-  const int key = (transposed ? 100000 : 0) + Cout * 100 + cblk * 10 + KH;
+  const int key = (u8in ? 1000000 : 0) + (transposed ? 100000 : 0) + Cout * 100 + cblk * 10 + KH;
   switch (key) {
+    case 1003212: launch_shiftconv<32, 1, 2, 0, true>(mi, mw, g, num_kb, sms, st); break;  // conv1 fwd, uint8 input
     case 3212: launch_shiftconv<32, 1, 2, 0>(mi, mw, g, num_kb, sms, st); break;          // conv1 fwd
     case 6422: launch_shiftconv<64, 2, 2, 0>(mi, mw, g, num_kb, sms, st); break;          // conv2 fwd
     case 6413: launch_shiftconv<64, 1, 3, 0>(mi, mw, g, num_kb, sms, st); break;          // conv3 fwd
@@ -419,6 +464,17 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_fwd(const void* in, const void* weight_krs
                "conv2d_s1: out_mode 1 is the 20x20 -> [12,12,4*Cout] layout");
   return shiftconv_launch(in, weight_krsc, bias, out, N, H, W, Cin, Cout, KH, KW, relu, out_mode, H - KH + 1, W - KW + 1,
                           H - KH + 1, W - KW + 1, 0, nullptr, stream, "conv2d_s1");
+}
+
+extern "C" int rl_conv2d_s1_u8in_bf16_fwd(const void* in_u8, float in_scale, const void* weight_krsc, const float* bias,
+                                          void* out, int N, int H, int W, int Cout, int KH, int KW, int relu,
+                                          int out_mode, rl_stream_t stream) {
+  RL_CHECK_ARG(bias, "conv2d_s1_u8in: bias required");
+  RL_CHECK_ARG(Cout == 32 && KH == 2 && KW == 2, "conv2d_s1_u8in: built for the 2x2, 64 -> 32 layer (conv1, space-to-depth)");
+  RL_CHECK_ARG(out_mode == 0 || (out_mode == 1 && H - KH + 1 == 20 && W - KW + 1 == 20),
+               "conv2d_s1_u8in: out_mode 1 is the 20x20 -> [12,12,4*Cout] layout");
+  return shiftconv_launch(in_u8, weight_krsc, bias, out, N, H, W, 64, Cout, KH, KW, relu, out_mode, H - KH + 1,
+                          W - KW + 1, H - KH + 1, W - KW + 1, 0, nullptr, stream, "conv2d_s1_u8in", 1, in_scale);
 }
 
 extern "C" int rl_conv2d_s1_nhwc_bf16_dgrad(const void* dout_grid, const void* weight_t_krsc, const void* act_mask,

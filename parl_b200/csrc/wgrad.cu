@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "tma.cuh"
+#include "u8win.cuh"
 
 namespace rl {
 
@@ -63,6 +64,9 @@ __device__ __forceinline__ void w_tmem_ld16(uint32_t taddr, float (&v)[16]) {
 //     128-byte row per K index, 8 rows per 1024-byte swizzle atom (SBO = 1024 B between K-groups of 8); LBO unused.
 //   MN-major SWIZZLE_64B  (((4,n),(8,k)):((1,LBO),(4,SBO)), layout_type 4): 32 MN-elements = one 64-byte row per
 //     K index, 8 rows per 512-byte atom.
+__device__ __forceinline__ void w_mbar_arrive(void* mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(mbar)) : "memory");
+}
 constexpr uint32_t kWgLoLbo1 = 1u << 16;
 constexpr uint32_t kWgHiSw128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
 constexpr uint32_t kWgHiSw64 = (uint32_t)(512 >> 4) | (1u << 14) | (4u << 29);
@@ -347,18 +351,23 @@ struct WgradPairArgs {
   int wrows, num_tiles, stages;
   int npairs, ncols;                  // ncols = npairs * CBLK * COUT (+ 2 * COUT bias-gradient columns)
   int bias;                           // 1: also accumulate the column sums of dout (bias gradient) in TMEM
+  float in_scale;                     // U8X: input operand = bf16(byte * in_scale)
 };
 
-template <int COUT, int CBLK>
+// U8X (conv1 on the uint8 observation): map_x is the uint8 [Q][64] matrix; the producer fills a dense staging ring
+// and the four dump warps (idle until the last tile) convert each window into the bf16 SWIZZLE_128B slot (u8win.cuh).
+template <int COUT, int CBLK, bool U8X = false>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_pair_kernel(const __grid_constant__ CUtensorMap map_dout,
                                                                    const __grid_constant__ CUtensorMap map_x,
                                                                    const WgradPairArgs g) {
+  static_assert(!U8X || CBLK == 1, "the uint8 window is one 64-channel block");
   constexpr int DOUT_BYTES = kWgBM * COUT * 2;                        // 16 KB (SW128) or 8 KB (SW64)
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int win_bytes = (g.wrows * 128 + 1023) & ~1023;
   const int stage_bytes = CBLK * win_bytes + DOUT_BYTES;              // windows first (1024-byte aligned), then dout
   __shared__ __align__(8) unsigned long long full_bar[kWgMaxStages], empty_bar[kWgMaxStages], done_bar;
+  __shared__ __align__(8) unsigned long long u8_full[kU8Stages], u8_empty[kU8Stages];
   __shared__ uint32_t tmem_base_smem;
   const uint32_t nstages = (uint32_t)g.stages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -368,8 +377,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_pair_kernel(const __grid_
     tma_prefetch_desc(&map_dout);
     tma_prefetch_desc(&map_x);
     for (int s = 0; s < kWgMaxStages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], U8X ? 1 + kU8Threads : 1);   // U8X: the dout TMA + every converter thread
       mbar_init(&empty_bar[s], 2);          // both issuers commit
+    }
+    for (int s = 0; s < kU8Stages; ++s) {
+      mbar_init(&u8_full[s], 1);
+      mbar_init(&u8_empty[s], kU8Threads);
     }
     mbar_init(&done_bar, 2);
     fence_mbar_init();
@@ -377,6 +390,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_pair_kernel(const __grid_
   if (warp == 1) w_tmem_alloc(&tmem_base_smem, tmem_cols);
   // constant A operand of the bias-gradient instruction: 16 K-rows x 64 bf16 ones, after the stage ring
   unsigned char* s_ones = smem + nstages * stage_bytes;
+  unsigned char* sStage = s_ones + 2048;                              // U8X: [kU8Stages][wrows][64 B]
   if (g.bias) {
     for (int i = threadIdx.x; i < 512; i += kWgThreads) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3F803F80u;
     fence_proxy_async_smem();               // generic-proxy stores -> visible to the tensor core's async proxy
@@ -388,13 +402,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_pair_kernel(const __grid_
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t s = 0, par = 1;
+      uint32_t s = 0, par = 1, ss = 0, spar = 1;
+      const int sbytes = u8_stage_bytes(g.wrows);
       for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        if (U8X) {
+          mbar_wait(&u8_empty[ss], spar);
+          mbar_arrive_expect_tx(&u8_full[ss], (uint32_t)(g.wrows * 64));
+          tma_load_2d(sStage + ss * sbytes, &map_x, 0, tile * kWgBM, &u8_full[ss]);
+          if (++ss == kU8Stages) ss = 0, spar ^= 1u;
+        }
         mbar_wait(&empty_bar[s], par);
-        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(DOUT_BYTES + CBLK * g.wrows * 128));
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(DOUT_BYTES + (U8X ? 0 : CBLK * g.wrows * 128)));
         unsigned char* st = smem + s * stage_bytes;
+        if (!U8X) {
 #pragma unroll
-        for (int cb = 0; cb < CBLK; ++cb) tma_load_2d(st + cb * win_bytes, &map_x, cb * 64, tile * kWgBM, &full_bar[s]);
+          for (int cb = 0; cb < CBLK; ++cb) tma_load_2d(st + cb * win_bytes, &map_x, cb * 64, tile * kWgBM, &full_bar[s]);
+        }
         tma_load_2d(st + CBLK * win_bytes, &map_dout, 0, tile * kWgBM, &full_bar[s]);
         if (++s == nstages) s = 0, par ^= 1u;
       }
@@ -456,6 +479,24 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_pair_kernel(const __grid_
   } else if (warp < 6) {
     // ===== dump the TMEM accumulators once: [128 lanes][ncols] =====
     const int qd = warp & 3;
+    if (U8X) {
+      // uint8 -> bf16 window converters (these warps have nothing else to do until the accumulators are final)
+      const int ct = threadIdx.x - 64;
+      const int sbytes = u8_stage_bytes(g.wrows);
+      const float cbias = -8388608.0f * g.in_scale;
+      uint32_t s = 0, epar = 1, ss = 0, fpar = 0;
+      for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        mbar_wait(&u8_full[ss], fpar);
+        mbar_wait(&empty_bar[s], epar);            // the MMAs that read this slot have completed
+        w_fence_after();
+        u8_window_to_bf16_sw128(sStage + ss * sbytes, smem + s * stage_bytes, g.wrows, ct, g.in_scale, cbias);
+        fence_proxy_async_smem();
+        w_mbar_arrive(&full_bar[s]);
+        w_mbar_arrive(&u8_empty[ss]);
+        if (++s == nstages) s = 0, epar ^= 1u;
+        if (++ss == kU8Stages) ss = 0, fpar ^= 1u;
+      }
+    }
     mbar_wait(&done_bar, 0);
     w_fence_after();
     float* dst = g.partials + ((size_t)blockIdx.x * 128 + qd * 32 + lane) * g.ncols;
@@ -601,9 +642,9 @@ static int wgrad_legacy_bias(const void* dout_grid, long long Q, int Cout, float
   return rl_colsum_bf16(dout_grid, Q, Cout, db, workspace, workspace_bytes, stream);
 }
 
-extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* in, float* dw_krsc, float* db, int N,
-                                            int H, int W, int Cin, int Cout, int KH, int KW, int accumulate,
-                                            void* workspace, size_t workspace_bytes, rl_stream_t stream) {
+static int wgrad_dispatch(const void* dout_grid, const void* in, float* dw_krsc, float* db, int N, int H, int W, int Cin,
+                          int Cout, int KH, int KW, int accumulate, void* workspace, size_t workspace_bytes,
+                          rl_stream_t stream, int u8in, float in_scale) {
   RL_CHECK_ARG(dout_grid && in && dw_krsc && workspace && N > 0, "conv2d_s1_wgrad: bad argument");
   RL_CHECK_ARG(aligned16(dout_grid) && aligned16(in) && aligned16(workspace), "conv2d_s1_wgrad: alignment");
   RL_CHECK_ARG((Cout == 64 && (Cin == 64 || Cin == 128)) || (Cout == 32 && Cin == 64),
@@ -618,12 +659,12 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
   RL_CHECK_ARG(g.wrows <= 256, "conv2d_s1_wgrad: window too tall");
   g.num_tiles = (int)((Q + kWgBM - 1) / kWgBM);
   const int npairs = (ntaps + 1) / 2;
-  if (!(g_wg_lane_map & 2) && npairs * cblk <= 2 * kWgSlotsPerIssuer && npairs * cblk * Cout <= 512) {
+  if (u8in || (!(g_wg_lane_map & 2) && npairs * cblk <= 2 * kWgSlotsPerIssuer && npairs * cblk * Cout <= 512)) {
     // ---- paired-tap form (default) ----
     WgradPairArgs a;
     a.partials = reinterpret_cast<float*>(workspace);
     a.W = W, a.KW = KW, a.ntaps = ntaps, a.wrows = g.wrows + 1;       // + the dummy partner row of an odd last tap
-    a.num_tiles = g.num_tiles, a.npairs = npairs, a.bias = db ? 1 : 0;
+    a.num_tiles = g.num_tiles, a.npairs = npairs, a.bias = db ? 1 : 0, a.in_scale = in_scale;
     a.ncols = npairs * cblk * Cout + (db ? 2 * Cout : 0);            // + one bias accumulator per issuer
     RL_CHECK_ARG(a.ncols <= 512, "conv2d_s1_wgrad: accumulators exceed the 512 TMEM columns");
     RL_CHECK_ARG(a.wrows <= 256, "conv2d_s1_wgrad: window too tall");
@@ -639,17 +680,23 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
     alignas(64) CUtensorMap mdp, mxp;
     if (wg_make_map(&mdp, dout_grid, (uint64_t)Cout, (uint64_t)Q, kWgBM, (uint32_t)Cout,
                     Cout == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B) ||
-        wg_make_map(&mxp, in, (uint64_t)Cin, (uint64_t)Q, (uint32_t)a.wrows)) {
+        (u8in ? make_tensor_map_u8_rows64(&mxp, in, (uint64_t)Q, (uint32_t)a.wrows)
+              : wg_make_map(&mxp, in, (uint64_t)Cin, (uint64_t)Q, (uint32_t)a.wrows))) {
       set_error("conv2d_s1_wgrad: cuTensorMapEncodeTiled failed");
       return RL_ERR_CUDA;
     }
     const size_t winp = (size_t)((a.wrows * 128 + 1023) & ~1023);
     const size_t stagep = (size_t)cblk * winp + (size_t)kWgBM * Cout * 2;
-    long long nstp = (long long)((216 * 1024) / stagep);
+    const size_t u8ring = u8in ? (size_t)kU8Stages * (size_t)((a.wrows * 64 + 1023) & ~1023) : 0;
+    long long nstp = (long long)((216 * 1024 - u8ring) / stagep);
     a.stages = (int)(nstp > kWgMaxStages ? kWgMaxStages : (nstp < 2 ? 2 : nstp));
-    const size_t smemp = (size_t)a.stages * stagep + 2048 + 1024;      // + the 2 KB tile of ones
+    const size_t smemp = (size_t)a.stages * stagep + 2048 + 1024 + u8ring;   // + the 2 KB tile of ones (+ uint8 staging)
     cudaStream_t stp = (cudaStream_t)stream;
-    if (Cout == 64 && cblk == 1) {
+    if (u8in) {
+      auto kern = wgrad_pair_kernel<32, 1, true>;
+      RL_SMEM_OPTIN(kern);
+      kern<<<gridp, kWgThreads, smemp, stp>>>(mdp, mxp, a);
+    } else if (Cout == 64 && cblk == 1) {
       RL_SMEM_OPTIN(wgrad_pair_kernel<64, 1>);
       wgrad_pair_kernel<64, 1><<<gridp, kWgThreads, smemp, stp>>>(mdp, mxp, a);
     } else if (Cout == 64) {
@@ -735,6 +782,21 @@ extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* i
                                                            g.ncols_max, g_wg_lane_map & 1, dw_krsc, accumulate);
   RL_CHECK_LAUNCH("rl_conv2d_s1_nhwc_bf16_wgrad");
   return wgrad_legacy_bias(dout_grid, Q, Cout, db, accumulate, workspace, workspace_bytes, stream);
+}
+
+extern "C" int rl_conv2d_s1_nhwc_bf16_wgrad(const void* dout_grid, const void* in, float* dw_krsc, float* db, int N,
+                                            int H, int W, int Cin, int Cout, int KH, int KW, int accumulate,
+                                            void* workspace, size_t workspace_bytes, rl_stream_t stream) {
+  return wgrad_dispatch(dout_grid, in, dw_krsc, db, N, H, W, Cin, Cout, KH, KW, accumulate, workspace, workspace_bytes,
+                        stream, 0, 1.f);
+}
+
+extern "C" int rl_conv2d_s1_u8in_bf16_wgrad(const void* dout_grid, const void* in_u8, float in_scale, float* dw_krsc,
+                                            float* db, int N, int H, int W, int Cout, int KH, int KW, int accumulate,
+                                            void* workspace, size_t workspace_bytes, rl_stream_t stream) {
+  RL_CHECK_ARG(Cout == 32 && KH == 2 && KW == 2, "conv2d_s1_u8in_wgrad: built for the 2x2, 64 -> 32 layer (conv1, space-to-depth)");
+  return wgrad_dispatch(dout_grid, in_u8, dw_krsc, db, N, H, W, 64, Cout, KH, KW, accumulate, workspace, workspace_bytes,
+                        stream, 1, in_scale);
 }
 
 extern "C" int rl_colsum_bf16(const void* x, long long rows, int C, float* out, void* workspace, size_t workspace_bytes,

@@ -74,7 +74,9 @@ def test_two_gpu_impala_replicas_match_single_gpu_global_batch():
     eng, grads = _run_engine(dev, B_TOTAL, 0, 2, None)
     g2, g1 = res[0][2][0].to(dev), grads[0]
     rel = ((g2 - g1).norm() / g1.norm()).item()
-    assert rel < 1e-3, rel                                 # first update: identical weights -> same global gradient
+    # first update: identical weights -> same global gradient, up to the bf16 rounding of each rank's partial fc/head
+    # weight gradient (the bf16 GEMM output is rounded per shard before the fp32 all-reduce: ~2^-9 per element)
+    assert rel < 4e-3, rel
     # after two Adam updates the weights agree except where a ~0 gradient flipped sign at rounding level (each such
     # element moves by up to 2 lr = 2e-3): the bulk must agree tightly, the outliers must stay rare and bounded
     w1 = eng.alg.optimizer.flat.detach().cpu()
