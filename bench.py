@@ -357,7 +357,7 @@ def main():
                                 eng.train_net is not None else 'torch',
                                 l2_policy='per-step working set (frame ring %.1f GB + observation plane %.1f GB + '
                                           'activations %.1f GB per GPU) >> 126 MB L2; K1 timed alone with L2 flushed' %
-                                          ((T_STEPS + 4) * B * 7056 / 1e9, T_STEPS * B * 56448 / 1e9,
+                                          ((T_STEPS + 4) * B * 7056 / 1e9, T_STEPS * B * 28224 * eng.obs_step.element_size() / 1e9,
                                            T_STEPS * B * 120e3 / 1e9)),
                     gpu_launches=launches, clocks=clocks, roofline=dom if dom is not None else roof, roofline_k1=roof,
                     roofline_network=net_roof, roofline_step=step_roof,
@@ -369,9 +369,15 @@ def main():
         dist.destroy_process_group()
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per sample of conv1 forward from the committed ncu captures:
+# bf16 input (profiles/r01_learner_kernels_final.txt: 2.948 GB + 1.282 GB at 51 200 samples); uint8 input
+# (profiles/r02_conv1_u8_ncu.txt: 1.445 GB + 1.270 GB)
+CONV1_NCU_TRAFFIC_PER_SAMPLE = {False: (2.947656e9 + 1.281806e9) / 51200.0, True: (1.445169e9 + 1.269890e9) / 51200.0}
+
+
 def measure_dominant_kernel(eng, kernels, torch, B, peak, peak_src):
     """Roofline entry of the step's dominant kernel, shiftconv_fwd_kernel<32,1,2,0> (conv1 forward): algorithmic bytes
-    per launch = samples x (21*21*64*2 B of space-to-depth input read + 20*20*32*2 B of outputs written)."""
+    per launch = samples x (4*84*84 B of uint8 observation read + 20*20*32*2 B of outputs written)."""
     net = eng.train_net
     if net is None:
         return None
@@ -388,20 +394,24 @@ def measure_dominant_kernel(eng, kernels, torch, B, peak, peak_src):
     ms = sorted(x.elapsed_time(y) for x, y in spans[1:])
     sec = sum(ms) / len(ms) * 1e-3
     # algorithmic bytes per sample as SURVEY.md 8(d) counts them: the stacked uint8 observation (4 x 84 x 84 = 28 224 B)
-    # read + the bf16 feature map written (20 x 20 x 32 x 2 = 25 600 B).  The kernel as built reads the observation as a
-    # bf16 space-to-depth plane (56 448 B per sample): that inflation is WASTE and is reported as traffic, not credited.
+    # read + the bf16 feature map written (20 x 20 x 32 x 2 = 25 600 B).  As built the kernel reads the uint8
+    # space-to-depth plane (21 x 21 x 64 = 28 224 B per sample, widened to bf16 in shared memory) and writes conv2's
+    # zero-padded 2x2-block input (12 x 12 x 128 x 2 = 36 864 B, of which 25 600 B are written, the border stays zero).
+    u8 = x0.dtype == torch.uint8
+    in_bytes = 21 * 21 * 64 * (1 if u8 else 2)
     alg_bytes = n * (4 * 84 * 84 + 20 * 20 * 32 * 2)
     ach = alg_bytes / sec / 1e9
     # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel in the committed `ncu --set full` capture
-    # (profiles/r01_learner_kernels_final.txt: 2.948 GB + 1.282 GB at 51 200 samples), scaled to this launch's samples
-    traffic = (2.947656e9 + 1.281806e9) * n / 51200.0
-    return dict(bound='hbm', kernel='shiftconv_fwd_kernel<32,1,2,0> (rl_conv2d_s1_nhwc_bf16_fwd, conv1 forward at the '
-                                    'learner batch): largest share of the step (15 % of kernel time)',
+    # (CONV1_NCU_TRAFFIC: bytes per sample), scaled to this launch's samples
+    traffic = CONV1_NCU_TRAFFIC_PER_SAMPLE[u8] * n if CONV1_NCU_TRAFFIC_PER_SAMPLE[u8] else None
+    name = 'shiftconv_fwd_kernel<32,1,2,0,%s> (%s, conv1 forward at the learner batch)' % (
+        'true' if u8 else 'false', 'rl_conv2d_s1_u8in_bf16_fwd' if u8 else 'rl_conv2d_s1_nhwc_bf16_fwd')
+    return dict(bound='hbm', kernel=name,
                 achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=traffic, peak_source=peak_src,
                 algorithmic_bytes_per_launch=alg_bytes, us_per_launch=sec * 1e6, samples_per_launch=n,
-                bytes_moved_per_launch_as_built=n * (21 * 21 * 64 * 2 + 20 * 20 * 32 * 2),
-                frac_of_peak_as_built=n * (21 * 21 * 64 * 2 + 20 * 20 * 32 * 2) / sec / 1e9 / peak,
-                l2='operands (11.6 GB + 7.5 GB at 204 800 samples) far beyond the 126 MB L2')
+                bytes_moved_per_launch_as_built=n * (in_bytes + 20 * 20 * 32 * 2),
+                frac_of_peak_as_built=n * (in_bytes + 20 * 20 * 32 * 2) / sec / 1e9 / peak,
+                l2='operands (%.1f GB + 7.5 GB at 204 800 samples) far beyond the 126 MB L2' % (204800 * in_bytes / 1e9))
 
 
 def numa_pin(gpu_index):

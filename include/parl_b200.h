@@ -344,6 +344,10 @@ int rl_conv2d_s1_nhwc_bf16_fwd(const void* in, const void* weight_krsc, const fl
                                int N, int H, int W, int Cin, int Cout, int KH, int KW, int relu, int out_mode,
                                rl_stream_t stream);
 int rl_debug_set_shiftconv_base_offset(int enable);
+/* 0 (default): one MMA group per filter tap; 1: column-tap-fused tile (the KW taps of a filter row share one
+ * A-operand read, N' = KW*Cout accumulator columns, shifted sum in the epilogue) — measured slower on B200, kept as
+ * an experiment and cross-check. */
+int rl_debug_set_shiftconv_form(int form);
 /* The same forward for conv1 of the Atari models on the uint8 observation: in_u8 [N,H,W,64] uint8 (space-to-depth,
  * rl_obs_stack_gather out_dtype 4); operand = bf16(byte * in_scale), converted in shared memory by four extra warps,
  * bit-identical to feeding rl_conv2d_s1_nhwc_bf16_fwd the out_dtype-3 tensor at half the input traffic.

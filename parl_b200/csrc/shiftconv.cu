@@ -257,6 +257,13 @@ __global__ void __launch_bounds__(U8IN ? kScThreads + kU8Threads : kScThreads, 1
     const int qd = warp & 3;                        // TMEM lane quarter this warp may read
     const int grp = (warp - 2) >> 2;                // epilogue group: tiles it = grp, grp + 2, ...
     const int HW = g.H * g.W;
+    // the bias lives in registers: a broadcast LDS per 4 channels per tile would cost shared-memory wavefronts on
+    // the pipe that already limits these kernels (tensor-core operand reads + TMEM reads, ncu round 2)
+    float bias_r[MODE == 0 ? COUT : 1];
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < COUT; ++i) bias_r[i] = s_bias[i];
+    }
     for (uint32_t it = (uint32_t)grp; blockIdx.x + (long long)it * gridDim.x < g.num_tiles; it += kScEpiGroups) {
       const int tile = blockIdx.x + (int)it * gridDim.x;
       const uint32_t buf = it % kScAcc;
@@ -302,10 +309,7 @@ __global__ void __launch_bounds__(U8IN ? kScThreads + kU8Threads : kScThreads, 1
           uint32_t pk[8];
           if (MODE == 0) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * i]);      // broadcast LDS.128
-              v[4 * i] += b4.x, v[4 * i + 1] += b4.y, v[4 * i + 2] += b4.z, v[4 * i + 3] += b4.w;
-            }
+            for (int i = 0; i < 16; ++i) v[i] += bias_r[c0 + i];
             if (relu) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) pk[i] = s_pack_relu_bf16x2(v[2 * i], v[2 * i + 1]);
@@ -332,6 +336,316 @@ __global__ void __launch_bounds__(U8IN ? kScThreads + kU8Threads : kScThreads, 1
       }
       s_fence_before();
       s_mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+  s_fence_before();
+  __syncthreads();
+  if (warp == 1) s_tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Column-tap-fused form (opt-in experiment, rl_debug_set_shiftconv_form(1)).  ncu on the form above
+// (profiles/r02_conv_forms.txt): these small-N layers run at ~1 shared-memory wavefront per clock per SM — the
+// shared-memory data pipe is the bound — of which two thirds are the tensor core's OPERAND reads (every tcgen05.mma
+// streams its 128-row A slice, 32 wavefronts of 128 B, for only N = 32..64 output columns, once per filter tap) and
+// one quarter the epilogue's TMEM reads (tcgen05.ld goes through the same pipe: 32 wavefronts per 32x32b.x16).
+// Here the KS taps of one filter ROW share one A read: the B tile of a (row r, channel block)
+// step stacks the weights of its KS column taps, N' = KS * COUT, so the accumulator row of window row p holds
+//     D[p, (s, co)] = sum_{r, ci} in[p + r*W, ci] * W[co, (r, s, ci)]
+// and the epilogue finishes out[p, co] = sum_s D[p + s, (s, co)]: the accumulator row of window row p + s sits in
+// TMEM lane p + s, i.e. in the NEIGHBOURING thread of the epilogue warp, so the shift is a warp shuffle; the last
+// KS-1 lanes of each warp get their neighbours' values from the next warp through a small shared-memory exchange
+// (one named barrier per tile and epilogue group), and a tile of 128 window rows yields 128-(KS-1) output rows.
+// MMAs per tile: KS*CBLK*4 instead of KS*KS*CBLK*4; A wavefronts divided by KS.
+// MEASURED (51 200 samples, B200): conv1 865 vs 686 us, conv2 758 vs 562, conv3 752 vs 416 — slower: the operand
+// wavefronts do drop (conv1 113 M -> 68 M, tensor pipe busy 85 % -> 43 %) but the accumulator is KS times wider, so
+// the TMEM reads grow by what the operand reads shrink (conv1: 45 M -> 80 M LSU-pipe wavefronts) and the epilogue's
+// instruction chain (shuffles, exchange, barrier) becomes the critical path.  Bit-exact on the integer tests.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void s_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int COUT, int KS>
+struct SfShape {
+  static constexpr int NP = KS * COUT;                          // accumulator columns (s, co)
+  static constexpr int NACC = (512 / NP) >= 4 ? 4 : 2;          // accumulators in flight
+  static constexpr int ST = kScBM - (KS - 1);                   // output rows per 128-row tile
+  static constexpr int XCH = 4 * (KS - 1) * (KS - 1) * COUT;    // [warp][shift-1][lane][co] floats handed to the previous warp
+  static constexpr int PART = 4 * (KS - 1) * COUT;              // [warp][boundary lane][co] partial sums
+  static constexpr int XCH_FLOATS = XCH + PART;                 // one exchange buffer
+  static constexpr int XCH_BYTES = kScEpiGroups * 2 * XCH_FLOATS * 4;
+};
+
+template <int COUT, int CBLK, int KS, int MODE, bool U8IN = false>
+__global__ void __launch_bounds__(U8IN ? kScThreads + kU8Threads : kScThreads, 1)
+    shiftconv_sfused_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
+                            const ShiftConvArgs g) {
+  static_assert(!U8IN || CBLK == 1, "the uint8 window is one 64-channel block");
+  using SH = SfShape<COUT, KS>;
+  constexpr int NP = SH::NP, NACC = SH::NACC, ST = SH::ST;
+  constexpr int W_KB = COUT * 128;                        // one (tap, 64-channel block) weight tile
+  constexpr int TMEM_COLS = NACC * NP <= 128 ? 128 : (NACC * NP <= 256 ? 256 : 512);
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  constexpr int num_kb = KS * KS * CBLK;
+  const int win_bytes = (g.wrows * 128 + 1023) & ~1023;
+  unsigned char* sW = smem;                               // [r][cb][s][COUT][128 B]
+  unsigned char* sWin = smem + ((num_kb * W_KB + 1023) & ~1023);
+  __shared__ __align__(8) unsigned long long full_bar[kScMaxStages], empty_bar[kScMaxStages], w_bar, tmem_full[kScAcc], tmem_empty[kScAcc];
+  __shared__ __align__(8) unsigned long long u8_full[kU8Stages], u8_empty[kU8Stages];
+  const uint32_t nstages = (uint32_t)g.stages;
+  unsigned char* sStage = sWin + nstages * CBLK * win_bytes;                       // U8IN: [kU8Stages][wrows][64 B]
+  float* sXch = reinterpret_cast<float*>(sStage + (U8IN ? kU8Stages * u8_stage_bytes(g.wrows) : 0));
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_bias[COUT];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (MODE == 0 && threadIdx.x < COUT) s_bias[threadIdx.x] = g.bias[threadIdx.x];
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_in);
+    tma_prefetch_desc(&map_w);
+    for (int s = 0; s < kScMaxStages; ++s) {
+      mbar_init(&full_bar[s], U8IN ? kU8Threads : 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kU8Stages; ++s) {
+      mbar_init(&u8_full[s], 1);
+      mbar_init(&u8_empty[s], kU8Threads);
+    }
+    mbar_init(&w_bar, 1);
+    for (int b = 0; b < kScAcc; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) s_tmem_alloc(&tmem_base_smem, TMEM_COLS);
+  s_fence_before();
+  __syncthreads();
+  s_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer: one window per tile; tiles advance by ST rows =====
+    if (lane == 0) {
+      uint32_t s = 0, par = 1;
+      if (U8IN) {
+        const int sbytes = u8_stage_bytes(g.wrows);
+        for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+          mbar_wait(&u8_empty[s], par);
+          mbar_arrive_expect_tx(&u8_full[s], (uint32_t)(g.wrows * 64));
+          tma_load_2d(sStage + s * sbytes, &map_in, 0, tile * ST + g.row_shift, &u8_full[s]);
+          if (++s == kU8Stages) s = 0, par ^= 1u;
+        }
+      } else {
+        for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+          mbar_wait(&empty_bar[s], par);
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(CBLK * g.wrows * 128));
+#pragma unroll
+          for (int cb = 0; cb < CBLK; ++cb)
+            tma_load_2d(sWin + (s * CBLK + cb) * win_bytes, &map_in, cb * 64, tile * ST + g.row_shift, &full_bar[s]);
+          if (++s == nstages) s = 0, par ^= 1u;
+        }
+      }
+    }
+  } else if (U8IN && warp > kScIssuer2) {
+    // ===== uint8 -> bf16 window converters =====
+    const int ct = threadIdx.x - kScThreads;
+    const int sbytes = u8_stage_bytes(g.wrows);
+    const float bias = -8388608.0f * g.in_scale;
+    uint32_t s = 0, epar = 1, ss = 0, fpar = 0;
+    for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      mbar_wait(&u8_full[ss], fpar);
+      mbar_wait(&empty_bar[s], epar);              // the MMAs that read this window slot have completed
+      s_fence_after();
+      u8_window_to_bf16_sw128(sStage + ss * sbytes, sWin + s * win_bytes, g.wrows, ct, g.in_scale, bias);
+      fence_proxy_async_smem();                    // generic-proxy stores -> visible to the tensor core's async proxy
+      s_mbar_arrive(&full_bar[s]);
+      s_mbar_arrive(&u8_empty[ss]);
+      if (++s == nstages) s = 0, epar ^= 1u;
+      if (++ss == kU8Stages) ss = 0, fpar ^= 1u;
+    }
+  } else if (warp == 1 || warp == kScIssuer2) {
+    // ===== resident weights + MMA issue (issuer 0: even tiles of this CTA, issuer 1: odd tiles) =====
+    if (lane == 0) {
+      const uint32_t issuer = warp == 1 ? 0u : 1u;
+      if (issuer == 0) {
+        mbar_arrive_expect_tx(&w_bar, (uint32_t)(num_kb * W_KB));
+        // slot ((r * CBLK + cb) * KS + s) <- columns of tap (r, s), channel block cb of the [Cout, (r,s,ci)] matrix
+        for (int r = 0; r < KS; ++r)
+          for (int cb = 0; cb < CBLK; ++cb)
+            for (int sx = 0; sx < KS; ++sx)
+              tma_load_2d(sW + ((r * CBLK + cb) * KS + sx) * W_KB, &map_w, ((r * KS + sx) * CBLK + cb) * 64, 0, &w_bar);
+      }
+      mbar_wait(&w_bar, 0);
+      constexpr uint32_t idesc = s_idesc_bf16(kScBM, NP);
+      uint32_t row_off[KS];                            // window-row shift of filter row r, 16-byte units
+#pragma unroll
+      for (int r = 0; r < KS; ++r) row_off[r] = (uint32_t)((g.flip ? KS - 1 - r : r) * g.W) * 8u;
+      const uint32_t w_lo = (smem_u32(sW) >> 4) + kDescLoLbo1, win_lo0 = (smem_u32(sWin) >> 4) + kDescLoLbo1;
+      const uint32_t win16 = (uint32_t)win_bytes >> 4;
+      uint32_t s = issuer, buf = issuer % NACC, full_par = 0, empty_par = 1;
+      for (long long tile = blockIdx.x + (long long)issuer * gridDim.x; tile < g.num_tiles; tile += 2 * gridDim.x) {
+        mbar_wait(&tmem_empty[buf], empty_par);
+        mbar_wait(&full_bar[s], full_par);
+        s_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * NP;
+        const uint32_t a_lo = win_lo0 + s * (CBLK * win16);
+#pragma unroll
+        for (int r = 0; r < KS; ++r) {
+#pragma unroll
+          for (int cb = 0; cb < CBLK; ++cb) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              s_umma(d_tmem, s_desc_from_lo(a_lo + cb * win16 + row_off[r] + 2u * k),
+                     s_desc_from_lo(w_lo + (uint32_t)((r * CBLK + cb) * KS * (W_KB >> 4) + 2 * k)), idesc,
+                     (r | cb | k) != 0 ? 1u : 0u);
+          }
+        }
+        s_commit(&empty_bar[s]);
+        s_commit(&tmem_full[buf]);
+        s += 2;
+        if (s >= nstages) s -= nstages, full_par ^= 1u;
+        buf += 2;
+        if (buf >= (uint32_t)NACC) buf -= NACC, empty_par ^= 1u;
+      }
+    }
+  } else {
+    // ===== epilogue (warps 2 .. 2 + 4 * kScEpiGroups - 1) =====
+    const int qd = warp & 3;                        // TMEM lane quarter this warp may read
+    const int grp = (warp - 2) >> 2;                // epilogue group: tiles it = grp, grp + 2, ...
+    const int HW = g.H * g.W;
+    constexpr int BL0 = 32 - (KS - 1);              // first lane whose column taps reach into the next warp
+    const bool bnd = lane >= BL0;
+    const bool has_mask = MODE == 1 && g.mask != nullptr;
+    const bool relu = g.relu != 0;
+    for (uint32_t it = (uint32_t)grp; blockIdx.x + (long long)it * gridDim.x < g.num_tiles; it += kScEpiGroups) {
+      const int tile = blockIdx.x + (int)it * gridDim.x;
+      const uint32_t buf = it % NACC;
+      const int row = qd * 32 + lane;
+      const int q = tile * ST + row;
+      const bool inrange = row < ST && q < g.Q;
+      uint4 mk[COUT / 8];
+      if (has_mask && inrange) {
+        const uint4* mp = reinterpret_cast<const uint4*>(g.mask + (size_t)q * COUT);
+#pragma unroll
+        for (int i = 0; i < COUT / 8; ++i) mk[i] = __ldg(mp + i);
+      }
+      const int n = q / HW;
+      const int rem = q - n * HW;
+      const int y = rem / g.W, x = rem - y * g.W;
+      const bool valid = inrange && y < g.Hout && x < g.Wout;
+      size_t obase = 0;
+      if (g.out_mode == 0) {
+        obase = ((size_t)(n * g.OGH + y) * g.OGW + x) * COUT;
+      } else if (g.out_mode == 1) {
+        const int yp = y + 2, xp = x + 2;
+        obase = (((size_t)n * 12 + (yp >> 1)) * 12 + (xp >> 1)) * (4 * COUT) + (size_t)(((yp & 1) * 2 + (xp & 1)) * COUT);
+      }
+      // bias / activation / mask, bf16 pack and the layout-aware store of 16 channels of this thread's output row
+      auto emit = [&](int c0, float (&v)[16]) {
+        bool ok = valid;
+        size_t dst_off = obase + c0;
+        if (g.out_mode == 2) {
+          const int blk = c0 >> 5, py = 2 * y + (blk >> 1) - 2, px = 2 * x + (blk & 1) - 2;
+          ok = inrange && py >= 0 && py < 20 && px >= 0 && px < 20;
+          dst_off = (((size_t)n * 21 + py) * 21 + px) * 32 + (c0 & 31);
+        }
+        if (!ok) return;
+        uint32_t pk[8];
+        if (MODE == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[c0 + 4 * i]);
+            v[4 * i] += b4.x, v[4 * i + 1] += b4.y, v[4 * i + 2] += b4.z, v[4 * i + 3] += b4.w;
+          }
+          if (relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[i] = s_pack_relu_bf16x2(v[2 * i], v[2 * i + 1]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[i] = s_pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pk[i] = s_pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          if (has_mask) {
+            const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 m4 = mk[c0 / 8 + (i >> 2)];
+              const uint32_t mw = (i & 3) == 0 ? m4.x : ((i & 3) == 1 ? m4.y : ((i & 3) == 2 ? m4.z : m4.w));
+              pk[i] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&mw), zero2);
+            }
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(g.out + dst_off);
+        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      };
+      float* xb = sXch + (grp * 2 + (int)((it >> 1) & 1u)) * SH::XCH_FLOATS;     // exchange buffer of this tile
+      float* part = xb + SH::XCH;
+      mbar_wait(&tmem_full[buf], (it / NACC) & 1u);
+      s_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + buf * NP;
+#pragma unroll
+      for (int c0 = 0; c0 < COUT; c0 += 16) {
+        float v[16];
+        // the column tap whose window shift is 0: s = 0 (forward) or KS-1 (transposed)
+        s_tmem_ld16(taddr + (uint32_t)((g.flip ? KS - 1 : 0) * COUT + c0), v);
+#pragma unroll
+        for (int sh = 1; sh < KS; ++sh) {
+          float u[16];
+          s_tmem_ld16(taddr + (uint32_t)((g.flip ? KS - 1 - sh : sh) * COUT + c0), u);
+          if (qd > 0 && lane < sh) {                 // rows the previous warp's last lanes need
+            float4* d = reinterpret_cast<float4*>(xb + ((qd * (KS - 1) + (sh - 1)) * (KS - 1) + lane) * COUT + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] = make_float4(u[4 * i], u[4 * i + 1], u[4 * i + 2], u[4 * i + 3]);
+          }
+          const bool have = lane + sh < 32;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float t = __shfl_down_sync(0xffffffffu, u[i], sh);
+            v[i] += have ? t : 0.f;
+          }
+        }
+        if (!bnd) {
+          emit(c0, v);
+        } else {
+          float4* d = reinterpret_cast<float4*>(part + (qd * (KS - 1) + (lane - BL0)) * COUT + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+      }
+      s_fence_before();
+      s_mbar_arrive(&tmem_empty[buf]);               // the accumulator is free: the rest works from shared memory
+      s_bar_sync(1 + grp, 128);
+      if (bnd && qd < 3) {                           // qd == 3: rows >= ST, no output
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 16) {
+          float v[16];
+          const float4* pp = reinterpret_cast<const float4*>(part + (qd * (KS - 1) + (lane - BL0)) * COUT + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 t = pp[i];
+            v[4 * i] = t.x, v[4 * i + 1] = t.y, v[4 * i + 2] = t.z, v[4 * i + 3] = t.w;
+          }
+#pragma unroll
+          for (int sh = 1; sh < KS; ++sh) {
+            if (lane + sh >= 32) {
+              const float4* xp = reinterpret_cast<const float4*>(
+                  xb + (((qd + 1) * (KS - 1) + (sh - 1)) * (KS - 1) + (lane + sh - 32)) * COUT + c0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 t = xp[i];
+                v[4 * i] += t.x, v[4 * i + 1] += t.y, v[4 * i + 2] += t.z, v[4 * i + 3] += t.w;
+              }
+            }
+          }
+          emit(c0, v);
+        }
+      }
     }
   }
   s_fence_before();
@@ -375,9 +689,31 @@ static void launch_shiftconv(const CUtensorMap& mi, const CUtensorMap& mw, const
   kern<<<grid, U8IN ? kScThreads + kU8Threads : kScThreads, smem, st>>>(mi, mw, g);
 }
 
+template <int COUT, int CBLK, int KS, int MODE, bool U8IN = false>
+static void launch_sfused(const CUtensorMap& mi, const CUtensorMap& mw, const ShiftConvArgs& g, int num_kb, int sms,
+                          cudaStream_t st) {
+  const size_t win = (size_t)((g.wrows * 128 + 1023) & ~1023);
+  const size_t smem = (size_t)((num_kb * COUT * 128 + 1023) & ~1023) + (size_t)g.stages * CBLK * win + 1024 +
+                      (U8IN ? u8_ring_bytes(g.wrows) : 0) + SfShape<COUT, KS>::XCH_BYTES;
+  auto kern = shiftconv_sfused_kernel<COUT, CBLK, KS, MODE, U8IN>;
+  RL_SMEM_OPTIN(kern);
+  const int grid = g.num_tiles < sms ? g.num_tiles : sms;
+  kern<<<grid, U8IN ? kScThreads + kU8Threads : kScThreads, smem, st>>>(mi, mw, g);
+}
+
 }  // namespace rl
 
 using namespace rl;
+
+// 0 (default): one tcgen05.mma group per filter tap (shiftconv_fwd_kernel); 1: column-tap-fused form
+// (shiftconv_sfused_kernel) — measured SLOWER on B200 (see its header), kept as the documented experiment and as
+// an independent cross-check of the tap/shift bookkeeping.
+static int g_sc_form = 0;
+extern "C" int rl_debug_set_shiftconv_form(int form) {
+  RL_CHECK_ARG(form == 0 || form == 1, "shiftconv form must be 0 (per-tap) or 1 (column taps fused)");
+  g_sc_form = form;
+  return RL_OK;
+}
 
 // Former triage hook.  Measured on B200 (round 1): the tensor core swizzles on ABSOLUTE shared-memory address
 // bits, so a descriptor that starts at an arbitrary 128-byte row of a 1024-byte aligned swizzled buffer needs NO
@@ -403,15 +739,19 @@ static int shiftconv_launch(const void* in, const void* weight, const float* bia
   g.Hout = Hout, g.Wout = Wout, g.OGH = OGH, g.OGW = OGW;
   const long long Q = (long long)N * H * W;
   RL_CHECK_ARG(Q < (1LL << 31), "%s: too many positions", name);
-  g.Q = (int)Q, g.wrows = kScBM + (KH - 1) * W + (KW - 1), g.relu = relu, g.out_mode = out_mode;
+  const int fused = g_sc_form && KW * Cout <= 256;                    // N' = KW * Cout accumulator columns per tile
+  const int tile_rows = fused ? kScBM - (KW - 1) : kScBM;             // output rows per 128-row tile
+  g.Q = (int)Q, g.wrows = kScBM + (KH - 1) * W + (fused ? 0 : KW - 1), g.relu = relu, g.out_mode = out_mode;
   g.row_shift = transposed ? -((KH - 1) * W + (KW - 1)) : 0, g.flip = transposed;
   g.mask = (const __nv_bfloat16*)mask, g.in_scale = in_scale;
   RL_CHECK_ARG(g.wrows <= 256, "%s: window of %d rows exceeds the TMA box limit", name, g.wrows);
-  g.num_tiles = (int)((Q + kScBM - 1) / kScBM);
+  g.num_tiles = (int)((Q + tile_rows - 1) / tile_rows);
   const int cblk = Cin / 64, num_kb = KH * KW * cblk;
   const size_t win = (size_t)((g.wrows * 128 + 1023) & ~1023);
   {
-    const size_t budget = 220 * 1024 - ((size_t)num_kb * Cout * 128 + 2048) - (u8in ? u8_ring_bytes(g.wrows) : 0);
+    // exchange buffers of the fused epilogue: 2 groups x 2 buffers x 4 warps x (KW-1) lanes x KW x Cout floats
+    const size_t xch = fused ? (size_t)2 * 2 * 4 * (KW - 1) * KW * Cout * 4 : 0;
+    const size_t budget = 220 * 1024 - ((size_t)num_kb * Cout * 128 + 2048) - (u8in ? u8_ring_bytes(g.wrows) : 0) - xch;
     long long st = (long long)(budget / ((size_t)cblk * win));
     if (st > kScMaxStages) st = kScMaxStages;
     // the dgrad epilogue reads the ReLU mask through L1: leave the unified L1/shared array some cache
@@ -433,6 +773,22 @@ static int shiftconv_launch(const void* in, const void* weight, const float* bia
   cudaStream_t st = (cudaStream_t)stream;
   // instantiations: the layers of the Atari actor-critic and their data gradients (2x2 and 3x3 filters)
   const int key = (u8in ? 1000000 : 0) + (transposed ? 100000 : 0) + Cout * 100 + cblk * 10 + KH;
+  if (fused) {
+    switch (key) {
+      case 1003212: launch_sfused<32, 1, 2, 0, true>(mi, mw, g, num_kb, sms, st); break;  // conv1 fwd, uint8 input
+      case 3212: launch_sfused<32, 1, 2, 0>(mi, mw, g, num_kb, sms, st); break;          // conv1 fwd
+      case 6422: launch_sfused<64, 2, 2, 0>(mi, mw, g, num_kb, sms, st); break;          // conv2 fwd
+      case 6413: launch_sfused<64, 1, 3, 0>(mi, mw, g, num_kb, sms, st); break;          // conv3 fwd
+      case 6412: launch_sfused<64, 1, 2, 0>(mi, mw, g, num_kb, sms, st); break;
+      case 6423: launch_sfused<64, 2, 3, 0>(mi, mw, g, num_kb, sms, st); break;
+      case 106413: launch_sfused<64, 1, 3, 1>(mi, mw, g, num_kb, sms, st); break;        // conv3 dgrad
+      case 112812: launch_sfused<128, 1, 2, 1>(mi, mw, g, num_kb, sms, st); break;       // conv2 dgrad
+      case 106412: launch_sfused<64, 1, 2, 1>(mi, mw, g, num_kb, sms, st); break;
+      default:
+        set_error("%s: no instantiation for Cout=%d Cin=%d %dx%d", name, Cout, Cin, KH, KW);
+        return RL_ERR_BAD_ARG;
+    }
+  } else
   switch (key) {
     case 1003212: launch_shiftconv<32, 1, 2, 0, true>(mi, mw, g, num_kb, sms, st); break;  // conv1 fwd, uint8 input
     case 3212: launch_shiftconv<32, 1, 2, 0>(mi, mw, g, num_kb, sms, st); break;          // conv1 fwd

@@ -355,9 +355,11 @@ struct WgradPairArgs {
 };
 
 // U8X (conv1 on the uint8 observation): map_x is the uint8 [Q][64] matrix; the producer fills a dense staging ring
-// and the four dump warps (idle until the last tile) convert each window into the bf16 SWIZZLE_128B slot (u8win.cuh).
+// and eight warps — the four dump warps (idle until the last tile) plus four extra ones (7-10) — convert each window
+// into the bf16 SWIZZLE_128B slot (u8win.cuh).
+constexpr int kWgU8Threads = kWgThreads + kU8Threads - 128;
 template <int COUT, int CBLK, bool U8X = false>
-__global__ void __launch_bounds__(kWgThreads, 1) wgrad_pair_kernel(const __grid_constant__ CUtensorMap map_dout,
+__global__ void __launch_bounds__(U8X ? kWgU8Threads : kWgThreads, 1) wgrad_pair_kernel(const __grid_constant__ CUtensorMap map_dout,
                                                                    const __grid_constant__ CUtensorMap map_x,
                                                                    const WgradPairArgs g) {
   static_assert(!U8X || CBLK == 1, "the uint8 window is one 64-channel block");
@@ -476,12 +478,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_pair_kernel(const __grid_
       }
       w_commit(&done_bar);
     }
-  } else if (warp < 6) {
+  } else {
     // ===== dump the TMEM accumulators once: [128 lanes][ncols] =====
     const int qd = warp & 3;
     if (U8X) {
       // uint8 -> bf16 window converters (these warps have nothing else to do until the accumulators are final)
-      const int ct = threadIdx.x - 64;
+      const int ct = warp < 6 ? threadIdx.x - 64 : threadIdx.x - kWgThreads + 128;
       const int sbytes = u8_stage_bytes(g.wrows);
       const float cbias = -8388608.0f * g.in_scale;
       uint32_t s = 0, epar = 1, ss = 0, fpar = 0;
@@ -497,15 +499,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_pair_kernel(const __grid_
         if (++ss == kU8Stages) ss = 0, fpar ^= 1u;
       }
     }
-    mbar_wait(&done_bar, 0);
-    w_fence_after();
-    float* dst = g.partials + ((size_t)blockIdx.x * 128 + qd * 32 + lane) * g.ncols;
-    const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
-    for (int c0 = 0; c0 < g.ncols; c0 += 16) {
-      float v[16];
-      w_tmem_ld16(taddr + (uint32_t)c0, v);
+    if (warp < 6) {
+      mbar_wait(&done_bar, 0);
+      w_fence_after();
+      float* dst = g.partials + ((size_t)blockIdx.x * 128 + qd * 32 + lane) * g.ncols;
+      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
+      for (int c0 = 0; c0 < g.ncols; c0 += 16) {
+        float v[16];
+        w_tmem_ld16(taddr + (uint32_t)c0, v);
 #pragma unroll
-      for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
     }
   }
   w_fence_before();
@@ -695,7 +699,7 @@ static int wgrad_dispatch(const void* dout_grid, const void* in, float* dw_krsc,
     if (u8in) {
       auto kern = wgrad_pair_kernel<32, 1, true>;
       RL_SMEM_OPTIN(kern);
-      kern<<<gridp, kWgThreads, smemp, stp>>>(mdp, mxp, a);
+      kern<<<gridp, kWgU8Threads, smemp, stp>>>(mdp, mxp, a);
     } else if (Cout == 64 && cblk == 1) {
       RL_SMEM_OPTIN(wgrad_pair_kernel<64, 1>);
       wgrad_pair_kernel<64, 1><<<gridp, kWgThreads, smemp, stp>>>(mdp, mxp, a);

@@ -62,7 +62,8 @@ class AtariActorNet(object):
         self.bfc.copy_(m.fc.bias), self.bpi.copy_(m.fc_pi.bias), self.bv.copy_(m.fc_v.bias)
 
     def policy(self, obs_s2d, logits_out):
-        """obs_s2d [B,21,21,64] bf16 (already scaled by 1/255) -> logits_out [B,A] float32."""
+        """obs_s2d [B,21,21,64] uint8 (bytes; conv1 scales by 1/255 while widening) or bf16 (already scaled)
+        -> logits_out [B,A] float32."""
         K = kernels
         if self.window_form:
             K.conv2d_s1_nhwc_bf16_fwd(obs_s2d, self.w1, self.b1, 2, 2, relu=True, out=self.a1, out_mode=1)

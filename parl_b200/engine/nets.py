@@ -34,12 +34,14 @@ class AtariActorCritic(Model):
 
     def _trunk(self, x):
         """Accepts (a) bf16 [N,21,21,64]: conv1's space-to-depth input from rl_obs_stack_gather(s2d=True),
-        already scaled by 1/255; (b) bf16 [N,84,84,4] NHWC, already scaled; (c) uint8/float [N,4,84,84] as in
+        already scaled by 1/255, or the same layout in uint8 (unscaled bytes, scaled here); (b) bf16 [N,84,84,4] NHWC, already scaled; (c) uint8/float [N,4,84,84] as in
         the reference (scaled here by 1/255).  Activations stay NHWC (channels_last); the flatten before
         ``fc`` is taken in (H,W,C) order with the weight columns permuted accordingly, which is the same
         function as the reference's (C,H,W) nn.Flatten + nn.Linear."""
         dt = self.compute_dtype if x.is_cuda else torch.float32
         with torch.autocast(device_type=x.device.type, dtype=dt, enabled=dt != torch.float32):
+            if x.dtype == torch.uint8 and x.dim() == 4 and x.shape[-1] == 64:
+                x = (x.float() * (1.0 / 255.0)).to(torch.bfloat16)     # the rounding the u8in conv kernels apply
             if x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[-1] == 64:
                 # 8x8/4/pad-1 conv == 2x2/1 conv over 4x4 pixel blocks: W1[o,c,4a+dy,4b+dx] -> W1'[o,(dy,dx,c),a,b]
                 w1 = self.conv1.weight.view(32, 4, 2, 4, 2, 4).permute(0, 3, 5, 1, 2, 4).reshape(32, 64, 2, 2)

@@ -2,7 +2,7 @@
 no cuDNN on the convolution path.
 
 Layers (a13: benchmark/torch/a2c/atari_model.py:23-96), all stride-1 in TMA-window form after space-to-depth:
-    x0 [N,21,21,64] --conv1' 2x2--> a1 (padded 2x2-block layout [N,12,12,128]) --conv2' 2x2--> a2 [N,11,11,64]
+    x0 [N,21,21,64] bf16 pre-scaled by 1/255 (or uint8 bytes, widened inside the conv1 kernels) --conv1' 2x2--> a1 (padded 2x2-block layout [N,12,12,128]) --conv2' 2x2--> a2 [N,11,11,64]
        --conv3 3x3--> a3 [N,9,9,64] == [N,5184] --fc--> h [N,512] --heads--> logits [N,A], values [N]
 Backward (after the fused loss kernel delivered d_logits / d_values):
     heads/fc data gradients : rl_gemm_bf16_tn_masked (ReLU masks fused in the epilogue)
@@ -19,8 +19,10 @@ from .. import kernels as K
 
 
 class AtariTrainNet(object):
-    def __init__(self, model, n_samples, device, fc_backend='auto'):
+    def __init__(self, model, n_samples, device, fc_backend='auto', obs_dtype=torch.bfloat16):
         self.model = model
+        assert obs_dtype in (torch.uint8, torch.bfloat16)
+        self.obs_dtype = obs_dtype          # bfloat16: pre-scaled operand (default); uint8: conv1 reads bytes (u8in kernels)
         N = self.N = int(n_samples)
         dev = self.device = torch.device(device)
         bf, f32 = torch.bfloat16, torch.float32
@@ -59,7 +61,7 @@ class AtariTrainNet(object):
     @property
     def x0(self):
         if self._x0 is None:
-            self._x0 = torch.empty((self.N, 21, 21, 64), dtype=torch.bfloat16, device=self.device)
+            self._x0 = torch.empty((self.N, 21, 21, 64), dtype=self.obs_dtype, device=self.device)
         return self._x0
 
     @torch.no_grad()
@@ -89,7 +91,8 @@ class AtariTrainNet(object):
         return self.forward_from_x0()
 
     def forward_from_x0(self, x0=None):
-        """x0 [N,21,21,64] bf16 (default: this net's own buffer); kept by reference for conv1's weight gradient."""
+        """x0 [N,21,21,64] uint8 or pre-scaled bf16 (default: this net's own buffer); kept by reference for conv1's
+        weight gradient."""
         N = self.N
         x0 = self._x0_in = self.x0 if x0 is None else x0
         K.conv2d_s1_nhwc_bf16_fwd(x0, self.w1, self.b1, 2, 2, relu=True, out=self.a1, out_mode=1)

@@ -31,6 +31,12 @@ def add_graph_launches(n):
     _graph_launches += int(n)
 
 
+def set_shiftconv_form(form):
+    """0 (default): one MMA group per filter tap; 1: column-tap-fused TMA-window conv tiles (measured slower; kept as
+    an experiment and cross-check)."""
+    check(_lib.load().rl_debug_set_shiftconv_form(int(form)), 'debug_set_shiftconv_form')
+
+
 def set_sm_limit(max_ctas):
     """Cap the CTAs of the persistent network kernels launched from now on (0 = one per SM)."""
     check(_lib.load().rl_set_sm_limit(int(max_ctas)), 'set_sm_limit')
@@ -168,8 +174,9 @@ def obs_stack_gather(planes, ages, t_begin, t_count, out, layout=TIME_MAJOR, sca
         P, B, HW = planes.shape[0], planes.shape[1], planes[0, 0].numel()
     dt = {torch.uint8: 0, torch.float32: 1, torch.bfloat16: 2}[out.dtype]
     if s2d:
-        assert out.dtype == torch.bfloat16 and out.numel() == t_count * B * 21 * 21 * 64
-        dt = 3
+        # bfloat16: value * scale; uint8: bytes untouched (the conv1 kernels scale while widening, u8in variants)
+        assert out.dtype in (torch.bfloat16, torch.uint8) and out.numel() == t_count * B * 21 * 21 * 64
+        dt = 3 if out.dtype == torch.bfloat16 else 4
     else:
         assert out.numel() == t_count * B * 4 * HW
     check(_lib.load().rl_obs_stack_gather(ptr(planes), ptr(ages), B, HW, int(t_begin), int(t_count), layout, dt,
@@ -506,15 +513,22 @@ def conv2d_nhwc_bf16_fwd(x, weight_krsc, bias, KH, KW, stride, pad, relu=True, o
     return out
 
 
-def conv2d_s1_nhwc_bf16_fwd(x, weight_krsc, bias, KH, KW, relu=True, out=None, out_mode=0):
-    """Stride-1 NHWC bf16 conv forward in TMA-window form (rl_conv2d_s1_nhwc_bf16_fwd)."""
+def conv2d_s1_nhwc_bf16_fwd(x, weight_krsc, bias, KH, KW, relu=True, out=None, out_mode=0, in_scale=1.0 / 255.0):
+    """Stride-1 NHWC bf16 conv forward in TMA-window form (rl_conv2d_s1_nhwc_bf16_fwd); a uint8 ``x`` (conv1 on the
+    space-to-depth observation) goes to rl_conv2d_s1_u8in_bf16_fwd, operand = bf16(byte * in_scale)."""
     require_cuda(x, weight_krsc, bias)
-    assert x.dtype == torch.bfloat16 and weight_krsc.dtype == torch.bfloat16 and bias.dtype == torch.float32
+    assert x.dtype in (torch.bfloat16, torch.uint8) and weight_krsc.dtype == torch.bfloat16 and bias.dtype == torch.float32
     N, H, W, Cin = x.shape
     Cout = weight_krsc.shape[0]
     if out is None:
         assert out_mode == 0
         out = torch.empty((N, H - KH + 1, W - KW + 1, Cout), dtype=torch.bfloat16, device=x.device)
+    if x.dtype == torch.uint8:
+        assert Cin == 64
+        check(_lib.load().rl_conv2d_s1_u8in_bf16_fwd(ptr(x), float(in_scale), ptr(weight_krsc), ptr(bias), ptr(out), N, H, W,
+                                                     Cout, KH, KW, 1 if relu else 0, int(out_mode), stream()),
+              'conv2d_s1_u8in_bf16_fwd')
+        return out
     check(_lib.load().rl_conv2d_s1_nhwc_bf16_fwd(ptr(x), ptr(weight_krsc), ptr(bias), ptr(out), N, H, W, Cin, Cout, KH,
                                                  KW, 1 if relu else 0, int(out_mode), stream()), 'conv2d_s1_nhwc_bf16_fwd')
     return out
@@ -542,16 +556,23 @@ def _raw_ws(device, nbytes, key):
     return ws
 
 
-def conv2d_s1_nhwc_bf16_wgrad(dout_grid, x, KH, KW, dw_krsc=None, accumulate=False, db=None):
+def conv2d_s1_nhwc_bf16_wgrad(dout_grid, x, KH, KW, dw_krsc=None, accumulate=False, db=None, in_scale=1.0 / 255.0):
     """Weight gradient of the TMA-window conv (rl_conv2d_s1_nhwc_bf16_wgrad) -> dw [Cout, KH*KW*Cin] float32;
-    db (optional [Cout] float32) receives the bias gradient from the same pass."""
+    db (optional [Cout] float32) receives the bias gradient from the same pass.  A uint8 ``x`` goes to
+    rl_conv2d_s1_u8in_bf16_wgrad (operand = bf16(byte * in_scale))."""
     require_cuda(dout_grid, x, dw_krsc, db)
     N, H, W, Cout = dout_grid.shape
     Cin = x.shape[-1]
-    assert x.shape[:3] == dout_grid.shape[:3]
+    assert x.shape[:3] == dout_grid.shape[:3] and x.dtype in (torch.bfloat16, torch.uint8)
     if dw_krsc is None:
         dw_krsc = torch.empty((Cout, KH * KW * Cin), dtype=torch.float32, device=x.device)
     ws = _raw_ws(x.device, _lib.load().rl_conv_wgrad_workspace_bytes(KH, KW, Cin), 'wgrad')
+    if x.dtype == torch.uint8:
+        assert Cin == 64
+        check(_lib.load().rl_conv2d_s1_u8in_bf16_wgrad(ptr(dout_grid), ptr(x), float(in_scale), ptr(dw_krsc), ptr(db), N, H,
+                                                       W, Cout, KH, KW, 1 if accumulate else 0, ptr(ws), ws.numel(),
+                                                       stream()), 'conv2d_s1_u8in_bf16_wgrad')
+        return dw_krsc
     check(_lib.load().rl_conv2d_s1_nhwc_bf16_wgrad(ptr(dout_grid), ptr(x), ptr(dw_krsc), ptr(db), N, H, W, Cin, Cout, KH, KW,
                                                    1 if accumulate else 0, ptr(ws), ws.numel(), stream()),
           'conv2d_s1_nhwc_bf16_wgrad')

@@ -26,8 +26,17 @@ LAYERS = [(33, 21, 64, 32, 2), (200, 21, 64, 32, 2), (17, 12, 128, 64, 2), (130,
           (260, 11, 64, 64, 3)]
 
 
+@pytest.fixture(params=[0, 1], ids=['per_tap', 'coltaps_fused'])
+def conv_form(request):
+    """Both tile forms of the TMA-window conv (rl_debug_set_shiftconv_form); the default is restored afterwards."""
+    from parl_b200 import kernels as K
+    K.set_shiftconv_form(request.param)
+    yield request.param
+    K.set_shiftconv_form(0)
+
+
 @pytest.mark.parametrize('N,H,Cin,Cout,k', LAYERS)
-def test_conv_forward_exact_on_integers(N, H, Cin, Cout, k):
+def test_conv_forward_exact_on_integers(N, H, Cin, Cout, k, conv_form):
     from parl_b200 import kernels as K
     g = torch.Generator(device=DEV).manual_seed(N * 7 + H)
     x = _ints((N, H, H, Cin), -2, 2, g)
@@ -41,9 +50,28 @@ def test_conv_forward_exact_on_integers(N, H, Cin, Cout, k):
     assert torch.equal(out.float(), ref)
 
 
+@pytest.mark.parametrize('N', [5, 150])
+def test_conv1_block_layout_output_exact_on_integers(N, conv_form):
+    """out_mode 1: conv1's 20x20x32 map written as conv2's zero-padded 2x2 space-to-depth input [N,12,12,128]."""
+    from parl_b200 import kernels as K
+    g = torch.Generator(device=DEV).manual_seed(N)
+    x = _ints((N, 21, 21, 64), -2, 2, g)
+    w = _ints((32, 64, 2, 2), -1, 1, g, density=0.08)
+    b = _ints((32, ), -3, 3, g)
+    ref = torch.relu(F.conv2d(x.permute(0, 3, 1, 2), w, b)).permute(0, 2, 3, 1)            # [N,20,20,32]
+    pad = torch.zeros(N, 24, 24, 32, device=DEV)
+    pad[:, 2:22, 2:22] = ref
+    blocks = pad.view(N, 12, 2, 12, 2, 32).permute(0, 1, 3, 2, 4, 5).reshape(N, 12, 12, 128)
+    w_krsc = w.permute(0, 2, 3, 1).reshape(32, 256).contiguous().to(torch.bfloat16)
+    out = torch.zeros(N, 12, 12, 128, device=DEV, dtype=torch.bfloat16)
+    K.conv2d_s1_nhwc_bf16_fwd(x.to(torch.bfloat16), w_krsc, b, 2, 2, relu=True, out=out, out_mode=1)
+    torch.cuda.synchronize()
+    assert torch.equal(out.float(), blocks)
+
+
 @pytest.mark.parametrize('N,H,Cin,Cout,k', [(9, 11, 64, 64, 3), (160, 11, 64, 64, 3), (11, 12, 128, 64, 2),
                                             (90, 12, 128, 64, 2)])
-def test_conv_dgrad_exact_on_integers(N, H, Cin, Cout, k):
+def test_conv_dgrad_exact_on_integers(N, H, Cin, Cout, k, conv_form):
     from parl_b200 import kernels as K
     g = torch.Generator(device=DEV).manual_seed(N * 3 + H)
     Ho = H - k + 1
