@@ -312,6 +312,9 @@ int rl_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, l
  * ---------------------------------------------------------------------- */
 int rl_gemm_bf16_tn(const void* A, const void* B, const float* bias, void* C, int M, int N, int K,
                     int lda, int ldb, int ldc, int relu, int out_f32, rl_stream_t stream);
+/* 1 (default): outputs of at least 2 x 2 tiles of width >= 128 run as 2 x 2 thread-block clusters whose CTAs multicast
+ * their operand half-tiles to each other (each operand byte leaves L2 once per cluster); 0: single-CTA form only. */
+int rl_debug_set_gemm_cluster(int enable);
 /* rl_gemm_bf16_tn with an optional split-K workspace — the actor-side nn.Linear (atari_model.py:46-49 evaluated on
  *  the 5-env batch of examples/IMPALA/actor.py:60-62; here 512..4096 envs per GPU).  Workspace (>= splits * ceil(M/128)*128 * ceil(N/BN)*BN * 4 bytes; 8 MB
  * covers every shape that splits): when the output has fewer tiles than half the SMs and K >= 1024, the reduction is

@@ -72,6 +72,7 @@ SIGNATURES = {
     'rl_conv2d_s1_u8in_bf16_fwd': (c_i, [c_p, c_f, c_p, c_p, c_p] + [c_i] * 8 + [c_p]),
     'rl_debug_set_shiftconv_base_offset': (c_i, [c_i]),
     'rl_debug_set_shiftconv_form': (c_i, [c_i]),
+    'rl_debug_set_gemm_cluster': (c_i, [c_i]),
     'rl_conv2d_s1_nhwc_bf16_dgrad': (c_i, [c_p, c_p, c_p, c_p] + [c_i] * 10 + [c_p]),
     'rl_conv_wgrad_workspace_bytes': (c_sz, [c_i, c_i, c_i]),
     'rl_conv2d_s1_nhwc_bf16_wgrad': (c_i, [c_p, c_p, c_p, c_p] + [c_i] * 8 + [c_p, c_sz, c_p]),

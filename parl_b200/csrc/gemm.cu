@@ -4,7 +4,7 @@
 //
 // sm_100a structure (one 128 x BN output tile per CTA, BK = 64 bf16 = one 128-byte swizzle atom):
 //   warp 0   : TMA producer — cp.async.bulk.tensor 2-D tiles of A and B (SWIZZLE_128B) into a
-//              4-stage shared-memory ring, completion on per-stage "full" mbarriers
+//              4..8-stage shared-memory ring, completion on per-stage "full" mbarriers
 //   warp 1   : allocates TMEM, issues tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN, K=16) from
 //              ONE elected thread, 4 per stage; tcgen05.commit releases the stage ("empty") and,
 //              after the last k-block, signals "tmem_full"
@@ -20,7 +20,9 @@ namespace rl {
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;          // bf16 elements per k-block = 128 bytes
-constexpr int kGemmStages = 4;
+// ring depth by tile width: the loop is bound by the L2/HBM latency of the TMA loads (bytes in flight per SM), so the
+// ring takes what shared memory allows — 8 stages up to BN = 64, 6 at BN = 128, 4 at BN = 256 (~200 KB)
+__host__ __device__ constexpr int gemm_stages(int bn) { return bn <= 64 ? 8 : (bn <= 128 ? 6 : 4); }
 constexpr int kGemmThreads = 192;    // 6 warps
 
 __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, int c0, int c1, void* mbar) {
@@ -56,6 +58,33 @@ __device__ __forceinline__ void umma_commit(void* mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(mbar))
                : "memory");
 }
+// ---- thread-block cluster helpers (2 x 2 multicast form) ---------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// 2-D tile load delivered to the same shared-memory offset (and mbarrier) of every CTA in cta_mask
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* map, int c0, int c1, void* mbar,
+                                                      uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], "
+      "[%4], %5;\n" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(mbar)), "h"(cta_mask)
+      : "memory");
+}
+// arrive on the mbarrier at this offset in every CTA of cta_mask once this thread's MMAs have completed
+__device__ __forceinline__ void umma_commit_multicast(void* mbar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+                   smem_u32(mbar)),
+               "h"(cta_mask)
+               : "memory");
+}
+
 // 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread (thread = lane/row)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
@@ -100,13 +129,20 @@ struct GemmArgs {
   int kb_per_split, ldp, mpad;
 };
 
-template <int BN>
+// CL (2 x 2 thread-block cluster, TMA multicast): the four CTAs of a cluster own a 256 x 2BN block of C.  The two CTAs
+// of one m-block need the same A tile, the two of one n-block the same B tile: each CTA loads HALF of its A tile
+// (map_a then has 64-row boxes) and half of its B tile and multicasts them to its partner, so every operand byte is
+// read from L2 once per cluster instead of once per CTA — the single-CTA form is L2-bandwidth bound at these shapes
+// (340 MB of operand re-reads for 4096 x 512 x 5184).  A stage of CTA X is written by X and its two partners, so X's
+// issuer releases it with ONE multicast tcgen05.commit to the three of them (empty barrier count 3).
+template <int BN, bool CL = false>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                       const __grid_constant__ CUtensorMap map_b,
                                                                       const GemmArgs g) {
   constexpr int A_STAGE = kGemmBM * kGemmBK * 2;     // 16 KB
   constexpr int B_STAGE = BN * kGemmBK * 2;
   constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr int kGemmStages = gemm_stages(BN);
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   // SWIZZLE_128B atoms need 1024-byte alignment: align by hand (the launch reserves the slack)
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -126,7 +162,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tn_kernel(const __g
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < kGemmStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL ? 3 : 1);
     }
     mbar_init(&tmem_full_bar, 1);
     fence_mbar_init();
@@ -134,6 +170,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tn_kernel(const __g
   if (warp == 1) tmem_alloc(&tmem_base_smem, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  // cluster rank = x + 2 y: x = position along M (blockIdx.x & 1), y = along N; partners: rank ^ 2 shares this
+  // CTA's m-block (A tile), rank ^ 1 its n-block (B tile)
+  const uint32_t crank = CL ? cluster_ctarank() : 0u;
+  const uint16_t mask_a = (uint16_t)((1u << crank) | (1u << (crank ^ 2u)));
+  const uint16_t mask_b = (uint16_t)((1u << crank) | (1u << (crank ^ 1u)));
+  if (CL) cluster_sync_all();          // every CTA's barriers exist before a partner's TMA or commit can reach them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
@@ -145,8 +187,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tn_kernel(const __g
         const uint32_t ph = (kb / kGemmStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1u);                                  // slot free (first pass: immediately)
         mbar_arrive_expect_tx(&full_bar[s], A_STAGE + B_STAGE);
-        tma_load_2d(sA + s * A_STAGE, &map_a, (kb0 + kb) * kGemmBK, m0, &full_bar[s]);
-        tma_load_2d(sB + s * B_STAGE, &map_b, (kb0 + kb) * kGemmBK, n0, &full_bar[s]);
+        if (CL) {
+          const int ha = (int)(crank >> 1), hb = (int)(crank & 1u);        // which half of the shared tile this CTA fetches
+          tma_load_2d_multicast(sA + s * A_STAGE + ha * (A_STAGE / 2), &map_a, (kb0 + kb) * kGemmBK, m0 + ha * (kGemmBM / 2),
+                                &full_bar[s], mask_a);
+          tma_load_2d_multicast(sB + s * B_STAGE + hb * (B_STAGE / 2), &map_b, (kb0 + kb) * kGemmBK, n0 + hb * (BN / 2),
+                                &full_bar[s], mask_b);
+        } else {
+          tma_load_2d(sA + s * A_STAGE, &map_a, (kb0 + kb) * kGemmBK, m0, &full_bar[s]);
+          tma_load_2d(sB + s * B_STAGE, &map_b, (kb0 + kb) * kGemmBK, n0, &full_bar[s]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -165,7 +215,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tn_kernel(const __g
           // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
           umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty_bar[s]);                                         // frees the smem stage when the MMAs retire
+        if (CL)
+          umma_commit_multicast(&empty_bar[s], (uint16_t)(mask_a | mask_b));  // ... in this CTA and in both partners
+        else
+          umma_commit(&empty_bar[s]);                                       // frees the smem stage when the MMAs retire
       }
       umma_commit(&tmem_full_bar);                                          // accumulator complete
     }
@@ -239,6 +292,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tn_kernel(const __g
   }
   tc_fence_before();
   __syncthreads();
+  if (CL) cluster_sync_all();          // no CTA leaves while a partner may still multicast into it or signal its barriers
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -291,11 +345,29 @@ static int make_tensor_map_bf16_sw128(CUtensorMap* map, const void* base, uint64
 
 template <int BN>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, int splits, cudaStream_t st) {
-  const size_t smem = (size_t)kGemmStages * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 1024;
+  const size_t smem = (size_t)gemm_stages(BN) * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 1024;
   RL_SMEM_OPTIN(gemm_bf16_tn_kernel<BN>);
   dim3 grid((g.M + kGemmBM - 1) / kGemmBM, (g.N + BN - 1) / BN, splits);
   gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, smem, st>>>(ma, mb, g);
   return 0;
+}
+
+// 2 x 2 cluster form: the tile grid is rounded up to even counts (out-of-range tiles load zeros and store nothing)
+template <int BN>
+static int launch_gemm_cluster(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& g, cudaStream_t st) {
+  const size_t smem = (size_t)gemm_stages(BN) * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 1024;
+  auto kern = gemm_bf16_tn_kernel<BN, true>;
+  RL_SMEM_OPTIN(kern);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(((g.M + kGemmBM - 1) / kGemmBM + 1) & ~1), (unsigned)(((g.N + BN - 1) / BN + 1) & ~1), 1);
+  cfg.blockDim = dim3(kGemmThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 2, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, ma, mb, g) == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace rl
@@ -305,6 +377,13 @@ using namespace rl;
 static int gemm_launch(const void* A, const void* B, const float* bias, void* C, int M, int N, int K, int lda, int ldb,
                        int ldc, int relu, int out_f32, const void* mask, int ldm, void* workspace, size_t workspace_bytes,
                        rl_stream_t stream);
+
+// 1 (default): 2 x 2 cluster + TMA multicast form for outputs of at least 2 x 2 tiles of width >= 128; 0: never.
+static int g_gemm_cluster = 1;
+extern "C" int rl_debug_set_gemm_cluster(int enable) {
+  g_gemm_cluster = enable ? 1 : 0;
+  return RL_OK;
+}
 
 extern "C" int rl_gemm_bf16_tn(const void* A, const void* B, const float* bias, void* C, int M, int N, int K, int lda,
                                int ldb, int ldc, int relu, int out_f32, rl_stream_t stream) {
@@ -365,6 +444,21 @@ static int gemm_launch(const void* A, const void* B, const float* bias, void* C,
     }
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_gemm_cluster && splits == 1 && BN >= 128 && mt >= 2 && nt >= 2) {
+    // 2 x 2 cluster: half-tile boxes, each half multicast to the partner CTA
+    if (make_tensor_map_bf16_sw128(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kGemmBM / 2) ||
+        make_tensor_map_bf16_sw128(&mb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, (uint32_t)BN / 2)) {
+      set_error("gemm_bf16_tn: cuTensorMapEncodeTiled failed");
+      return RL_ERR_CUDA;
+    }
+    const int rc = BN == 256 ? launch_gemm_cluster<256>(ma, mb, g, st) : launch_gemm_cluster<128>(ma, mb, g, st);
+    if (rc) {
+      set_error("gemm_bf16_tn: cluster launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return RL_ERR_CUDA;
+    }
+    RL_CHECK_LAUNCH("rl_gemm_bf16_tn");
+    return RL_OK;
+  }
   switch (BN) {
     case 256: launch_gemm<256>(ma, mb, g, splits, st); break;
     case 128: launch_gemm<128>(ma, mb, g, splits, st); break;

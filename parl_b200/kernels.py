@@ -37,6 +37,11 @@ def set_shiftconv_form(form):
     check(_lib.load().rl_debug_set_shiftconv_form(int(form)), 'debug_set_shiftconv_form')
 
 
+def set_gemm_cluster(enable):
+    """1 (default): 2 x 2 cluster + TMA multicast form of rl_gemm_bf16_tn where the output has >= 2 x 2 wide tiles."""
+    check(_lib.load().rl_debug_set_gemm_cluster(1 if enable else 0), 'debug_set_gemm_cluster')
+
+
 def set_sm_limit(max_ctas):
     """Cap the CTAs of the persistent network kernels launched from now on (0 = one per SM)."""
     check(_lib.load().rl_set_sm_limit(int(max_ctas)), 'set_sm_limit')
