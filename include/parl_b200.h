@@ -56,6 +56,11 @@ size_t rl_loss_workspace_bytes(int n_cols);
 
 /* Triage hook: 1 forces the cp.async tile path of rl_vtrace_loss_fwd_bwd, 0 (default) lets the
  * TMA tensor-map path run when the layout allows it. */
+/* 1: the per-env-step chain kernels (observation gather, TMA-window convs, GEMMs, env step) are launched with
+ * programmatic stream serialization: each starts its prologue while the previous kernel of the stream drains and
+ * blocks on griddepcontrol.wait before touching dependent memory.  0 (default): plain stream order — measured equal
+ * for the graph-replayed rollout and slower for the pipelined step (profiles/r02_pdl_ab.txt). */
+int rl_debug_set_pdl(int enable);
 int rl_debug_set_tma(int disable);
 /* Triage hook for rl_vtrace_loss_fwd_bwd: 0 = default kernel (v4), 6 = the v6 kernel (one 8-row TMA chunk per
  * warp, single block sync; time-major, TMA-able shapes with T <= 56; slower than v4 at every measured shape). */
@@ -303,6 +308,11 @@ int rl_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, l
                  const float* lr_device, float lr, float beta1, float beta2, float eps, int step,
                  float grad_div, const float* grad_norm, float max_norm, int clip_mode, int zero_grad,
                  const int32_t* step_device, rl_stream_t stream);
+
+/* out[i] = cast(src[idx[i]]) (idx < 0 -> 0): rebuilds every bf16 (out_bf16 = 1) or float32 (0) operand copy of the
+ * network kernels from the flat float32 master buffer in one launch; idx is the index permutation of the copies,
+ * built once by the host (parl_b200.kernels.PackPlan).  idx and out 16-byte aligned. */
+int rl_gather_cast(const float* src, const int32_t* idx, long long n, void* out, int out_bf16, rl_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * a13 / K6  Dense contraction on the tcgen05 tensor cores (TMA-staged tiles, fp32 accumulation in TMEM):

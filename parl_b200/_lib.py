@@ -31,6 +31,7 @@ SIGNATURES = {
     'rl_set_sm_limit': (c_i, [c_i]),
     'rl_loss_workspace_bytes': (c_sz, [c_i]),
     'rl_debug_set_tma': (c_i, [c_i]),
+    'rl_debug_set_pdl': (c_i, [c_i]),
     'rl_debug_set_vtrace_path': (c_i, [c_i]),
     'rl_vtrace_from_importance_weights': (c_i, [c_p] * 6 + [c_i, c_i, c_f, c_f, c_p, c_p, c_p]),
     'rl_vtrace_loss_fwd_bwd': (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_i,
@@ -63,6 +64,7 @@ SIGNATURES = {
     'rl_replay_gather_frames': (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     'rl_gather_rows': (c_i, [c_p, c_p, ctypes.c_longlong, c_i, c_p, c_p]),
     'rl_grad_global_norm': (c_i, [c_p, ctypes.c_longlong, c_p, c_p, c_sz, c_p]),
+    'rl_gather_cast': (c_i, [c_p, c_p, ctypes.c_longlong, c_p, c_i, c_p]),
     'rl_adam_step': (c_i, [c_p, c_p, c_p, c_p, ctypes.c_longlong, c_p, c_f, c_f, c_f, c_f, c_i, c_f, c_p, c_f, c_i,
                            c_i, c_p, c_p]),
     'rl_gemm_bf16_tn': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
@@ -106,6 +108,11 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    # triage switches from the environment (defaults live in the library)
+    if os.environ.get('PARL_B200_PDL', '') == '1':
+        lib.rl_debug_set_pdl(1)
+    if os.environ.get('PARL_B200_GEMM_CLUSTER', '') == '0':
+        lib.rl_debug_set_gemm_cluster(0)
     return lib
 
 

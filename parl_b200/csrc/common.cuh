@@ -10,6 +10,7 @@ namespace rl {
 
 void set_error(const char* fmt, ...);
 int effective_sms(int sms);          // SM count capped by rl_set_sm_limit
+int pdl_enabled();                   // 1: chain kernels are launched with programmatic stream serialization
 
 #define RL_CHECK_ARG(cond, ...)            \
   do {                                     \
@@ -54,6 +55,27 @@ static inline void opt_in_max_dynamic_smem(Kernel kernel, unsigned long long* do
   } while (0)
 
 #ifdef __CUDACC__
+// Programmatic dependent launch (actor chain: 7 short kernels per env step).  A kernel launched through launch_chain
+// may begin while its predecessor in the stream is still draining: its prologue (barrier init, TMEM allocation,
+// tensor-map prefetch, weight loads — nothing a predecessor writes) runs ahead, pdl_wait() then blocks until the
+// predecessor grid has completed and its writes are visible, and pdl_trigger() lets the NEXT kernel in the stream start
+// its own prologue.  Every kernel launched this way MUST call pdl_wait() before its first access to memory another
+// kernel of the stream produces (or still reads) — and before it exits.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                       Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));

@@ -46,6 +46,8 @@ struct AtariStepArgs {
 };
 
 __global__ void __launch_bounds__(256) atari_synth_step_kernel(AtariStepArgs p) {
+  pdl_wait();            // chain kernel (launch_chain): the logits / step counter come from the previous kernels
+  pdl_trigger();
   if (p.step_dev) p.step = *p.step_dev;
   const int nblk = p.HW >> 4;
   const long long total = (long long)p.B * nblk;
@@ -214,6 +216,8 @@ __global__ void __launch_bounds__(256) obs_stack_gather_s2d_kernel(const uint8_t
                                                                    void* __restrict__ out_v) {
   constexpr int W = 84, G = 21, ITEMS = G * G * 4, FRAME = W * W, CHUNKS = FRAME / 16;     // 7056 B = 441 x 16
   __shared__ __align__(16) uint8_t sfr[4][FRAME];
+  pdl_wait();            // chain kernel (launch_chain): the frames / ages come from the env-step kernel before it
+  pdl_trigger();
   const long long nsamples = (long long)t_count * B;
   const float bias = -8388608.0f * scale;
   for (long long r = blockIdx.x; r < nsamples; r += gridDim.x) {      // sample index in output order
@@ -453,7 +457,7 @@ extern "C" int rl_env_atari_synth_step(uint8_t* frame_out, float* reward_out, ui
   const long long cap = 148LL * 8 * 4;      // 4 waves of 8 CTAs/SM, grid-stride beyond
   if (blocks > cap) blocks = cap;
   if (blocks < (B + 255) / 256) blocks = (B + 255) / 256;
-  atari_synth_step_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+  launch_chain(atari_synth_step_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, a);
   RL_CHECK_LAUNCH("rl_env_atari_synth_step");
   return RL_OK;
 }
@@ -485,11 +489,11 @@ extern "C" int rl_obs_stack_gather(const uint8_t* planes, const uint8_t* ages, i
     long long b3 = (long long)t_count * B;              // one CTA per sample, grid-stride beyond 8 CTAs per SM
     if (b3 > 148LL * 7) b3 = 148LL * 7;                 // 28 KB of staged frames per CTA: 7 CTAs per SM
     if (out_dtype == 3)
-      obs_stack_gather_s2d_kernel<false><<<(unsigned)b3, 256, 0, (cudaStream_t)stream>>>(planes, ages, B, t_begin, t_count,
-                                                                                         em, scale, out);
+      launch_chain(obs_stack_gather_s2d_kernel<false>, dim3((unsigned)b3), dim3(256), 0, (cudaStream_t)stream, planes, ages,
+                   B, t_begin, t_count, em, scale, out);
     else
-      obs_stack_gather_s2d_kernel<true><<<(unsigned)b3, 256, 0, (cudaStream_t)stream>>>(planes, ages, B, t_begin, t_count,
-                                                                                        em, scale, out);
+      launch_chain(obs_stack_gather_s2d_kernel<true>, dim3((unsigned)b3), dim3(256), 0, (cudaStream_t)stream, planes, ages,
+                   B, t_begin, t_count, em, scale, out);
   } else {
     set_error("obs_stack_gather: out_dtype %d unsupported (0=u8, 1=f32, 2=bf16 NHWC, 3=bf16 space-to-depth, 4=u8 space-to-depth)",
               out_dtype);

@@ -178,6 +178,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tn_kernel(const __g
   if (CL) cluster_sync_all();          // every CTA's barriers exist before a partner's TMA or commit can reach them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();            // chain kernel (launch_chain): A comes from the previous kernel of the stream
+  pdl_trigger();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -299,6 +301,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tn_kernel(const __g
 // C[row, col] = act(sum_z partial[z][row][col] + bias[col]) in split order (deterministic)
 __global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(const float* __restrict__ partial, int splits, int mpad,
                                                                  int ldp, const GemmArgs g) {
+  pdl_wait();            // chain kernel (launch_chain)
+  pdl_trigger();
   const int n4 = (g.N + 3) >> 2;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)g.M * n4) return;
@@ -348,7 +352,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmA
   const size_t smem = (size_t)gemm_stages(BN) * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 1024;
   RL_SMEM_OPTIN(gemm_bf16_tn_kernel<BN>);
   dim3 grid((g.M + kGemmBM - 1) / kGemmBM, (g.N + BN - 1) / BN, splits);
-  gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, smem, st>>>(ma, mb, g);
+  launch_chain(gemm_bf16_tn_kernel<BN>, grid, dim3(kGemmThreads), smem, st, ma, mb, g);
   return 0;
 }
 
@@ -363,10 +367,12 @@ static int launch_gemm_cluster(const CUtensorMap& ma, const CUtensorMap& mb, con
   cfg.blockDim = dim3(kGemmThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 2, attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr, cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled();
+  cfg.attrs = attr, cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, kern, ma, mb, g) == cudaSuccess ? 0 : -1;
 }
 
@@ -467,7 +473,8 @@ static int gemm_launch(const void* A, const void* B, const float* bias, void* C,
   }
   if (splits > 1) {
     const long long items = (long long)M * ((N + 3) / 4);
-    gemm_splitk_reduce_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(g.partial, splits, g.mpad, g.ldp, g);
+    launch_chain(gemm_splitk_reduce_kernel, dim3((unsigned)((items + 255) / 256)), dim3(256), 0, st,
+                 (const float*)g.partial, splits, g.mpad, g.ldp, g);
   }
   RL_CHECK_LAUNCH("rl_gemm_bf16_tn");
   return RL_OK;

@@ -10,6 +10,8 @@
 // Adam (torch.optim.Adam / paddle.optimizer.Adam, identical algebra):
 //   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
 // Bytes per parameter: read 16 (p,g,m,v) + write 12 (p,m,v); norm pass reads 4.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "reduce.cuh"
 
@@ -73,6 +75,56 @@ __global__ void __launch_bounds__(kOT) adam_step_kernel(float* __restrict__ p, c
 }  // namespace rl
 
 using namespace rl;
+
+// Operand refresh after a learner update: every bf16 / fp32 operand copy the network kernels keep (KRSC conv
+// filters, their space-to-depth and transposed forms, (H,W,C)-ordered fc columns, bias vectors) is an index
+// permutation of the flat fp32 master buffer, so ONE gather launch rebuilds them all: out[i] = cast(src[idx[i]]),
+// idx < 0 -> 0 (padding, unused head columns).  Replaces ~26 permute+copy launches per update.
+__global__ void __launch_bounds__(256) gather_cast_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
+                                                          long long n, void* __restrict__ out, int out_bf16) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (out_bf16) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i * 8 < n; i += stride) {
+      const long long e = i * 8;
+      float v[8];
+      if (e + 8 <= n) {
+        const int4 a = __ldg(reinterpret_cast<const int4*>(idx + e)), b = __ldg(reinterpret_cast<const int4*>(idx + e) + 1);
+        const int j[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = j[k] >= 0 ? __ldg(src + j[k]) : 0.f;
+        uint32_t pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+          pk[k] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + e) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      } else {
+        for (long long t = e; t < n; ++t) {
+          const int jj = idx[t];
+          reinterpret_cast<__nv_bfloat16*>(out)[t] = __float2bfloat16(jj >= 0 ? src[jj] : 0.f);
+        }
+      }
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const int jj = idx[i];
+      reinterpret_cast<float*>(out)[i] = jj >= 0 ? __ldg(src + jj) : 0.f;
+    }
+  }
+}
+
+extern "C" int rl_gather_cast(const float* src, const int32_t* idx, long long n, void* out, int out_bf16,
+                              rl_stream_t stream) {
+  RL_CHECK_ARG(src && idx && out && n > 0, "gather_cast: bad argument");
+  RL_CHECK_ARG(aligned16(idx) && aligned16(out), "gather_cast: idx and out must be 16-byte aligned");
+  const long long work = out_bf16 ? (n + 7) / 8 : n;
+  long long blocks = (work + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gather_cast_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, idx, n, out, out_bf16);
+  RL_CHECK_LAUNCH("rl_gather_cast");
+  return RL_OK;
+}
 
 extern "C" int rl_grad_global_norm(const float* grad, long long n, float* out_norm, void* workspace,
                                    size_t workspace_bytes, rl_stream_t stream) {

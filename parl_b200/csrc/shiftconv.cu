@@ -165,6 +165,14 @@ __global__ void __launch_bounds__(U8IN ? kScThreads + kU8Threads : kScThreads, 1
   __syncthreads();
   s_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // resident weights: requested BEFORE the dependency wait (they are written by the operand refresh, at least two
+  // kernels back in the stream), so the load overlaps the tail of the previous kernel
+  if (warp == 1 && lane == 0) {
+    mbar_arrive_expect_tx(&w_bar, (uint32_t)(num_kb * W_KB));
+    for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sW + kb * W_KB, &map_w, kb * 64, 0, &w_bar);
+  }
+  pdl_wait();            // chain kernel (launch_chain): the input activations come from the previous kernel
+  pdl_trigger();
 
   if (warp == 0) {
     // ===== TMA producer: one window (CBLK column blocks) per tile =====
@@ -210,10 +218,6 @@ __global__ void __launch_bounds__(U8IN ? kScThreads + kU8Threads : kScThreads, 1
     // ===== resident weights + MMA issue (issuer 0: even tiles of this CTA, issuer 1: odd tiles) =====
     if (lane == 0) {
       const uint32_t issuer = warp == 1 ? 0u : 1u;
-      if (issuer == 0) {
-        mbar_arrive_expect_tx(&w_bar, (uint32_t)(num_kb * W_KB));
-        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(sW + kb * W_KB, &map_w, kb * 64, 0, &w_bar);
-      }
       mbar_wait(&w_bar, 0);
       constexpr uint32_t idesc = s_idesc_bf16(kScBM, COUT);
       // the issue loop is ONE thread's instruction stream: keep it to "add, add, mma" — tap shifts are
@@ -686,7 +690,7 @@ static void launch_shiftconv(const CUtensorMap& mi, const CUtensorMap& mw, const
   auto kern = shiftconv_fwd_kernel<COUT, CBLK, KS, MODE, U8IN>;
   RL_SMEM_OPTIN(kern);
   const int grid = g.num_tiles < sms ? g.num_tiles : sms;
-  kern<<<grid, U8IN ? kScThreads + kU8Threads : kScThreads, smem, st>>>(mi, mw, g);
+  launch_chain(kern, dim3(grid), dim3(U8IN ? kScThreads + kU8Threads : kScThreads), smem, st, mi, mw, g);
 }
 
 template <int COUT, int CBLK, int KS, int MODE, bool U8IN = false>

@@ -11,10 +11,11 @@ fc weight with (H,W,C)-ordered columns.
 import torch
 
 from .. import kernels
+from .packing import PackedOperands
 
 
 class AtariActorNet(object):
-    def __init__(self, model, batch, device, window_form=True):
+    def __init__(self, model, batch, device, window_form=True, flat=None):
         self.model = model
         self.B = int(batch)
         dev = self.device = torch.device(device)
@@ -28,38 +29,37 @@ class AtariActorNet(object):
         self.h = torch.empty((self.B, 512), dtype=bf, device=dev)
         A = model.fc_pi.weight.shape[0]
         self.A = A
-        self.w1 = torch.empty((32, 256), dtype=bf, device=dev)
-        self.w2 = torch.empty((64, 512), dtype=bf, device=dev)
-        self.w3 = torch.empty((64, 576), dtype=bf, device=dev)
-        self.wfc = torch.empty((512, 5184), dtype=bf, device=dev)
-        self.wpi = torch.empty((A, 512), dtype=bf, device=dev)
-        self.wv = torch.empty((1, 512), dtype=bf, device=dev)
-        self.b1 = torch.empty(32, dtype=torch.float32, device=dev)
-        self.b2 = torch.empty(64, dtype=torch.float32, device=dev)
-        self.b3 = torch.empty(64, dtype=torch.float32, device=dev)
-        self.bfc = torch.empty(512, dtype=torch.float32, device=dev)
-        self.bpi = torch.empty(A, dtype=torch.float32, device=dev)
-        self.bv = torch.empty(1, dtype=torch.float32, device=dev)
+        f32 = torch.float32
+        self.ops = PackedOperands(dev)
+        for name, shape, dt in (('w1', (32, 256), bf), ('w2', (64, 512), bf), ('w3', (64, 576), bf),
+                                ('wfc', (512, 5184), bf), ('wpi', (A, 512), bf), ('wv', (1, 512), bf),
+                                ('b1', (32, ), f32), ('b2', (64, ), f32), ('b3', (64, ), f32), ('bfc', (512, ), f32),
+                                ('bpi', (A, ), f32), ('bv', (1, ), f32)):
+            self.ops.declare(name, shape, dt)
+        self.ops.materialize(self)
+        if flat is not None:
+            self.ops.bind_flat(flat, model, self._sources)
         self.pack()
+
+    def _sources(self, P, full):
+        """The operand copies as tensor expressions over the parameters (see engine/packing.py)."""
+        # conv1 8x8/4 -> 2x2/1 on 4x4 pixel blocks: W1[o,c,4a+dy,4b+dx] -> [o, (a,b), (dy,dx,c)]
+        w1 = P('conv1.weight').view(32, 4, 2, 4, 2, 4).permute(0, 2, 4, 3, 5, 1).reshape(32, 256)    # (o, a, b, dy, dx, c)
+        if self.window_form:
+            # conv2 4x4/2/p2 -> 2x2/1 on 2x2 pixel blocks: W2[o,c,2a+dy,2b+dx] -> [o, (a,b), (dy,dx,c)]
+            w2 = P('conv2.weight').view(64, 32, 2, 2, 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(64, 512)
+        else:
+            w2 = P('conv2.weight').permute(0, 2, 3, 1).reshape(64, 512)                             # (o, r, s, c)
+        return [('w1', w1), ('w2', w2), ('w3', P('conv3.weight').permute(0, 2, 3, 1).reshape(64, 576)),
+                ('wfc', P('fc.weight').view(512, 64, 9, 9).permute(0, 2, 3, 1).reshape(512, 5184)),
+                ('wpi', P('fc_pi.weight')), ('wv', P('fc_v.weight')), ('b1', P('conv1.bias')), ('b2', P('conv2.bias')),
+                ('b3', P('conv3.bias')), ('bfc', P('fc.bias')), ('bpi', P('fc_pi.bias')), ('bv', P('fc_v.bias'))]
 
     @torch.no_grad()
     def pack(self):
-        """fp32 master weights -> bf16 kernel operands (in place: safe to call between CUDA-graph replays)."""
-        m = self.model
-        # conv1 8x8/4 -> 2x2/1 on 4x4 pixel blocks: W1[o,c,4a+dy,4b+dx] -> [o, (a,b), (dy,dx,c)]
-        w1 = m.conv1.weight.view(32, 4, 2, 4, 2, 4).permute(0, 2, 4, 3, 5, 1)      # (o, a, b, dy, dx, c)
-        self.w1.copy_(w1.reshape(32, 256))
-        if self.window_form:
-            # conv2 4x4/2/p2 -> 2x2/1 on 2x2 pixel blocks: W2[o,c,2a+dy,2b+dx] -> [o, (a,b), (dy,dx,c)]
-            self.w2.copy_(m.conv2.weight.view(64, 32, 2, 2, 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(64, 512))
-        else:
-            self.w2.copy_(m.conv2.weight.permute(0, 2, 3, 1).reshape(64, 512))     # (o, r, s, c)
-        self.w3.copy_(m.conv3.weight.permute(0, 2, 3, 1).reshape(64, 576))
-        self.wfc.copy_(m.fc.weight.view(512, 64, 9, 9).permute(0, 2, 3, 1).reshape(512, 5184))
-        self.wpi.copy_(m.fc_pi.weight)
-        self.wv.copy_(m.fc_v.weight)
-        self.b1.copy_(m.conv1.bias), self.b2.copy_(m.conv2.bias), self.b3.copy_(m.conv3.bias)
-        self.bfc.copy_(m.fc.bias), self.bpi.copy_(m.fc_pi.bias), self.bv.copy_(m.fc_v.bias)
+        """fp32 master weights -> bf16 kernel operands, in place (safe between CUDA-graph replays): one gather launch
+        per dtype when the parameters live in the optimizer's flat buffer, else one copy per operand."""
+        self.ops.refresh(self.model, self._sources)
 
     def policy(self, obs_s2d, logits_out):
         """obs_s2d [B,21,21,64] uint8 (bytes; conv1 scales by 1/255 while widening) or bf16 (already scaled)

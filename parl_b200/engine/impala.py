@@ -92,7 +92,8 @@ class ImpalaEngine(object):
         native_ok = (self.h, self.w) == (84, 84) and isinstance(self.model, AtariActorCritic)
         use_native_learner = role != 'actor' and (learner_kernels is True or (learner_kernels == 'auto' and native_ok))
         # learner forward+backward on hand-written tcgen05 kernels (no autograd) when the model is the Atari net
-        self.train_net = AtariTrainNet(self.model, T * B, dev, obs_dtype=self.obs_dtype if self.s2d else torch.bfloat16) \
+        self.train_net = AtariTrainNet(self.model, T * B, dev, obs_dtype=self.obs_dtype if self.s2d else torch.bfloat16,
+                                       flat=self._flat_master()) \
             if use_native_learner else None
         # learner inputs: one pre-scaled bf16 NHWC buffer per chunk (each is saved by autograd for conv1's
         # weight gradient, so chunks must not share storage): T*B*56 KB in total
@@ -108,7 +109,7 @@ class ImpalaEngine(object):
         # actor-critic on 84x84 frames ('auto'), else the user's torch Model
         use_native = role != 'learner' and (actor_kernels is True or (actor_kernels == 'auto' and self.s2d and
                                                                      isinstance(self.model, AtariActorCritic)))
-        self.actor_net = AtariActorNet(self.model, B, dev) if use_native else None
+        self.actor_net = AtariActorNet(self.model, B, dev, flat=self._flat_master()) if use_native else None
         # Shared observation plane: the actor's per-step conv1 input (space-to-depth uint8, 28 KB per env step) is
         # written straight into row t of a (T,B) plane of the rollout buffer set and the learner's conv1 forward /
         # weight gradient read it from there — the learner never re-gathers the frame ring.  5.8 GB per set at
@@ -137,6 +138,11 @@ class ImpalaEngine(object):
             self._ev_pack = torch.cuda.Event()
         if role != 'learner':
             self.reset()
+
+    def _flat_master(self):
+        """The optimizer's flat fp32 parameter buffer (operand copies are refreshed from it in one launch)."""
+        opt = getattr(self.alg, 'optimizer', None)
+        return getattr(opt, 'flat', None)
 
     def _bind(self, i):
         """Make buffer set i the one the attribute names (planes, ages, beh_logits, ...) refer to."""

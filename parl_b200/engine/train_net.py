@@ -16,10 +16,11 @@ Gradients are written into the parameters' ``.grad`` views of the FlatAdam buffe
 import torch
 
 from .. import kernels as K
+from .packing import PackedOperands
 
 
 class AtariTrainNet(object):
-    def __init__(self, model, n_samples, device, fc_backend='auto', obs_dtype=torch.bfloat16):
+    def __init__(self, model, n_samples, device, fc_backend='auto', obs_dtype=torch.bfloat16, flat=None):
         self.model = model
         assert obs_dtype in (torch.uint8, torch.bfloat16)
         self.obs_dtype = obs_dtype          # bfloat16: pre-scaled operand (default); uint8: conv1 reads bytes (u8in kernels)
@@ -40,13 +41,17 @@ class AtariTrainNet(object):
         # gradients of activations (grids are zero where no valid output exists and are never written there)
         self.dheads, self.dh = z(N, 32), e(N, 512)
         self.da3g, self.da2g, self.da1g = z(N, 11, 11, 64), z(N, 12, 12, 64), z(N, 21, 21, 32)
-        # operand copies of the weights
-        self.w1, self.w2, self.w3 = e(32, 256), e(64, 512), e(64, 576)
-        self.wfc, self.wpi, self.wv = e(512, 5184), e(A, 512), e(1, 512)
-        self.wfcT, self.whT = e(5184, 512), z(512, 32)
-        self.w3T, self.w2T = e(64, 576), e(128, 256)
-        self.b1, self.b2, self.b3 = [torch.empty(n, dtype=f32, device=dev) for n in (32, 64, 64)]
-        self.bfc, self.bpi, self.bv = [torch.empty(n, dtype=f32, device=dev) for n in (512, A, 1)]
+        # operand copies of the weights (carved from two arenas, refreshed by one gather launch per dtype: packing.py)
+        self.ops = PackedOperands(dev)
+        for name, shape, dt in (('w1', (32, 256), bf), ('w2', (64, 512), bf), ('w3', (64, 576), bf),
+                                ('wfc', (512, 5184), bf), ('wpi', (A, 512), bf), ('wv', (1, 512), bf),
+                                ('wfcT', (5184, 512), bf), ('whT', (512, 32), bf), ('w3T', (64, 576), bf),
+                                ('w2T', (128, 256), bf), ('b1', (32, ), f32), ('b2', (64, ), f32), ('b3', (64, ), f32),
+                                ('bfc', (512, ), f32), ('bpi', (A, ), f32), ('bv', (1, ), f32)):
+            self.ops.declare(name, shape, dt)
+        self.ops.materialize(self)
+        if flat is not None:
+            self.ops.bind_flat(flat, model, self._sources)
         # weight-gradient scratch (KRSC, float32)
         self.dw1 = torch.empty((32, 256), dtype=f32, device=dev)
         self.dw2 = torch.empty((64, 512), dtype=f32, device=dev)
@@ -64,24 +69,26 @@ class AtariTrainNet(object):
             self._x0 = torch.empty((self.N, 21, 21, 64), dtype=self.obs_dtype, device=self.device)
         return self._x0
 
+    def _sources(self, P, full):
+        """The operand copies as tensor expressions over the parameters (see engine/packing.py)."""
+        A = self.A
+        w2p = P('conv2.weight').view(64, 32, 2, 2, 2, 2).permute(0, 2, 4, 3, 5, 1)        # (o, a, b, dy, dx, c)
+        wfc = P('fc.weight').view(512, 64, 9, 9).permute(0, 2, 3, 1).reshape(512, 5184)   # columns in (h,w,c) order
+        whT = full((512, 32))
+        whT[:, :A] = P('fc_pi.weight').t()
+        whT[:, A:A + 1] = P('fc_v.weight').t()
+        return [('w1', P('conv1.weight').view(32, 4, 2, 4, 2, 4).permute(0, 2, 4, 3, 5, 1).reshape(32, 256)),
+                ('w2', w2p.reshape(64, 512)),
+                ('w2T', w2p.permute(3, 4, 5, 1, 2, 0).reshape(128, 256)),                 # [(dy,dx,c)][(a,b,o)]
+                ('w3', P('conv3.weight').permute(0, 2, 3, 1).reshape(64, 576)),           # (o, r, s, c)
+                ('w3T', P('conv3.weight').permute(1, 2, 3, 0).reshape(64, 576)),          # [c][(r,s,o)]
+                ('wfc', wfc), ('wfcT', wfc.t()), ('wpi', P('fc_pi.weight')), ('wv', P('fc_v.weight')), ('whT', whT),
+                ('b1', P('conv1.bias')), ('b2', P('conv2.bias')), ('b3', P('conv3.bias')), ('bfc', P('fc.bias')),
+                ('bpi', P('fc_pi.bias')), ('bv', P('fc_v.bias'))]
+
     @torch.no_grad()
     def pack(self):
-        m = self.model
-        self.w1.copy_(m.conv1.weight.view(32, 4, 2, 4, 2, 4).permute(0, 2, 4, 3, 5, 1).reshape(32, 256))
-        w2p = m.conv2.weight.view(64, 32, 2, 2, 2, 2).permute(0, 2, 4, 3, 5, 1)          # (o, a, b, dy, dx, c)
-        self.w2.copy_(w2p.reshape(64, 512))
-        self.w2T.copy_(w2p.permute(3, 4, 5, 1, 2, 0).reshape(128, 256))                  # [(dy,dx,c)][(a,b,o)]
-        self.w3.copy_(m.conv3.weight.permute(0, 2, 3, 1).reshape(64, 576))               # (o, r, s, c)
-        self.w3T.copy_(m.conv3.weight.permute(1, 2, 3, 0).reshape(64, 576))              # [c][(r,s,o)]
-        wfc = m.fc.weight.view(512, 64, 9, 9).permute(0, 2, 3, 1).reshape(512, 5184)     # columns in (h,w,c) order
-        self.wfc.copy_(wfc)
-        self.wfcT.copy_(wfc.t())
-        self.wpi.copy_(m.fc_pi.weight)
-        self.wv.copy_(m.fc_v.weight)
-        self.whT[:, :self.A].copy_(m.fc_pi.weight.t())
-        self.whT[:, self.A:self.A + 1].copy_(m.fc_v.weight.t())
-        self.b1.copy_(m.conv1.bias), self.b2.copy_(m.conv2.bias), self.b3.copy_(m.conv3.bias)
-        self.bfc.copy_(m.fc.bias), self.bpi.copy_(m.fc_pi.bias), self.bv.copy_(m.fc_v.bias)
+        self.ops.refresh(self.model, self._sources)
 
     # ------------------------------------------------------------------ forward
     def forward(self, planes, ages, t_count, layout=K.TIME_MAJOR):

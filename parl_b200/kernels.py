@@ -42,6 +42,11 @@ def set_gemm_cluster(enable):
     check(_lib.load().rl_debug_set_gemm_cluster(1 if enable else 0), 'debug_set_gemm_cluster')
 
 
+def set_pdl(enable):
+    """1: programmatic dependent launch of the per-env-step chain kernels; 0 (default): plain stream order."""
+    check(_lib.load().rl_debug_set_pdl(1 if enable else 0), 'debug_set_pdl')
+
+
 def set_sm_limit(max_ctas):
     """Cap the CTAs of the persistent network kernels launched from now on (0 = one per SM)."""
     check(_lib.load().rl_set_sm_limit(int(max_ctas)), 'set_sm_limit')
@@ -451,6 +456,18 @@ def gather_rows(src, idx):
     row_bytes = src[0].numel() * src.element_size()
     out = torch.empty((idx.numel(), ) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
     check(_lib.load().rl_gather_rows(ptr(src), ptr(idx), idx.numel(), row_bytes, ptr(out), stream()), 'gather_rows')
+    return out
+
+
+def gather_cast(src_flat, idx, out):
+    """out[i] = cast(src_flat[idx[i]]) (idx < 0 -> 0), out bfloat16 or float32 (rl_gather_cast): the one-launch refresh
+    of the network kernels' operand copies from the flat float32 master buffer."""
+    require_cuda(src_flat, idx, out)
+    _chk('src', src_flat, torch.float32)
+    _chk('idx', idx, torch.int32)
+    assert out.dtype in (torch.bfloat16, torch.float32) and out.numel() == idx.numel() and out.is_contiguous()
+    check(_lib.load().rl_gather_cast(ptr(src_flat), ptr(idx), idx.numel(), ptr(out), 1 if out.dtype == torch.bfloat16 else 0,
+                                     stream()), 'gather_cast')
     return out
 
 

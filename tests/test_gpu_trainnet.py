@@ -117,3 +117,30 @@ def test_pipelined_engine_is_deterministic_and_matches_host_contract():
     want = s0['rewards'].cpu().t()
     # hosts[0] was last written by rollout 2 (set 0): the device buffer of set 0 still holds that rollout
     assert torch.equal(got, want)
+
+
+def test_one_launch_operand_refresh_matches_per_operand_copies():
+    """engine/packing.py: the index-permutation gather (rl_gather_cast) rebuilds every operand copy exactly as the
+    permute + copy expressions do, for the learner's and the actor's net, before and after a weight change."""
+    from parl_b200.algorithms import IMPALA
+    from parl_b200.engine.actor_net import AtariActorNet
+    torch.manual_seed(3)
+    model = AtariActorCritic(18).to(DEV)
+    alg = IMPALA(model, sample_batch_steps=4, gamma=0.99, vf_loss_coeff=0.5, clip_rho_threshold=1.0,
+                 clip_pg_rho_threshold=1.0)
+    flat = alg.optimizer.flat
+    names = ['w1', 'w2', 'w3', 'wfc', 'wpi', 'wv', 'b1', 'b2', 'b3', 'bfc', 'bpi', 'bv']
+    pairs = [(AtariTrainNet(model, 128, DEV, flat=flat), AtariTrainNet(model, 128, DEV), names + ['wfcT', 'whT', 'w3T', 'w2T']),
+             (AtariActorNet(model, 128, DEV, flat=flat), AtariActorNet(model, 128, DEV), names)]
+    for fast, ref, ns in pairs:
+        assert fast.ops.flat is not None and ref.ops.flat is None
+    for rnd in range(2):
+        for fast, ref, ns in pairs:
+            fast.pack(), ref.pack()
+            torch.cuda.synchronize()
+            for n in ns:
+                a, b = getattr(fast, n), getattr(ref, n)
+                assert a.dtype == b.dtype and torch.equal(a, b), (rnd, n)
+                assert a.float().abs().sum().item() > 0 or n.startswith('b'), n
+        with torch.no_grad():
+            flat.add_(torch.randn_like(flat) * 0.01)          # "a learner update"
