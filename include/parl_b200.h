@@ -139,6 +139,18 @@ int rl_env_atari_synth_step(
     int B, int HW, uint64_t seed, uint32_t step, const uint32_t* step_dev, uint32_t env_offset, float p_done,
     int reset, rl_stream_t stream);
 
+/* rl_env_atari_synth_step for step row t of a frame ring `planes` [P,B,7056] (84x84 frames; the new frame goes to
+ * planes[t+4]) fused with rl_obs_stack_gather(out_dtype 4) of the NEXT step: obs_next [B,21,21,64] uint8 receives
+ * obs(t+1) — the new frame is taken from shared memory, the older frames of the stack from the ring.  Bit-identical to
+ * the two separate calls; saves one launch per env step of the actor chain (VectorEnv.step + the agent's obs handling,
+ * parl/env/vector_env.py:41-63, examples/IMPALA/actor.py:60-75). */
+int rl_env_atari_synth_step_gather(
+    uint8_t* planes, int t, float* reward_out, uint8_t* done_out, const uint8_t* age_in, uint8_t* age_out,
+    const float* logits, int A, int32_t* actions_out,
+    float* ep_ret, int32_t* ep_len, float* totals, float* ring_ret, int32_t* ring_len, uint32_t* ring_head, int ring_cap,
+    int B, uint64_t seed, uint32_t step, const uint32_t* step_dev, uint32_t env_offset, float p_done,
+    uint8_t* obs_next, rl_stream_t stream);
+
 /* Materialise observations from the frame ring: obs(t,b) channel j (0 = oldest)
  * = plane[t + 3 - min(3-j, age[t,b])].  planes [P,B,HW] u8, ages [>=t_begin+t_count, B] u8.
  * Output [t_count*B, 4, HW] in time-major or env-major sample order;
@@ -325,6 +337,14 @@ int rl_gemm_bf16_tn(const void* A, const void* B, const float* bias, void* C, in
 /* 1 (default): outputs of at least 2 x 2 tiles of width >= 128 run as 2 x 2 thread-block clusters whose CTAs multicast
  * their operand half-tiles to each other (each operand byte leaves L2 once per cluster); 0: single-CTA form only. */
 int rl_debug_set_gemm_cluster(int enable);
+/* Hidden layer + small heads in one call (the actor's fc 5184->512 followed by the policy head,
+ * benchmark/torch/a2c/atari_model.py:46-49,60-66): H = act(A.B^T + bias) [M,N] bf16 as rl_gemm_bf16_tn(_splitk), then
+ * out2 = bf16(H).W2^T + b2 for N2 <= 32 head rows (W2 [N2,N] bf16, out2 [M,ldo2] float32, fp32 accumulation in a fixed
+ * order).  With split-K the reduce, bias, ReLU, H store and the heads are ONE kernel (warp per row); otherwise the heads
+ * kernel follows the GEMM.  N % 128 == 0, N <= 1024, N2*N*2 <= 48 KB.  workspace as rl_gemm_bf16_tn_splitk (may be NULL). */
+int rl_gemm_bf16_tn_heads(const void* A, const void* B, const float* bias, void* H, int M, int N, int K, int lda, int ldb,
+                          int ldh, int relu, const void* W2, const float* b2, int N2, float* out2, int ldo2,
+                          void* workspace, size_t workspace_bytes, rl_stream_t stream);
 /* rl_gemm_bf16_tn with an optional split-K workspace — the actor-side nn.Linear (atari_model.py:46-49 evaluated on
  *  the 5-env batch of examples/IMPALA/actor.py:60-62; here 512..4096 envs per GPU).  Workspace (>= splits * ceil(M/128)*128 * ceil(N/BN)*BN * 4 bytes; 8 MB
  * covers every shape that splits): when the output has fewer tiles than half the SMs and K >= 1024, the reduction is

@@ -38,6 +38,8 @@ SIGNATURES = {
                                      c_f, c_f, c_f, c_f, c_f, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
     'rl_env_atari_synth_step': (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i,
                                       c_i, c_i, c_u64, c_u32, c_p, c_u32, c_f, c_i, c_p]),
+    'rl_env_atari_synth_step_gather': (c_i, [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
+                                             c_i, c_i, c_u64, c_u32, c_p, c_u32, c_f, c_p, c_p]),
     'rl_obs_stack_gather': (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p]),
     'rl_env_mujoco_synth_step': (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i,
                                        c_u64, c_u32, c_u32, c_f, c_i, c_p]),
@@ -75,6 +77,7 @@ SIGNATURES = {
     'rl_debug_set_shiftconv_base_offset': (c_i, [c_i]),
     'rl_debug_set_shiftconv_form': (c_i, [c_i]),
     'rl_debug_set_gemm_cluster': (c_i, [c_i]),
+    'rl_gemm_bf16_tn_heads': (c_i, [c_p, c_p, c_p, c_p] + [c_i] * 7 + [c_p, c_p, c_i, c_p, c_i, c_p, c_sz, c_p]),
     'rl_conv2d_s1_nhwc_bf16_dgrad': (c_i, [c_p, c_p, c_p, c_p] + [c_i] * 10 + [c_p]),
     'rl_conv_wgrad_workspace_bytes': (c_sz, [c_i, c_i, c_i]),
     'rl_conv2d_s1_nhwc_bf16_wgrad': (c_i, [c_p, c_p, c_p, c_p] + [c_i] * 8 + [c_p, c_sz, c_p]),

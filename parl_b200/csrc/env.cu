@@ -284,6 +284,112 @@ __global__ void __launch_bounds__(256) obs_stack_gather_s2d_kernel(const uint8_t
 }
 
 // ---------------------------------------------------------------------------
+// Env step t fused with the observation gather of step t+1 (uint8 space-to-depth form): the per-env-step chain of the
+// actor loses one launch, and the new frame is used from shared memory instead of being read back from HBM.
+//   CTAs [0, nscalar)   : the per-env scalar part of atari_synth_step_kernel, unchanged (reward, done, age, action
+//                         sampling from the logits, episode statistics) — 256 envs per CTA;
+//   CTAs [nscalar, ...) : one env at a time (grid-stride): generate frame (step+1) into shared memory AND the frame
+//                         ring (the ring stays the system of record: later steps' stacks, the learner-side and host
+//                         paths read it), recompute this env's done flag (a pure function of (env, step)) to get
+//                         age(t+1), fetch the up to three older frames of the stack from the ring with cp.async, and
+//                         write obs(t+1) as [21,21,64] uint8 blocks — bit-identical to rl_env_atari_synth_step
+//                         followed by rl_obs_stack_gather(out_dtype 4).
+// ---------------------------------------------------------------------------
+struct AtariStepGatherArgs {
+  AtariStepArgs s;
+  const uint8_t* planes;     // ring base [P, B, 7056]; s.frame_out = planes[t + 4]
+  int t;                     // row of this step: the older frames of obs(t+1) are planes[t + 4 - k], k = 1..3
+  uint8_t* obs_next;         // [B, 21, 21, 64] uint8
+  int nscalar;
+};
+
+__global__ void __launch_bounds__(256) atari_step_gather_kernel(AtariStepGatherArgs a) {
+  constexpr int W = 84, G = 21, ITEMS = G * G * 4, FRAME = W * W, CHUNKS = FRAME / 16;
+  __shared__ __align__(16) uint8_t sfr[4][FRAME];
+  pdl_wait();            // chain kernel (launch_chain)
+  pdl_trigger();
+  AtariStepArgs& p = a.s;
+  if (p.step_dev) p.step = *p.step_dev;
+  if ((int)blockIdx.x < a.nscalar) {
+    const int b = blockIdx.x * 256 + threadIdx.x;
+    const bool valid = b < p.B;
+    float reward = 0.f;
+    bool done = false;
+    if (valid) {
+      const uint32_t env = p.env_offset + (uint32_t)b;
+      const uint4 x = philox4x32_10(env, p.step, 0u, STREAM_REWDONE, p.k0, p.k1);
+      reward = (float)(x.x & 1u);
+      done = x.y < p.done_thr;
+      p.reward_out[b] = reward;
+      p.done_out[b] = done ? 1 : 0;
+      const int age = p.age_in[b];
+      p.age_out[b] = done ? 0 : (uint8_t)min(age + 1, 3);
+      if (p.logits) {
+        const uint4 ua = philox4x32_10(env, p.step, 0u, STREAM_ACTION, p.k0, p.k1);
+        p.actions_out[b] = sample_categorical_exact(p.logits + (long long)b * p.A, p.A, u01_24(ua.x));
+      }
+    }
+    episode_update(p.st, b, valid, reward, done);
+    return;
+  }
+  const uint32_t n = p.step + 1u;
+  for (int b = blockIdx.x - a.nscalar; b < p.B; b += gridDim.x - a.nscalar) {
+    const uint32_t env = p.env_offset + (uint32_t)b;
+    // age of obs(t+1): same arithmetic as the scalar part (done is a pure function of (env, step))
+    const uint4 x = philox4x32_10(env, p.step, 0u, STREAM_REWDONE, p.k0, p.k1);
+    const int age = (x.y < p.done_thr) ? 0 : min((int)p.age_in[b] + 1, 3);
+    // newest frame: generate once, keep in shared memory (channel 3), write to the ring
+    uint4* ring = reinterpret_cast<uint4*>(p.frame_out + (long long)b * FRAME);
+    for (int k = threadIdx.x; k < CHUNKS; k += 256) {
+      const uint4 v = frame_block(env, n, (uint32_t)k, p.k0, p.k1);
+      *reinterpret_cast<uint4*>(&sfr[3][k * 16]) = v;
+      ring[k] = v;
+    }
+    // older channels c = 0..2: plane[t + 4 - min(3 - c, age)]; min(..) == 0 is the new frame itself
+    for (int i = threadIdx.x; i < 3 * CHUNKS; i += 256) {
+      const int c = i / CHUNKS, k = i - c * CHUNKS;
+      const int back = min(3 - c, age);
+      if (back > 0)
+        cp_async16(&sfr[c][k * 16], a.planes + ((long long)(a.t + 4 - back) * p.B + b) * FRAME + k * 16);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    if (age < 3) {                                   // channels that repeat the new frame (after a reset)
+      for (int i = threadIdx.x; i < 3 * CHUNKS; i += 256) {
+        const int c = i / CHUNKS, k = i - c * CHUNKS;
+        if (min(3 - c, age) == 0) *reinterpret_cast<uint4*>(&sfr[c][k * 16]) = *reinterpret_cast<const uint4*>(&sfr[3][k * 16]);
+      }
+      __syncthreads();
+    }
+    uint8_t* dst_sample = a.obs_next + (long long)b * (G * G * 64);
+    for (int j = threadIdx.x; j < ITEMS; j += 256) {
+      const int dy = j & 3, pq = j >> 2, Y = pq / G, X = pq - Y * G;
+      const int y = 4 * Y + dy - 1;
+      uint32_t px[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        px[c] = 0u;
+        if (y >= 0) {
+          const uint32_t* row = reinterpret_cast<const uint32_t*>(&sfr[c][0]) + y * (W / 4);
+          const uint32_t w0 = X > 0 ? row[X - 1] : 0u;
+          const uint32_t w1 = row[X];
+          px[c] = (w0 >> 24) | (w1 << 8);
+        }
+      }
+      uint32_t wd[4];
+#pragma unroll
+      for (int dx = 0; dx < 4; ++dx) {
+        const uint32_t sel = (uint32_t)dx | ((uint32_t)(4 + dx) << 4);
+        wd[dx] = __byte_perm(__byte_perm(px[0], px[1], sel), __byte_perm(px[2], px[3], sel), 0x5410u);
+      }
+      *reinterpret_cast<uint4*>(dst_sample + pq * 64 + dy * 16) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    }
+    __syncthreads();                                 // the next env overwrites the staged frames
+  }
+}
+
+// ---------------------------------------------------------------------------
 // MuJoCo-shaped synthetic env (obs N(0,1)^D) and CartPole physics: one lane per env.
 // ---------------------------------------------------------------------------
 struct VecStepArgs {
@@ -459,6 +565,31 @@ extern "C" int rl_env_atari_synth_step(uint8_t* frame_out, float* reward_out, ui
   if (blocks < (B + 255) / 256) blocks = (B + 255) / 256;
   launch_chain(atari_synth_step_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, a);
   RL_CHECK_LAUNCH("rl_env_atari_synth_step");
+  return RL_OK;
+}
+
+extern "C" int rl_env_atari_synth_step_gather(uint8_t* planes, int t, float* reward_out, uint8_t* done_out,
+                                              const uint8_t* age_in, uint8_t* age_out, const float* logits, int A,
+                                              int32_t* actions_out, float* ep_ret, int32_t* ep_len, float* totals,
+                                              float* ring_ret, int32_t* ring_len, uint32_t* ring_head, int ring_cap,
+                                              int B, uint64_t seed, uint32_t step, const uint32_t* step_dev,
+                                              uint32_t env_offset, float p_done, uint8_t* obs_next, rl_stream_t stream) {
+  RL_CHECK_ARG(planes && reward_out && done_out && age_in && age_out && ep_ret && ep_len && totals && obs_next && t >= 0,
+               "atari_synth_step_gather: null pointer");
+  RL_CHECK_ARG(B > 0 && aligned16(planes) && aligned16(obs_next), "atari_synth_step_gather: bad shape / alignment");
+  RL_CHECK_ARG(!logits || (A >= 1 && actions_out), "atari_synth_step_gather: logits given but A=%d / actions_out null", A);
+  AtariStepGatherArgs g;
+  AtariStepArgs& a = g.s;
+  a.frame_out = planes + (size_t)(t + 4) * B * 7056, a.reward_out = reward_out, a.done_out = done_out;
+  a.age_in = age_in, a.age_out = age_out, a.logits = logits, a.actions_out = actions_out, a.A = A;
+  a.st = make_stats(ep_ret, ep_len, totals, ring_ret, ring_len, ring_head, ring_cap);
+  a.B = B, a.HW = 7056, a.k0 = (uint32_t)seed, a.k1 = (uint32_t)(seed >> 32), a.step = step, a.env_offset = env_offset;
+  a.done_thr = prob_thr(p_done), a.reset = 0, a.step_dev = step_dev;
+  g.planes = planes, g.t = t, g.obs_next = obs_next, g.nscalar = (B + 255) / 256;
+  long long env_ctas = B;
+  if (env_ctas > 148LL * 7) env_ctas = 148LL * 7;          // 28 KB of staged frames per CTA: 7 CTAs per SM
+  launch_chain(atari_step_gather_kernel, dim3((unsigned)(g.nscalar + env_ctas)), dim3(256), 0, (cudaStream_t)stream, g);
+  RL_CHECK_LAUNCH("rl_env_atari_synth_step_gather");
   return RL_OK;
 }
 

@@ -323,6 +323,84 @@ __global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(const float* __
   }
 }
 
+// Hidden layer + small heads of the actor step in one pass (examples/IMPALA/atari_model.py policy head after the fc
+// layer): a warp owns one row.  H[row, :] = relu(sum_z partial[z][row][:] + bias) (split-K reduce; or, with
+// partial == NULL, H is read as written by the GEMM epilogue), rounded to bf16 and stored; then
+// out2[row, n] = b2[n] + sum_c bf16(H[row, c]) * W2[n, c] for the N2 <= 32 head rows — fp32, fixed order (16-column
+// lane partials, xor-shuffle tree), so the per-step chain has one launch instead of reduce + a tensor-core GEMM whose
+// 7-8 us are all prologue at N2 = 18.
+struct HeadsArgs {
+  const __nv_bfloat16* W2;   // [N2, N] bf16
+  const float* b2;           // [N2] or NULL
+  float* out2;               // [M, ldo2]
+  int N2, ldo2;
+};
+constexpr int kHeadsMaxN = 1024, kHeadsMaxN2 = 32;
+
+__global__ void __launch_bounds__(256) fc_reduce_heads_kernel(const float* __restrict__ partial, int splits, int mpad, int ldp,
+                                                              const float* __restrict__ bias, __nv_bfloat16* __restrict__ H,
+                                                              int ldh, int M, int N, int relu, const HeadsArgs hd) {
+  extern __shared__ __align__(16) unsigned char heads_smem[];
+  __nv_bfloat16* sW = reinterpret_cast<__nv_bfloat16*>(heads_smem);          // [N2][N]
+  for (int i = threadIdx.x; i < hd.N2 * N / 8; i += blockDim.x)            // head weights: written by the operand refresh
+    reinterpret_cast<uint4*>(sW)[i] = __ldg(reinterpret_cast<const uint4*>(hd.W2) + i);
+  pdl_wait();            // chain kernel (launch_chain)
+  pdl_trigger();
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int nchunk = N >> 7;                                               // 128 columns per pass: 4 per lane
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
+    float acc[kHeadsMaxN2];
+#pragma unroll
+    for (int n = 0; n < kHeadsMaxN2; ++n) acc[n] = 0.f;
+    for (int j = 0; j < nchunk; ++j) {
+      const int col = j * 128 + lane * 4;
+      float hv[4];
+      if (partial) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z = 0; z < splits; ++z) {
+          const float4 p = *reinterpret_cast<const float4*>(partial + ((size_t)z * mpad + row) * ldp + col);
+          a.x += p.x, a.y += p.y, a.z += p.z, a.w += p.w;
+        }
+        const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        hv[0] = a.x + b4.x, hv[1] = a.y + b4.y, hv[2] = a.z + b4.z, hv[3] = a.w + b4.w;
+        if (relu) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hv[i] = fmaxf(hv[i], 0.f);
+        }
+        __nv_bfloat162 lo = __floats2bfloat162_rn(hv[0], hv[1]), hi = __floats2bfloat162_rn(hv[2], hv[3]);
+        *reinterpret_cast<uint2*>(H + (size_t)row * ldh + col) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        hv[0] = __low2float(lo), hv[1] = __high2float(lo), hv[2] = __low2float(hi), hv[3] = __high2float(hi);
+      } else {
+        const uint2 u = *reinterpret_cast<const uint2*>(H + (size_t)row * ldh + col);
+        const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+        hv[0] = __low2float(lo), hv[1] = __high2float(lo), hv[2] = __low2float(hi), hv[3] = __high2float(hi);
+      }
+#pragma unroll
+      for (int n = 0; n < kHeadsMaxN2; ++n) {
+        if (n < hd.N2) {
+          const uint2 w = *reinterpret_cast<const uint2*>(sW + (size_t)n * N + col);
+          const __nv_bfloat162 wl = *reinterpret_cast<const __nv_bfloat162*>(&w.x), wh = *reinterpret_cast<const __nv_bfloat162*>(&w.y);
+          acc[n] = fmaf(hv[0], __low2float(wl), acc[n]);
+          acc[n] = fmaf(hv[1], __high2float(wl), acc[n]);
+          acc[n] = fmaf(hv[2], __low2float(wh), acc[n]);
+          acc[n] = fmaf(hv[3], __high2float(wh), acc[n]);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < kHeadsMaxN2; ++n) {
+      if (n < hd.N2) {
+        float v = acc[n];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) hd.out2[(size_t)row * hd.ldo2 + n] = v + (hd.b2 ? hd.b2[n] : 0.f);
+      }
+    }
+  }
+}
+
 // rank-2 bf16 tensor map {K (contiguous), rows}, box {64, box_rows}, SWIZZLE_128B
 static int make_tensor_map_bf16_sw128(CUtensorMap* map, const void* base, uint64_t K, uint64_t rows, uint64_t pitch_bytes,
                                       uint32_t box_rows) {
@@ -382,7 +460,7 @@ using namespace rl;
 
 static int gemm_launch(const void* A, const void* B, const float* bias, void* C, int M, int N, int K, int lda, int ldb,
                        int ldc, int relu, int out_f32, const void* mask, int ldm, void* workspace, size_t workspace_bytes,
-                       rl_stream_t stream);
+                       rl_stream_t stream, const HeadsArgs* heads = nullptr);
 
 // 1 (default): 2 x 2 cluster + TMA multicast form for outputs of at least 2 x 2 tiles of width >= 128; 0: never.
 static int g_gemm_cluster = 1;
@@ -403,15 +481,39 @@ extern "C" int rl_gemm_bf16_tn_splitk(const void* A, const void* B, const float*
   return gemm_launch(A, B, bias, C, M, N, K, lda, ldb, ldc, relu, out_f32, nullptr, 0, workspace, workspace_bytes, stream);
 }
 
+extern "C" int rl_gemm_bf16_tn_heads(const void* A, const void* B, const float* bias, void* H, int M, int N, int K, int lda,
+                                     int ldb, int ldh, int relu, const void* W2, const float* b2, int N2, float* out2,
+                                     int ldo2, void* workspace, size_t workspace_bytes, rl_stream_t stream) {
+  RL_CHECK_ARG(W2 && out2 && N2 >= 1 && N2 <= kHeadsMaxN2 && ldo2 >= N2, "gemm_bf16_tn_heads: 1 <= N2 <= 32 heads required");
+  RL_CHECK_ARG(N % 128 == 0 && N <= kHeadsMaxN && ldh % 4 == 0 && (size_t)N2 * N * 2 <= 48 * 1024 && aligned16(W2) &&
+                   (!bias || aligned16(bias)),
+               "gemm_bf16_tn_heads: N must be a multiple of 128 (<= 1024), N2*N*2 <= 48 KB, ldh % 4 == 0");
+  RL_CHECK_ARG(!workspace || aligned16(workspace), "gemm_bf16_tn_heads: workspace must be 16-byte aligned");
+  HeadsArgs hd;
+  hd.W2 = (const __nv_bfloat16*)W2, hd.b2 = b2, hd.out2 = out2, hd.N2 = N2, hd.ldo2 = ldo2;
+  return gemm_launch(A, B, bias, H, M, N, K, lda, ldb, ldh, relu, 0, nullptr, 0, workspace, workspace_bytes, stream, &hd);
+}
+
 extern "C" int rl_gemm_bf16_tn_masked(const void* A, const void* B, void* C, const void* mask, int M, int N, int K,
                                       int lda, int ldb, int ldc, int ldm, int out_f32, rl_stream_t stream) {
   RL_CHECK_ARG(mask && ldm >= N, "gemm_bf16_tn_masked: mask required, ldm >= N");
   return gemm_launch(A, B, nullptr, C, M, N, K, lda, ldb, ldc, 0, out_f32, mask, ldm, nullptr, 0, stream);
 }
 
+static int launch_heads(const float* partial, int splits, int mpad, int ldp, const float* bias, void* H, int ldh, int M,
+                        int N, int relu, const HeadsArgs& hd, cudaStream_t st) {
+  const size_t smem = (size_t)hd.N2 * N * 2;
+  int blocks = (M + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  return launch_chain(fc_reduce_heads_kernel, dim3((unsigned)blocks), dim3(256), smem, st, partial, splits, mpad, ldp, bias,
+                      (__nv_bfloat16*)H, ldh, M, N, relu, hd) == cudaSuccess
+             ? 0
+             : -1;
+}
+
 static int gemm_launch(const void* A, const void* B, const float* bias, void* C, int M, int N, int K, int lda, int ldb,
                        int ldc, int relu, int out_f32, const void* mask, int ldm, void* workspace, size_t workspace_bytes,
-                       rl_stream_t stream) {
+                       rl_stream_t stream, const HeadsArgs* heads) {
   RL_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "gemm_bf16_tn: bad argument");
   RL_CHECK_ARG(aligned16(A) && aligned16(B) && aligned16(C), "gemm_bf16_tn: pointers must be 16-byte aligned");
   RL_CHECK_ARG(lda >= K && ldb >= K && ldc >= N && (lda % 8) == 0 && (ldb % 8) == 0,
@@ -463,6 +565,10 @@ static int gemm_launch(const void* A, const void* B, const float* bias, void* C,
       return RL_ERR_CUDA;
     }
     RL_CHECK_LAUNCH("rl_gemm_bf16_tn");
+    if (heads && launch_heads(nullptr, 0, 0, 0, nullptr, C, ldc, M, N, 0, *heads, st)) {
+      set_error("gemm_bf16_tn_heads: heads launch failed");
+      return RL_ERR_CUDA;
+    }
     return RL_OK;
   }
   switch (BN) {
@@ -472,10 +578,23 @@ static int gemm_launch(const void* A, const void* B, const float* bias, void* C,
     default: launch_gemm<32>(ma, mb, g, splits, st); break;
   }
   if (splits > 1) {
+    if (heads) {
+      // split-K reduce, bias, ReLU, bf16 H and the heads in ONE kernel
+      if (launch_heads(g.partial, splits, g.mpad, g.ldp, bias, C, ldc, M, N, relu, *heads, st)) {
+        set_error("gemm_bf16_tn_heads: heads launch failed");
+        return RL_ERR_CUDA;
+      }
+      RL_CHECK_LAUNCH("rl_gemm_bf16_tn_heads");
+      return RL_OK;
+    }
     const long long items = (long long)M * ((N + 3) / 4);
     launch_chain(gemm_splitk_reduce_kernel, dim3((unsigned)((items + 255) / 256)), dim3(256), 0, st,
                  (const float*)g.partial, splits, g.mpad, g.ldp, g);
   }
   RL_CHECK_LAUNCH("rl_gemm_bf16_tn");
+  if (heads && launch_heads(nullptr, 0, 0, 0, nullptr, C, ldc, M, N, 0, *heads, st)) {
+    set_error("gemm_bf16_tn_heads: heads launch failed");
+    return RL_ERR_CUDA;
+  }
   return RL_OK;
 }

@@ -8,6 +8,8 @@ The bf16 operand copies of the parameters are re-packed from the fp32 master wei
 update (``pack``): conv kernels in (r,s,c)-ordered [Cout, K] form, conv1 in its space-to-depth form, the
 fc weight with (H,W,C)-ordered columns.
 """
+import os
+
 import torch
 
 from .. import kernels
@@ -21,6 +23,11 @@ class AtariActorNet(object):
         dev = self.device = torch.device(device)
         bf = torch.bfloat16
         self.window_form = window_form
+        # fc + policy head in one call (rl_gemm_bf16_tn_heads: split-K reduce and head in ONE warp-per-row kernel).  OFF
+        # by default: measured slower on B200 (rollout of 512 envs 3.04 vs 2.64 ms, 4096 envs 12.0 vs 11.6 ms,
+        # profiles/r02_chain_ab.txt) — the CUDA-core head costs ~900 instructions per row against a tcgen05 GEMM whose
+        # 7-8 us are almost all prologue
+        self.fuse_heads = os.environ.get('PARL_B200_FUSE_HEADS', '0') == '1'
         # window form: conv1 writes conv2's zero-padded 2x2-block input [B,12,12,128] (border stays zero)
         self.a1 = (torch.zeros((self.B, 12, 12, 128), dtype=bf, device=dev) if window_form else
                    torch.empty((self.B, 20, 20, 32), dtype=bf, device=dev))
@@ -73,8 +80,11 @@ class AtariActorNet(object):
             K.conv2d_nhwc_bf16_fwd(obs_s2d, self.w1, self.b1, 2, 2, 1, 0, relu=True, out=self.a1)
             K.conv2d_nhwc_bf16_fwd(self.a1, self.w2, self.b2, 4, 4, 2, 2, relu=True, out=self.a2)
             K.conv2d_nhwc_bf16_fwd(self.a2, self.w3, self.b3, 3, 3, 1, 0, relu=True, out=self.a3)
-        K.gemm_bf16_tn(self.a3.view(self.B, 5184), self.wfc, self.bfc, relu=True, out=self.h)
-        K.gemm_bf16_tn(self.h, self.wpi, self.bpi, relu=False, out=logits_out)
+        if self.fuse_heads:
+            K.gemm_bf16_tn_heads(self.a3.view(self.B, 5184), self.wfc, self.bfc, self.h, self.wpi, self.bpi, logits_out)
+        else:
+            K.gemm_bf16_tn(self.a3.view(self.B, 5184), self.wfc, self.bfc, relu=True, out=self.h)
+            K.gemm_bf16_tn(self.h, self.wpi, self.bpi, relu=False, out=logits_out)
         return logits_out
 
     def value(self, values_out):

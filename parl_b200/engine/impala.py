@@ -82,6 +82,8 @@ class ImpalaEngine(object):
         # per-step policy input, pre-scaled bf16 (space-to-depth blocks on 84x84 frames, else NHWC) or uint8 blocks
         self.obs_dtype = torch.uint8 if (self.s2d and obs_dtype in ('uint8', 'u8', torch.uint8)) else torch.bfloat16
         self.obs_step = torch.empty((B, ) + obs_shape, dtype=self.obs_dtype, device=dev)
+        self.fuse_step_gather = os.environ.get('PARL_B200_FUSE_STEP_GATHER', '1') != '0'
+
         self.step_dev = torch.zeros(T, dtype=torch.int32, device=dev)      # global env-step index of row t
         self.step_dev.copy_(torch.arange(T, dtype=torch.int32))
         self.model = model if model is not None else AtariActorCritic(A)
@@ -168,18 +170,29 @@ class ImpalaEngine(object):
             self.planes[0:4].copy_(prev['planes'][T:T + 4])
             self.ages[0].copy_(prev['ages'][T])
             self.step_dev.add_(T)
+            # per env step: [obs gather ->] policy forward -> env step.  On 84x84 uint8 observations the env step of
+            # row t also produces obs(t+1) (rl_env_atari_synth_step_gather): one launch less per step
+            fuse = self.s2d and self.obs_dtype == torch.uint8 and self.fuse_step_gather
             for t in range(T):
                 obs_t = self.x0[t] if self.share_obs else self.obs_step
-                kernels.obs_stack_gather(self.planes, self.ages, t, 1, obs_t, scale=1.0 / 255.0, s2d=self.s2d)
+                if t == 0 or not fuse:
+                    kernels.obs_stack_gather(self.planes, self.ages, t, 1, obs_t, scale=1.0 / 255.0, s2d=self.s2d)
                 if self.actor_net is not None:
                     self.actor_net.policy(obs_t, self.beh_logits[t])
                 else:
                     pol = self._actor_model if self._actor_model is not None else self.model
                     self.beh_logits[t].copy_(pol.policy(obs_t))
-                kernels.env_atari_synth_step(self.planes[t + 4], self.rewards[t], self.dones[t], self.ages[t],
-                                             self.ages[t + 1], self.stats, self.seed, 0, p_done=self.p_done,
-                                             env_offset=self.env_offset, logits=self.beh_logits[t],
-                                             actions_out=self.actions[t], step_dev=self.step_dev[t:])
+                if fuse and t + 1 < T:
+                    obs_n = self.x0[t + 1] if self.share_obs else self.obs_step
+                    kernels.env_atari_synth_step_gather(self.planes, t, self.rewards[t], self.dones[t], self.ages[t],
+                                                        self.ages[t + 1], self.stats, self.seed, obs_n, p_done=self.p_done,
+                                                        env_offset=self.env_offset, logits=self.beh_logits[t],
+                                                        actions_out=self.actions[t], step_dev=self.step_dev[t:])
+                else:
+                    kernels.env_atari_synth_step(self.planes[t + 4], self.rewards[t], self.dones[t], self.ages[t],
+                                                 self.ages[t + 1], self.stats, self.seed, 0, p_done=self.p_done,
+                                                 env_offset=self.env_offset, logits=self.beh_logits[t],
+                                                 actions_out=self.actions[t], step_dev=self.step_dev[t:])
 
     def _run_rollout(self, i):
         """Rollout into buffer set i on the current stream (graph replay after the first, eager, run)."""

@@ -174,6 +174,21 @@ def env_atari_synth_step(frame_out, reward_out, done_out, age_in, age_out, stats
         1 if reset else 0, stream()), 'env_atari_synth_step')
 
 
+def env_atari_synth_step_gather(planes, t, reward_out, done_out, age_in, age_out, stats, seed, obs_next, p_done=0.1,
+                                env_offset=0, logits=None, actions_out=None, step_dev=None, step=0):
+    """Env step of row t (new frame -> planes[t+4]) fused with the uint8 space-to-depth gather of obs(t+1) into
+    ``obs_next`` [B,21,21,64] (rl_env_atari_synth_step_gather); 84x84 frames."""
+    require_cuda(planes, obs_next)
+    P, B = planes.shape[0], planes.shape[1]
+    assert planes[0, 0].numel() == 84 * 84 and planes.dtype == torch.uint8 and 0 <= t and t + 4 < P
+    assert obs_next.dtype == torch.uint8 and obs_next.numel() == B * 21 * 21 * 64 and obs_next.is_contiguous()
+    A = logits.shape[-1] if logits is not None else 0
+    check(_lib.load().rl_env_atari_synth_step_gather(
+        ptr(planes), int(t), ptr(reward_out), ptr(done_out), ptr(age_in), ptr(age_out), ptr(logits), A, ptr(actions_out),
+        *stats.args(), B, int(seed), int(step), ptr(step_dev), int(env_offset), float(p_done), ptr(obs_next), stream()),
+        'env_atari_synth_step_gather')
+
+
 def obs_stack_gather(planes, ages, t_begin, t_count, out, layout=TIME_MAJOR, scale=1.0, s2d=False):
     """planes [P,B,HW] u8, ages [T+1,B] u8 -> out [t_count*B, 4, HW] (uint8 / float32, NCHW) or
     [t_count*B, HW, 4] (bfloat16, NHWC, value*scale)."""
@@ -519,6 +534,24 @@ def gemm_bf16_tn(a, b, bias=None, relu=False, out_dtype=torch.bfloat16, out=None
                                       out.stride(0), 1 if relu else 0, 1 if out.dtype == torch.float32 else 0,
                                       stream()), 'gemm_bf16_tn')
     return out
+
+
+def gemm_bf16_tn_heads(a, b, bias, h_out, w2, b2, out2, relu=True):
+    """h_out = act(a @ b.T + bias) (bf16) and out2 = h_out @ w2.T + b2 (float32, <= 32 head rows) in one call
+    (rl_gemm_bf16_tn_heads): at small batch the split-K reduce and the heads are a single kernel."""
+    require_cuda(a, b, bias, h_out, w2, b2, out2)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16
+    assert h_out.dtype == torch.bfloat16 and out2.dtype == torch.float32 and bias.dtype == torch.float32
+    M, K = a.shape
+    N, N2 = b.shape[0], w2.shape[0]
+    assert h_out.shape == (M, N) and out2.shape == (M, N2) and w2.shape[1] == N and w2.is_contiguous()
+    ws = _raw_ws(a.device, 8 << 20, 'gemm_splitk_%d' % torch.cuda.current_stream(a.device).cuda_stream) \
+        if (M <= 2048 and K >= 1024) else None
+    check(_lib.load().rl_gemm_bf16_tn_heads(ptr(a), ptr(b), ptr(bias), ptr(h_out), M, N, K, a.stride(0), b.stride(0),
+                                            h_out.stride(0), 1 if relu else 0, ptr(w2), ptr(b2), N2, ptr(out2),
+                                            out2.stride(0), ptr(ws), ws.numel() if ws is not None else 0, stream()),
+          'gemm_bf16_tn_heads')
+    return out2
 
 
 def conv2d_nhwc_bf16_fwd(x, weight_krsc, bias, KH, KW, stride, pad, relu=True, out=None):

@@ -204,3 +204,45 @@ def test_obs_gather_nhwc_and_space_to_depth():
     s2d_em = torch.empty(T * B, 21, 21, 64, dtype=torch.bfloat16, device=DEV)
     K.obs_stack_gather(planes, ages, 0, T, s2d_em, layout=K.ENV_MAJOR, scale=1.0 / 255.0, s2d=True)
     assert torch.equal(s2d_em.cpu().reshape(B, T, -1), want.reshape(T, B, -1).transpose(0, 1))
+
+
+@pytest.mark.parametrize('B', [5, 300, 1200])
+def test_fused_step_gather_is_bit_identical_to_separate_kernels(B):
+    """rl_env_atari_synth_step_gather == rl_env_atari_synth_step followed by rl_obs_stack_gather(uint8 space-to-depth)
+    of the next step: frames, scalars, actions, episode statistics and obs(t+1), over several steps with resets."""
+    import torch
+    from parl_b200 import kernels as K
+    dev = torch.device('cuda', 0)
+    T, A, seed = 6, 18, 1234
+
+    def fresh():
+        planes = torch.zeros((T + 4, B, 84 * 84), dtype=torch.uint8, device=dev)
+        ages = torch.zeros((T + 1, B), dtype=torch.uint8, device=dev)
+        st = K.EpisodeStats(B, dev)
+        K.env_atari_synth_step(planes[3], None, None, None, ages[0], st, seed, 0, env_offset=7, reset=True)
+        return dict(planes=planes, ages=ages, st=st, rew=torch.zeros((T, B), device=dev),
+                    done=torch.zeros((T, B), dtype=torch.uint8, device=dev),
+                    act=torch.zeros((T, B), dtype=torch.int32, device=dev),
+                    obs=torch.zeros((T + 1, B, 21, 21, 64), dtype=torch.uint8, device=dev))
+
+    g = torch.Generator(device=dev).manual_seed(B)
+    logits = torch.randn((T, B, A), device=dev, generator=g)
+    a, b = fresh(), fresh()
+    step_dev = torch.arange(T, dtype=torch.int32, device=dev)
+    for s_, fused in ((a, False), (b, True)):
+        K.obs_stack_gather(s_['planes'], s_['ages'], 0, 1, s_['obs'][0], s2d=True)
+        for t in range(T):
+            if fused:
+                K.env_atari_synth_step_gather(s_['planes'], t, s_['rew'][t], s_['done'][t], s_['ages'][t], s_['ages'][t + 1],
+                                              s_['st'], seed, s_['obs'][t + 1], p_done=0.3, env_offset=7, logits=logits[t],
+                                              actions_out=s_['act'][t], step_dev=step_dev[t:])
+            else:
+                K.env_atari_synth_step(s_['planes'][t + 4], s_['rew'][t], s_['done'][t], s_['ages'][t], s_['ages'][t + 1],
+                                       s_['st'], seed, 0, p_done=0.3, env_offset=7, logits=logits[t],
+                                       actions_out=s_['act'][t], step_dev=step_dev[t:])
+                K.obs_stack_gather(s_['planes'], s_['ages'], t + 1, 1, s_['obs'][t + 1], s2d=True)
+    torch.cuda.synchronize()
+    for k in ('planes', 'ages', 'rew', 'done', 'act', 'obs'):
+        assert torch.equal(a[k], b[k]), k
+    assert a['done'].sum().item() > 0 and a['obs'].float().abs().sum().item() > 0
+    assert torch.equal(a['st'].totals, b['st'].totals) and torch.equal(a['st'].ep_len, b['st'].ep_len)

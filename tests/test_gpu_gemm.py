@@ -216,3 +216,25 @@ def test_obs_gather_s2d_matches_reference_layout():
     ref = (pad[:, :, :84, :84] * (1.0 / 255.0)).view(n, 4, 21, 4, 21, 4).permute(0, 2, 4, 3, 5, 1).reshape(n, 21, 21, 64)
     torch.cuda.synchronize()
     assert torch.equal(out, ref.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize('M', [96, 512, 4096])
+def test_gemm_heads_fused_matches_separate_calls(M):
+    """rl_gemm_bf16_tn_heads (actor fc + policy head; split-K reduce and heads in one kernel at small M) against the
+    two separate tcgen05 GEMMs for H (bit-identical) and an fp32 product of the stored bf16 H for the heads."""
+    from parl_b200 import kernels as K_
+    torch.manual_seed(M)
+    N, Kd, N2 = 512, 5184, 18
+    a = (torch.randn(M, Kd, device=DEV) * 0.05).to(torch.bfloat16)
+    b = (torch.randn(N, Kd, device=DEV) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV) * 0.1
+    w2 = (torch.randn(N2, N, device=DEV) * 0.1).to(torch.bfloat16)
+    b2 = torch.randn(N2, device=DEV)
+    h = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    out2 = torch.empty(M, N2, device=DEV)
+    K_.gemm_bf16_tn_heads(a, b, bias, h, w2, b2, out2)
+    h_ref = K_.gemm_bf16_tn(a, b, bias, relu=True)
+    torch.cuda.synchronize()
+    assert torch.equal(h, h_ref)
+    ref2 = h.float() @ w2.float().t() + b2
+    assert (out2 - ref2).abs().max().item() < 1e-3 * max(1.0, ref2.abs().max().item())

@@ -124,6 +124,8 @@ def test_one_launch_operand_refresh_matches_per_operand_copies():
     permute + copy expressions do, for the learner's and the actor's net, before and after a weight change."""
     from parl_b200.algorithms import IMPALA
     from parl_b200.engine.actor_net import AtariActorNet
+    from parl_b200.engine.nets import AtariActorCritic
+    from parl_b200.engine.train_net import AtariTrainNet
     torch.manual_seed(3)
     model = AtariActorCritic(18).to(DEV)
     alg = IMPALA(model, sample_batch_steps=4, gamma=0.99, vf_loss_coeff=0.5, clip_rho_threshold=1.0,
