@@ -330,11 +330,15 @@ def main():
     # (bf16 activations, every tensor read/written once per kernel that needs it):
     #   rollout 264 KB (gather 84.7, conv1 82.0, conv2 52.4, conv3 25.9, fc+heads 12.4, env frame 7.1)
     #   learner 538 KB (forward 172.7, mask/scatter + fc products 61.1, dgrad 132.9, wgrad 170.9)
-    step_bytes = (264.5e3 + 537.6e3) * T_STEPS * B
+    # with the observation plane kept uint8 (the default) the gather writes, and conv1 forward (actor + learner) and
+    # conv1's weight gradient read, 28.2 KB less each: 208 KB + 481 KB
+    u8_obs = eng.obs_step.dtype == torch.uint8
+    per_env_step = (264.5e3 + 537.6e3) - (4 * 28224 if u8_obs else 0)
+    step_bytes = per_env_step * T_STEPS * B
     ach_hbm = step_bytes * args.steps / elapsed / 1e9
     step_roof = dict(bound='hbm', what='whole step: activation traffic of the network kernels, per GPU',
                      achieved=ach_hbm, peak=peak, unit='GB/s', frac=ach_hbm / peak, peak_source=peak_src,
-                     algorithmic_bytes_per_env_step=802.1e3) if eng.train_net is not None else None
+                     algorithmic_bytes_per_env_step=per_env_step) if eng.train_net is not None else None
 
     e2e = None
     if not args.no_e2e:

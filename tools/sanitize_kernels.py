@@ -59,3 +59,37 @@ e = PolicyGradientEngine(num_envs=40, rollout_steps=12, device=dev)
 e.step()
 torch.cuda.synchronize()
 print('mlp engines ok')
+
+# round-2 additions: conv1 on uint8 observations (forward + weight gradient), the fused env step + next-observation
+# gather, the one-launch operand refresh, the 2x2-cluster GEMM, the fc + head call
+obs = torch.randint(0, 256, (40, 4, 84, 84), dtype=torch.uint8, device=dev)
+u8 = torch.empty((40, 21, 21, 64), dtype=torch.uint8, device=dev)
+K.obs_stack_gather(obs, None, 0, 1, u8, s2d=True)
+w1 = (torch.randn(32, 256, device=dev) * 0.05).to(torch.bfloat16)
+a1 = torch.zeros((40, 12, 12, 128), dtype=torch.bfloat16, device=dev)
+K.conv2d_s1_nhwc_bf16_fwd(u8, w1, torch.zeros(32, device=dev), 2, 2, relu=True, out=a1, out_mode=1)
+dout = torch.zeros((40, 21, 21, 32), dtype=torch.bfloat16, device=dev)
+dout[:, :20, :20] = 0.1
+K.conv2d_s1_nhwc_bf16_wgrad(dout, u8, 2, 2, db=torch.empty(32, device=dev))
+Bq, Tq = 37, 3
+planes = torch.zeros((Tq + 4, Bq, 7056), dtype=torch.uint8, device=dev)
+ages = torch.zeros((Tq + 1, Bq), dtype=torch.uint8, device=dev)
+st = K.EpisodeStats(Bq, dev)
+K.env_atari_synth_step(planes[3], None, None, None, ages[0], st, 5, 0, reset=True)
+nxt = torch.empty((Bq, 21, 21, 64), dtype=torch.uint8, device=dev)
+for t in range(Tq):
+    K.env_atari_synth_step_gather(planes, t, torch.empty(Bq, device=dev), torch.empty(Bq, dtype=torch.uint8, device=dev),
+                                  ages[t], ages[t + 1], st, 5, nxt, p_done=0.3, logits=torch.randn(Bq, 18, device=dev),
+                                  actions_out=torch.empty(Bq, dtype=torch.int32, device=dev), step=t)
+flat = torch.randn(5000, device=dev)
+idx = torch.randint(-1, 5000, (4099, ), dtype=torch.int32, device=dev)
+K.gather_cast(flat, idx, torch.empty(4099, dtype=torch.bfloat16, device=dev))
+K.gather_cast(flat, idx, torch.empty(4099, dtype=torch.float32, device=dev))
+a = (torch.randn(300, 512, device=dev) * 0.1).to(torch.bfloat16)
+b = (torch.randn(512, 512, device=dev) * 0.1).to(torch.bfloat16)
+K.gemm_bf16_tn(a, b, torch.zeros(512, device=dev), relu=True)                 # 3 x 4 tiles of 128 x 128: cluster form
+K.gemm_bf16_tn_heads(a, b, torch.zeros(512, device=dev), torch.empty(300, 512, dtype=torch.bfloat16, device=dev),
+                     (torch.randn(18, 512, device=dev) * 0.1).to(torch.bfloat16), torch.zeros(18, device=dev),
+                     torch.empty(300, 18, device=dev))
+torch.cuda.synchronize()
+print('round-2 kernels ok')
