@@ -340,11 +340,14 @@ int rl_debug_set_gemm_cluster(int enable);
 /* Hidden layer + small heads in one call (the actor's fc 5184->512 followed by the policy head,
  * benchmark/torch/a2c/atari_model.py:46-49,60-66): H = act(A.B^T + bias) [M,N] bf16 as rl_gemm_bf16_tn(_splitk), then
  * out2 = bf16(H).W2^T + b2 for N2 <= 32 head rows (W2 [N2,N] bf16, out2 [M,ldo2] float32, fp32 accumulation in a fixed
- * order).  With split-K the reduce, bias, ReLU, H store and the heads are ONE kernel (warp per row); otherwise the heads
- * kernel follows the GEMM.  N % 128 == 0, N <= 1024, N2*N*2 <= 48 KB.  workspace as rl_gemm_bf16_tn_splitk (may be NULL). */
+ * order).  The heads kernel follows the GEMM (and its split-K reduce): mma.sync.m16n8k16 tiles of 16 rows, four warps
+ * each reducing a quarter of N, for N2 <= 24; otherwise a warp-per-row kernel.  N % 128 == 0, N <= 1024, N2*N*2 <= 48 KB.  workspace as rl_gemm_bf16_tn_splitk (may be NULL). */
 int rl_gemm_bf16_tn_heads(const void* A, const void* B, const float* bias, void* H, int M, int N, int K, int lda, int ldb,
                           int ldh, int relu, const void* W2, const float* b2, int N2, float* out2, int ldo2,
                           void* workspace, size_t workspace_bytes, rl_stream_t stream);
+/* 1 (default): the heads of rl_gemm_bf16_tn_heads run as a warp-level mma.sync kernel after H is complete; 0: the
+ * warp-per-row CUDA-core kernel (fused with the split-K reduce where that applies). */
+int rl_debug_set_heads_mma(int enable);
 /* rl_gemm_bf16_tn with an optional split-K workspace — the actor-side nn.Linear (atari_model.py:46-49 evaluated on
  *  the 5-env batch of examples/IMPALA/actor.py:60-62; here 512..4096 envs per GPU).  Workspace (>= splits * ceil(M/128)*128 * ceil(N/BN)*BN * 4 bytes; 8 MB
  * covers every shape that splits): when the output has fewer tiles than half the SMs and K >= 1024, the reduction is

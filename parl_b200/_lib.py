@@ -77,6 +77,7 @@ SIGNATURES = {
     'rl_debug_set_shiftconv_base_offset': (c_i, [c_i]),
     'rl_debug_set_shiftconv_form': (c_i, [c_i]),
     'rl_debug_set_gemm_cluster': (c_i, [c_i]),
+    'rl_debug_set_heads_mma': (c_i, [c_i]),
     'rl_gemm_bf16_tn_heads': (c_i, [c_p, c_p, c_p, c_p] + [c_i] * 7 + [c_p, c_p, c_i, c_p, c_i, c_p, c_sz, c_p]),
     'rl_conv2d_s1_nhwc_bf16_dgrad': (c_i, [c_p, c_p, c_p, c_p] + [c_i] * 10 + [c_p]),
     'rl_conv_wgrad_workspace_bytes': (c_sz, [c_i, c_i, c_i]),
@@ -116,6 +117,8 @@ def load():
         lib.rl_debug_set_pdl(1)
     if os.environ.get('PARL_B200_GEMM_CLUSTER', '') == '0':
         lib.rl_debug_set_gemm_cluster(0)
+    if os.environ.get('PARL_B200_HEADS_MMA', '') == '0':
+        lib.rl_debug_set_heads_mma(0)
     return lib
 
 

@@ -401,6 +401,64 @@ __global__ void __launch_bounds__(256) fc_reduce_heads_kernel(const float* __res
   }
 }
 
+// The head alone, when H already exists (after the GEMM epilogue or the plain split-K reduce): out2 = H . W2^T + b2 with
+// warp-level mma.sync.m16n8k16 (bf16 x bf16 -> f32).  N2 <= 24 columns are a sliver of a tcgen05 tile — the UMMA kernel
+// spends its 7-8 us on barrier setup, TMEM allocation and the TMA ring for 8 k-blocks — while here a 16-row tile is
+// four warps, each reducing a quarter of K straight from global memory (fragments are 4-byte loads in the operands'
+// native row-major layouts), then one shared-memory pass adds the four partial tiles in a fixed order.
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int kHeadsMmaNT = 3;       // n-tiles of 8 head rows: N2 <= 24
+
+__global__ void __launch_bounds__(128) heads_mma_kernel(const __nv_bfloat16* __restrict__ H, int ldh, int M, int N,
+                                                        const HeadsArgs hd) {
+  __shared__ float red[4][16][kHeadsMmaNT * 8];
+  pdl_wait();            // chain kernel (launch_chain)
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+  const int row0 = blockIdx.x * 16;
+  const int kper = N >> 2, kb = warp * kper;                       // this warp's quarter of the reduction
+  const __nv_bfloat16* h0 = H + (size_t)min(row0 + g, M - 1) * ldh + tig * 2;
+  const __nv_bfloat16* h1 = H + (size_t)min(row0 + g + 8, M - 1) * ldh + tig * 2;
+  const __nv_bfloat16* wr[kHeadsMmaNT];
+  bool wok[kHeadsMmaNT];
+#pragma unroll
+  for (int nt = 0; nt < kHeadsMmaNT; ++nt) {
+    wok[nt] = nt * 8 + g < hd.N2;
+    wr[nt] = hd.W2 + (size_t)min(nt * 8 + g, hd.N2 - 1) * N + tig * 2;
+  }
+  float c[kHeadsMmaNT][4];
+#pragma unroll
+  for (int nt = 0; nt < kHeadsMmaNT; ++nt) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+#pragma unroll 4
+  for (int k0 = kb; k0 < kb + kper; k0 += 16) {
+    const uint32_t a0 = *reinterpret_cast<const uint32_t*>(h0 + k0), a1 = *reinterpret_cast<const uint32_t*>(h1 + k0);
+    const uint32_t a2 = *reinterpret_cast<const uint32_t*>(h0 + k0 + 8), a3 = *reinterpret_cast<const uint32_t*>(h1 + k0 + 8);
+#pragma unroll
+    for (int nt = 0; nt < kHeadsMmaNT; ++nt) {
+      uint32_t b0 = __ldg(reinterpret_cast<const uint32_t*>(wr[nt] + k0)), b1 = __ldg(reinterpret_cast<const uint32_t*>(wr[nt] + k0 + 8));
+      if (!wok[nt]) b0 = b1 = 0u;
+      mma_bf16_16816(c[nt], a0, a1, a2, a3, b0, b1);
+    }
+  }
+#pragma unroll
+  for (int nt = 0; nt < kHeadsMmaNT; ++nt) {
+    red[warp][g][nt * 8 + tig * 2] = c[nt][0], red[warp][g][nt * 8 + tig * 2 + 1] = c[nt][1];
+    red[warp][g + 8][nt * 8 + tig * 2] = c[nt][2], red[warp][g + 8][nt * 8 + tig * 2 + 1] = c[nt][3];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 16 * kHeadsMmaNT * 8; i += 128) {
+    const int r = i / (kHeadsMmaNT * 8), n = i - r * (kHeadsMmaNT * 8), row = row0 + r;
+    if (row < M && n < hd.N2)
+      hd.out2[(size_t)row * hd.ldo2 + n] = ((red[0][r][n] + red[1][r][n]) + (red[2][r][n] + red[3][r][n])) + (hd.b2 ? hd.b2[n] : 0.f);
+  }
+}
+
 // rank-2 bf16 tensor map {K (contiguous), rows}, box {64, box_rows}, SWIZZLE_128B
 static int make_tensor_map_bf16_sw128(CUtensorMap* map, const void* base, uint64_t K, uint64_t rows, uint64_t pitch_bytes,
                                       uint32_t box_rows) {
@@ -464,6 +522,7 @@ static int gemm_launch(const void* A, const void* B, const float* bias, void* C,
 
 // 1 (default): 2 x 2 cluster + TMA multicast form for outputs of at least 2 x 2 tiles of width >= 128; 0: never.
 static int g_gemm_cluster = 1;
+static int g_heads_mma = 1;      // 1: mma.sync head kernel after the plain reduce; 0: warp-per-row CUDA-core kernel(s)
 extern "C" int rl_debug_set_gemm_cluster(int enable) {
   g_gemm_cluster = enable ? 1 : 0;
   return RL_OK;
@@ -479,6 +538,11 @@ extern "C" int rl_gemm_bf16_tn_splitk(const void* A, const void* B, const float*
                                       size_t workspace_bytes, rl_stream_t stream) {
   RL_CHECK_ARG(!workspace || aligned16(workspace), "gemm_bf16_tn_splitk: workspace must be 16-byte aligned");
   return gemm_launch(A, B, bias, C, M, N, K, lda, ldb, ldc, relu, out_f32, nullptr, 0, workspace, workspace_bytes, stream);
+}
+
+extern "C" int rl_debug_set_heads_mma(int enable) {
+  g_heads_mma = enable ? 1 : 0;
+  return RL_OK;
 }
 
 extern "C" int rl_gemm_bf16_tn_heads(const void* A, const void* B, const float* bias, void* H, int M, int N, int K, int lda,
@@ -502,6 +566,11 @@ extern "C" int rl_gemm_bf16_tn_masked(const void* A, const void* B, void* C, con
 
 static int launch_heads(const float* partial, int splits, int mpad, int ldp, const float* bias, void* H, int ldh, int M,
                         int N, int relu, const HeadsArgs& hd, cudaStream_t st) {
+  if (!partial && g_heads_mma && hd.N2 <= 8 * kHeadsMmaNT && N % 64 == 0 && ldh % 2 == 0)
+    return launch_chain(heads_mma_kernel, dim3((unsigned)((M + 15) / 16)), dim3(128), 0, st, (const __nv_bfloat16*)H, ldh, M, N,
+                        hd) == cudaSuccess
+               ? 0
+               : -1;
   const size_t smem = (size_t)hd.N2 * N * 2;
   int blocks = (M + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -578,8 +647,8 @@ static int gemm_launch(const void* A, const void* B, const float* bias, void* C,
     default: launch_gemm<32>(ma, mb, g, splits, st); break;
   }
   if (splits > 1) {
-    if (heads) {
-      // split-K reduce, bias, ReLU, bf16 H and the heads in ONE kernel
+    if (heads && !(g_heads_mma && heads->N2 <= 8 * kHeadsMmaNT && N % 64 == 0)) {
+      // split-K reduce, bias, ReLU, bf16 H and the heads in ONE warp-per-row kernel
       if (launch_heads(g.partial, splits, g.mpad, g.ldp, bias, C, ldc, M, N, relu, *heads, st)) {
         set_error("gemm_bf16_tn_heads: heads launch failed");
         return RL_ERR_CUDA;

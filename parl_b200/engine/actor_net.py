@@ -23,11 +23,11 @@ class AtariActorNet(object):
         dev = self.device = torch.device(device)
         bf = torch.bfloat16
         self.window_form = window_form
-        # fc + policy head in one call (rl_gemm_bf16_tn_heads: split-K reduce and head in ONE warp-per-row kernel).  OFF
-        # by default: measured slower on B200 (rollout of 512 envs 3.04 vs 2.64 ms, 4096 envs 12.0 vs 11.6 ms,
-        # profiles/r02_chain_ab.txt) — the CUDA-core head costs ~900 instructions per row against a tcgen05 GEMM whose
-        # 7-8 us are almost all prologue
-        self.fuse_heads = os.environ.get('PARL_B200_FUSE_HEADS', '0') == '1'
+        # fc + policy head in one call (rl_gemm_bf16_tn_heads): the head is a warp-level mma.sync kernel instead of a
+        # tcgen05 GEMM whose 7-8 us are all prologue — rollout of 512 envs 2.55 vs 2.65 ms, neutral at 4096
+        # (profiles/r02_chain_ab.txt; the first attempt, a warp-per-row CUDA-core head fused into the split-K reduce,
+        # was slower: 3.04 ms)
+        self.fuse_heads = os.environ.get('PARL_B200_FUSE_HEADS', '1') != '0'
         # window form: conv1 writes conv2's zero-padded 2x2-block input [B,12,12,128] (border stays zero)
         self.a1 = (torch.zeros((self.B, 12, 12, 128), dtype=bf, device=dev) if window_form else
                    torch.empty((self.B, 20, 20, 32), dtype=bf, device=dev))

@@ -218,8 +218,9 @@ def test_obs_gather_s2d_matches_reference_layout():
     assert torch.equal(out, ref.to(torch.bfloat16))
 
 
+@pytest.mark.parametrize('heads_mma', [1, 0])
 @pytest.mark.parametrize('M', [96, 512, 4096])
-def test_gemm_heads_fused_matches_separate_calls(M):
+def test_gemm_heads_fused_matches_separate_calls(M, heads_mma):
     """rl_gemm_bf16_tn_heads (actor fc + policy head; split-K reduce and heads in one kernel at small M) against the
     two separate tcgen05 GEMMs for H (bit-identical) and an fp32 product of the stored bf16 H for the heads."""
     from parl_b200 import kernels as K_
@@ -232,7 +233,12 @@ def test_gemm_heads_fused_matches_separate_calls(M):
     b2 = torch.randn(N2, device=DEV)
     h = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
     out2 = torch.empty(M, N2, device=DEV)
-    K_.gemm_bf16_tn_heads(a, b, bias, h, w2, b2, out2)
+    from parl_b200 import _lib
+    _lib.load().rl_debug_set_heads_mma(heads_mma)
+    try:
+        K_.gemm_bf16_tn_heads(a, b, bias, h, w2, b2, out2)
+    finally:
+        _lib.load().rl_debug_set_heads_mma(1)
     h_ref = K_.gemm_bf16_tn(a, b, bias, relu=True)
     torch.cuda.synchronize()
     assert torch.equal(h, h_ref)
