@@ -50,6 +50,11 @@ class PackedOperands(object):
         """``sources(P, full)`` -> [(name, tensor expression over the parameters)]; P(name) is the parameter (or its
         index tensor), full(shape) a zero (or -1) tensor of the matching kind for partially filled copies."""
         if self.flat is not None:
+            # the index permutation addresses the flat buffer: a model whose parameters were re-homed since (model.to(),
+            # a new optimizer) would silently be refreshed from stale memory
+            if self._probe.data_ptr() != self._probe_ptr:
+                raise RuntimeError('parl_b200: the model parameters no longer live in the flat buffer the operand refresh '
+                                   'was bound to (rebuild the net / engine after re-homing the parameters)')
             for dtype, idx in self.idx.items():
                 K.gather_cast(self.flat, idx, self.arenas[dtype])
             return
@@ -77,4 +82,6 @@ class PackedOperands(object):
             assert tuple(src.shape) == shape, (name, tuple(src.shape), shape)
             idx[dtype][off:off + n] = src.reshape(-1)
         self.idx, self.flat = idx, flat
+        self._probe = next(iter(model.parameters()))
+        self._probe_ptr = self._probe.data_ptr()
         return True
