@@ -146,6 +146,13 @@ def check(code, what):
         raise RuntimeError('parl_b200.%s failed (code %d): %s' % (what, code, msg))
 
 
+def check_config(code, what):
+    """check() for calls that only set a library switch (no kernel launch: not counted in ``launches``)."""
+    global launches
+    check(code, what)
+    launches -= 1
+
+
 def require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:

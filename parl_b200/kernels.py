@@ -34,17 +34,17 @@ def add_graph_launches(n):
 def set_shiftconv_form(form):
     """0 (default): one MMA group per filter tap; 1: column-tap-fused TMA-window conv tiles (measured slower; kept as
     an experiment and cross-check)."""
-    check(_lib.load().rl_debug_set_shiftconv_form(int(form)), 'debug_set_shiftconv_form')
+    _lib.check_config(_lib.load().rl_debug_set_shiftconv_form(int(form)), 'debug_set_shiftconv_form')
 
 
 def set_gemm_cluster(enable):
     """1 (default): 2 x 2 cluster + TMA multicast form of rl_gemm_bf16_tn where the output has >= 2 x 2 wide tiles."""
-    check(_lib.load().rl_debug_set_gemm_cluster(1 if enable else 0), 'debug_set_gemm_cluster')
+    _lib.check_config(_lib.load().rl_debug_set_gemm_cluster(1 if enable else 0), 'debug_set_gemm_cluster')
 
 
 def set_pdl(enable):
     """1: programmatic dependent launch of the per-env-step chain kernels; 0 (default): plain stream order."""
-    check(_lib.load().rl_debug_set_pdl(1 if enable else 0), 'debug_set_pdl')
+    _lib.check_config(_lib.load().rl_debug_set_pdl(1 if enable else 0), 'debug_set_pdl')
 
 
 def set_sm_limit(max_ctas):
