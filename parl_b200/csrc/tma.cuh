@@ -85,4 +85,33 @@ inline int make_tensor_map_2d_f32(CUtensorMap* map, const void* base, uint64_t d
   return 0;
 }
 
+// Same, through a small per-thread cache keyed by (base, dims, pitch, box): the loss kernels are launched every
+// learner step on the same buffers, and six driver encodes per launch are several microseconds of host time.
+inline int cached_tensor_map_2d_f32(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t dim1, uint64_t pitch_bytes,
+                                    uint32_t box0, uint32_t box1, const char** err) {
+  struct Entry {
+    const void* base;
+    uint64_t dim0, dim1, pitch;
+    uint32_t box0, box1;
+    CUtensorMap map;
+  };
+  constexpr int kN = 64;
+  static thread_local Entry cache[kN];
+  static thread_local int used = 0, next = 0;
+  for (int i = 0; i < used; ++i) {
+    const Entry& e = cache[i];
+    if (e.base == base && e.dim0 == dim0 && e.dim1 == dim1 && e.pitch == pitch_bytes && e.box0 == box0 && e.box1 == box1) {
+      *map = e.map;
+      return 0;
+    }
+  }
+  const int rc = make_tensor_map_2d_f32(map, base, dim0, dim1, pitch_bytes, box0, box1, err);
+  if (rc) return rc;
+  Entry& e = cache[next];
+  e.base = base, e.dim0 = dim0, e.dim1 = dim1, e.pitch = pitch_bytes, e.box0 = box0, e.box1 = box1, e.map = *map;
+  next = (next + 1) % kN;
+  if (used < kN) ++used;
+  return 0;
+}
+
 }  // namespace rl

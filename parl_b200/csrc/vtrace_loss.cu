@@ -9,16 +9,15 @@
 //
 // Layout in HBM: logits [T,B,A] f32, per-step scalars [T,B].  Two kernels:
 //
-//  * vtrace_loss_kernel (v4, the default): a CTA owns 4 adjacent env columns for ALL T rows (the scan never leaves
-//    the CTA); the logits tiles [T, 4*A] move by 2-D TMA tensor maps (cp.async for env-major / unaligned shapes),
-//    one (t,b) element per thread, array-free two-sweep softmax, warp-shuffle segmented suffix scan, gradient tile
-//    written in place and TMA-stored, deterministic loss reduction (CTA partials -> last CTA, fp64).
-//  * vtrace_loss_cta_kernel (v6, opt-in via rl_debug_set_vtrace_path(6)): same CTA shape, but every warp owns ONE
-//    8-row TMA chunk (own mbarrier, own store) and the scan is composed from per-warp affine maps after a single
-//    __syncthreads.  Round-2 measurements (profiles/r02_k1_*): 23.5 us vs 20.4 us for v4 at T=50, B=4096 — the
-//    instruction count per element did not drop (777 vs 815 warp-instructions per warp) and 40 registers round up
-//    to 6 CTAs per SM (1.15 waves); a warp-autonomous variant (v5: one warp per column block, 7 warps per SM) was
-//    latency-bound at 24.8 us and was removed.  DESIGN.md section 4 has the analysis.
+//  * vtrace_loss_v8_kernel (default where eligible: time-major, TMA-aligned, T <= 64, B % 4 == 0, even A <= 18 — the
+//    C3 learner batch): a CTA owns 4 adjacent env columns for ALL T rows, fetched as two half-tiles in time that are
+//    all in flight from the first instruction; one element per thread per half with its logits register-resident
+//    as packed pairs; in-warp shuffle suffix scan composed across warps after one block sync per half.
+//  * vtrace_loss_kernel (v4, every other shape and the env-major layout; rl_debug_set_vtrace_path(4) forces it):
+//    same CTA shape, chunks of <= 56 rows staged by 2-D TMA tensor maps (cp.async for env-major / unaligned shapes),
+//    array-free two-sweep softmax, scan on warp 0, gradient tile written in place and TMA-stored.
+//  Both: deterministic loss reduction (CTA partials -> last CTA, fp64).  Earlier designs (v5 warp-autonomous, v6
+//  warp-per-8-row-chunk with 32 registers) were measured slower and removed: DESIGN.md section 4.
 // Algorithmic traffic: (12A+17) bytes per kept (t,b) element.
 #include <stdarg.h>
 #include <string.h>
@@ -467,47 +466,54 @@ __global__ void __launch_bounds__(128) vtrace_returns_kernel(const float* __rest
 }
 
 // ---------------------------------------------------------------------------
-// v6: CTA per 4-column block, ONE 8-row pass per warp (the default fast path).  v5 showed that a warp walking
-// all of T alone is bound by its own instruction latency (7 warps per SM cannot hide LDS -> MUFU -> FADD chains),
-// so the rows of a column block are spread over ceil(T/8) warps: every warp waits only for ITS 8-row TMA chunk,
-// computes the softmax statistics of its 32 elements (two register-light sweeps: 7 CTAs = 49 warps stay resident
-// per SM), reduces its rows to one affine map per column (3 shuffle steps), and after the CTA's single
-// __syncthreads composes the maps of the later warps (<= 6 FMAs) to get its incoming accumulator.  The gradient
-// rows are recomputed in place and each warp TMA-stores its own chunk at once.
+// v8 (default for time-major TMA shapes with T <= 64, B % 4 == 0, even A <= 18): the K1 of the C3 learner batch.
+//
+// What bounded v4 at T=50, B=4096 (profiles/r02_k1_ncu.txt): 914 warp-instructions per 32 elements at 38 % issue
+// utilisation (three shared-memory sweeps with loop overhead, 3 block syncs per tile, a scan on warp 0 only) inside
+// ONE wave in which every CTA loads, then computes, then stores in lock-step — DRAM busy 20 %.  v8 keeps the CTA
+// shape "4 env columns x all T rows" (the scan never leaves the CTA, one wave of B/4 CTAs, 7 resident per SM) and
+// changes what happens inside it:
+//   * the tile is fetched as TWO half-tiles in time (later half first: it heads the backward recurrence), each with
+//     its own mbarrier; all four TMA loads are in flight from the first instruction, so the second half streams in
+//     while the first is being computed, and its gradient rows leave by TMA while the second half is computed;
+//   * 4 warps = one (t,b) element per thread per half; the element's 2A logits are read from shared memory ONCE
+//     into registers as 64-bit pairs (stride-18-word LDS.64: conflict-free), all arithmetic on packed pairs
+//     (fma/add/mul.f32x2), exponentials kept in registers for the gradient (no second MUFU pass, no re-read);
+//   * the recurrence acc_t = delta_t + k_t acc_{t+1} is a 3-step shuffle suffix scan of affine maps inside each warp
+//     (8 rows), composed across the 4 warps after ONE block sync per half, carry between the halves in shared memory;
+//   * loss partials: one float4 per CTA, last CTA (ticket) reduces them in fixed order in fp64, overlapped with
+//     the drain of the gradient stores.
 // ---------------------------------------------------------------------------
-constexpr int kV6Rows = 8;                 // rows per warp / per TMA chunk
-constexpr int kV6MaxWarps = 7;             // T <= 56
-
-// packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2): two lanes of arithmetic per issue slot
-__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
-  unsigned long long ra, rb, rc, rd;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-  float2 d;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
-__device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
-  unsigned long long ra, rb, rd;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-  float2 d;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
-  unsigned long long ra, rb, rd;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-  float2 d;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-// mbarrier wait that lets the hardware suspend the warp for up to ~1 ms per probe instead of spinning
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// mbarrier wait with a hardware suspend-time hint (the warp sleeps instead of spinning on the LSU)
 __device__ __forceinline__ void mbar_wait_suspend(void* mbar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -522,179 +528,235 @@ __device__ __forceinline__ void mbar_wait_suspend(void* mbar, uint32_t parity) {
       : "memory");
 }
 
+constexpr int kV8Warps = 4;                // 128 threads: 32 rows x 4 columns per pass
+constexpr int kV8Rows = 32;                // rows of the later (first processed) pass
+constexpr int kV8MaxT = 64;
+
+struct V8Maps {                            // [0] = box of the earlier rows [0, T-R1), [1] = box of the later rows [T-R1, T)
+  CUtensorMap tl[2], bl[2], dl[2];
+};
+
 template <int A_>
-__global__ void __maxnreg__(32)          // 7 CTAs x 7 warps x 32 registers: one wave of 1024 CTAs on 148 SMs
-    vtrace_loss_cta_kernel(const VtraceLossArgs p, const __grid_constant__ CUtensorMap map_tl,
-                           const __grid_constant__ CUtensorMap map_bl, const __grid_constant__ CUtensorMap map_dl,
-                           const __grid_constant__ CUtensorMap map_tl_tail, const __grid_constant__ CUtensorMap map_bl_tail,
-                           const __grid_constant__ CUtensorMap map_dl_tail) {
-  static_assert(A_ >= 2 && (A_ & 1) == 0, "v6 needs an even compile-time A");
-  constexpr int CW = 4, R = kV6Rows;
+__global__ void __launch_bounds__(kV8Warps * 32, 7)     // 7 CTAs x 4 warps per SM: B/4 CTAs = one wave at B = 4096
+    vtrace_loss_v8_kernel(const VtraceLossArgs p, const __grid_constant__ V8Maps maps) {
+  static_assert(A_ >= 2 && (A_ & 1) == 0, "v8 needs an even compile-time A");
+  constexpr int CW = 4, NW = kV8Warps, NP = A_ / 2;
+  constexpr int kRowBytes = CW * A_ * 4;
   constexpr uint32_t FULL = 0xffffffffu;
-  constexpr int kChunkBytes = R * CW * A_ * 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) unsigned long long s_bar[kV6MaxWarps];
-  __shared__ float2 s_comp[kV6MaxWarps][CW];
-  __shared__ float s_red[4][kV6MaxWarps];
-  __shared__ bool s_last;
+  __shared__ __align__(8) u64 s_bar[2];
+  __shared__ float2 s_comp[2][NW][CW];
+  __shared__ float s_carry[CW];
+  __shared__ float s_red[4][NW];
+  __shared__ double s_dred[4][NW];
+  __shared__ int s_last;
   const int T = p.T, B = p.B;
-  const int P = (T + R - 1) / R, nfull = T / R, tail_rows = T - nfull * R;
+  const int R1 = min(T, kV8Rows), R0 = T - R1;           // pass 1 = rows [R0, T) (first), pass 0 = rows [0, R0)
+  // shared-memory tiles: [R1 later rows | R0 earlier rows] x [CW*A] floats; R1 * kRowBytes is a multiple of 128 when
+  // R0 > 0 (R1 = 32), so both TMA destinations are 128-byte aligned
+  unsigned char* s_x = smem_raw;                         // target logits, overwritten by the gradient
+  unsigned char* s_y = smem_raw + ((T * kRowBytes + 127) & ~127);     // behaviour logits
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b0 = blockIdx.x * CW;
-  unsigned char* s_tl = smem_raw;
-  unsigned char* s_bl = smem_raw + (((size_t)T * CW * A_ * 4 + 127) & ~(size_t)127);   // TMA tiles: 128-byte aligned
 
   if (tid == 0) {
-    for (int c = 0; c < P; ++c) mbar_init(&s_bar[c], 1);
+    tma_prefetch_desc(&maps.tl[1]);
+    tma_prefetch_desc(&maps.bl[1]);
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
     fence_mbar_init();
-  }
-  __syncthreads();
-  if (tid == 0) {
-    for (int c = P - 1; c >= 0; --c) {                  // latest rows first: they head the dependency chain
-      const bool full = c < nfull;
-      const uint32_t bytes = (uint32_t)((full ? R : tail_rows) * CW * A_ * 4);
-      mbar_arrive_expect_tx(&s_bar[c], 2u * bytes);
-      tma_load_2d(s_tl + c * kChunkBytes, full ? &map_tl : &map_tl_tail, b0 * A_, c * R, &s_bar[c]);
-      tma_load_2d(s_bl + c * kChunkBytes, full ? &map_bl : &map_bl_tail, b0 * A_, c * R, &s_bar[c]);
+    mbar_arrive_expect_tx(&s_bar[1], 2u * (uint32_t)(R1 * kRowBytes));        // later rows first: they head the chain
+    tma_load_2d(s_x, &maps.tl[1], b0 * A_, R0, &s_bar[1]);
+    tma_load_2d(s_y, &maps.bl[1], b0 * A_, R0, &s_bar[1]);
+    if (R0 > 0) {
+      mbar_arrive_expect_tx(&s_bar[0], 2u * (uint32_t)(R0 * kRowBytes));
+      tma_load_2d(s_x + R1 * kRowBytes, &maps.tl[0], b0 * A_, 0, &s_bar[0]);
+      tma_load_2d(s_y + R1 * kRowBytes, &maps.bl[0], b0 * A_, 0, &s_bar[0]);
     }
+    tma_prefetch_desc(&maps.dl[1]);
   }
-  // ---- this lane's element: (t, b) = (warp*8 + lane/4, b0 + lane%4).  Lanes past the last row are CLAMPED onto
-  //      row T-1 (they read valid memory and compute throw-away values) so that the hot path has no branches;
-  //      fv / fl are the 0/1 masks "row exists" / "row carries a loss term".
-  const int r = lane >> 2, c = lane & 3;
-  const int t_raw = warp * R + r;
-  const int t = min(t_raw, T - 1);
-  const float fv = t_raw < T ? 1.f : 0.f;
-  const float fl = t_raw < T - 1 ? 1.f : 0.f;
-  const int g = t * B + b0 + c;
-  const int act = p.act64 ? (int)reinterpret_cast<const long long*>(p.actions)[g] : reinterpret_cast<const int*>(p.actions)[g];
-  const float e_r = p.rewards[g];
-  const float e_v = p.values[g];
-  const float e_g = p.dones[g] ? 0.0f : p.gamma;          // impala.py:59  (~dones) * discount
-  const float e_vn = p.values[min(g + B, (T - 1) * B + b0 + c)];
-  mbar_wait_suspend(&s_bar[warp], 0);
+  // ---- this thread's element of each pass: (row r of the pass, column c).  Rows past the pass's last row are
+  //      CLAMPED onto it (valid memory, throw-away arithmetic) so that the hot path is branch-free; warps that hold
+  //      no row at all skip the arithmetic and contribute identity maps.
+  const int r = tid >> 2, c = tid & 3;
+  int e_act[2];
+  float e_r[2], e_v[2], e_g[2], e_vn[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int nrows = h ? R1 : R0;
+    const int t = (h ? R0 : 0) + max(min(r, nrows - 1), 0);
+    const int g = t * B + b0 + c;
+    e_act[h] = p.act64 ? (int)reinterpret_cast<const long long*>(p.actions)[g] : reinterpret_cast<const int*>(p.actions)[g];
+    e_r[h] = p.rewards[g];
+    e_v[h] = p.values[g];
+    e_g[h] = p.dones[g] ? 0.0f : p.gamma;                // impala.py:59  (~dones) * discount
+    e_vn[h] = p.values[min(g + B, (T - 1) * B + b0 + c)];
+  }
+  __syncthreads();                                       // barrier initialisation visible to every waiter
 
-  // ---- phase A: softmax statistics.  Sweep 1: maxima.  Sweep 2 (packed pairs): exponentials, S, W = sum e xs,
-  //      Y = sum e y, Sy; the target exponentials are parked over the (dead) behaviour logits for phase C.
-  float* pt = reinterpret_cast<float*>(s_tl) + (size_t)(t * CW + c) * A_;
-  float* pb = reinterpret_cast<float*>(s_bl) + (size_t)(t * CW + c) * A_;
-  float m = -INFINITY, my = -INFINITY;
+  float sum_pi = 0.f, sum_vf = 0.f, sum_ent = 0.f, sum_kl = 0.f;
+  const int h_last = R0 > 0 ? 0 : 1;
+#pragma unroll 1
+  for (int h = 1; h >= h_last; --h) {
+    const int nrows = h ? R1 : R0;
+    float D = 0.f, K = 1.f;                              // identity map: rows that do not exist
+    float l2S = 0.f, inv = 0.f, H = 0.f, la = 0.f, rpg = 0.f;
+    u64 X[NP], E[NP];
 #pragma unroll
-  for (int j = 0; j < A_; j += 2) {
-    const float2 a = *reinterpret_cast<const float2*>(pt + j);
-    const float2 y = *reinterpret_cast<const float2*>(pb + j);
-    m = fmaxf(m, fmaxf(a.x, a.y));
-    my = fmaxf(my, fmaxf(y.x, y.y));
-  }
-  const float nm = -m * kL2E, nmy = -my * kL2E;
-  const float x_act = pt[act], y_act = pb[act];
-  const float2 cL = make_float2(kL2E, kL2E), cnm = make_float2(nm, nm), cnmy = make_float2(nmy, nmy);
-  float2 S2 = make_float2(0.f, 0.f), W2 = S2, Y2 = S2, Sy2 = S2;
+    for (int j = 0; j < NP; ++j) X[j] = 0ull, E[j] = 0ull;
+    const bool warp_on = warp * 8 < nrows;               // warp-uniform
+    const int rc = min(r, nrows - 1);
+    const int t = (h ? R0 : 0) + rc;
+    const bool valid = r < nrows;
+    const bool loss = valid && t < T - 1;
+    const int g = t * B + b0 + c;
+    const int act = h ? e_act[1] : e_act[0];
+    const float er = h ? e_r[1] : e_r[0], ev = h ? e_v[1] : e_v[0], eg = h ? e_g[1] : e_g[0], evn = h ? e_vn[1] : e_vn[0];
+    const int soff = ((h ? 0 : R1) + rc) * kRowBytes + c * (A_ * 4);
+    float* px = reinterpret_cast<float*>(s_x + soff);
+    const float* py = reinterpret_cast<const float*>(s_y + soff);
+    if (warp_on) {
+      mbar_wait_suspend(&s_bar[h], 0);
+      // ---- phase A: one read of the 2A logits, maxima, then (packed pairs) xs = (x - m) log2e, e = 2^xs,
+      //      S = sum e, W = sum e xs, Y = sum e y, Sy = sum 2^((y - my) log2e)
+      u64 Y[NP];
 #pragma unroll
-  for (int j = 0; j < A_; j += 2) {
-    const float2 a = *reinterpret_cast<const float2*>(pt + j);
-    const float2 y = *reinterpret_cast<const float2*>(pb + j);
-    const float2 xs = f2_fma(a, cL, cnm);
-    const float2 e = make_float2(ex2_approx(xs.x), ex2_approx(xs.y));
-    const float2 ys = f2_fma(y, cL, cnmy);
-    const float2 ey = make_float2(ex2_approx(ys.x), ex2_approx(ys.y));
-    S2 = f2_add(S2, e);
-    W2 = f2_fma(e, xs, W2);
-    Y2 = f2_fma(e, y, Y2);
-    Sy2 = f2_add(Sy2, ey);
-    *reinterpret_cast<float2*>(pb + j) = e;              // this lane's own row: no cross-lane hazard
-  }
-  const float S = S2.x + S2.y, Wt = W2.x + W2.y, Y = Y2.x + Y2.y, Sy = Sy2.x + Sy2.y;
-  const float l2S = lg2_approx(S);
-  const float inv = __fdividef(1.0f, S);
-  const float logSy = lg2_approx(Sy) * kLN2;
-  const float Hn = (Wt * inv - l2S) * kLN2;              // sum_j p_j log p_j
-  const float H = -Hn;
-  float sum_kl = fv * (Hn - Y * inv + my + logSy);       // impala.py:160-162: every row
-  const float la = (fmaf(x_act, kL2E, nm) - l2S) * kLN2;
-  const float lma = y_act - my - logSy;
-  const float rho = ex2_approx((la - lma) * kL2E);       // vtrace.py:101-103
-  const float rhoc = p.clip_rho >= 0.f ? fminf(rho, p.clip_rho) : rho;
-  const float rpg = p.clip_pg >= 0.f ? fminf(rho, p.clip_pg) : rho;
-  float D = fl * __fmul_rn(rhoc, __fsub_rn(__fadd_rn(e_r, __fmul_rn(e_g, e_vn)), e_v));     // :115 (0 past T-2)
-  float K = fl * __fmul_rn(e_g, fminf(rho, 1.0f));                                          // :109
-  float sum_ent = fl * H;
-  // suffix scan of the affine maps acc -> D + K acc over the warp's 8 rows (later time = higher lane)
+      for (int j = 0; j < NP; ++j) {
+        X[j] = *reinterpret_cast<const u64*>(px + 2 * j);
+        Y[j] = *reinterpret_cast<const u64*>(py + 2 * j);
+      }
+      const float x_act = px[act], y_act = py[act];
+      float m, my;
+      {
+        float a0, a1, c0_, c1_;
+        upk2(X[0], a0, a1);
+        upk2(Y[0], c0_, c1_);
+        m = fmaxf(a0, a1), my = fmaxf(c0_, c1_);
 #pragma unroll
-  for (int off = CW; off < 32; off <<= 1) {
-    const float Dn = __shfl_down_sync(FULL, D, off);
-    const float Kn = __shfl_down_sync(FULL, K, off);
-    const bool in = lane + off < 32;
-    D = in ? fmaf(K, Dn, D) : D;
-    K = in ? K * Kn : K;
-  }
-  if (lane < CW) s_comp[warp][lane] = make_float2(D, K);   // the whole pass as one map, per column
-  __syncthreads();
-  // ---- phase B: accumulator entering this warp's rows = later warps' maps applied to 0, latest first
-  float cin = 0.f;
-  for (int w2 = P - 1; w2 > warp; --w2) {
-    const float2 m2 = s_comp[w2][c];
-    cin = fmaf(m2.y, cin, m2.x);
-  }
-  const float acc = fmaf(K, cin, D);
-  float acc_n = __shfl_down_sync(FULL, acc, CW);
-  acc_n = r == R - 1 ? cin : acc_n;
-  // ---- phase C: advantages, losses, gradient row (exponentials read back, no second MUFU pass)
-  const float vs = __fadd_rn(acc, e_v);                              // vtrace.py:125
-  const float vs_n = __fadd_rn(acc_n, e_vn);                         // :128-129 (bootstrap at the end)
-  const float adv = fl * __fmul_rn(rpg, __fsub_rn(__fadd_rn(e_r, __fmul_rn(e_g, vs_n)), e_v));   // :136-137
-  const float dv = fl * (e_v - vs);
-  float sum_pi = -la * adv;                                           // impala.py:67-68
-  float sum_vf = 0.5f * dv * dv;                                      // :71-72
-  if (fv != 0.f) {
-    p.d_values[g] = p.vf_coeff * dv;
-    if (p.vs_out) p.vs_out[g] = vs;
-    if (p.pg_out) p.pg_out[g] = adv;
-  }
-  {
-    const float ce2 = fl * p.ent_coeff * kLN2;
-    const float c0 = fmaf(ce2, l2S, adv - fl * p.ent_coeff * H) * inv;   // folded with 1/S; 0 on the bootstrap row
-    const float c1 = -ce2 * inv;
-    const float2 c02 = make_float2(c0, c0), c12 = make_float2(c1, c1);
+        for (int j = 1; j < NP; ++j) {
+          upk2(X[j], a0, a1);
+          upk2(Y[j], c0_, c1_);
+          m = max3(m, a0, a1);
+          my = max3(my, c0_, c1_);
+        }
+      }
+      const float nm = -m * kL2E, nmy = -my * kL2E;
+      const u64 cL = pk2(kL2E, kL2E), cnm = pk2(nm, nm), cnmy = pk2(nmy, nmy);
+      u64 S2 = pk2(0.f, 0.f), W2 = S2, Y2 = S2, Sy2 = S2;
 #pragma unroll
-    for (int j = 0; j < A_; j += 2) {
-      const float2 a = *reinterpret_cast<const float2*>(pt + j);
-      const float2 e = *reinterpret_cast<const float2*>(pb + j);
-      const float2 xs = f2_fma(a, cL, cnm);
-      *reinterpret_cast<float2*>(pt + j) = f2_mul(e, f2_fma(c12, xs, c02));
+      for (int j = 0; j < NP; ++j) {
+        const u64 xs = fma2(X[j], cL, cnm);
+        const u64 ys = fma2(Y[j], cL, cnmy);
+        float a0, a1, c0_, c1_;
+        upk2(xs, a0, a1);
+        upk2(ys, c0_, c1_);
+        const u64 e = pk2(ex2_approx(a0), ex2_approx(a1));
+        const u64 ey = pk2(ex2_approx(c0_), ex2_approx(c1_));
+        S2 = add2(S2, e);
+        W2 = fma2(e, xs, W2);
+        Y2 = fma2(e, Y[j], Y2);
+        Sy2 = add2(Sy2, ey);
+        X[j] = xs;
+        E[j] = e;
+      }
+      float s0, s1, w0, w1, y0, y1, q0, q1;
+      upk2(S2, s0, s1);
+      upk2(W2, w0, w1);
+      upk2(Y2, y0, y1);
+      upk2(Sy2, q0, q1);
+      const float S = s0 + s1, Wt = w0 + w1, Yt = y0 + y1, Sy = q0 + q1;
+      l2S = lg2_approx(S);
+      inv = __fdividef(1.0f, S);
+      const float logSy = lg2_approx(Sy) * kLN2;
+      const float Hn = (Wt * inv - l2S) * kLN2;            // sum_j p_j log p_j
+      H = -Hn;
+      sum_kl += valid ? Hn - Yt * inv + my + logSy : 0.f;  // impala.py:160-162: every row
+      la = (fmaf(x_act, kL2E, nm) - l2S) * kLN2;
+      const float lma = y_act - my - logSy;
+      const float rho = ex2_approx((la - lma) * kL2E);     // vtrace.py:101-103
+      const float rhoc = p.clip_rho >= 0.f ? fminf(rho, p.clip_rho) : rho;
+      rpg = p.clip_pg >= 0.f ? fminf(rho, p.clip_pg) : rho;
+      // deltas = clipped_rhos * (rewards + discounts * values_t_plus_1 - values)   :115 ; k = discount * min(rho, 1)  :109
+      D = loss ? __fmul_rn(rhoc, __fsub_rn(__fadd_rn(er, __fmul_rn(eg, evn)), ev)) : 0.f;
+      K = loss ? __fmul_rn(eg, fminf(rho, 1.0f)) : (valid ? 0.f : 1.f);
+      sum_ent += loss ? H : 0.f;
+      // ---- phase B: suffix scan of the affine maps acc -> D + K acc over the warp's 8 rows (later time = higher lane)
+#pragma unroll
+      for (int off = CW; off < 32; off <<= 1) {
+        const float Dn = __shfl_down_sync(FULL, D, off);
+        const float Kn = __shfl_down_sync(FULL, K, off);
+        const bool in = lane + off < 32;
+        D = in ? fmaf(K, Dn, D) : D;
+        K = in ? K * Kn : K;
+      }
     }
-    pt[act] -= adv;
+    if (lane < CW) s_comp[h][warp][lane] = make_float2(D, K);          // the warp's 8 rows as one map, per column
+    __syncthreads();
+    if (h == 0 && tid == 0) {                              // the later rows' gradient is complete: send it
+      tma_store_2d(&maps.dl[1], b0 * A_, R0, s_x);
+      tma_store_commit();
+    }
+    // accumulator entering this warp's rows = later warps' maps applied to the later pass's carry, latest first
+    float cin = h ? 0.f : s_carry[c];
+    for (int w2 = NW - 1; w2 > warp; --w2) {
+      const float2 m2 = s_comp[h][w2][c];
+      cin = fmaf(m2.y, cin, m2.x);
+    }
+    const float acc = fmaf(K, cin, D);
+    float acc_n = __shfl_down_sync(FULL, acc, CW);
+    acc_n = lane >= 32 - CW ? cin : acc_n;
+    if (h == 1 && tid < CW) s_carry[tid] = acc;            // acc at the first row of the later pass
+    // ---- phase C: advantages, losses, gradient row in place of the target logits
+    const float vs = __fadd_rn(acc, ev);                               // vtrace.py:125
+    const float vs_n = __fadd_rn(acc_n, evn);                          // :128-129 (bootstrap at the end)
+    const float adv = loss ? __fmul_rn(rpg, __fsub_rn(__fadd_rn(er, __fmul_rn(eg, vs_n)), ev)) : 0.f;   // :136-137
+    const float dv = loss ? ev - vs : 0.f;
+    sum_pi -= la * adv;                                                 // impala.py:67-68
+    sum_vf = fmaf(0.5f * dv, dv, sum_vf);                               // :71-72
+    if (valid) {
+      p.d_values[g] = p.vf_coeff * dv;
+      if (loss) {
+        if (p.vs_out) p.vs_out[g] = vs;
+        if (p.pg_out) p.pg_out[g] = adv;
+      }
+      // dL/dz_j = p_j (adv - c_e (H + log p_j)) - adv [j == a],  log p_j = ln2 (xs_j - log2 S); all 0 on the last row
+      const float ce2 = loss ? p.ent_coeff * kLN2 : 0.f;
+      const float c0 = fmaf(ce2, l2S, adv - (loss ? p.ent_coeff * H : 0.f)) * inv;   // folded with 1/S
+      const float c1 = -ce2 * inv;
+      const u64 c02 = pk2(c0, c0), c12 = pk2(c1, c1);
+#pragma unroll
+      for (int j = 0; j < NP; ++j) *reinterpret_cast<u64*>(px + 2 * j) = mul2(E[j], fma2(c12, X[j], c02));
+      px[act] -= adv;
+    }
+    fence_proxy_async_smem();            // generic-proxy writes of the gradient rows -> visible to the TMA engine
   }
-  fence_proxy_async_smem();              // generic-proxy writes of the gradient rows -> visible to the TMA engine
-  __syncwarp();
-  if (lane == 0) {
-    tma_store_2d(warp < nfull ? &map_dl : &map_dl_tail, b0 * A_, warp * R, s_tl + warp * kChunkBytes);
-    tma_store_commit();
-  }
+
   // ---- loss reduction: warp -> CTA -> (last CTA) grid, fixed order, fp64 at the end
   sum_pi = warp_sum(sum_pi), sum_vf = warp_sum(sum_vf), sum_ent = warp_sum(sum_ent), sum_kl = warp_sum(sum_kl);
-  if (lane == 0) {
-    s_red[0][warp] = sum_pi, s_red[1][warp] = sum_vf, s_red[2][warp] = sum_ent, s_red[3][warp] = sum_kl;
-    tma_store_wait_read();               // the shared-memory rows must outlive the bulk read
-  }
+  if (lane == 0) s_red[0][warp] = sum_pi, s_red[1][warp] = sum_vf, s_red[2][warp] = sum_ent, s_red[3][warp] = sum_kl;
   __syncthreads();
-  if (tid < 4) {
-    float a = 0.f;
-    for (int x = 0; x < P; ++x) a += s_red[tid][x];
-    p.partials[blockIdx.x * 4 + tid] = a;
+  if (tid == 0) {
+    if (R0 > 0) tma_store_2d(&maps.dl[0], b0 * A_, 0, s_x + R1 * kRowBytes);
+    else tma_store_2d(&maps.dl[1], b0 * A_, 0, s_x);
+    tma_store_commit();
+    float4 part;
+    part.x = (s_red[0][0] + s_red[0][1]) + (s_red[0][2] + s_red[0][3]);
+    part.y = (s_red[1][0] + s_red[1][1]) + (s_red[1][2] + s_red[1][3]);
+    part.z = (s_red[2][0] + s_red[2][1]) + (s_red[2][2] + s_red[2][3]);
+    part.w = (s_red[3][0] + s_red[3][1]) + (s_red[3][2] + s_red[3][3]);
+    reinterpret_cast<float4*>(p.partials)[blockIdx.x] = part;
     __threadfence();
+    s_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
   }
-  __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
   __syncthreads();
   if (s_last) {
     __threadfence();
     double accd[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int i = tid; i < (int)gridDim.x; i += blockDim.x) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) accd[q] += (double)__ldcg(p.partials + i * 4 + q);
+#pragma unroll 2
+    for (int i = tid; i < (int)gridDim.x; i += NW * 32) {
+      const float4 q = __ldcg(reinterpret_cast<const float4*>(p.partials) + i);
+      accd[0] += (double)q.x, accd[1] += (double)q.y, accd[2] += (double)q.z, accd[3] += (double)q.w;
     }
-    __shared__ double s_dred[4][kV6MaxWarps];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       double v = accd[q];
@@ -706,10 +768,7 @@ __global__ void __maxnreg__(32)          // 7 CTAs x 7 warps x 32 registers: one
     if (tid == 0) {
       double rr[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        rr[q] = 0.0;
-        for (int x = 0; x < P; ++x) rr[q] += s_dred[q][x];
-      }
+      for (int q = 0; q < 4; ++q) rr[q] = (s_dred[q][0] + s_dred[q][1]) + (s_dred[q][2] + s_dred[q][3]);
       const float pi = (float)rr[0], vf = (float)rr[1], ent = (float)rr[2];
       p.losses[0] = pi + vf * p.vf_coeff + ent * p.ent_coeff;      // impala.py:78-79
       p.losses[1] = pi;
@@ -719,42 +778,41 @@ __global__ void __maxnreg__(32)          // 7 CTAs x 7 warps x 32 registers: one
       *p.ticket = 0u;
     }
   }
+  if (tid == 0) tma_store_wait_read();   // the shared-memory rows must outlive the bulk reads
 }
 
 template <int A_>
-static bool try_launch_v6(const VtraceLossArgs& a, const float* tl, const float* bl, float* dl, cudaStream_t st) {
-  if constexpr (A_ >= 2 && (A_ & 1) == 0 && A_ <= 64) {
-    constexpr int CW = 4, R = kV6Rows;
+static bool try_launch_v8(const VtraceLossArgs& a, const float* tl, const float* bl, float* dl, cudaStream_t st) {
+  if constexpr (A_ >= 2 && (A_ & 1) == 0 && A_ <= 18) {
+    constexpr int CW = 4;
     const int T = a.T, B = a.B;
-    if (B % CW != 0 || T > R * kV6MaxWarps || ((CW * A_ * 4) % 16) != 0 || CW * A_ > 256) return false;
-    if ((R * CW * A_ * 4) % 128 != 0) return false;          // every chunk starts 128-byte aligned in shared memory
-    const int P = (T + R - 1) / R, nfull = T / R, tail = T - nfull * R;
-    alignas(64) CUtensorMap maps[6];
+    if (B % CW != 0 || T > kV8MaxT || T < 2) return false;
+    const int R1 = T < kV8Rows ? T : kV8Rows, R0 = T - R1;
+    alignas(64) V8Maps maps;
     const char* err = nullptr;
     const uint64_t pitch = (uint64_t)B * A_ * sizeof(float);
+    CUtensorMap* dst[3] = {maps.tl, maps.bl, maps.dl};
     const float* bases[3] = {tl, bl, dl};
     for (int i = 0; i < 3; ++i) {
-      if (make_tensor_map_2d_f32(&maps[i], bases[i], (uint64_t)B * A_, (uint64_t)T, pitch, CW * A_, R, &err)) return false;
-      if (make_tensor_map_2d_f32(&maps[3 + i], bases[i], (uint64_t)B * A_, (uint64_t)T, pitch, CW * A_, tail > 0 ? tail : R,
-                                 &err))
+      if (cached_tensor_map_2d_f32(&dst[i][1], bases[i], (uint64_t)B * A_, (uint64_t)T, pitch, CW * A_, R1, &err)) return false;
+      if (cached_tensor_map_2d_f32(&dst[i][0], bases[i], (uint64_t)B * A_, (uint64_t)T, pitch, CW * A_, R0 > 0 ? R0 : R1, &err))
         return false;
     }
-    const size_t smem = 2 * (((size_t)T * CW * A_ * 4 + 127) & ~(size_t)127);
-    if (smem > 200 * 1024) return false;
-    RL_SMEM_OPTIN(vtrace_loss_cta_kernel<A_>);
-    static bool carve = false;
-    if (!carve) {
-      cudaFuncSetAttribute(vtrace_loss_cta_kernel<A_>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    const size_t tile = ((size_t)T * CW * A_ * 4 + 127) & ~(size_t)127;
+    static bool attr_done = false;
+    if (!attr_done) {
+      RL_SMEM_OPTIN(vtrace_loss_v8_kernel<A_>);
+      cudaFuncSetAttribute(vtrace_loss_v8_kernel<A_>, cudaFuncAttributePreferredSharedMemoryCarveout,
                            cudaSharedmemCarveoutMaxShared);
-      carve = true;
+      attr_done = true;
     }
-    vtrace_loss_cta_kernel<A_><<<B / CW, P * 32, smem, st>>>(a, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5]);
+    vtrace_loss_v8_kernel<A_><<<B / CW, kV8Warps * 32, 2 * tile, st>>>(a, maps);
     return true;
   }
   return false;
 }
 
-static int g_v6_enable = 0;      // rl_debug_set_vtrace_path(6): opt in to the v6 kernel
+static int g_vtrace_path = 0;    // rl_debug_set_vtrace_path: 0 = v8 where eligible, else v4; 4 = v4 always
 
 template <int A_>
 static int launch_vtrace_loss(const VtraceLossArgs& a, int layout, bool tma, const CUtensorMap* maps, int grid,
@@ -783,14 +841,13 @@ extern "C" int rl_debug_set_tma(int disable) {
   return RL_OK;
 }
 
-// Triage hook: 0 = default (the CTA-per-4-columns kernel with block-level phases, v4: the fastest measured path at
-// every shape, profiles/r02_k1_matrix_b.jsonl), 6 = the v6 kernel (one 8-row TMA chunk per warp, single block sync).
+// Triage hook: 0 = default (v8 where eligible, else v4), 4 = the general v4 kernel always, 8 = same as 0.
 extern "C" int rl_debug_set_vtrace_path(int mode) {
-  if (mode != 0 && mode != 6) {
-    rl::set_error("rl_debug_set_vtrace_path: mode %d not in {0, 6}", mode);
+  if (mode != 0 && mode != 4 && mode != 8) {
+    rl::set_error("rl_debug_set_vtrace_path: mode %d not in {0, 4, 8}", mode);
     return RL_ERR_BAD_ARG;
   }
-  rl::g_v6_enable = mode == 6;
+  rl::g_vtrace_path = mode;
   return RL_OK;
 }
 
@@ -852,32 +909,38 @@ extern "C" int rl_vtrace_loss_fwd_bwd(const float* target_logits, const float* b
   } else {
     a.vec = ptr_ok && (((long long)T * A) % 4 == 0) && (((long long)TC * A) % 4 == 0);
   }
-  // TMA tile path: time-major, 16-byte aligned bases, row pitch a multiple of 16 bytes, box <= 256 elements
-  alignas(64) CUtensorMap maps[3];
-  memset(maps, 0, sizeof(maps));
+  // TMA tile paths: time-major, 16-byte aligned bases, row pitch a multiple of 16 bytes, box <= 256 elements
   bool tma = layout == RL_LAYOUT_TIME_MAJOR && ptr_ok && (((long long)B * A) % 4 == 0) && kBW * A <= 256 && TC <= 256 &&
              !g_disable_tma;
-  if (tma) {
-    const char* err = nullptr;
-    const uint64_t pitch = (uint64_t)B * A * sizeof(float);
-    if (make_tensor_map_2d_f32(&maps[0], target_logits, (uint64_t)B * A, (uint64_t)T, pitch, kBW * A, TC, &err) ||
-        make_tensor_map_2d_f32(&maps[1], behaviour_logits, (uint64_t)B * A, (uint64_t)T, pitch, kBW * A, TC, &err) ||
-        make_tensor_map_2d_f32(&maps[2], d_logits, (uint64_t)B * A, (uint64_t)T, pitch, kBW * A, TC, &err)) {
-      tma = false;                       // fall back to the cp.async tile path
+  cudaStream_t st = (cudaStream_t)stream;
+  bool done = false;
+  if (tma && g_vtrace_path != 4) {
+    switch (A) {
+#define RL_CASE(N) case N: done = try_launch_v8<N>(a, target_logits, behaviour_logits, d_logits, st); break;
+      RL_CASE(2) RL_CASE(4) RL_CASE(6) RL_CASE(8) RL_CASE(10) RL_CASE(12) RL_CASE(14) RL_CASE(16) RL_CASE(18)
+#undef RL_CASE
+      default: break;
     }
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  const bool v6_ok = tma && g_v6_enable;
-  switch (A) {
-#define RL_CASE(N)                                                                                     \
-  case N:                                                                                              \
-    if (!(v6_ok && try_launch_v6<N>(a, target_logits, behaviour_logits, d_logits, st)))                 \
-      launch_vtrace_loss<N>(a, layout, tma, maps, grid, smem, st);                                      \
-    break;
-    RL_CASE(2) RL_CASE(3) RL_CASE(4) RL_CASE(5) RL_CASE(6) RL_CASE(7) RL_CASE(8) RL_CASE(9) RL_CASE(10) RL_CASE(12)
-    RL_CASE(14) RL_CASE(16) RL_CASE(18)
+  if (!done) {
+    alignas(64) CUtensorMap maps[3];
+    memset(maps, 0, sizeof(maps));
+    if (tma) {
+      const char* err = nullptr;
+      const uint64_t pitch = (uint64_t)B * A * sizeof(float);
+      if (cached_tensor_map_2d_f32(&maps[0], target_logits, (uint64_t)B * A, (uint64_t)T, pitch, kBW * A, TC, &err) ||
+          cached_tensor_map_2d_f32(&maps[1], behaviour_logits, (uint64_t)B * A, (uint64_t)T, pitch, kBW * A, TC, &err) ||
+          cached_tensor_map_2d_f32(&maps[2], d_logits, (uint64_t)B * A, (uint64_t)T, pitch, kBW * A, TC, &err)) {
+        tma = false;                       // fall back to the cp.async tile path
+      }
+    }
+    switch (A) {
+#define RL_CASE(N) case N: launch_vtrace_loss<N>(a, layout, tma, maps, grid, smem, st); break;
+      RL_CASE(2) RL_CASE(3) RL_CASE(4) RL_CASE(5) RL_CASE(6) RL_CASE(7) RL_CASE(8) RL_CASE(9) RL_CASE(10) RL_CASE(12)
+      RL_CASE(14) RL_CASE(16) RL_CASE(18)
 #undef RL_CASE
-    default: launch_vtrace_loss<0>(a, layout, tma, maps, grid, smem, st); break;
+      default: launch_vtrace_loss<0>(a, layout, tma, maps, grid, smem, st); break;
+    }
   }
   RL_CHECK_LAUNCH("rl_vtrace_loss_fwd_bwd");
   return RL_OK;

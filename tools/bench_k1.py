@@ -1,6 +1,7 @@
 """K1 (rl_vtrace_loss_fwd_bwd) timing matrix: kernel path x shape, two timing methods.
     python tools/bench_k1.py
- a) 'rot':   64 back-to-back launches over 8 rotating buffer sets (8 x 47 MB > 126 MB L2), one event pair
+ a) 'rot':   64 back-to-back launches over 8 rotating buffer sets (8 x 47 MB > 126 MB L2), captured in one CUDA graph,
+             one event pair around the replay (the eager Python loop next to it: host-launch-rate bound)
  b) 'flush': one event pair per launch, a 256 MB fill between launches evicts L2
 """
 import json
@@ -41,12 +42,13 @@ if __name__ == '__main__':
     lib = _lib.load()
     peak = 6571.6
     for (T, B, A) in [(50, 4096, 18), (50, 512, 18), (50, 65536, 18)]:
-        for mode in (0, 6):
+        for mode in (0, 4):
             lib.rl_debug_set_vtrace_path(mode)
             nbuf = 8 if B <= 4096 else 2
             r = bench_vtrace(T, B, A, nbuf=nbuf)
+            r_eager = bench_vtrace(T, B, A, nbuf=nbuf, graph=False)
             us_f = flushed(T, B, A)
-            r.update(mode=mode, frac_rot=r['gbps'] / peak, us_flushed=us_f,
+            r.update(mode=mode, frac_rot=r['gbps'] / peak, us_eager_loop=r_eager['us'], us_flushed=us_f,
                      frac_flushed=r['alg_bytes'] / us_f / 1e3 / peak)
             print(json.dumps(r))
     lib.rl_debug_set_vtrace_path(0)

@@ -9,7 +9,7 @@ from parl_b200 import kernels as K, _lib  # noqa
 
 T, A = 50, 18
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-modes = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [0, 6]
+modes = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [0, 4]
 dev = 'cuda:0'
 tl = 2 * torch.randn(T * B, A, device=dev)
 bl = tl + 0.5 * torch.randn(T * B, A, device=dev)
