@@ -57,7 +57,7 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 // Host: encode a rank-2 float32 tensor map {dim0 (contiguous), dim1} with row pitch `pitch_bytes` and box {box0, box1}.
 // Returns 0 on success; on failure `err` (if non-NULL) receives a static message.
 inline int make_tensor_map_2d_f32(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t dim1, uint64_t pitch_bytes,
-                                  uint32_t box0, uint32_t box1, const char** err) {
+                                  uint32_t box0, uint32_t box1, const char** err, bool as_int32 = false) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -75,7 +75,8 @@ inline int make_tensor_map_2d_f32(CUtensorMap* map, const void* base, uint64_t d
   const cuuint64_t gstride[1] = {pitch_bytes};
   const cuuint32_t box[2] = {box0, box1};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  const CUresult r = fn(map, as_int32 ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void*>(base), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -88,27 +89,30 @@ inline int make_tensor_map_2d_f32(CUtensorMap* map, const void* base, uint64_t d
 // Same, through a small per-thread cache keyed by (base, dims, pitch, box): the loss kernels are launched every
 // learner step on the same buffers, and six driver encodes per launch are several microseconds of host time.
 inline int cached_tensor_map_2d_f32(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t dim1, uint64_t pitch_bytes,
-                                    uint32_t box0, uint32_t box1, const char** err) {
+                                    uint32_t box0, uint32_t box1, const char** err, bool as_int32 = false) {
   struct Entry {
     const void* base;
     uint64_t dim0, dim1, pitch;
     uint32_t box0, box1;
+    bool as_int32;
     CUtensorMap map;
   };
-  constexpr int kN = 64;
+  constexpr int kN = 128;
   static thread_local Entry cache[kN];
   static thread_local int used = 0, next = 0;
   for (int i = 0; i < used; ++i) {
     const Entry& e = cache[i];
-    if (e.base == base && e.dim0 == dim0 && e.dim1 == dim1 && e.pitch == pitch_bytes && e.box0 == box0 && e.box1 == box1) {
+    if (e.base == base && e.dim0 == dim0 && e.dim1 == dim1 && e.pitch == pitch_bytes && e.box0 == box0 && e.box1 == box1 &&
+        e.as_int32 == as_int32) {
       *map = e.map;
       return 0;
     }
   }
-  const int rc = make_tensor_map_2d_f32(map, base, dim0, dim1, pitch_bytes, box0, box1, err);
+  const int rc = make_tensor_map_2d_f32(map, base, dim0, dim1, pitch_bytes, box0, box1, err, as_int32);
   if (rc) return rc;
   Entry& e = cache[next];
-  e.base = base, e.dim0 = dim0, e.dim1 = dim1, e.pitch = pitch_bytes, e.box0 = box0, e.box1 = box1, e.map = *map;
+  e.base = base, e.dim0 = dim0, e.dim1 = dim1, e.pitch = pitch_bytes, e.box0 = box0, e.box1 = box1, e.as_int32 = as_int32,
+  e.map = *map;
   next = (next + 1) % kN;
   if (used < kN) ++used;
   return 0;

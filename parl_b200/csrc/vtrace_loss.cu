@@ -534,6 +534,7 @@ constexpr int kV8MaxT = 64;
 
 struct V8Maps {                            // [0] = box of the earlier rows [0, T-R1), [1] = box of the later rows [T-R1, T)
   CUtensorMap tl[2], bl[2], dl[2];
+  CUtensorMap act, rew, val, dval;         // per-step scalars [T, B]: box = all T rows x 4 columns (16 bytes)
 };
 
 template <int A_>
@@ -548,24 +549,33 @@ __global__ void __launch_bounds__(kV8Warps * 32, 7)     // 7 CTAs x 4 warps per 
   __shared__ float2 s_comp[2][NW][CW];
   __shared__ float s_carry[CW];
   __shared__ float s_red[4][NW];
-  __shared__ double s_dred[4][NW];
-  __shared__ int s_last;
   const int T = p.T, B = p.B;
   const int R1 = min(T, kV8Rows), R0 = T - R1;           // pass 1 = rows [R0, T) (first), pass 0 = rows [0, R0)
-  // shared-memory tiles: [R1 later rows | R0 earlier rows] x [CW*A] floats; R1 * kRowBytes is a multiple of 128 when
-  // R0 > 0 (R1 = 32), so both TMA destinations are 128-byte aligned
+  // shared memory: logits tiles [R1 later rows | R0 earlier rows] x [CW*A] floats (R1 * kRowBytes is a multiple of
+  // 128 when R0 > 0, so both TMA destinations are 128-byte aligned), then the scalar tiles [T][CW] in row order
+  const int tile_pad = (T * kRowBytes + 127) & ~127;
+  const int sc_pad = (T * CW * 4 + 127) & ~127;
   unsigned char* s_x = smem_raw;                         // target logits, overwritten by the gradient
-  unsigned char* s_y = smem_raw + ((T * kRowBytes + 127) & ~127);     // behaviour logits
+  unsigned char* s_y = smem_raw + tile_pad;              // behaviour logits
+  const int* s_act = reinterpret_cast<const int*>(smem_raw + 2 * tile_pad);
+  float* s_rew = reinterpret_cast<float*>(smem_raw + 2 * tile_pad + sc_pad);      // rewards, overwritten by d_values
+  const float* s_val = reinterpret_cast<const float*>(smem_raw + 2 * tile_pad + 2 * sc_pad);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b0 = blockIdx.x * CW;
 
+  // Every input of the CTA arrives by TMA (no per-thread global loads on the critical path: 16-byte rows of the
+  // [T, B] scalar arrays fetched by LDG cost one L1 miss entry each and were what the warps waited for).
   if (tid == 0) {
     tma_prefetch_desc(&maps.tl[1]);
     tma_prefetch_desc(&maps.bl[1]);
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
     fence_mbar_init();
-    mbar_arrive_expect_tx(&s_bar[1], 2u * (uint32_t)(R1 * kRowBytes));        // later rows first: they head the chain
+    // later rows first (they head the recurrence), with the scalars of all rows
+    mbar_arrive_expect_tx(&s_bar[1], 2u * (uint32_t)(R1 * kRowBytes) + 3u * (uint32_t)(T * CW * 4));
+    tma_load_2d(const_cast<int*>(s_act), &maps.act, b0, 0, &s_bar[1]);
+    tma_load_2d(s_rew, &maps.rew, b0, 0, &s_bar[1]);
+    tma_load_2d(const_cast<float*>(s_val), &maps.val, b0, 0, &s_bar[1]);
     tma_load_2d(s_x, &maps.tl[1], b0 * A_, R0, &s_bar[1]);
     tma_load_2d(s_y, &maps.bl[1], b0 * A_, R0, &s_bar[1]);
     if (R0 > 0) {
@@ -579,18 +589,11 @@ __global__ void __launch_bounds__(kV8Warps * 32, 7)     // 7 CTAs x 4 warps per 
   //      CLAMPED onto it (valid memory, throw-away arithmetic) so that the hot path is branch-free; warps that hold
   //      no row at all skip the arithmetic and contribute identity maps.
   const int r = tid >> 2, c = tid & 3;
-  int e_act[2];
-  float e_r[2], e_v[2], e_g[2], e_vn[2];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int nrows = h ? R1 : R0;
-    const int t = (h ? R0 : 0) + max(min(r, nrows - 1), 0);
-    const int g = t * B + b0 + c;
-    e_act[h] = p.act64 ? (int)reinterpret_cast<const long long*>(p.actions)[g] : reinterpret_cast<const int*>(p.actions)[g];
-    e_r[h] = p.rewards[g];
-    e_v[h] = p.values[g];
-    e_g[h] = p.dones[g] ? 0.0f : p.gamma;                // impala.py:59  (~dones) * discount
-    e_vn[h] = p.values[min(g + B, (T - 1) * B + b0 + c)];
+  // done flags: the 4 columns of a row are one aligned 32-bit word; lane c == 0 of each row fetches it
+  uint32_t dn1 = 0, dn0 = 0;
+  if (c == 0) {
+    dn1 = *reinterpret_cast<const uint32_t*>(p.dones + (size_t)(R0 + min(r, R1 - 1)) * B + b0);
+    if (R0 > 0) dn0 = *reinterpret_cast<const uint32_t*>(p.dones + (size_t)min(r, R0 - 1) * B + b0);
   }
   __syncthreads();                                       // barrier initialisation visible to every waiter
 
@@ -601,6 +604,8 @@ __global__ void __launch_bounds__(kV8Warps * 32, 7)     // 7 CTAs x 4 warps per 
     const int nrows = h ? R1 : R0;
     float D = 0.f, K = 1.f;                              // identity map: rows that do not exist
     float l2S = 0.f, inv = 0.f, H = 0.f, la = 0.f, rpg = 0.f;
+    float er = 0.f, ev = 0.f, eg = 0.f, evn = 0.f;
+    int act = 0;
     u64 X[NP], E[NP];
 #pragma unroll
     for (int j = 0; j < NP; ++j) X[j] = 0ull, E[j] = 0ull;
@@ -609,14 +614,19 @@ __global__ void __launch_bounds__(kV8Warps * 32, 7)     // 7 CTAs x 4 warps per 
     const int t = (h ? R0 : 0) + rc;
     const bool valid = r < nrows;
     const bool loss = valid && t < T - 1;
-    const int g = t * B + b0 + c;
-    const int act = h ? e_act[1] : e_act[0];
-    const float er = h ? e_r[1] : e_r[0], ev = h ? e_v[1] : e_v[0], eg = h ? e_g[1] : e_g[0], evn = h ? e_vn[1] : e_vn[0];
     const int soff = ((h ? 0 : R1) + rc) * kRowBytes + c * (A_ * 4);
     float* px = reinterpret_cast<float*>(s_x + soff);
     const float* py = reinterpret_cast<const float*>(s_y + soff);
     if (warp_on) {
-      mbar_wait_suspend(&s_bar[h], 0);
+      if (h) mbar_wait_suspend(&s_bar[1], 0);
+      else mbar_wait_suspend(&s_bar[0], 0);
+      // ---- scalars of the element (shared memory; the done word comes from the row's first lane)
+      const uint32_t dw = __shfl_sync(FULL, h ? dn1 : dn0, lane & ~3);
+      act = s_act[t * CW + c];
+      er = s_rew[t * CW + c];
+      ev = s_val[t * CW + c];
+      evn = s_val[min(t + 1, T - 1) * CW + c];
+      eg = ((dw >> (8 * c)) & 0xffu) ? 0.0f : p.gamma;       // impala.py:59  (~dones) * discount
       // ---- phase A: one read of the 2A logits, maxima, then (packed pairs) xs = (x - m) log2e, e = 2^xs,
       //      S = sum e, W = sum e xs, Y = sum e y, Sy = sum 2^((y - my) log2e)
       u64 Y[NP];
@@ -714,10 +724,10 @@ __global__ void __launch_bounds__(kV8Warps * 32, 7)     // 7 CTAs x 4 warps per 
     sum_pi -= la * adv;                                                 // impala.py:67-68
     sum_vf = fmaf(0.5f * dv, dv, sum_vf);                               // :71-72
     if (valid) {
-      p.d_values[g] = p.vf_coeff * dv;
+      s_rew[t * CW + c] = p.vf_coeff * dv;                              // d_values tile (the reward was consumed above)
       if (loss) {
-        if (p.vs_out) p.vs_out[g] = vs;
-        if (p.pg_out) p.pg_out[g] = adv;
+        if (p.vs_out) p.vs_out[t * B + b0 + c] = vs;
+        if (p.pg_out) p.pg_out[t * B + b0 + c] = adv;
       }
       // dL/dz_j = p_j (adv - c_e (H + log p_j)) - adv [j == a],  log p_j = ln2 (xs_j - log2 S); all 0 on the last row
       const float ce2 = loss ? p.ent_coeff * kLN2 : 0.f;
@@ -735,9 +745,14 @@ __global__ void __launch_bounds__(kV8Warps * 32, 7)     // 7 CTAs x 4 warps per 
   sum_pi = warp_sum(sum_pi), sum_vf = warp_sum(sum_vf), sum_ent = warp_sum(sum_ent), sum_kl = warp_sum(sum_kl);
   if (lane == 0) s_red[0][warp] = sum_pi, s_red[1][warp] = sum_vf, s_red[2][warp] = sum_ent, s_red[3][warp] = sum_kl;
   __syncthreads();
-  if (tid == 0) {
+  if (warp != 0) return;
+  // warp 0 finishes alone: gradient stores, the CTA's partial, the ticket; the warp that draws the last ticket
+  // reduces all partials (L2-resident, float4 per CTA) while the other CTAs' stores drain
+  unsigned ticket = 0;
+  if (lane == 0) {
     if (R0 > 0) tma_store_2d(&maps.dl[0], b0 * A_, 0, s_x + R1 * kRowBytes);
     else tma_store_2d(&maps.dl[1], b0 * A_, 0, s_x);
+    tma_store_2d(&maps.dval, b0, 0, s_rew);
     tma_store_commit();
     float4 part;
     part.x = (s_red[0][0] + s_red[0][1]) + (s_red[0][2] + s_red[0][3]);
@@ -745,40 +760,34 @@ __global__ void __launch_bounds__(kV8Warps * 32, 7)     // 7 CTAs x 4 warps per 
     part.z = (s_red[2][0] + s_red[2][1]) + (s_red[2][2] + s_red[2][3]);
     part.w = (s_red[3][0] + s_red[3][1]) + (s_red[3][2] + s_red[3][3]);
     reinterpret_cast<float4*>(p.partials)[blockIdx.x] = part;
-    __threadfence();
-    s_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+    // release: the partial is visible to whoever observes the incremented ticket (acquire side below)
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(p.ticket) : "memory");
   }
-  __syncthreads();
-  if (s_last) {
-    __threadfence();
+  ticket = __shfl_sync(FULL, ticket, 0);
+  if (ticket == gridDim.x - 1) {
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
     double accd[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 2
-    for (int i = tid; i < (int)gridDim.x; i += NW * 32) {
+#pragma unroll 4
+    for (int i = lane; i < (int)gridDim.x; i += 32) {
       const float4 q = __ldcg(reinterpret_cast<const float4*>(p.partials) + i);
       accd[0] += (double)q.x, accd[1] += (double)q.y, accd[2] += (double)q.z, accd[3] += (double)q.w;
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      double v = accd[q];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-      if (lane == 0) s_dred[q][warp] = v;
+      for (int o = 16; o > 0; o >>= 1) accd[q] += __shfl_xor_sync(FULL, accd[q], o);
     }
-    __syncthreads();
-    if (tid == 0) {
-      double rr[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) rr[q] = (s_dred[q][0] + s_dred[q][1]) + (s_dred[q][2] + s_dred[q][3]);
-      const float pi = (float)rr[0], vf = (float)rr[1], ent = (float)rr[2];
+    if (lane == 0) {
+      const float pi = (float)accd[0], vf = (float)accd[1], ent = (float)accd[2];
       p.losses[0] = pi + vf * p.vf_coeff + ent * p.ent_coeff;      // impala.py:78-79
       p.losses[1] = pi;
       p.losses[2] = vf;
       p.losses[3] = ent;
-      p.losses[4] = (float)(rr[3] / ((double)T * (double)B));
+      p.losses[4] = (float)(accd[3] / ((double)T * (double)B));
       *p.ticket = 0u;
     }
   }
-  if (tid == 0) tma_store_wait_read();   // the shared-memory rows must outlive the bulk reads
+  if (lane == 0) tma_store_wait_read();  // the shared-memory rows must outlive the bulk reads
 }
 
 template <int A_>
@@ -786,7 +795,9 @@ static bool try_launch_v8(const VtraceLossArgs& a, const float* tl, const float*
   if constexpr (A_ >= 2 && (A_ & 1) == 0 && A_ <= 18) {
     constexpr int CW = 4;
     const int T = a.T, B = a.B;
-    if (B % CW != 0 || T > kV8MaxT || T < 2) return false;
+    if (B % CW != 0 || T > kV8MaxT || T < 2 || a.act64) return false;
+    if (!aligned16(a.actions) || !aligned16(a.rewards) || !aligned16(a.values) || !aligned16(a.d_values)) return false;
+    if ((reinterpret_cast<uintptr_t>(a.dones) & 3u) != 0) return false;
     const int R1 = T < kV8Rows ? T : kV8Rows, R0 = T - R1;
     alignas(64) V8Maps maps;
     const char* err = nullptr;
@@ -798,7 +809,14 @@ static bool try_launch_v8(const VtraceLossArgs& a, const float* tl, const float*
       if (cached_tensor_map_2d_f32(&dst[i][0], bases[i], (uint64_t)B * A_, (uint64_t)T, pitch, CW * A_, R0 > 0 ? R0 : R1, &err))
         return false;
     }
+    const uint64_t spitch = (uint64_t)B * 4;
+    if (cached_tensor_map_2d_f32(&maps.act, a.actions, (uint64_t)B, (uint64_t)T, spitch, CW, T, &err, true) ||
+        cached_tensor_map_2d_f32(&maps.rew, a.rewards, (uint64_t)B, (uint64_t)T, spitch, CW, T, &err) ||
+        cached_tensor_map_2d_f32(&maps.val, a.values, (uint64_t)B, (uint64_t)T, spitch, CW, T, &err) ||
+        cached_tensor_map_2d_f32(&maps.dval, a.d_values, (uint64_t)B, (uint64_t)T, spitch, CW, T, &err))
+      return false;
     const size_t tile = ((size_t)T * CW * A_ * 4 + 127) & ~(size_t)127;
+    const size_t sc = ((size_t)T * CW * 4 + 127) & ~(size_t)127;
     static bool attr_done = false;
     if (!attr_done) {
       RL_SMEM_OPTIN(vtrace_loss_v8_kernel<A_>);
@@ -806,7 +824,7 @@ static bool try_launch_v8(const VtraceLossArgs& a, const float* tl, const float*
                            cudaSharedmemCarveoutMaxShared);
       attr_done = true;
     }
-    vtrace_loss_v8_kernel<A_><<<B / CW, kV8Warps * 32, 2 * tile, st>>>(a, maps);
+    vtrace_loss_v8_kernel<A_><<<B / CW, kV8Warps * 32, 2 * tile + 3 * sc, st>>>(a, maps);
     return true;
   }
   return false;
