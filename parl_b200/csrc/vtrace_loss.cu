@@ -403,9 +403,21 @@ __global__ void __launch_bounds__(kNT, 7) vtrace_loss_kernel(const VtraceLossArg
   if (s_last) {
     __threadfence();
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int i = tid; i < (int)gridDim.x; i += kNT) {
+    {
+      // all loads of a pass in flight at once (a loop of dependent L2 round trips is microseconds of single-CTA tail)
+      const float4* parts = reinterpret_cast<const float4*>(p.partials);
+      const int n = (int)gridDim.x;
+      for (int base = 0; base < n; base += kNT * 4) {
+        float4 q[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q] += (double)__ldcg(p.partials + i * 4 + q);
+        for (int u = 0; u < 4; ++u) {
+          const int i = base + u * kNT + tid;
+          q[u] = i < n ? __ldcg(parts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          acc[0] += (double)q[u].x, acc[1] += (double)q[u].y, acc[2] += (double)q[u].z, acc[3] += (double)q[u].w;
+      }
     }
     __shared__ double s_dred[4][kNT / 32];
 #pragma unroll
@@ -549,6 +561,8 @@ __global__ void __launch_bounds__(kV8Warps * 32, 7)     // 7 CTAs x 4 warps per 
   __shared__ float2 s_comp[2][NW][CW];
   __shared__ float s_carry[CW];
   __shared__ float s_red[4][NW];
+  __shared__ double s_dred[4][NW];
+  __shared__ int s_last;
   const int T = p.T, B = p.B;
   const int R1 = min(T, kV8Rows), R0 = T - R1;           // pass 1 = rows [R0, T) (first), pass 0 = rows [0, R0)
   // shared memory: logits tiles [R1 later rows | R0 earlier rows] x [CW*A] floats (R1 * kRowBytes is a multiple of
@@ -745,11 +759,10 @@ __global__ void __launch_bounds__(kV8Warps * 32, 7)     // 7 CTAs x 4 warps per 
   sum_pi = warp_sum(sum_pi), sum_vf = warp_sum(sum_vf), sum_ent = warp_sum(sum_ent), sum_kl = warp_sum(sum_kl);
   if (lane == 0) s_red[0][warp] = sum_pi, s_red[1][warp] = sum_vf, s_red[2][warp] = sum_ent, s_red[3][warp] = sum_kl;
   __syncthreads();
-  if (warp != 0) return;
-  // warp 0 finishes alone: gradient stores, the CTA's partial, the ticket; the warp that draws the last ticket
-  // reduces all partials (L2-resident, float4 per CTA) while the other CTAs' stores drain
-  unsigned ticket = 0;
-  if (lane == 0) {
+  // thread 0: gradient stores, the CTA's partial (one float4), the ticket.  The CTA that draws the last ticket reduces
+  // all partials (L2-resident) with EVERY load in flight at once: 8 independent float4 loads per thread — a loop of
+  // dependent L2 round trips here was 5 us of single-warp tail in the first v8 capture (profiles/r02_k1_v8_ncu.txt).
+  if (tid == 0) {
     if (R0 > 0) tma_store_2d(&maps.dl[0], b0 * A_, 0, s_x + R1 * kRowBytes);
     else tma_store_2d(&maps.dl[1], b0 * A_, 0, s_x);
     tma_store_2d(&maps.dval, b0, 0, s_rew);
@@ -761,33 +774,49 @@ __global__ void __launch_bounds__(kV8Warps * 32, 7)     // 7 CTAs x 4 warps per 
     part.w = (s_red[3][0] + s_red[3][1]) + (s_red[3][2] + s_red[3][3]);
     reinterpret_cast<float4*>(p.partials)[blockIdx.x] = part;
     // release: the partial is visible to whoever observes the incremented ticket (acquire side below)
+    unsigned ticket;
     asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(p.ticket) : "memory");
+    s_last = ticket == gridDim.x - 1;
   }
-  ticket = __shfl_sync(FULL, ticket, 0);
-  if (ticket == gridDim.x - 1) {
+  __syncthreads();
+  if (s_last) {
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
-    double accd[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
-    for (int i = lane; i < (int)gridDim.x; i += 32) {
-      const float4 q = __ldcg(reinterpret_cast<const float4*>(p.partials) + i);
-      accd[0] += (double)q.x, accd[1] += (double)q.y, accd[2] += (double)q.z, accd[3] += (double)q.w;
+    const int n = (int)gridDim.x;
+    const float4* parts = reinterpret_cast<const float4*>(p.partials);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    for (int base = 0; base < n; base += NW * 32 * 8) {
+      float4 q[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = base + u * (NW * 32) + tid;
+        q[u] = i < n ? __ldcg(parts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a0 += (double)q[u].x, a1 += (double)q[u].y, a2 += (double)q[u].z, a3 += (double)q[u].w;
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) accd[q] += __shfl_xor_sync(FULL, accd[q], o);
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(FULL, a0, o);
+      a1 += __shfl_xor_sync(FULL, a1, o);
+      a2 += __shfl_xor_sync(FULL, a2, o);
+      a3 += __shfl_xor_sync(FULL, a3, o);
     }
-    if (lane == 0) {
-      const float pi = (float)accd[0], vf = (float)accd[1], ent = (float)accd[2];
+    if (lane == 0) s_dred[0][warp] = a0, s_dred[1][warp] = a1, s_dred[2][warp] = a2, s_dred[3][warp] = a3;
+    __syncthreads();
+    if (tid == 0) {
+      double rr[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) rr[q] = (s_dred[q][0] + s_dred[q][1]) + (s_dred[q][2] + s_dred[q][3]);
+      const float pi = (float)rr[0], vf = (float)rr[1], ent = (float)rr[2];
       p.losses[0] = pi + vf * p.vf_coeff + ent * p.ent_coeff;      // impala.py:78-79
       p.losses[1] = pi;
       p.losses[2] = vf;
       p.losses[3] = ent;
-      p.losses[4] = (float)(accd[3] / ((double)T * (double)B));
+      p.losses[4] = (float)(rr[3] / ((double)T * (double)B));
       *p.ticket = 0u;
     }
   }
-  if (lane == 0) tma_store_wait_read();  // the shared-memory rows must outlive the bulk reads
+  if (tid == 0) tma_store_wait_read();   // the shared-memory rows must outlive the bulk reads
 }
 
 template <int A_>

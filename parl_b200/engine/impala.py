@@ -281,6 +281,9 @@ class ImpalaEngine(object):
         model's parameters (set_weights, load_state_dict, Agent.restore, sync_weights_to into this model)."""
         if self.train_net is not None:
             self.train_net.pack()
+        st = getattr(self, '_host_slab_state', None)
+        if st is not None:
+            st['net'].pack()
         self._snapshot_actor_weights()
 
     def get_weights(self):
@@ -453,6 +456,8 @@ class ImpalaEngine(object):
         bl = host['behaviour_logits'].to(dev, non_blocking=True)
         rew = host['rewards'].to(dev, non_blocking=True)
         dones = host['dones'].to(dev, non_blocking=True)
+        if self.train_net is not None and self._host_slab_plan() is not None:
+            return self._learn_from_host_slabs(host, acts, bl, rew, dones, learning_rate, entropy_coeff)
         if self.train_net is not None:
             # native learner: stacked uint8 observations -> conv1's space-to-depth input -> tcgen05 forward/backward
             net = self.train_net
@@ -494,6 +499,88 @@ class ImpalaEngine(object):
         if self.actor_net is not None and not self.pipeline:
             self.actor_net.pack()
         return res['losses'].clone()
+
+    def _host_slab_plan(self):
+        """(number of slabs, env columns per slab) of the slab-pipelined host learner, or None when the batch is too
+        small to be worth it.  A slab is a whole number of env columns (V-trace scans a column over all T rows), all
+        slabs are equal, about 320 columns (16 000 samples at T = 50: ~8 ms of H2D, ~2 ms of compute)."""
+        samples = getattr(self, 'host_slab_samples', None)
+        if samples is None:
+            samples = int(os.environ.get('PARL_B200_HOST_SLAB_SAMPLES', '16384'))
+        if samples <= 0:
+            return None                           # 0: the one-shot path (whole batch uploaded, then one forward/backward)
+        T, B = self.T, self.B
+        target = max(1, samples // T)
+        if B < 2 * target:
+            return None
+        n = -(-B // target)
+        while B % n:
+            n += 1
+        return n, B // n
+
+    def _learn_from_host_slabs(self, host, acts, bl, rew, dones, learning_rate, entropy_coeff):
+        """learn_from_host with the H2D copy of the observations PIPELINED against the learner's compute: the batch
+        is cut into equal slabs of whole env columns; a copy stream uploads slab i+1 into one of two staging buffers
+        while the compute stream runs gather -> forward -> V-trace loss -> backward on slab i (a slab-sized
+        AtariTrainNet) and adds its parameter gradient into an accumulator.  IMPALA's loss is a SUM over samples
+        (impala.py:67-79), so per-slab gradients add up to the whole-batch gradient (fp32 summation order differs from
+        the one-shot path: round-off only); one optimizer step per call, as before.  With 5.8 GB of observations per
+        4096x50 batch the PCIe copy (~104 ms) was serialised in front of ~25 ms of compute; now only the last slab's
+        compute is exposed."""
+        T, B, A = self.T, self.B, self.A
+        dev = self.device
+        nsl, cols = self._host_slab_plan()
+        ns = cols * T
+        st = getattr(self, '_host_slab_state', None)
+        if st is None or st['ns'] != ns:
+            grad = self.alg.optimizer.grad
+            st = self._host_slab_state = dict(
+                ns=ns,
+                net=AtariTrainNet(self.model, ns, dev, obs_dtype=self.obs_dtype if self.s2d else torch.bfloat16,
+                                  flat=self._flat_master()),
+                obs=[torch.empty((ns, 4, self.h, self.w), dtype=torch.uint8, device=dev) for _ in range(2)],
+                copy_stream=torch.cuda.Stream(device=dev),
+                ev_h2d=[torch.cuda.Event() for _ in range(2)], ev_free=[torch.cuda.Event() for _ in range(2)],
+                acc=torch.empty_like(grad), losses=torch.zeros((nsl, 8), dtype=torch.float32, device=dev),
+                d_logits=torch.empty((ns, A), dtype=torch.float32, device=dev),
+                d_values=torch.empty(ns, dtype=torch.float32, device=dev))
+        net, cs = st['net'], st['copy_stream']
+        cur = torch.cuda.current_stream()
+        cs.wait_stream(cur)                       # the staging buffers are free once the previous call's work is done
+        grad = self.alg.optimizer.grad
+        for i in range(nsl):
+            s0, j = i * ns, i % 2
+            with torch.cuda.stream(cs):
+                if i >= 2:
+                    cs.wait_event(st['ev_free'][j])
+                st['obs'][j].copy_(host['obs'][s0:s0 + ns], non_blocking=True)
+                st['ev_h2d'][j].record(cs)
+            cur.wait_event(st['ev_h2d'][j])
+            kernels.obs_stack_gather(st['obs'][j], None, 0, 1, net.x0, scale=1.0 / 255.0, s2d=True)
+            st['ev_free'][j].record(cur)          # the staging buffer is consumed once the gather has run
+            logits, values = net.forward_from_x0()
+            res = kernels.vtrace_loss_fwd_bwd(logits, bl[s0:s0 + ns], acts[s0:s0 + ns], rew[s0:s0 + ns], dones[s0:s0 + ns],
+                                              values.view(-1), T, cols, self.alg.gamma, self.alg.vf_loss_coeff,
+                                              entropy_coeff, self.alg.clip_rho_threshold, self.alg.clip_pg_rho_threshold,
+                                              layout=kernels.ENV_MAJOR,
+                                              out=dict(losses=st['losses'][i], d_logits=st['d_logits'],
+                                                       d_values=st['d_values']))
+            net.backward(res['d_logits'], res['d_values'])
+            if i == 0:
+                st['acc'].copy_(grad)
+            else:
+                st['acc'].add_(grad)
+        grad.copy_(st['acc'])
+        if self.alg.grad_sync is not None:
+            self.alg.grad_sync(grad)
+        self.alg.optimizer.step(lr=learning_rate)
+        net.pack()
+        self.train_net.pack()
+        if self.actor_net is not None and not self.pipeline:
+            self.actor_net.pack()
+        losses = st['losses'].sum(0)
+        losses[4] = losses[4] / nsl               # KL is a mean over samples; the slabs are equal
+        return losses
 
     # ------------------------------------------------------------------ metrics (Actor.get_metrics analogue)
     def get_metrics(self):

@@ -55,3 +55,32 @@ def test_remote_actor_and_agent_learn_through_numpy_contract():
     m = actor.get_metrics().get()
     assert set(m) == {'episode_rewards', 'episode_steps'} and len(m['episode_rewards']) == len(m['episode_steps']) > 0
     actor.destroy()
+
+
+def test_slab_pipelined_host_learner_matches_one_shot():
+    """AtariAgent.learn with the observation upload pipelined slab by slab against the compute (the default at the
+    C3 batch) gives the one-shot path's losses and parameter update up to fp32 summation order."""
+    from parl_b200.engine.impala_host import DeviceImpalaActor, AtariAgent
+    B, T, A = 256, 8, 18
+    cfg = dict(env_num=B, sample_batch_steps=T, act_dim=A, seed=5)
+    actor = DeviceImpalaActor(cfg, device=DEV)
+    torch.manual_seed(1)
+    ag0 = AtariAgent(cfg, device=DEV)
+    torch.manual_seed(1)
+    ag1 = AtariAgent(cfg, device=DEV)
+    ag0.engine.host_slab_samples = 0               # one-shot
+    ag1.engine.host_slab_samples = 64 * T          # 4 slabs of 64 env columns
+    assert ag0.engine._host_slab_plan() is None and ag1.engine._host_slab_plan() == (4, 64)
+    actor.set_weights(ag0.get_weights())
+    for it in range(2):
+        batch = actor.sample()
+        args = (batch['obs'], batch['actions'], batch['behaviour_logits'], batch['rewards'], batch['dones'], 0.001, -0.01)
+        l0, l1 = ag0.learn(*args), ag1.learn(*args)
+        np.testing.assert_allclose(l1, l0, rtol=2e-4, atol=1e-3)
+        w0, w1 = ag0.get_weights(), ag1.get_weights()
+        for k in w0:
+            # Adam's first steps move every weight by ~lr = 1e-3 (update = lr * m / sqrt(v) ~ lr * sign(g)); the two
+            # paths must agree far inside that, except for the odd component whose gradient is round-off sized
+            d = np.abs(w0[k] - w1[k])
+            assert d.mean() < 2e-5 and (d > 2e-4).mean() < 2e-3, (it, k, d.mean(), d.max(), (d > 2e-4).mean())
+        actor.set_weights(ag0.get_weights())
