@@ -585,19 +585,30 @@ __global__ void __launch_bounds__(kV8Warps * 32, 7)     // 7 CTAs x 4 warps per 
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
     fence_mbar_init();
-    // later rows first (they head the recurrence), with the scalars of all rows
-    mbar_arrive_expect_tx(&s_bar[1], 2u * (uint32_t)(R1 * kRowBytes) + 3u * (uint32_t)(T * CW * 4));
-    tma_load_2d(const_cast<int*>(s_act), &maps.act, b0, 0, &s_bar[1]);
-    tma_load_2d(s_rew, &maps.rew, b0, 0, &s_bar[1]);
-    tma_load_2d(const_cast<float*>(s_val), &maps.val, b0, 0, &s_bar[1]);
-    tma_load_2d(s_x, &maps.tl[1], b0 * A_, R0, &s_bar[1]);
-    tma_load_2d(s_y, &maps.bl[1], b0 * A_, R0, &s_bar[1]);
-    if (R0 > 0) {
-      mbar_arrive_expect_tx(&s_bar[0], 2u * (uint32_t)(R0 * kRowBytes));
+  }
+  // Programmatic dependent launch (when the launch carries the attribute; no-ops otherwise): the prologue above ran
+  // while the predecessor in the stream was still draining; nothing it produced has been touched yet.
+  pdl_trigger();
+  pdl_wait();
+  __syncthreads();                                       // barrier initialisation visible to every waiter / issuer
+  // one elected lane per warp issues its share of the seven loads (a single thread needs ~0.4 us for all of them);
+  // the transaction bytes are posted by warp 0 — a complete_tx that lands first only drives the count negative, the
+  // phase cannot complete before the pending arrival
+  if (lane == 0) {
+    if (warp == 0) {
+      mbar_arrive_expect_tx(&s_bar[1], 2u * (uint32_t)(R1 * kRowBytes) + 3u * (uint32_t)(T * CW * 4));
+      if (R0 > 0) mbar_arrive_expect_tx(&s_bar[0], 2u * (uint32_t)(R0 * kRowBytes));
+      tma_load_2d(s_x, &maps.tl[1], b0 * A_, R0, &s_bar[1]);            // later rows first: they head the recurrence
+    } else if (warp == 1) {
+      tma_load_2d(s_y, &maps.bl[1], b0 * A_, R0, &s_bar[1]);
+    } else if (warp == 2) {
+      tma_load_2d(const_cast<int*>(s_act), &maps.act, b0, 0, &s_bar[1]);
+      tma_load_2d(s_rew, &maps.rew, b0, 0, &s_bar[1]);
+      tma_load_2d(const_cast<float*>(s_val), &maps.val, b0, 0, &s_bar[1]);
+    } else if (R0 > 0) {
       tma_load_2d(s_x + R1 * kRowBytes, &maps.tl[0], b0 * A_, 0, &s_bar[0]);
       tma_load_2d(s_y + R1 * kRowBytes, &maps.bl[0], b0 * A_, 0, &s_bar[0]);
     }
-    tma_prefetch_desc(&maps.dl[1]);
   }
   // ---- this thread's element of each pass: (row r of the pass, column c).  Rows past the pass's last row are
   //      CLAMPED onto it (valid memory, throw-away arithmetic) so that the hot path is branch-free; warps that hold
@@ -609,7 +620,6 @@ __global__ void __launch_bounds__(kV8Warps * 32, 7)     // 7 CTAs x 4 warps per 
     dn1 = *reinterpret_cast<const uint32_t*>(p.dones + (size_t)(R0 + min(r, R1 - 1)) * B + b0);
     if (R0 > 0) dn0 = *reinterpret_cast<const uint32_t*>(p.dones + (size_t)min(r, R0 - 1) * B + b0);
   }
-  __syncthreads();                                       // barrier initialisation visible to every waiter
 
   float sum_pi = 0.f, sum_vf = 0.f, sum_ent = 0.f, sum_kl = 0.f;
   const int h_last = R0 > 0 ? 0 : 1;
@@ -780,7 +790,8 @@ __global__ void __launch_bounds__(kV8Warps * 32, 7)     // 7 CTAs x 4 warps per 
   }
   __syncthreads();
   if (s_last) {
-    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    // acquire: thread 0's acq_rel atomic observed every other CTA's release; the block barrier above extends that
+    // order to the whole CTA, and the loads below go to L2 (ld.cg), so no further fence is needed
     const int n = (int)gridDim.x;
     const float4* parts = reinterpret_cast<const float4*>(p.partials);
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
@@ -819,6 +830,11 @@ __global__ void __launch_bounds__(kV8Warps * 32, 7)     // 7 CTAs x 4 warps per 
   if (tid == 0) tma_store_wait_read();   // the shared-memory rows must outlive the bulk reads
 }
 
+static int g_vtrace_path = 0;    // rl_debug_set_vtrace_path: 0 = default (v8 where eligible, else v4), 4 = v4 always,
+                                 // 8 = v8 without / 9 = v8 with programmatic dependent launch
+constexpr bool kK1PdlDefault = false;
+static bool k1_pdl() { return g_vtrace_path == 9 || (g_vtrace_path == 0 && kK1PdlDefault); }
+
 template <int A_>
 static bool try_launch_v8(const VtraceLossArgs& a, const float* tl, const float* bl, float* dl, cudaStream_t st) {
   if constexpr (A_ >= 2 && (A_ & 1) == 0 && A_ <= 18) {
@@ -853,13 +869,19 @@ static bool try_launch_v8(const VtraceLossArgs& a, const float* tl, const float*
                            cudaSharedmemCarveoutMaxShared);
       attr_done = true;
     }
-    vtrace_loss_v8_kernel<A_><<<B / CW, kV8Warps * 32, 2 * tile + 3 * sc, st>>>(a, maps);
+    // programmatic dependent launch: the CTAs may become resident (barrier init, descriptor prefetch) while the
+    // predecessor in the stream drains; griddepcontrol.wait orders every global access behind its completion
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B / CW), cfg.blockDim = dim3(kV8Warps * 32), cfg.dynamicSmemBytes = 2 * tile + 3 * sc, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = k1_pdl() ? 1 : 0;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, vtrace_loss_v8_kernel<A_>, a, maps) != cudaSuccess) return false;
     return true;
   }
   return false;
 }
-
-static int g_vtrace_path = 0;    // rl_debug_set_vtrace_path: 0 = v8 where eligible, else v4; 4 = v4 always
 
 template <int A_>
 static int launch_vtrace_loss(const VtraceLossArgs& a, int layout, bool tma, const CUtensorMap* maps, int grid,
@@ -888,10 +910,11 @@ extern "C" int rl_debug_set_tma(int disable) {
   return RL_OK;
 }
 
-// Triage hook: 0 = default (v8 where eligible, else v4), 4 = the general v4 kernel always, 8 = same as 0.
+// Triage hook: 0 = default (v8 where eligible, else v4), 4 = the general v4 kernel always, 8 / 9 = v8 without / with
+// programmatic dependent launch.
 extern "C" int rl_debug_set_vtrace_path(int mode) {
-  if (mode != 0 && mode != 4 && mode != 8) {
-    rl::set_error("rl_debug_set_vtrace_path: mode %d not in {0, 4, 8}", mode);
+  if (mode != 0 && mode != 4 && mode != 8 && mode != 9) {
+    rl::set_error("rl_debug_set_vtrace_path: mode %d not in {0, 4, 8, 9}", mode);
     return RL_ERR_BAD_ARG;
   }
   rl::g_vtrace_path = mode;

@@ -158,7 +158,7 @@ def test_tma_and_cpasync_tile_paths_agree():
             for k in ('d_logits', 'd_values', 'vs', 'pg_advantages'):
                 assert torch.equal(r0[k], r1[k]), (k, T, B, A)
             assert torch.equal(r0['losses'][:5], r1['losses'][:5])
-            for mode in (0, ):
+            for mode in (0, 9):
                 lib.rl_debug_set_vtrace_path(mode)
                 r5 = kernels.vtrace_loss_fwd_bwd(*args, T, B, 0.99, 0.5, -0.01, want_returns=True)
                 torch.cuda.synchronize()

@@ -42,7 +42,7 @@ if __name__ == '__main__':
     lib = _lib.load()
     peak = 6571.6
     for (T, B, A) in [(50, 4096, 18), (50, 512, 18), (50, 65536, 18)]:
-        for mode in (0, 4):
+        for mode in (0, 4, 9):
             lib.rl_debug_set_vtrace_path(mode)
             nbuf = 8 if B <= 4096 else 2
             r = bench_vtrace(T, B, A, nbuf=nbuf)
