@@ -501,12 +501,21 @@ def run_e2e(eng, args, world, dev):
     actor.set_weights(agent.get_weights()).get()
     fut = actor.sample()
 
+    phase = dict(wait_sample=0.0, set_weights=0.0, learn=0.0)     # host wall-clock per phase (timed steps only)
+
     def one_step(fut):
+        t0 = time.time()
         batch = fut.get()
+        t1 = time.time()
         actor.set_weights(agent.get_weights())            # queued on the actor's worker: applies before its next sample
         nxt = actor.sample()
+        t2 = time.time()
         losses = agent.learn(batch['obs'], batch['actions'], batch['behaviour_logits'], batch['rewards'],
                              batch['dones'], 0.001, -0.01)  # returns Python floats: a D2H read of the step's result
+        t3 = time.time()
+        phase['wait_sample'] += t1 - t0
+        phase['set_weights'] += t2 - t1
+        phase['learn'] += t3 - t2
         return nxt, losses, batch
 
     for _ in range(3):                                    # warm-up (graph capture, allocator, both host buffer sets)
@@ -514,6 +523,8 @@ def run_e2e(eng, args, world, dev):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    for k in phase:
+        phase[k] = 0.0
     t0 = time.time()
     for _ in range(steps):
         fut, losses, batch = one_step(fut)
@@ -523,6 +534,7 @@ def run_e2e(eng, args, world, dev):
         dist.barrier()
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
     fut.get()
+    last_sample_ms = float(actor.last_sample_s) * 1e3     # host wall clock of the actor's last sample() call
     nbytes = sum(v.nbytes for v in batch.values())
     wbytes = sum(v.nbytes for v in agent.get_weights().values())
     bw = copy_bandwidth(torch, dev) if rank == 0 else None
@@ -538,6 +550,8 @@ def run_e2e(eng, args, world, dev):
                      '-> AtariAgent.learn(numpy) ; actor.set_weights(agent.get_weights()) numpy weight dicts '
                      '(examples/IMPALA/train.py:165-194)',
                 host_buffers=pin, copy_bandwidth_gbs=bw, pcie_ceiling_env_steps_per_s=ceiling,
+                learner_thread_ms_per_step={k: v * 1e3 / steps for k, v in phase.items()},
+                actor_groups=int(os.environ.get('PARL_B200_ACTOR_GROUPS', 0)) or 'auto', actor_last_sample_ms=last_sample_ms,
                 sample_dict_bytes=nbytes, last_losses=[float(x) for x in losses])
 
 

@@ -271,6 +271,18 @@ int rl_td_loss_fwd_bwd(
     long long M, int A, float gamma, float* losses, float* d_q, float* td_abs,
     void* workspace, size_t workspace_bytes, rl_stream_t stream);
 
+/* f4  Continuous-control critic TD (DDPG / TD3 / SAC).  Replaces parl/algorithms/torch/ddpg.py:63-73,
+ * td3.py:78-94, sac.py:90-99:
+ *   target = reward + (1 - terminal) * gamma * (min(Q1', Q2') - alpha * log pi(a'|s'))
+ *   loss   = mse(Q1, target) + mse(Q2, target)          (means over the N samples)
+ * q2 / d_q2 NULL: single critic (DDPG); q2_target_next NULL: no min; next_log_prob NULL: no entropy term.
+ *   all arrays [N] f32, terminal 0/1; losses [3] = total, mse1, mse2; d_q = 2 (Q - target) / N; target_out [N] or NULL */
+int rl_twin_q_td_loss_fwd_bwd(
+    const float* q1, const float* q2, const float* q1_target_next, const float* q2_target_next,
+    const float* next_log_prob, const float* reward, const float* terminal, long long N, float gamma, float alpha,
+    float* losses, float* d_q1, float* d_q2, float* target_out,
+    void* workspace, size_t workspace_bytes, rl_stream_t stream);
+
 /* REINFORCE on probabilities.  Replaces parl/algorithms/torch/policy_gradient.py:54-75. */
 int rl_pg_loss_fwd_bwd(
     const float* prob, const void* action, int action_i64, const float* reward, long long N, int A,

@@ -59,6 +59,8 @@ SIGNATURES = {
     'rl_td_loss_fwd_bwd': (c_i, [c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, ctypes.c_longlong, c_i, c_f, c_p, c_p,
                                  c_p, c_p, c_sz, c_p]),
     'rl_pg_loss_fwd_bwd': (c_i, [c_p, c_p, c_i, c_p, ctypes.c_longlong, c_i, c_p, c_p, c_p, c_sz, c_p]),
+    'rl_twin_q_td_loss_fwd_bwd': (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, ctypes.c_longlong, c_f, c_f, c_p, c_p, c_p, c_p,
+                                        c_p, c_sz, c_p]),
     'rl_per_store': (c_i, [c_p, c_p, c_i, c_i, c_i, c_p, ctypes.c_double, ctypes.c_double, c_p]),
     'rl_per_update': (c_i, [c_p, c_p, c_i, c_p, c_p, c_i, ctypes.c_double, ctypes.c_double, c_p]),
     'rl_per_sample': (c_i, [c_p, c_p, c_i, c_i, c_p, c_u64, c_u32, ctypes.c_double, ctypes.c_double, c_p, c_p,

@@ -411,6 +411,55 @@ __global__ void __launch_bounds__(kFT) pg_prob_loss_kernel(const float* __restri
   if (grid_reduce<1, kFT>(sums, partials, ticket, tot)) losses[0] = (float)(tot[0] / (double)N);
 }
 
+// Continuous-control critic TD (DDPG / TD3 / SAC): target = r + gamma (1 - terminal) (min(Q1', Q2') - alpha log pi'),
+// loss = mse(Q1, target) + mse(Q2, target), gradients dQ = 2 (Q - target) / N.  One launch, thread per sample.
+struct TwinQArgs {
+  const float* q1;
+  const float* q2;          // NULL: single critic (DDPG)
+  const float* tq1;
+  const float* tq2;         // NULL: single target critic
+  const float* next_logp;   // NULL: no entropy term (DDPG / TD3)
+  const float* reward;
+  const float* terminal;
+  float* d_q1;
+  float* d_q2;
+  float* target_out;        // NULL or [N]
+  float* losses;
+  float* partials;
+  unsigned* ticket;
+  long long N;
+  float gamma, alpha;
+};
+
+__global__ void __launch_bounds__(kFT) twin_q_td_loss_kernel(const TwinQArgs p) {
+  const long long g = (long long)blockIdx.x * kFT + threadIdx.x;
+  float sums[2] = {0.f, 0.f};
+  if (g < p.N) {
+    float tq = p.tq1[g];
+    if (p.tq2) tq = fminf(tq, p.tq2[g]);                                       // td3.py:88, sac.py:94
+    if (p.next_logp) tq = __fsub_rn(tq, __fmul_rn(p.alpha, p.next_logp[g]));   // sac.py:94
+    // reward + (1 - terminal) * gamma * target_Q      td3.py:89, ddpg.py:67 (sac.py:95: gamma * (1 - terminal), same product)
+    const float target = __fadd_rn(p.reward[g], __fmul_rn(__fmul_rn(__fsub_rn(1.0f, p.terminal[g]), p.gamma), tq));
+    if (p.target_out) p.target_out[g] = target;
+    const float inv = 2.0f / (float)p.N;
+    const float d1 = p.q1[g] - target;
+    sums[0] = d1 * d1;
+    p.d_q1[g] = d1 * inv;
+    if (p.q2) {
+      const float d2 = p.q2[g] - target;
+      sums[1] = d2 * d2;
+      p.d_q2[g] = d2 * inv;
+    }
+  }
+  double tot[2];
+  if (grid_reduce<2, kFT>(sums, p.partials, p.ticket, tot)) {
+    const float m1 = (float)(tot[0] / (double)p.N), m2 = (float)(tot[1] / (double)p.N);
+    p.losses[0] = m1 + m2;                                                     // td3.py:93-94, sac.py:98-99
+    p.losses[1] = m1;
+    p.losses[2] = m2;
+  }
+}
+
 static unsigned* ws_ticket(void* ws) { return reinterpret_cast<unsigned*>(ws); }
 static float* ws_partials(void* ws) { return reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + 256); }
 
@@ -525,6 +574,28 @@ extern "C" int rl_td_loss_fwd_bwd(const float* q, const float* q_target_next, co
   a.M = M, a.A = A, a.act64 = action_i64, a.gamma = gamma;
   td_loss_kernel<<<(unsigned)((M + kFT - 1) / kFT), kFT, 0, (cudaStream_t)stream>>>(a);
   RL_CHECK_LAUNCH("rl_td_loss_fwd_bwd");
+  return RL_OK;
+}
+
+extern "C" int rl_twin_q_td_loss_fwd_bwd(const float* q1, const float* q2, const float* q1_target_next,
+                                         const float* q2_target_next, const float* next_log_prob, const float* reward,
+                                         const float* terminal, long long N, float gamma, float alpha, float* losses,
+                                         float* d_q1, float* d_q2, float* target_out, void* workspace,
+                                         size_t workspace_bytes, rl_stream_t stream) {
+  RL_CHECK_ARG(q1 && q1_target_next && reward && terminal && losses && d_q1 && workspace && N > 0,
+               "twin_q_td_loss: bad argument");
+  RL_CHECK_ARG((q2 == nullptr) == (d_q2 == nullptr), "twin_q_td_loss: q2 and d_q2 go together");
+  if (workspace_bytes < rl_flat_workspace_bytes(N, 0)) {
+    set_error("twin_q_td_loss: workspace too small");
+    return RL_ERR_WORKSPACE;
+  }
+  TwinQArgs a = {};
+  a.q1 = q1, a.q2 = q2, a.tq1 = q1_target_next, a.tq2 = q2_target_next, a.next_logp = next_log_prob;
+  a.reward = reward, a.terminal = terminal, a.d_q1 = d_q1, a.d_q2 = d_q2, a.target_out = target_out, a.losses = losses;
+  a.ticket = ws_ticket(workspace), a.partials = ws_partials(workspace);
+  a.N = N, a.gamma = gamma, a.alpha = alpha;
+  twin_q_td_loss_kernel<<<(unsigned)((N + kFT - 1) / kFT), kFT, 0, (cudaStream_t)stream>>>(a);
+  RL_CHECK_LAUNCH("rl_twin_q_td_loss_fwd_bwd");
   return RL_OK;
 }
 

@@ -15,6 +15,9 @@ on the actor's own CUDA stream and copies the sample dict — keys / dtypes / en
 pinned host memory (two alternating buffer sets: the dict handed out stays valid until the sample after next).
 ``AtariAgent.learn`` uploads the numpy arrays and runs IMPALA.learn with the network on the tcgen05 kernels.
 """
+import os
+import time
+
 import numpy as np
 import torch
 
@@ -37,8 +40,29 @@ def _engine(config, role, device):
                         p_done=c['p_done'], role=role)
 
 
+def _actor_groups(config):
+    """Number of env-column groups the actor pool is split into (see DeviceImpalaActor): config['actor_groups'] or
+    $PARL_B200_ACTOR_GROUPS, else the largest of 4 / 2 / 1 that divides env_num and leaves >= 512 envs per group."""
+    B = int(config['env_num'])
+    g = config.get('actor_groups') or os.environ.get('PARL_B200_ACTOR_GROUPS')
+    if g:
+        g = int(g)
+        assert g >= 1 and B % g == 0, 'actor_groups must divide env_num'
+        return g
+    for g in (4, 2):
+        if B % g == 0 and B // g >= 512:
+            return g
+    return 1
+
+
 class DeviceImpalaActor(object):
-    """Actor(config) with sample() / set_weights(weights) / get_metrics() (examples/IMPALA/actor.py:54-105)."""
+    """Actor(config) with sample() / set_weights(weights) / get_metrics() (examples/IMPALA/actor.py:54-105).
+
+    The pool is split into G groups of env columns (G engines with env_offset = first column: the Philox streams are
+    keyed by the global env index, so the env side is the same as one pool's).  sample() rolls the groups out one
+    after the other on the actor stream while a copy stream gathers and downloads the group before: rows
+    [g*B/G*T, (g+1)*B/G*T) of the env-major sample dict are one contiguous block per group.  Only the first group's
+    rollout is exposed in front of the PCIe copy (4 ms instead of 12 + 3 ms at 4096 envs)."""
 
     def __init__(self, config=None, device=None):
         if device is None:
@@ -48,41 +72,76 @@ class DeviceImpalaActor(object):
         self.config = dict(default_config)
         self.config.update(config or {})
         self.stream = torch.cuda.Stream(device=self.device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        G = self.groups = _actor_groups(self.config)
+        B, T = int(self.config['env_num']), int(self.config['sample_batch_steps'])
+        Bg = B // G
         with torch.cuda.stream(self.stream):
-            self.pool = _engine(self.config, 'actor', self.device)
-            self.hosts = [self.pool.make_host_sample_buffers() for _ in range(2)]
+            self.pools = []
+            for g in range(G):
+                c = dict(self.config)
+                c['env_num'], c['env_offset'] = Bg, int(self.config['env_offset']) + g * Bg
+                self.pools.append(_engine(c, 'actor', self.device))
+            for q in self.pools[1:]:                    # one set of weights for all groups until set_weights arrives
+                q.set_weights(self.pools[0].get_weights())
+            self.hosts = [self._make_host_buffers(B * T) for _ in range(2)]
+        self.pool = self.pools[0]
+        n = Bg * T
+        self._views = [[{k: v[g * n:(g + 1) * n] for k, v in h.items()} for g in range(G)] for h in self.hosts]
+        self._ev = [torch.cuda.Event() for _ in range(G)]
         self.stream.synchronize()
         self._n = 0
-        self._metrics_read = 0
+        self._metrics_read = [0] * G
+
+    def _make_host_buffers(self, N):
+        """Pinned host arrays with the keys / dtypes / env-major order of Actor.sample() (actor.py:54-91)."""
+        p0 = self.pools[0]
+        pin = dict(pin_memory=True)
+        return dict(obs=torch.empty((N, 4, p0.h, p0.w), dtype=torch.uint8, **pin),
+                    actions=torch.empty(N, dtype=torch.int64, **pin),
+                    behaviour_logits=torch.empty((N, p0.A), dtype=torch.float32, **pin),
+                    rewards=torch.empty(N, dtype=torch.float32, **pin),
+                    dones=torch.empty(N, dtype=torch.bool, **pin))
 
     def sample(self):
-        host = self.hosts[self._n % 2]
+        t_begin = time.time()
+        which = self._n % 2
+        host = self.hosts[which]
         self._n += 1
         torch.cuda.set_device(self.device)
         with torch.cuda.stream(self.stream):
-            self.pool.rollout()
-            self.pool._sample_dict_to_host(host)
-        self.stream.synchronize()
+            for g, pool in enumerate(self.pools):
+                pool.rollout()
+                self._ev[g].record(self.stream)
+                with torch.cuda.stream(self.copy_stream):
+                    self.copy_stream.wait_event(self._ev[g])
+                    pool._sample_dict_to_host(self._views[which][g])
+        self.copy_stream.synchronize()                  # every group is on the host; the pools are free again
+        self.last_sample_s = time.time() - t_begin      # host wall clock of this call (rollouts + download)
         return {k: v.numpy() for k, v in host.items()}
 
     def set_weights(self, weights):
         torch.cuda.set_device(self.device)
         with torch.cuda.stream(self.stream):
-            self.pool.set_weights(weights)
+            for pool in self.pools:
+                pool.set_weights(weights)
         self.stream.synchronize()
 
     def get_metrics(self):
         """{'episode_rewards': [...], 'episode_steps': [...]} of the episodes finished since the last call
         (actor.py:93-102: MonitorEnv.next_episode_results of every env)."""
-        st = self.pool.stats
-        head = int(st.ring_head.item())
-        cap = st.ring_cap
-        lo = max(self._metrics_read, head - cap)
-        idx = [i % cap for i in range(lo, head)]
-        self._metrics_read = head
-        if not idx:
-            return {'episode_rewards': [], 'episode_steps': []}
-        return {'episode_rewards': st.ring_ret.cpu()[idx].tolist(), 'episode_steps': st.ring_len.cpu()[idx].tolist()}
+        rets, lens = [], []
+        for g, pool in enumerate(self.pools):
+            st = pool.stats
+            head = int(st.ring_head.item())
+            cap = st.ring_cap
+            lo = max(self._metrics_read[g], head - cap)
+            idx = [i % cap for i in range(lo, head)]
+            self._metrics_read[g] = head
+            if idx:
+                rets += st.ring_ret.cpu()[idx].tolist()
+                lens += st.ring_len.cpu()[idx].tolist()
+        return {'episode_rewards': rets, 'episode_steps': lens}
 
 
 class AtariAgent(Agent):

@@ -398,6 +398,34 @@ def td_loss_fwd_bwd(q, q_target_next, action, reward, terminal, gamma, q_online_
     return dict(losses=losses, d_q=d_q, td_abs=td)
 
 
+def twin_q_td_loss_fwd_bwd(q1, q1_target_next, reward, terminal, gamma, q2=None, q2_target_next=None,
+                           next_log_prob=None, alpha=0.0, want_target=False):
+    """Continuous-control critic TD (ddpg.py:63-73 / td3.py:78-94 / sac.py:90-99) ->
+    dict(losses[3] = total, mse1, mse2; d_q1; d_q2 or None; target or None).  All inputs are [N] (or [N,1]) float32."""
+    require_cuda(q1, q1_target_next, reward, terminal, q2, q2_target_next, next_log_prob)
+    N = q1.numel()
+    dev = q1.device
+    _chk('q1', q1, torch.float32)
+    _chk('q2', q2, torch.float32, N, optional=True)
+    _chk('q1_target_next', q1_target_next, torch.float32, N)
+    _chk('q2_target_next', q2_target_next, torch.float32, N, optional=True)
+    _chk('next_log_prob', next_log_prob, torch.float32, N, optional=True)
+    _chk('reward', reward, torch.float32, N)
+    _chk('terminal', terminal, torch.float32, N)
+    for t in (q1, q2, q1_target_next, q2_target_next, next_log_prob, reward, terminal):
+        assert t is None or t.is_contiguous(), 'twin_q_td_loss: tensors must be contiguous'
+    losses = torch.zeros(3, dtype=torch.float32, device=dev)
+    d_q1 = torch.empty_like(q1)
+    d_q2 = torch.empty_like(q2) if q2 is not None else None
+    target = torch.empty(N, dtype=torch.float32, device=dev) if want_target else None
+    ws = _flat_ws(dev, N)
+    check(_lib.load().rl_twin_q_td_loss_fwd_bwd(ptr(q1), ptr(q2), ptr(q1_target_next), ptr(q2_target_next),
+                                                ptr(next_log_prob), ptr(reward), ptr(terminal), N, float(gamma),
+                                                float(alpha), ptr(losses), ptr(d_q1), ptr(d_q2), ptr(target), ptr(ws),
+                                                ws.numel(), stream()), 'twin_q_td_loss_fwd_bwd')
+    return dict(losses=losses, d_q1=d_q1, d_q2=d_q2, target=target)
+
+
 def pg_loss_fwd_bwd(prob, action, reward):
     """policy_gradient.py:54-75 -> dict(losses[1], d_prob)."""
     require_cuda(prob, action, reward)

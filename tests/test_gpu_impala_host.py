@@ -9,13 +9,16 @@ pytestmark = pytest.mark.gpu
 DEV = torch.device('cuda:0')
 
 
-def test_remote_actor_and_agent_learn_through_numpy_contract():
+@pytest.mark.parametrize('groups', [1, 2])
+def test_remote_actor_and_agent_learn_through_numpy_contract(groups):
+    """groups = 2: the pool is split into two column groups whose rollouts overlap the download of the group before;
+    the env-major sample dict (and the env side, keyed by the global env index) is the same."""
     import parl_b200 as parl
     from parl_b200.engine.impala_host import DeviceImpalaActor, AtariAgent
     from oracle import envs as oenv
     torch.manual_seed(0)
     B, T, A, seed = 64, 8, 18, 77
-    cfg = dict(env_num=B, sample_batch_steps=T, act_dim=A, seed=seed)
+    cfg = dict(env_num=B, sample_batch_steps=T, act_dim=A, seed=seed, actor_groups=groups)
     parl.connect('localhost:8010')
     agent = AtariAgent(cfg, device=DEV)
     Actor = parl.remote_class(wait=False)(DeviceImpalaActor)
