@@ -115,3 +115,28 @@ def pg_loss(prob, action, reward):
     loss = torch.mean(-1 * logp * _t(reward))
     loss.backward()
     return dict(loss=loss.item(), d_prob=p.grad.numpy())
+
+
+def twin_q_td(q1, q1_target_next, reward, terminal, gamma, q2=None, q2_target_next=None, next_log_prob=None, alpha=0.0):
+    """Continuous-control critic TD in float32 numpy, operation order of the reference:
+    DDPG ddpg.py:63-73 (single critic), TD3 td3.py:86-94 (min of the twin target critics), SAC sac.py:92-99
+    (min - alpha * log pi, then reward + gamma * (1 - terminal) * target).  Gradients of the mean-squared errors
+    are written out by hand: d mse / d q = 2 (q - target) / N."""
+    f = np.float32
+    q1 = np.asarray(q1, f).reshape(-1)
+    tq = np.asarray(q1_target_next, f).reshape(-1)
+    if q2_target_next is not None:
+        tq = np.minimum(tq, np.asarray(q2_target_next, f).reshape(-1))
+    if next_log_prob is not None:
+        tq = (tq - f(alpha) * np.asarray(next_log_prob, f).reshape(-1)).astype(f)
+    r, term = np.asarray(reward, f).reshape(-1), np.asarray(terminal, f).reshape(-1)
+    target = (r + ((f(1.0) - term) * f(gamma)).astype(f) * tq).astype(f)
+    n = q1.size
+    d1 = q1 - target
+    out = dict(target=target, mse1=float(np.mean(d1.astype(np.float64) ** 2)), d_q1=(d1 * f(2.0 / n)).astype(f))
+    out['loss'] = out['mse1']
+    if q2 is not None:
+        d2 = np.asarray(q2, f).reshape(-1) - target
+        out.update(mse2=float(np.mean(d2.astype(np.float64) ** 2)), d_q2=(d2 * f(2.0 / n)).astype(f))
+        out['loss'] = out['mse1'] + out['mse2']
+    return out

@@ -1,4 +1,5 @@
-"""``parl.algorithms`` for the hot path: IMPALA, A2C, PPO, DQN, DDQN, PolicyGradient.
+"""``parl.algorithms`` for the hot path: IMPALA, A2C, PPO, DQN, DDQN, PolicyGradient, and the continuous-control
+family DDPG / TD3 / SAC.
 
 Signatures follow the reference; the network forward/backward goes through the
 user's ``parl.Model`` (torch autograd), everything after the network outputs — returns scan,
@@ -9,5 +10,8 @@ from .ppo import PPO
 from .dqn import DQN
 from .ddqn import DDQN
 from .policy_gradient import PolicyGradient
+from .ddpg import DDPG
+from .td3 import TD3
+from .sac import SAC
 
-__all__ = ['IMPALA', 'A2C', 'PPO', 'DQN', 'DDQN', 'PolicyGradient']
+__all__ = ['IMPALA', 'A2C', 'PPO', 'DQN', 'DDQN', 'PolicyGradient', 'DDPG', 'TD3', 'SAC']

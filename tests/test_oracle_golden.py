@@ -173,3 +173,21 @@ def test_atari_replay_golden(golden):
     np.testing.assert_array_equal(act, g['action'])
     np.testing.assert_array_equal(rew, g['reward'])
     np.testing.assert_array_equal(over, g['isOver'])
+
+
+def test_twin_q_td_golden(golden):
+    """oracle.losses.twin_q_td against the critic TD arithmetic recorded from the reference's DDPG / TD3 / SAC
+    expressions (tests/golden/make_golden_cc.py)."""
+    g = golden('cc')
+    for name in ('ddpg', 'td3', 'sac'):
+        kw = {}
+        if name != 'ddpg':
+            kw.update(q2=g['tab_q2'], q2_target_next=g['tab_tq2'])
+        if name == 'sac':
+            kw.update(next_log_prob=g['tab_logp'], alpha=float(g['tab_sac_alpha']))
+        o = olo.twin_q_td(g['tab_q1'], g['tab_tq1'], g['tab_reward'], g['tab_terminal'], float(g['tab_%s_gamma' % name]), **kw)
+        np.testing.assert_allclose(o['target'], g['tab_%s_target' % name].reshape(-1), rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(o['loss'], g['tab_%s_loss' % name], rtol=1e-5)
+        np.testing.assert_allclose(o['d_q1'], g['tab_%s_d_q1' % name].reshape(-1), rtol=1e-5, atol=1e-8)
+        if name != 'ddpg':
+            np.testing.assert_allclose(o['d_q2'], g['tab_%s_d_q2' % name].reshape(-1), rtol=1e-5, atol=1e-8)
