@@ -27,7 +27,7 @@ UNIT = 'env-steps/s'
 TOTAL_ENVS = 4096
 T_STEPS = 50
 ACT_DIM = 18
-K1_NCU_TRAFFIC_BYTES = 32.24e6        # dram read + write of one K1 launch at B=4096 (ncu --set full, profiles/)
+K1_NCU_TRAFFIC_BYTES = 32.19e6        # dram read + write of one K1 (v8) launch at B=4096 (ncu --set full, profiles/r02_k1_v8_ncu.txt)
 
 
 def parse():
@@ -318,10 +318,10 @@ def main():
     if k1_s:
         ach = alg_bytes / k1_s / 1e9
         # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch at B=4096 from the committed
-        # `ncu --set full` capture of this kernel version (profiles/r02_k1_*.txt); the gradient tile (15.3 MB) is
+        # `ncu --set full` capture of this kernel version (profiles/r02_k1_v8_ncu.txt); the gradient tile (15.3 MB) is
         # mostly still in the 126 MB L2 when the launch ends, so the write half shows up only partly
         traffic = K1_NCU_TRAFFIC_BYTES if B == 4096 else None
-        roof = dict(bound='hbm', kernel='vtrace_loss_kernel (rl_vtrace_loss_fwd_bwd)', achieved=ach, peak=peak,
+        roof = dict(bound='hbm', kernel='vtrace_loss_v8_kernel (rl_vtrace_loss_fwd_bwd)', achieved=ach, peak=peak,
                     unit='GB/s', frac=ach / peak, traffic=traffic, peak_source=peak_src,
                     algorithmic_bytes_per_launch=alg_bytes, us_per_launch=k1_s * 1e6,
                     us_per_launch_l2_flushed_single_event_pair=k1_flushed_s * 1e6,
