@@ -82,8 +82,10 @@ class DeviceImpalaActor(object):
                 c = dict(self.config)
                 c['env_num'], c['env_offset'] = Bg, int(self.config['env_offset']) + g * Bg
                 self.pools.append(_engine(c, 'actor', self.device))
-            for q in self.pools[1:]:                    # one set of weights for all groups until set_weights arrives
-                q.set_weights(self.pools[0].get_weights())
+            if G > 1:                                   # one set of weights for all groups until set_weights arrives
+                w0 = self.pools[0].get_weights()
+                for q in self.pools[1:]:
+                    q.set_weights(w0)
             self.hosts = [self._make_host_buffers(B * T) for _ in range(2)]
         self.pool = self.pools[0]
         n = Bg * T
@@ -123,8 +125,19 @@ class DeviceImpalaActor(object):
     def set_weights(self, weights):
         torch.cuda.set_device(self.device)
         with torch.cuda.stream(self.stream):
-            for pool in self.pools:
-                pool.set_weights(weights)
+            p0 = self.pools[0]
+            p0.set_weights(weights)                     # numpy dict -> device (the only host->device copy)
+            for q in self.pools[1:]:                    # the other groups take theirs device-to-device
+                f0, fq = p0._flat_master(), q._flat_master()
+                with torch.no_grad():
+                    if f0 is not None and fq is not None and f0.numel() == fq.numel():
+                        fq.copy_(f0)
+                    else:
+                        for a, b in zip(q.model.parameters(), p0.model.parameters()):
+                            a.copy_(b)
+                    for a, b in zip(q.model.buffers(), p0.model.buffers()):
+                        a.copy_(b)
+                q.repack()
         self.stream.synchronize()
 
     def get_metrics(self):
