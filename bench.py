@@ -475,6 +475,35 @@ def copy_bandwidth(torch, dev, nbytes=1 << 30):
     return out
 
 
+def copy_bandwidth_bidir(torch, dev, nbytes=1 << 30):
+    """Pinned H2D and D2H copies running AT THE SAME TIME on two streams (what the host-contract path does: the actor
+    downloads sample k+1 while the learner uploads sample k), GB/s per direction.  Called by every rank at once, so
+    that GPUs behind a shared PCIe switch / one host memory system see each other's traffic."""
+    h_up = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h_dn = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d_up = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_dn = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    d_up.copy_(h_up, non_blocking=True)
+    h_dn.copy_(d_dn, non_blocking=True)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    reps = 3
+    with torch.cuda.stream(s_up):
+        ev[0].record()
+        for _ in range(reps):
+            d_up.copy_(h_up, non_blocking=True)
+        ev[1].record()
+    with torch.cuda.stream(s_dn):
+        ev[2].record()
+        for _ in range(reps):
+            h_dn.copy_(d_dn, non_blocking=True)
+        ev[3].record()
+    torch.cuda.synchronize()
+    return dict(h2d=reps * nbytes / (ev[0].elapsed_time(ev[1]) * 1e-3) / 1e9,
+                d2h=reps * nbytes / (ev[2].elapsed_time(ev[3]) * 1e-3) / 1e9)
+
+
 def run_e2e(eng, args, world, dev):
     """The same metric END TO END through the reference-facing surface with HOST buffers, exactly the Learner loop of
     examples/IMPALA/train.py:165-194: a ``@parl.remote_class(wait=False)`` Actor (the device actor pool) whose
@@ -540,16 +569,33 @@ def run_e2e(eng, args, world, dev):
     bw = copy_bandwidth(torch, dev) if rank == 0 else None
     actor.destroy()
     value = steps * T_STEPS * args.envs / el.item()
-    ceiling = None
+    ceiling = ceiling_bidir = bidir = None
     if bw:
-        # both directions run concurrently (full-duplex PCIe): the slower one bounds a step
+        # one direction at a time, this GPU alone: the slower one bounds a step if the link were full duplex at that rate
         ceiling = T_STEPS * B * world / (nbytes / (min(bw['h2d'], bw['d2h']) * 1e9))
+    # what the path actually sees: both directions at once, on every rank at the same time.  Every rank takes part in
+    # the collectives whatever happens to its own measurement (zeros mark a failed one).
+    if world > 1:
+        dist.barrier()
+    try:
+        b2 = copy_bandwidth_bidir(torch, dev)
+    except Exception as exc:                              # noqa: BLE001 - the ceiling is a report, not the metric
+        sys.stderr.write('bench: bidirectional copy bandwidth not measured (%r)\n' % (exc, ))
+        b2 = dict(h2d=0.0, d2h=0.0)
+    t = torch.tensor([b2['h2d'], b2['d2h'], 1.0 if b2['h2d'] > 0 else 0.0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    agg = t.tolist()
+    if agg[2] == world:
+        bidir = dict(h2d_per_gpu=agg[0] / world, d2h_per_gpu=agg[1] / world, h2d_all_gpus=agg[0], d2h_all_gpus=agg[1])
+        ceiling_bidir = T_STEPS * B * world / (nbytes / (min(agg[:2]) / world * 1e9))
     return dict(value=value, unit=UNIT, h2d_bytes_per_step=nbytes + wbytes, d2h_bytes_per_step=nbytes + wbytes + 40,
                 steps=steps, ms_per_step=el.item() * 1e3 / steps,
                 path='@parl.remote_class(wait=False) Actor.sample() -> numpy dict (uint8 stacked obs, env-major, pinned) '
                      '-> AtariAgent.learn(numpy) ; actor.set_weights(agent.get_weights()) numpy weight dicts '
                      '(examples/IMPALA/train.py:165-194)',
                 host_buffers=pin, copy_bandwidth_gbs=bw, pcie_ceiling_env_steps_per_s=ceiling,
+                copy_bandwidth_bidirectional_all_ranks_gbs=bidir, pcie_ceiling_bidirectional_env_steps_per_s=ceiling_bidir,
                 learner_thread_ms_per_step={k: v * 1e3 / steps for k, v in phase.items()},
                 actor_groups=int(os.environ.get('PARL_B200_ACTOR_GROUPS', 0)) or 'auto', actor_last_sample_ms=last_sample_ms,
                 sample_dict_bytes=nbytes, last_losses=[float(x) for x in losses])
