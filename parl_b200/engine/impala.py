@@ -25,6 +25,22 @@ from .actor_net import AtariActorNet
 from .train_net import AtariTrainNet
 
 
+def host_slab_plan(B, T, samples=16384):
+    """(number of slabs, env columns per slab) for uploading a [B*T] env-major batch slab by slab, or None when the
+    batch is too small to be worth it (or samples <= 0: the one-shot path).  A slab is a whole number of env columns
+    (V-trace scans a column over all T rows), all slabs are equal, about ``samples`` samples each (16 384 = 327 columns
+    at T = 50: ~7 ms of H2D, ~2 ms of compute)."""
+    if samples <= 0:
+        return None
+    target = max(1, samples // T)
+    if B < 2 * target:
+        return None
+    n = -(-B // target)
+    while B % n:
+        n += 1
+    return n, B // n
+
+
 class ImpalaEngine(object):
     def __init__(self, num_envs=4096, sample_batch_steps=50, act_dim=18, frame_hw=(84, 84), seed=0, device=None,
                  env_offset=0, gamma=0.99, vf_loss_coeff=0.5, clip_rho_threshold=1.0, clip_pg_rho_threshold=1.0,
@@ -501,22 +517,11 @@ class ImpalaEngine(object):
         return res['losses'].clone()
 
     def _host_slab_plan(self):
-        """(number of slabs, env columns per slab) of the slab-pipelined host learner, or None when the batch is too
-        small to be worth it.  A slab is a whole number of env columns (V-trace scans a column over all T rows), all
-        slabs are equal, about 320 columns (16 000 samples at T = 50: ~8 ms of H2D, ~2 ms of compute)."""
+        """(number of slabs, env columns per slab) of the slab-pipelined host learner, or None: see host_slab_plan."""
         samples = getattr(self, 'host_slab_samples', None)
         if samples is None:
             samples = int(os.environ.get('PARL_B200_HOST_SLAB_SAMPLES', '16384'))
-        if samples <= 0:
-            return None                           # 0: the one-shot path (whole batch uploaded, then one forward/backward)
-        T, B = self.T, self.B
-        target = max(1, samples // T)
-        if B < 2 * target:
-            return None
-        n = -(-B // target)
-        while B % n:
-            n += 1
-        return n, B // n
+        return host_slab_plan(self.B, self.T, samples)
 
     def _learn_from_host_slabs(self, host, acts, bl, rew, dones, learning_rate, entropy_coeff):
         """learn_from_host with the H2D copy of the observations PIPELINED against the learner's compute: the batch
