@@ -221,8 +221,6 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k1_events = []
-    eng.k1_events = k1_events
     ev0.record()
     for _ in range(args.steps):
         losses = step()
@@ -233,10 +231,17 @@ def main():
     elapsed_ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
-    eng.k1_events = None
     clocks = sampler.stop() if rank == 0 else None
     elapsed = elapsed_ms.item() * 1e-3
     launches = kernels.launch_count()
+    # K1 bracketed by events INSIDE a step: three extra, untimed steps (an event pair inside the update forces the
+    # eager launch path, so the timed region above runs without it)
+    k1_events = []
+    eng.k1_events = k1_events
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    eng.k1_events = None
     total_steps = args.steps * T_STEPS * args.envs
     value = total_steps / elapsed
 
@@ -385,6 +390,8 @@ def main():
                                 else 'sequential',
                                 network='hand-written tcgen05 kernels (actor fwd; learner fwd+dgrad+wgrad)' if
                                 eng.train_net is not None else 'torch',
+                                learner_update='2 CUDA graphs (fwd+loss+bwd | clip+Adam+refresh)' if
+                                eng._learn_graph_enabled() else 'eager launches',
                                 l2_policy='per-step working set (frame ring %.1f GB + observation plane %.1f GB + '
                                           'activations %.1f GB per GPU) >> 126 MB L2; K1 timed alone with L2 flushed' %
                                           ((T_STEPS + 4) * B * 7056 / 1e9, T_STEPS * B * 28224 * eng.obs_step.element_size() / 1e9,
