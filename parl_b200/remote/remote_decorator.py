@@ -62,7 +62,6 @@ class _NoWaitProxy(object):
         object.__setattr__(self, '_xparl_obj', None)
         object.__setattr__(self, '_xparl_init_error', None)
         object.__setattr__(self, '_xparl_closed', False)
-        object.__setattr__(self, '_xparl_methods', set())
         t = threading.Thread(target=self._xparl_loop, args=(cls, args, kwargs), daemon=True)
         object.__setattr__(self, '_xparl_thread', t)
         t.start()
@@ -106,22 +105,15 @@ class _NoWaitProxy(object):
     def __getattr__(self, name):
         # like the reference (proxy_wrapper_nowait.py:150-202): wait for the calls queued so far, then
         # an attribute read returns the VALUE, a method returns a wrapper producing FutureObjects.
-        # A name once seen to be a method stays a method (class attributes do not turn into data), so only the first
-        # access pays the round trip: `actor.set_weights(w); actor.sample()` then queues both calls without waiting
-        # for the first to finish.
-        methods = object.__getattribute__(self, '_xparl_methods')
-        if name not in methods:
-            is_attr, value = self._xparl_submit('probe', name).get()
-            if is_attr:
-                return value
-            methods.add(name)
+        is_attr, value = self._xparl_submit('probe', name).get()
+        if is_attr:
+            return value
 
         def _call(*a, **k):
             return self._xparl_submit('call', name, a, k)
         return _call
 
     def __setattr__(self, name, value):
-        object.__getattribute__(self, '_xparl_methods').discard(name)     # an instance attribute may now shadow a method
         self._xparl_submit('set', name, (value, )).get()
 
     def destroy(self):

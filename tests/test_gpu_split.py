@@ -58,9 +58,14 @@ def test_conv_wgrad_split_operands_reach_fp32(N, H, Cin, Cout, k):
     Ho = H - k + 1
     x = torch.randn(N, H, H, Cin, device=DEV, generator=g)
     dout = torch.randn(N, Ho, Ho, Cout, device=DEV, generator=g)
-    w = torch.zeros(Cout, Cin, k, k, device=DEV, dtype=torch.float64, requires_grad=True)
-    torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w).backward(dout.double().permute(0, 3, 1, 2))
-    ref = w.grad.permute(0, 2, 3, 1).reshape(Cout, -1).float()
+    # reference: dW[co, (r, s, ci)] = sum over samples and positions of dout[n, y, x, co] * x[n, y + r, x + s, ci], as k*k
+    # float64 matrix products (cuDNN's float64 convolution backward takes a minute at these shapes)
+    ref = torch.empty(Cout, k, k, Cin, device=DEV, dtype=torch.float64)
+    dflat = dout.double().reshape(-1, Cout)
+    for r in range(k):
+        for c in range(k):
+            ref[:, r, c, :] = dflat.t() @ x[:, r:r + Ho, c:c + Ho, :].double().reshape(-1, Cin)
+    ref = ref.reshape(Cout, -1).float()
     dw = torch.zeros(Cout, k * k * Cin, device=DEV)
     for px in split(x):
         for pd in split(dout):

@@ -240,31 +240,6 @@ def test_install_as_parl():
     assert p2 is parl
 
 
-def test_no_wait_proxy_queues_method_calls_without_a_round_trip():
-    """Once a name is known to be a method, `a.slow(); a.fast()` queues both calls at once (the IMPALA Learner's
-    `actor.set_weights(w); actor.sample()`); an instance attribute assigned through the proxy shadows the method again."""
-    parl.connect('localhost:8010')
-
-    @parl.remote_class(wait=False)
-    class Actor(object):
-        def slow(self):
-            time.sleep(0.3)
-            return 's'
-
-        def fast(self):
-            return 'f'
-    a = Actor()
-    assert a.fast().get() == 'f' and a.slow().get() == 's'      # first access of each name probes the hosted object
-    t0 = time.time()
-    f1 = a.slow()
-    f2 = a.fast()                                                # must not wait for slow() to finish
-    assert time.time() - t0 < 0.15
-    assert f1.get() == 's' and f2.get() == 'f'                   # FIFO on the hosted object's worker
-    a.fast = 7                                                   # instance attribute shadows the method (reference behaviour)
-    assert a.fast == 7
-    a.destroy()
-
-
 def test_host_slab_plan_and_actor_groups():
     from parl_b200.engine.impala import host_slab_plan
     from parl_b200.engine.impala_host import _actor_groups
