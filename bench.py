@@ -234,8 +234,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     elapsed = elapsed_ms.item() * 1e-3
     launches = kernels.launch_count()
-    # K1 bracketed by events INSIDE a step: three extra, untimed steps (an event pair inside the update forces the
-    # eager launch path, so the timed region above runs without it)
+    # K1 bracketed by events INSIDE a step: three extra, untimed steps (no event records inside the timed region)
     k1_events = []
     eng.k1_events = k1_events
     for _ in range(3):
@@ -390,8 +389,6 @@ def main():
                                 else 'sequential',
                                 network='hand-written tcgen05 kernels (actor fwd; learner fwd+dgrad+wgrad)' if
                                 eng.train_net is not None else 'torch',
-                                learner_update='2 CUDA graphs (fwd+loss+bwd | clip+Adam+refresh)' if
-                                eng._learn_graph_enabled() else 'eager launches',
                                 l2_policy='per-step working set (frame ring %.1f GB + observation plane %.1f GB + '
                                           'activations %.1f GB per GPU) >> 126 MB L2; K1 timed alone with L2 flushed' %
                                           ((T_STEPS + 4) * B * 7056 / 1e9, T_STEPS * B * 28224 * eng.obs_step.element_size() / 1e9,

@@ -367,12 +367,9 @@ class ImpalaEngine(object):
         return res['losses'].clone()
 
     def _learn_native(self, learning_rate, entropy_coeff):
-        """learn() with the network forward/backward on the hand-written kernels (AtariTrainNet).  At small per-GPU
-        batches (the 4- and 8-GPU shares of the 4096-actor workload) the ~60 kernels of an update are 5-70 us each and an
-        eager Python launch costs 10-15 us, so the update is captured once and replayed as CUDA graphs (see
-        _learn_native_graphed); larger batches and timed-K1 runs take the eager path."""
-        if self._learn_graph_enabled():
-            return self._learn_native_graphed(learning_rate, entropy_coeff)
+        """learn() with the network forward/backward on the hand-written kernels (AtariTrainNet).  (Replaying the
+        update as CUDA graphs was measured at the 4- and 8-GPU shares of the workload — 5.23 vs 5.20 ms per step at 512
+        envs, 9.93 vs 9.86 at 1024, profiles/r02_learn_graph_ab.txt: the learner is not launch-bound — and removed.)"""
         res = self._learn_fwd_bwd(entropy_coeff)
         if self.alg.grad_sync is not None:
             self.alg.grad_sync(self.alg.optimizer.grad)
@@ -380,7 +377,7 @@ class ImpalaEngine(object):
         return res['losses'].clone()
 
     def _learn_fwd_bwd(self, entropy_coeff):
-        """Forward, fused V-trace loss, backward: fills the flat gradient buffer (graph-safe: no host sync)."""
+        """Forward, fused V-trace loss, backward: fills the flat gradient buffer."""
         T, B, A = self.T, self.B, self.A
         net = self.train_net
         if self.share_obs:
@@ -408,75 +405,13 @@ class ImpalaEngine(object):
         opt = self.alg.optimizer
         if opt.lr_dev is not None:
             if learning_rate is not None and float(learning_rate) != opt.lr:
-                opt.set_lr(learning_rate)                 # device-resident rate (graph replay reads it from memory)
+                opt.set_lr(learning_rate)                 # device-resident rate
             opt.step()
         else:
             opt.step(lr=learning_rate)
         self.train_net.pack()
         if self.actor_net is not None and not self.pipeline:
             self.actor_net.pack()
-
-    def _learn_graph_enabled(self):
-        if not self.use_graph or self.train_net is None or getattr(self, 'k1_events', None) is not None:
-            return False
-        mode = os.environ.get('PARL_B200_LEARN_GRAPH', 'auto')
-        if mode in ('0', 'off'):
-            return False
-        return mode in ('1', 'on') or self.T * self.B <= 102400
-
-    def _learn_native_graphed(self, learning_rate, entropy_coeff):
-        """The update as two CUDA graphs: [forward, V-trace loss, backward] per (buffer set, entropy coefficient) and
-        [clip, Adam, operand refresh] once, with the gradient all-reduce (NCCL, when attached) launched eagerly in
-        between.  Learning rate and update count live on the device (FlatAdam.enable_device_state).  First call per key
-        runs eagerly (allocator / workspace warm-up), the second captures, later calls replay."""
-        opt = self.alg.optimizer
-        if opt.lr_dev is None:
-            opt.enable_device_state()
-        st = self.__dict__.setdefault('_learn_graphs', dict(fb={}, apply=None, warm=set(), launches={}))
-        key = (self._cur_set, float(entropy_coeff))
-        if key not in st['fb'] and len(st['fb']) >= 16:   # a schedule with many distinct coefficients: stay eager
-            res = self._learn_fwd_bwd(entropy_coeff)
-        elif key not in st['warm']:
-            st['warm'].add(key)
-            res = self._learn_fwd_bwd(entropy_coeff)
-        else:
-            if key not in st['fb']:
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                before = kernels.launch_count()
-                with torch.cuda.graph(g):
-                    self._learn_fwd_bwd(entropy_coeff)
-                st['launches'][key] = kernels.launch_count() - before
-                kernels.add_graph_launches(-st['launches'][key])          # capture is not execution
-                st['fb'][key] = g
-            st['fb'][key].replay()
-            kernels.add_graph_launches(st['launches'][key])
-            T, B, A = self.T, self.B, self.A
-            self.tgt_logits, self.values = self.train_net.logits.view(T, B, A), self.train_net.values.view(T, B)
-            res = dict(losses=self.loss_out['losses'])
-        if self.alg.grad_sync is not None:
-            self.alg.grad_sync(opt.grad)
-        if learning_rate is not None and float(learning_rate) != opt.lr:
-            opt.set_lr(learning_rate)
-        if 'apply' not in st['warm']:
-            st['warm'].add('apply')
-            self._learn_apply(None)
-        else:
-            if st['apply'] is None:
-                count = opt.step_count
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                before = kernels.launch_count()
-                with torch.cuda.graph(g):
-                    self._learn_apply(None)
-                st['launches']['apply'] = kernels.launch_count() - before
-                kernels.add_graph_launches(-st['launches']['apply'])
-                opt.step_count = count                    # capture is not execution (the device counter did not move)
-                st['apply'] = g
-            st['apply'].replay()
-            opt.step_count += 1
-            kernels.add_graph_launches(st['launches']['apply'])
-        return res['losses'].clone()
 
     # ------------------------------------------------------------------ reference-facing host contract
     def make_host_sample_buffers(self):
