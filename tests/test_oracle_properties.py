@@ -120,3 +120,34 @@ def test_sample_categorical_exact_edge_cases():
     assert lo[0] == 0 and hi[0] == 3
     assert lo[1] == 1 and hi[1] == 1
     assert 0 <= lo[2] <= hi[2] <= 3
+
+
+def test_twin_q_td_properties():
+    """Continuous-control critic TD oracle: the hand-written gradients are the derivative of the loss; terminal
+    transitions bootstrap nothing; the twin target is the smaller of the two; the entropy term shifts the target by
+    -gamma (1 - terminal) alpha log pi."""
+    from oracle import losses as olo
+    rng = np.random.RandomState(5)
+    N = 64
+    q1, q2, tq1, tq2, lp, rew = [rng.randn(N).astype(np.float32) for _ in range(6)]
+    term = (rng.rand(N) < 0.3).astype(np.float32)
+    o = olo.twin_q_td(q1, tq1, rew, term, 0.9, q2=q2, q2_target_next=tq2, next_log_prob=lp, alpha=0.25)
+    # finite differences of loss = mse1 + mse2 in float64
+    def loss(a, b):
+        t = o['target'].astype(np.float64)
+        return np.mean((a - t) ** 2) + np.mean((b - t) ** 2)
+    eps = 1e-3
+    for i in (0, 7, 63):
+        d = np.zeros(N)
+        d[i] = eps
+        g1 = (loss(q1 + d, q2) - loss(q1 - d, q2)) / (2 * eps)
+        g2 = (loss(q1, q2 + d) - loss(q1, q2 - d)) / (2 * eps)
+        np.testing.assert_allclose(o['d_q1'][i], g1, rtol=1e-4, atol=1e-7)
+        np.testing.assert_allclose(o['d_q2'][i], g2, rtol=1e-4, atol=1e-7)
+    np.testing.assert_array_equal(o['target'][term == 1], rew[term == 1])
+    plain = olo.twin_q_td(q1, tq1, rew, term, 0.9, q2=q2, q2_target_next=tq2)
+    live = term == 0
+    np.testing.assert_allclose(plain['target'][live], rew[live] + 0.9 * np.minimum(tq1, tq2)[live], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose((plain['target'] - o['target'])[live], 0.9 * 0.25 * lp[live], rtol=1e-4, atol=1e-6)
+    single = olo.twin_q_td(q1, tq1, rew, term, 0.9)
+    assert 'd_q2' not in single and abs(single['loss'] - single['mse1']) == 0.0
