@@ -62,8 +62,9 @@ size_t rl_loss_workspace_bytes(int n_cols);
  * for the graph-replayed rollout and slower for the pipelined step (profiles/r02_pdl_ab.txt). */
 int rl_debug_set_pdl(int enable);
 int rl_debug_set_tma(int disable);
-/* Triage hook for rl_vtrace_loss_fwd_bwd: 0 = default kernel (v4), 6 = the v6 kernel (one 8-row TMA chunk per
- * warp, single block sync; time-major, TMA-able shapes with T <= 56; slower than v4 at every measured shape). */
+/* Triage hook for rl_vtrace_loss_fwd_bwd: 0 = default (the v8 kernel for time-major, TMA-able shapes with T <= 64,
+ * B % 4 == 0, even A <= 18 and int32 actions; the general v4 kernel otherwise), 4 = v4 always, 8 / 9 = v8 without /
+ * with programmatic dependent launch (measured equal: profiles/r02_k1_matrix_g.jsonl). */
 int rl_debug_set_vtrace_path(int mode);
 
 /* ------------------------------------------------------------------------
