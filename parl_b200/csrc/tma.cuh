@@ -57,7 +57,7 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 // Host: encode a rank-2 float32 tensor map {dim0 (contiguous), dim1} with row pitch `pitch_bytes` and box {box0, box1}.
 // Returns 0 on success; on failure `err` (if non-NULL) receives a static message.
 inline int make_tensor_map_2d_f32(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t dim1, uint64_t pitch_bytes,
-                                  uint32_t box0, uint32_t box1, const char** err, bool as_int32 = false) {
+                                  uint32_t box0, uint32_t box1, const char** err, bool as_int32 = false, int l2_promo = 1) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -77,7 +77,9 @@ inline int make_tensor_map_2d_f32(CUtensorMap* map, const void* base, uint64_t d
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(map, as_int32 ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                         const_cast<void*>(base), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        l2_promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                      : (l2_promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B),
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (err) *err = "cuTensorMapEncodeTiled failed";
@@ -89,12 +91,13 @@ inline int make_tensor_map_2d_f32(CUtensorMap* map, const void* base, uint64_t d
 // Same, through a small per-thread cache keyed by (base, dims, pitch, box): the loss kernels are launched every
 // learner step on the same buffers, and six driver encodes per launch are several microseconds of host time.
 inline int cached_tensor_map_2d_f32(CUtensorMap* map, const void* base, uint64_t dim0, uint64_t dim1, uint64_t pitch_bytes,
-                                    uint32_t box0, uint32_t box1, const char** err, bool as_int32 = false) {
+                                    uint32_t box0, uint32_t box1, const char** err, bool as_int32 = false, int l2_promo = 1) {
   struct Entry {
     const void* base;
     uint64_t dim0, dim1, pitch;
     uint32_t box0, box1;
     bool as_int32;
+    int l2_promo;
     CUtensorMap map;
   };
   constexpr int kN = 128;
@@ -103,16 +106,16 @@ inline int cached_tensor_map_2d_f32(CUtensorMap* map, const void* base, uint64_t
   for (int i = 0; i < used; ++i) {
     const Entry& e = cache[i];
     if (e.base == base && e.dim0 == dim0 && e.dim1 == dim1 && e.pitch == pitch_bytes && e.box0 == box0 && e.box1 == box1 &&
-        e.as_int32 == as_int32) {
+        e.as_int32 == as_int32 && e.l2_promo == l2_promo) {
       *map = e.map;
       return 0;
     }
   }
-  const int rc = make_tensor_map_2d_f32(map, base, dim0, dim1, pitch_bytes, box0, box1, err, as_int32);
+  const int rc = make_tensor_map_2d_f32(map, base, dim0, dim1, pitch_bytes, box0, box1, err, as_int32, l2_promo);
   if (rc) return rc;
   Entry& e = cache[next];
   e.base = base, e.dim0 = dim0, e.dim1 = dim1, e.pitch = pitch_bytes, e.box0 = box0, e.box1 = box1, e.as_int32 = as_int32,
-  e.map = *map;
+  e.l2_promo = l2_promo, e.map = *map;
   next = (next + 1) % kN;
   if (used < kN) ++used;
   return 0;

@@ -834,6 +834,8 @@ static int g_vtrace_path = 0;    // rl_debug_set_vtrace_path: 0 = default (v8 wh
                                  // 8 = v8 without / 9 = v8 with programmatic dependent launch
 constexpr bool kK1PdlDefault = false;
 static bool k1_pdl() { return g_vtrace_path == 9 || (g_vtrace_path == 0 && kK1PdlDefault); }
+// L2 promotion of the logits tensor maps: 1 = 128 B (default), 2 = 256 B (mode 10), 0 = none (mode 11)
+static int k1_l2_promo() { return g_vtrace_path == 10 ? 2 : (g_vtrace_path == 11 ? 0 : 1); }
 
 template <int A_>
 static bool try_launch_v8(const VtraceLossArgs& a, const float* tl, const float* bl, float* dl, cudaStream_t st) {
@@ -850,8 +852,11 @@ static bool try_launch_v8(const VtraceLossArgs& a, const float* tl, const float*
     CUtensorMap* dst[3] = {maps.tl, maps.bl, maps.dl};
     const float* bases[3] = {tl, bl, dl};
     for (int i = 0; i < 3; ++i) {
-      if (cached_tensor_map_2d_f32(&dst[i][1], bases[i], (uint64_t)B * A_, (uint64_t)T, pitch, CW * A_, R1, &err)) return false;
-      if (cached_tensor_map_2d_f32(&dst[i][0], bases[i], (uint64_t)B * A_, (uint64_t)T, pitch, CW * A_, R0 > 0 ? R0 : R1, &err))
+      if (cached_tensor_map_2d_f32(&dst[i][1], bases[i], (uint64_t)B * A_, (uint64_t)T, pitch, CW * A_, R1, &err, false,
+                                   k1_l2_promo()))
+        return false;
+      if (cached_tensor_map_2d_f32(&dst[i][0], bases[i], (uint64_t)B * A_, (uint64_t)T, pitch, CW * A_, R0 > 0 ? R0 : R1, &err,
+                                   false, k1_l2_promo()))
         return false;
     }
     const uint64_t spitch = (uint64_t)B * 4;
@@ -913,8 +918,8 @@ extern "C" int rl_debug_set_tma(int disable) {
 // Triage hook: 0 = default (v8 where eligible, else v4), 4 = the general v4 kernel always, 8 / 9 = v8 without / with
 // programmatic dependent launch.
 extern "C" int rl_debug_set_vtrace_path(int mode) {
-  if (mode != 0 && mode != 4 && mode != 8 && mode != 9) {
-    rl::set_error("rl_debug_set_vtrace_path: mode %d not in {0, 4, 8, 9}", mode);
+  if (mode != 0 && mode != 4 && (mode < 8 || mode > 11)) {
+    rl::set_error("rl_debug_set_vtrace_path: mode %d not in {0, 4, 8, 9, 10, 11}", mode);
     return RL_ERR_BAD_ARG;
   }
   rl::g_vtrace_path = mode;
