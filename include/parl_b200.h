@@ -64,7 +64,8 @@ int rl_debug_set_pdl(int enable);
 int rl_debug_set_tma(int disable);
 /* Triage hook for rl_vtrace_loss_fwd_bwd: 0 = default (the v8 kernel for time-major, TMA-able shapes with T <= 64,
  * B % 4 == 0, even A <= 18 and int32 actions; the general v4 kernel otherwise), 4 = v4 always, 8 / 9 = v8 without /
- * with programmatic dependent launch (measured equal: profiles/r02_k1_matrix_g.jsonl). */
+ * with programmatic dependent launch (measured equal: profiles/r02_k1_matrix_g.jsonl), 10 / 11 = v8 with 256-byte / no L2
+ * promotion in the logits tensor maps (no effect: profiles/r02_k1_l2_promotion.jsonl). */
 int rl_debug_set_vtrace_path(int mode);
 
 /* ------------------------------------------------------------------------
